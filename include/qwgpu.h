@@ -1,0 +1,178 @@
+/*
+ * qwgpu.h — C ABI of libqwgpu.so: the B200-native drop-in for Quickwit's per-split leaf search.
+ *
+ * What each entry point replaces in the reference (paths relative to
+ * /root/reference/quickwit/):
+ *
+ *   qwgpu_leaf_search          SearchService::leaf_search(LeafSearchRequest) -> LeafSearchResponse
+ *                              quickwit-search/src/service.rs:81,177-203 (seam A)
+ *   qwgpu_invoke_leaf_search   LambdaLeafSearchInvoker::invoke_leaf_search(LeafSearchRequest)
+ *                              -> Vec<LambdaSingleSplitResult>; quickwit-search/src/invoker.rs:27-38
+ *                              (seam B; response = LambdaSearchResponses-shaped bytes)
+ *   qwgpu_split_search         searcher.search(&query, &collector) for ONE split,
+ *                              quickwit-search/src/leaf.rs:637 (seam C; plan in, hits/buckets out)
+ *   qwgpu_compile_plan         doc_mapper.query(...) + make_collector_for_split(...):
+ *                              quickwit-search/src/leaf.rs:562-580, collector.rs:1033-1052,
+ *                              quickwit-query/src/query_ast/tantivy_query_ast.rs:166-377
+ *   qwgpu_merge_leaf_responses QuickwitCollector::merge_fruits / merge_leaf_responses /
+ *                              IncrementalCollector, quickwit-search/src/collector.rs:832-974,1195-1313
+ *                              (leaf-level and root-level merge; called from root.rs:836-853)
+ *   qwgpu_finalize_aggregation finalize_aggregation, quickwit-search/src/root.rs:1105-1135
+ *   qwgpu_split_register       open_index_with_caches + warmup (leaf.rs:210-251,269-472): makes
+ *                              a split's postings / columns / fieldnorms resident — in HBM.
+ *   qwgpu_imgb_*               the split-image writer (the transcoding target for a tantivy
+ *                              segment). Not on the query path.
+ *
+ * Conventions: every function returns 0 on success, a negative QWGPU_E* code otherwise;
+ * qwgpu_last_error() returns a thread-local message (maps to SearchError::Internal /
+ * InvalidQuery / InvalidAggregationRequest / InvalidArgument, quickwit-search/src/error.rs:32-53).
+ * Buffers returned through `uint8_t** out` are malloc'ed by the library and released with
+ * qwgpu_buf_free. All entry points are thread-safe and re-entrant on a ctx
+ * (the reference calls leaf search concurrently from its rayon pool, SURVEY.md §8b "Threading").
+ * There is NO CPU fallback: search entry points fail with QWGPU_ENODEVICE without a CUDA device.
+ */
+#ifndef QWGPU_H
+#define QWGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "qwgpu_format.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QWGPU_OK 0
+#define QWGPU_EINTERNAL (-1)      /* SearchError::Internal */
+#define QWGPU_EINVALID_QUERY (-2) /* SearchError::InvalidQuery */
+#define QWGPU_EINVALID_AGG (-3)   /* SearchError::InvalidAggregationRequest */
+#define QWGPU_EINVALID_ARG (-4)   /* SearchError::InvalidArgument */
+#define QWGPU_ENODEVICE (-5)      /* no CUDA device: the product path never falls back to CPU */
+#define QWGPU_ENOTFOUND (-6)      /* unknown split id */
+#define QWGPU_EUNSUPPORTED (-7)   /* query/aggregation shape not implemented on the GPU path */
+
+typedef struct qwgpu_ctx qwgpu_ctx;
+typedef struct qwgpu_imgb qwgpu_imgb;
+
+const char* qwgpu_last_error(void);
+const char* qwgpu_version(void);
+void qwgpu_buf_free(void* buf);
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* device < 0: host-only context (plan compilation, merging; no search). */
+int qwgpu_init(int device, qwgpu_ctx** out);
+void qwgpu_shutdown(qwgpu_ctx* ctx);
+
+/* Copies the image's data region to the device; the host-side directory (term dictionary,
+ * column dictionaries, headers) is copied and owned by the ctx. `img` may be freed afterwards. */
+int qwgpu_split_register(qwgpu_ctx* ctx, const char* split_id, const uint8_t* img, uint64_t img_len);
+int qwgpu_split_unregister(qwgpu_ctx* ctx, const char* split_id);
+/* Bytes resident on the device for this ctx. */
+uint64_t qwgpu_resident_bytes(qwgpu_ctx* ctx);
+
+/* ---- seam A / B: protobuf in, protobuf out ---------------------------------------------------- */
+
+/* req = quickwit.search.LeafSearchRequest, resp = quickwit.search.LeafSearchResponse
+ * (quickwit-proto/protos/quickwit/search.proto:343-359,583-613). Per-split failures are reported
+ * in `failed_splits` (retryable_error = true), never as a non-zero return (leaf.rs:1989-2004). */
+int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp,
+                      size_t* resp_len);
+/* resp = quickwit.search.LambdaSearchResponses (one LambdaSingleSplitResult per split). */
+int qwgpu_invoke_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp,
+                             size_t* resp_len);
+
+/* ---- seam C: plan in, hits / buckets out ------------------------------------------------------- */
+
+/* Compiles (SearchRequest protobuf, doc mapper JSON) against ONE split image into a QwPlanHeader
+ * blob (host only; works on a device-less ctx). `img` is any registered-or-not split image. */
+int qwgpu_compile_plan(const uint8_t* img, uint64_t img_len, const char* split_id,
+                       const uint8_t* search_request_pb, size_t search_request_len,
+                       const char* doc_mapper_json, uint8_t** plan, size_t* plan_len);
+
+typedef struct qwgpu_split_result {
+  uint64_t num_hits;
+  uint32_t num_partial_hits; /* <= plan.max_hits */
+  uint32_t num_agg_cells;    /* total cells over all QwAggNode, node-major */
+  QwHit* hits;               /* malloc'ed; free with qwgpu_buf_free */
+  QwAggCell* agg_cells;      /* malloc'ed; free with qwgpu_buf_free */
+  /* measurement: device time of the search kernels of this call (CUDA events), microseconds */
+  float gpu_time_us;
+  uint32_t num_kernel_launches;
+  uint64_t postings_scored; /* Σ doc_freq of the plan's terms ("docs scored") */
+  uint64_t algorithmic_bytes; /* SURVEY.md §8d numerator for this split/plan */
+} qwgpu_split_result;
+
+/* Runs `num_splits` plans (plan i against split_ids[i]) in ONE batched launch sequence.
+ * results[i] is filled for every split; status[i] is 0 or a QWGPU_E* code for that split. */
+int qwgpu_split_search(qwgpu_ctx* ctx, uint32_t num_splits, const char* const* split_ids,
+                       const uint8_t* const* plans, const size_t* plan_lens,
+                       qwgpu_split_result* results, int* status);
+void qwgpu_split_result_free(qwgpu_split_result* r);
+
+/* ---- merge / finalize -------------------------------------------------------------------------- */
+
+/* Merges N LeafSearchResponse protobufs under `search_request_pb` (sort orders, max_hits,
+ * start_offset, aggregation request): semantics of merge_leaf_responses +
+ * QuickwitCollector::merge_fruits (collector.rs:832-974). */
+int qwgpu_merge_leaf_responses(const uint8_t* search_request_pb, size_t search_request_len,
+                               uint32_t n, const uint8_t* const* resps, const size_t* resp_lens,
+                               uint8_t** merged, size_t* merged_len);
+/* intermediate aggregation bytes -> final aggregation JSON (root.rs:1105-1135). */
+int qwgpu_finalize_aggregation(const char* aggregation_request_json, const uint8_t* intermediate,
+                               size_t intermediate_len, char** json_out);
+
+/* ---- multi-GPU partial exchange -------------------------------------------------
+ * Fixed-size per-rank partial: what one rank contributes to the single all-gather that stands in
+ * for the root merge. The caller (one process per GPU) all-gathers `partial_bytes` from every
+ * rank (NCCL) and calls qwgpu_merge_partials on the gathered buffer (every rank or rank 0). */
+int qwgpu_partial_size(const uint8_t* search_request_pb, size_t search_request_len,
+                       uint64_t* partial_bytes);
+int qwgpu_response_to_partial(const uint8_t* search_request_pb, size_t search_request_len,
+                              const uint8_t* resp, size_t resp_len, uint8_t* partial,
+                              uint64_t partial_bytes);
+int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request_len,
+                         uint32_t n_ranks, const uint8_t* gathered, uint64_t partial_bytes,
+                         uint8_t** merged, size_t* merged_len);
+
+/* ---- split image writer ------------------------------------------------------------------------ */
+
+qwgpu_imgb* qwgpu_imgb_new(uint32_t num_docs);
+void qwgpu_imgb_free(qwgpu_imgb* b);
+/* returns field id (>= 0) or a negative error. fieldnorm_ids: num_docs bytes or NULL. */
+int qwgpu_imgb_add_field(qwgpu_imgb* b, const char* name, uint32_t flags, uint32_t tokenizer,
+                         const uint8_t* fieldnorm_ids, uint64_t total_num_tokens);
+/* docs strictly increasing; tfs NULL when the field has no freqs. */
+int qwgpu_imgb_add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint32_t term_len,
+                        const uint32_t* docs, const uint32_t* tfs, uint32_t n);
+/* values: mapped-u64 values. index: FULL -> NULL (num_vals == num_docs);
+ * OPTIONAL -> sorted doc ids (num_vals of them); MULTI -> start offsets (num_docs + 1).
+ * STR columns pass ordinals as values plus the sorted dictionary. */
+int qwgpu_imgb_add_column(qwgpu_imgb* b, const char* name, uint32_t type, uint32_t cardinality,
+                          const uint64_t* values, uint64_t num_vals, const uint32_t* index,
+                          const uint8_t* dict_bytes, const uint32_t* dict_offs, uint32_t dict_n);
+int qwgpu_imgb_finish(qwgpu_imgb* b, uint8_t** img, uint64_t* img_len);
+
+/* Synthetic hdfs-logs-shaped split (SURVEY.md §8d corpus): see DESIGN.md "Synthetic corpus".
+ * term_fracs[i] is the doc-frequency fraction of body term "t<i>"; deterministic in `seed`. */
+typedef struct qwgpu_synth_spec {
+  uint32_t num_docs;
+  uint32_t split_ord;
+  uint64_t seed;
+  uint32_t num_terms;
+  const double* term_fracs;
+  int64_t ts_start_secs; /* first timestamp; docs advance monotonically, 1 s resolution */
+  uint32_t ts_span_secs; /* timestamps cover [ts_start, ts_start + span) */
+  uint32_t num_tenants;
+} qwgpu_synth_spec;
+int qwgpu_synth_split(const qwgpu_synth_spec* spec, uint8_t** img, uint64_t* img_len);
+
+/* tantivy fieldnorm <-> id table (tantivy::fieldnorm::{fieldnorm_to_id,id_to_fieldnorm}). */
+uint8_t qwgpu_fieldnorm_to_id(uint32_t fieldnorm);
+uint32_t qwgpu_id_to_fieldnorm(uint8_t id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QWGPU_H */
