@@ -27,6 +27,7 @@ extern "C" {
 #define QW_BLOCK_LEN 128u                  /* tantivy COMPRESSION_BLOCK_SIZE */
 #define QW_TERMINATED 0x7FFFFFFFu          /* tantivy TERMINATED sentinel (i32::MAX as u32) */
 #define QW_NO_PREV_DOC 0xFFFFFFFFu
+#define QW_MIN_WIN_SHIFT 12u /* evaluation windows are <= 4096 docs and never straddle an index window */
 
 /* ---------------------------------------------------------------- image ---------------------- */
 
@@ -69,11 +70,21 @@ typedef struct QwImgTerm {
   uint32_t bytes_off, bytes_len; /* into term bytes blob */
   uint32_t doc_freq;
   uint32_t num_blocks; /* ceil(doc_freq / 128) */
-  uint32_t reserved;
-  uint64_t skip_off; /* data-relative: QwSkip[num_blocks] */
-  uint64_t data_off; /* data-relative: packed blocks */
+  uint32_t win_shift;  /* window index granularity: one entry per 2^win_shift docs (>= 12) */
+  uint64_t skip_off; /* data-relative: QwSkip[num_blocks] (CPU-style seek structure) */
+  uint64_t data_off; /* data-relative: blocks, each [QwSkip header][packed docs][packed tfs] */
   uint64_t data_len;
-} QwImgTerm; /* 48 bytes */
+  uint64_t widx_off; /* data-relative: QwWinIdx[ceil(num_docs / 2^win_shift)] */
+  uint64_t tf_len;   /* bytes of data_len that are packed term frequencies (roofline accounting) */
+} QwImgTerm; /* 64 bytes */
+
+/* Window index: for index-window j (docs [j<<win_shift, (j+1)<<win_shift)) the byte range
+ * [start, end) of QwImgTerm data holding every block that overlaps it (start == end if none).
+ * This is what lets a GPU thread block that owns a doc-id window fetch exactly the posting bytes
+ * it needs with ONE dependent load instead of a binary search over the skip list. */
+typedef struct QwWinIdx {
+  uint32_t start, end;
+} QwWinIdx;
 
 /* One skip entry per posting block; 16 bytes = one coalesced 128-bit load.
  * A block holds `count` (1..128) postings. Doc ids are stored as strictly-sorted deltas:
@@ -87,7 +98,7 @@ typedef struct QwImgTerm {
 typedef struct QwSkip {
   uint32_t last_doc;
   uint32_t prev_last_doc;
-  uint32_t byte_off; /* relative to QwImgTerm.data_off */
+  uint32_t byte_off; /* of this block's inline header, relative to QwImgTerm.data_off */
   uint8_t doc_bits;
   uint8_t tf_bits;
   uint16_t count;
@@ -124,7 +135,7 @@ typedef struct QwImgColumn {
   uint64_t index_off, index_len;   /* data-relative */
   uint64_t dict_off, dict_len;     /* strings-blob relative: uint32 offs[n+1] then bytes */
   uint64_t reserved;
-} QwImgColumn; /* 104 bytes */
+} QwImgColumn; /* 112 bytes */
 
 /* ---------------------------------------------------------------- plan ----------------------- */
 

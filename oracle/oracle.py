@@ -36,7 +36,9 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
+        src = os.path.join(_HERE, "qw_oracle.c")
+        hdr = os.path.join(_HERE, "..", "include", "qwgpu_format.h")
+        if (not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
             build()
         L = C.CDLL(_LIB)
         L.qwo_split_search.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(OHit),

@@ -150,10 +150,10 @@ struct DocSet {
 static void term_load_block(DocSet* s) {
   const QwSkip* sk = &s->skips[s->blk];
   uint32_t deltas[QW_BLOCK_LEN];
-  o_unpack_4x(s->tdata + sk->byte_off, sk->doc_bits, deltas);
+  o_unpack_4x(s->tdata + sk->byte_off + 16u, sk->doc_bits, deltas);
   uint32_t prev = sk->prev_last_doc;
   for (uint32_t i = 0; i < sk->count; i++) { prev = prev + deltas[i] + 1; s->docs[i] = prev; }
-  if (s->has_tf && s->scoring) o_unpack_4x(s->tdata + sk->byte_off + 16u * sk->doc_bits, sk->tf_bits, s->tfs);
+  if (s->has_tf && s->scoring) o_unpack_4x(s->tdata + sk->byte_off + 16u + 16u * sk->doc_bits, sk->tf_bits, s->tfs);
   s->cnt = sk->count; s->pos = 0;
   if (s->visited) *s->visited += sk->count;
 }
@@ -623,8 +623,8 @@ int qwo_decode_postings(const uint8_t* img, uint64_t img_len, uint32_t term_ord,
   const QwSkip* sk = (const QwSkip*)(im.data + t->skip_off);
   uint32_t n = 0, d[QW_BLOCK_LEN], f[QW_BLOCK_LEN];
   for (uint32_t b = 0; b < t->num_blocks; b++) {
-    o_unpack_4x(im.data + t->data_off + sk[b].byte_off, sk[b].doc_bits, d);
-    o_unpack_4x(im.data + t->data_off + sk[b].byte_off + 16u * sk[b].doc_bits, sk[b].tf_bits, f);
+    o_unpack_4x(im.data + t->data_off + sk[b].byte_off + 16u, sk[b].doc_bits, d);
+    o_unpack_4x(im.data + t->data_off + sk[b].byte_off + 16u + 16u * sk[b].doc_bits, sk[b].tf_bits, f);
     uint32_t prev = sk[b].prev_last_doc;
     for (uint32_t i = 0; i < sk[b].count && n < cap; i++, n++) { prev = prev + d[i] + 1; docs[n] = prev; tfs[n] = sk[b].tf_bits ? f[i] : 1; }
   }

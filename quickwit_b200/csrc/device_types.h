@@ -1,0 +1,123 @@
+// device_types.h — structures shared by the host engine (engine.cu host half) and the kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/qwgpu_format.h"
+
+#define QW_THREADS 256
+#define QW_WARPS (QW_THREADS / 32)
+#define QW_MAX_INSTR 96
+#define QW_MAX_DCOLS 16
+#define QW_MAX_DAGGS 8
+#define QW_MAX_LEVELS QW_MAX_PLAN_DEPTH
+#define QW_MAX_TERMS 64      /* TERM instructions per plan */
+#define QW_BLK_TAB 48        /* staged blocks per (term, window) before falling back to direct mode */
+#define QW_STAGE_BYTES 16384 /* packed posting bytes staged per window */
+#define QW_HIST_BINS 2048    /* 11-bit radix digits */
+#define QW_DIGIT_BITS 11
+#define QW_KEY_BITS 192
+#define QW_CAND_CAP 8192     /* candidates kept per split before the final sort */
+#define QW_MAX_TOPK 4096
+#define QW_SMEM_AGG_CELLS 4096
+
+enum { OP_TERM = 1, OP_RANGE = 2, OP_EXISTS = 3, OP_ALL = 4, OP_BOOL_BEGIN = 5, OP_BOOL_END = 6 };
+enum { IF_SCORED = 1u, IF_HAS_TF = 2u, IF_HAS_FN = 4u };
+
+struct DInstr {  // 64 bytes
+  uint32_t op, level, occur, flags;
+  uint64_t a, b, c;  // TERM: data_off, widx_off, skip_off | RANGE: lo, hi
+  uint32_t n;        // TERM: num_blocks   | BOOL_END: n_req
+  uint32_t m;        // TERM: win_shift    | BOOL_END: n_should
+  uint32_t r;        // TERM: fn slot      | RANGE/EXISTS: column | BOOL_END: required_should
+  float f;           // TERM: bm25 weight  | const-score leaves: boost
+  uint32_t t;        // TERM: term slot (index among the plan's TERM instructions)
+  uint32_t pad;
+};
+
+struct DCol {  // 48 bytes
+  uint64_t values_off, index_off, min_value, gcd;
+  uint32_t bits, card, type, nwords64;
+};
+
+struct DAgg {
+  uint32_t kind, parent, first_child, num_children;
+  uint32_t col, num_buckets, has_bounds, num_ranges;
+  uint32_t has_missing, cell_base, is_f64, pad;
+  double interval, offset, bound_min, bound_max;
+  int64_t base_pos;
+  uint64_t range_from[QW_MAX_AGG_RANGES], range_to[QW_MAX_AGG_RANGES];
+};
+
+// Composite sort key: a 192-bit big-endian bit string, greater = better.
+//   [has1:1][lin1:10][pay1:64][has2:1][pay2:64][doc':32][0:20]
+// lin1 is a value-linear 10-bit bucket of the first sort value (so the first radix digit already
+// discriminates well), pay* are order-preserving payloads (complemented for ascending order) and
+// doc' is the doc id (complemented when the first order is ascending): exactly the total order of
+// SegmentPartialHitSortingKey (quickwit-search/src/collector.rs:1082-1112).
+struct DKeySpec {
+  uint32_t kind[2], order[2], col[2];
+  float score_scale;     // SCORE: lin = min(1023, (uint)(score * scale))
+  uint32_t lin_shr;      // COLUMN/DOCID: lin = min(1023, (r' >> shr) << shl)
+  uint32_t lin_shl;
+  uint32_t pad;
+  uint64_t raw_max;      // r' = order == DESC ? raw : raw_max - raw
+};
+
+struct DThresh {  // per split, device-resident, written by k_pick
+  uint64_t key[3];       // candidates are docs with composite key >= key
+  uint32_t prefix_bits;  // number of leading bits of `key` that are fixed so far
+  uint32_t above;        // docs strictly above the prefix (exact path bookkeeping)
+  uint32_t done;         // 1 when the candidate set fits QW_CAND_CAP
+  uint32_t matched;      // docs matching the prefix at the last level
+};
+
+struct DSplitPlan {
+  uint64_t data_base;  // device address of the split's data region
+  uint32_t num_docs, num_windows;
+  uint32_t n_instr, instr_base;
+  uint32_t n_cols, col_base;
+  uint32_t n_aggs, agg_base;
+  uint32_t n_terms, n_levels;
+  uint32_t max_hits, scoring;
+  uint32_t n_fn_slots, n_cells;
+  uint64_t fn_off[2];      // data-relative fieldnorm arrays staged per window
+  uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables
+  DKeySpec key;
+  QwSearchAfter sa;
+  uint64_t out_num_hits;   // device address of a uint64 counter
+  uint64_t out_hist;       // device address of uint32[QW_HIST_BINS]
+  uint64_t out_cand_count; // device address of a uint32 counter
+  uint64_t out_cands;      // device address of uint64[3 * QW_CAND_CAP]
+  uint64_t out_cells;      // device address of QwAggCell[n_cells]
+  uint64_t out_hits;       // device address of QwHit[max_hits]
+  uint64_t out_nhits;      // device address of uint32 (hits written by k_select)
+};
+
+struct SmemLevel {
+  uint32_t req, shd, nt, cnt, msum, ssum;  // byte offsets; 0xFFFFFFFF = not allocated
+};
+struct SmemLayout {
+  uint32_t instr, cols, aggs;
+  SmemLevel lvl[QW_MAX_LEVELS];
+  uint32_t tmp, fn[2], tab[2];
+  uint32_t rng, blktab, blkcnt, stage, hist, misc;
+  uint32_t total;
+};
+
+struct KParams {
+  const DSplitPlan* plans;
+  const DInstr* instrs;
+  const DCol* cols;
+  const DAgg* aggs;
+  DThresh* thresh;
+  const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
+  uint32_t n_splits;
+  uint32_t total_work;
+  uint32_t stride;   // sampling stride over windows (1 = all)
+  uint32_t W;        // window size in docs (power of two, <= 4096)
+  uint32_t level;    // MODE_HIST: radix level being histogrammed
+  uint32_t use_prefix;  // MODE_HIST: restrict to docs whose key matches thresh prefix
+  uint32_t smem_aggs;   // 1: aggregation counts privatised in shared memory
+  uint32_t pad;
+  SmemLayout sm;
+};

@@ -1,0 +1,671 @@
+// engine.cu — host engine: HBM residency of split images, lowering of seam-C plans into the
+// window-engine program, batched launches (one launch sequence covers every split of a request),
+// top-K threshold selection (sampled fast path + exact radix-select fallback) and result readback.
+//
+// Replaces, for one leaf request: open_index_with_caches + warmup (quickwit-search/src/leaf.rs:
+// 210-251,269-472) at register time, and searcher.search(&query,&collector) (leaf.rs:637) per call.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.h"
+#include "kernels.cuh"
+
+namespace qw {
+
+#define CUDA_CHECK(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      fail((_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? QWGPU_ENODEVICE       \
+                                                                           : QWGPU_EINTERNAL,     \
+           "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,               \
+           cudaGetErrorString(_e));                                                               \
+  } while (0)
+
+uint32_t id_to_fieldnorm(uint8_t id);  // image_builder.cpp
+
+SplitDev::~SplitDev() {
+  if (d_data) cudaFree(d_data);
+  if (d_tabs) cudaFree(d_tabs);
+}
+
+struct CallSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  uint8_t *d_blob = nullptr, *h_blob = nullptr;
+  size_t blob_cap = 0;
+  uint8_t* d_scratch = nullptr;
+  size_t scratch_cap = 0;
+  uint8_t *d_out = nullptr, *h_out = nullptr;
+  size_t out_cap = 0;
+  void ensure(size_t blob, size_t scratch, size_t out) {
+    if (blob > blob_cap) {
+      if (d_blob) cudaFree(d_blob);
+      if (h_blob) cudaFreeHost(h_blob);
+      blob_cap = blob * 2;
+      CUDA_CHECK(cudaMalloc(&d_blob, blob_cap));
+      CUDA_CHECK(cudaMallocHost(&h_blob, blob_cap));
+    }
+    if (scratch > scratch_cap) {
+      if (d_scratch) cudaFree(d_scratch);
+      scratch_cap = scratch * 2;
+      CUDA_CHECK(cudaMalloc(&d_scratch, scratch_cap));
+    }
+    if (out > out_cap) {
+      if (d_out) cudaFree(d_out);
+      if (h_out) cudaFreeHost(h_out);
+      out_cap = out * 2;
+      CUDA_CHECK(cudaMalloc(&d_out, out_cap));
+      CUDA_CHECK(cudaMallocHost(&h_out, out_cap));
+    }
+  }
+  ~CallSlot() {
+    if (d_blob) cudaFree(d_blob);
+    if (h_blob) cudaFreeHost(h_blob);
+    if (d_scratch) cudaFree(d_scratch);
+    if (d_out) cudaFree(d_out);
+    if (h_out) cudaFreeHost(h_out);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+Engine::Engine(int dev) : device(dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail(QWGPU_ENODEVICE, "no CUDA device available (%s); the qwgpu search path has no CPU fallback",
+         e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+  if (dev >= n) fail(QWGPU_EINVALID_ARG, "device %d out of range (%d devices)", dev, n);
+  CUDA_CHECK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  sm_count = prop.multiProcessorCount;
+  max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device);
+  for (CallSlot* s : free_slots) delete s;
+  splits.clear();
+}
+
+void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
+  ImageView full;
+  full.open(img, len);
+  auto sp = std::make_shared<SplitDev>();
+  sp->id = id;
+  sp->dir.assign(img, img + full.hdr->data_off);
+  // the directory-only view: relax the length check by opening over the original then rebasing
+  sp->view = full;
+  sp->view.base = sp->dir.data();
+  sp->view.hdr = (const QwImgHeader*)sp->dir.data();
+  sp->view.fields = (const QwImgField*)(sp->dir.data() + full.hdr->fields_off);
+  sp->view.terms = (const QwImgTerm*)(sp->dir.data() + full.hdr->terms_off);
+  sp->view.columns = (const QwImgColumn*)(sp->dir.data() + full.hdr->columns_off);
+  sp->view.term_bytes = sp->dir.data() + full.hdr->term_bytes_off;
+  sp->view.strings = sp->dir.data() + full.hdr->strings_off;
+  sp->view.data = nullptr;
+  sp->data_len = full.hdr->data_len;
+  CUDA_CHECK(cudaSetDevice(device));
+  CUDA_CHECK(cudaMalloc(&sp->d_data, std::max<uint64_t>(sp->data_len, 16)));
+  CUDA_CHECK(cudaMemcpy(sp->d_data, full.data, sp->data_len, cudaMemcpyHostToDevice));
+  // Bm25Weight cache per field: K1 * (1 - B + B * fieldnorm(id) / avg)
+  uint32_t nf = full.hdr->num_fields;
+  std::vector<float> tabs((size_t)std::max(nf, 1u) * 256);
+  for (uint32_t f = 0; f < nf; f++) {
+    float avg = (float)full.fields[f].total_num_tokens / (float)full.hdr->num_docs;
+    for (uint32_t i = 0; i < 256; i++)
+      tabs[f * 256 + i] = BM25_K1 * (1.0f - BM25_B + BM25_B * (float)id_to_fieldnorm((uint8_t)i) / avg);
+  }
+  CUDA_CHECK(cudaMalloc(&sp->d_tabs, tabs.size() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(sp->d_tabs, tabs.data(), tabs.size() * sizeof(float), cudaMemcpyHostToDevice));
+  std::lock_guard<std::mutex> g(mu);
+  auto it = splits.find(sp->id);
+  if (it != splits.end()) resident -= it->second->data_len;
+  splits[sp->id] = sp;
+  resident += sp->data_len;
+}
+
+void Engine::unregister_split(const char* id) {
+  std::lock_guard<std::mutex> g(mu);
+  auto it = splits.find(id);
+  if (it == splits.end()) fail(QWGPU_ENOTFOUND, "split '%s' is not registered", id);
+  resident -= it->second->data_len;
+  splits.erase(it);
+}
+
+std::shared_ptr<SplitDev> Engine::find(const std::string& id) {
+  std::lock_guard<std::mutex> g(mu);
+  auto it = splits.find(id);
+  return it == splits.end() ? nullptr : it->second;
+}
+
+uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t>* bases) {
+  uint64_t total = 0;
+  if (bases) bases->resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    uint64_t cells = aggs[i].kind == QW_AGG_STATS ? 1 : aggs[i].num_buckets;
+    uint32_t p = aggs[i].parent;
+    while (p != 0xFFFFFFFFu) { cells *= aggs[p].num_buckets; p = aggs[p].parent; }
+    if (bases) (*bases)[i] = (uint32_t)total;
+    total += cells;
+    if (total > (1ull << 26)) fail(QWGPU_EINVALID_AGG, "aggregation bucket space too large (%llu cells)", (unsigned long long)total);
+  }
+  return total;
+}
+
+// ---- lowering: QwPlan tree -> window-engine program ----------------------------------------------
+struct Lowered {
+  DSplitPlan P;
+  std::vector<DInstr> instrs;
+  std::vector<DCol> cols;
+  std::vector<DAgg> aggs;
+  std::vector<int> col_map;  // image column -> DCol index
+  uint32_t need_cnt = 0, need_ssum = 0, levels = 0;  // bit per level
+  float score_max = 0.f;
+  int fn_field[2] = {-1, -1};
+  uint64_t postings = 0, alg_bytes = 0, min_required_df = ~0ull;
+  std::vector<std::pair<uint32_t, uint64_t>> range_cols;  // (col, driver df) for roofline accounting
+};
+
+static uint32_t use_col(Lowered& L, const SplitDev& sp, uint32_t c) {
+  if (c == 0xFFFFFFFFu) return c;
+  if (c >= sp.view.hdr->num_columns) fail(QWGPU_EINVALID_ARG, "plan references column %u (split has %u)", c, sp.view.hdr->num_columns);
+  if (L.col_map[c] >= 0) return (uint32_t)L.col_map[c];
+  if (L.cols.size() >= QW_MAX_DCOLS) fail(QWGPU_EUNSUPPORTED, "plan uses more than %d columns", QW_MAX_DCOLS);
+  const QwImgColumn& ic = sp.view.columns[c];
+  DCol d;
+  d.values_off = ic.values_off; d.index_off = ic.index_off; d.min_value = ic.min_value; d.gcd = ic.gcd;
+  d.bits = ic.bits; d.card = ic.cardinality; d.type = ic.type; d.nwords64 = (sp.view.hdr->num_docs + 63) / 64;
+  L.col_map[c] = (int)L.cols.size();
+  L.cols.push_back(d);
+  return (uint32_t)L.col_map[c];
+}
+
+static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, uint32_t nn, uint32_t idx,
+                       uint32_t level, uint32_t occur, bool scored_ctx) {
+  if (idx >= nn) fail(QWGPU_EINVALID_ARG, "plan node index out of range");
+  const QwPlanNode& n = nodes[idx];
+  const bool scored = scored_ctx && (occur == QW_OCCUR_MUST || occur == QW_OCCUR_SHOULD);
+  DInstr in;
+  memset(&in, 0, sizeof in);
+  in.level = level;
+  in.occur = occur;
+  in.flags = scored ? IF_SCORED : 0;
+  switch (n.kind) {
+    case QW_NODE_TERM: {
+      in.op = OP_TERM;
+      in.t = L.P.n_terms++;
+      if (L.P.n_terms > QW_MAX_TERMS) fail(QWGPU_EUNSUPPORTED, "more than %d term clauses", QW_MAX_TERMS);
+      in.r = 0;
+      if (n.term_ord != 0xFFFFFFFFu) {
+        if (n.term_ord >= sp.view.hdr->num_terms) fail(QWGPU_EINVALID_ARG, "plan term ord out of range");
+        const QwImgTerm& t = sp.view.terms[n.term_ord];
+        const QwImgField& f = sp.view.fields[t.field_id];
+        in.a = t.data_off; in.b = t.widx_off; in.c = t.skip_off;
+        in.n = t.num_blocks; in.m = t.win_shift; in.f = n.bm25_weight;
+        if (f.flags & QW_FIELD_HAS_FREQS) in.flags |= IF_HAS_TF;
+        if (f.flags & QW_FIELD_HAS_FIELDNORMS) in.flags |= IF_HAS_FN;
+        L.postings += t.doc_freq;
+        L.alg_bytes += t.data_len - (scored ? 0 : t.tf_len);
+        if (occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER) L.min_required_df = std::min<uint64_t>(L.min_required_df, t.doc_freq);
+        if (scored) {
+          int slot = -1;
+          for (int s = 0; s < 2; s++) if (L.fn_field[s] == (int)t.field_id) slot = s;
+          if (slot < 0) {
+            for (int s = 0; s < 2 && slot < 0; s++) if (L.fn_field[s] < 0) { L.fn_field[s] = (int)t.field_id; slot = s; }
+            if (slot < 0) fail(QWGPU_EUNSUPPORTED, "scoring over more than 2 distinct text fields");
+          }
+          in.r = (uint32_t)slot;
+          L.score_max += n.bm25_weight > 0 ? n.bm25_weight : 0.f;
+        }
+      }
+      L.instrs.push_back(in);
+      break;
+    }
+    case QW_NODE_RANGE: case QW_NODE_EXISTS: case QW_NODE_ALL: case QW_NODE_NONE: {
+      if (n.kind == QW_NODE_NONE) { in.op = OP_EXISTS; in.r = 0xFFFFFFFFu; }  // matches nothing
+      else if (n.kind == QW_NODE_ALL) in.op = OP_ALL;
+      else {
+        in.op = n.kind == QW_NODE_RANGE ? OP_RANGE : OP_EXISTS;
+        in.r = use_col(L, sp, n.column);
+        in.a = n.lo; in.b = n.hi;
+        if (n.column != 0xFFFFFFFFu) L.range_cols.push_back({n.column, 0});
+      }
+      in.f = n.boost;
+      if (scored) L.score_max += n.boost > 0 ? n.boost : 0.f;
+      L.instrs.push_back(in);
+      break;
+    }
+    case QW_NODE_BOOL: {
+      if (level + 1 > QW_MAX_LEVELS) fail(QWGPU_EUNSUPPORTED, "boolean query nested deeper than %d levels", QW_MAX_LEVELS);
+      // the bool's own accumulators live at `level`; when it is a child, the caller passed level+1
+      DInstr bg;
+      memset(&bg, 0, sizeof bg);
+      bg.op = OP_BOOL_BEGIN; bg.level = level;
+      L.instrs.push_back(bg);
+      L.levels |= 1u << level;
+      uint32_t n_req = 0, n_should = 0;
+      if (n.first_child + n.num_children > nn) fail(QWGPU_EINVALID_ARG, "plan children out of range");
+      // required group: scored MUST clauses in plan order first (fixes the f32 summation order),
+      // then unscored required clauses, posting lists before column predicates (so range filters
+      // only probe surviving candidates)
+      std::vector<uint32_t> order;
+      auto child = [&](uint32_t c) -> const QwPlanNode& { return nodes[n.first_child + c]; };
+      auto is_req = [&](uint32_t c) { return child(c).occur == QW_OCCUR_MUST || child(c).occur == QW_OCCUR_FILTER; };
+      auto is_colpred = [&](uint32_t c) { return child(c).kind == QW_NODE_RANGE || child(c).kind == QW_NODE_EXISTS || child(c).kind == QW_NODE_ALL; };
+      const bool child_scored_ctx = scored_ctx;
+      for (uint32_t c = 0; c < n.num_children; c++) if (is_req(c) && child_scored_ctx && child(c).occur == QW_OCCUR_MUST) order.push_back(c);
+      for (int pass = 0; pass < 2; pass++)
+        for (uint32_t c = 0; c < n.num_children; c++)
+          if (is_req(c) && !(child_scored_ctx && child(c).occur == QW_OCCUR_MUST) && (is_colpred(c) ? pass == 1 : pass == 0)) order.push_back(c);
+      if (child_scored_ctx) {
+        // scored column predicates must also come after posting lists only when that keeps order;
+        // scored clauses keep plan order, so nothing to do here
+      }
+      n_req = (uint32_t)order.size();
+      for (uint32_t c = 0; c < n.num_children; c++) if (child(c).occur == QW_OCCUR_SHOULD) { order.push_back(c); n_should++; }
+      for (uint32_t c = 0; c < n.num_children; c++) if (child(c).occur == QW_OCCUR_MUST_NOT) order.push_back(c);
+      for (uint32_t c : order) {
+        const QwPlanNode& cn = child(c);
+        uint32_t child_level = cn.kind == QW_NODE_BOOL ? level + 1 : level;
+        lower_node(L, sp, nodes, nn, n.first_child + c, child_level, cn.occur, scored);
+      }
+      uint32_t msm = n.min_should_match == 0xFFFFFFFFu ? 0 : n.min_should_match;
+      uint32_t need = msm > 0 ? msm : (n_req == 0 ? 1 : 0);
+      if (need >= 2) L.need_cnt |= 1u << level;
+      if (n_should) L.need_ssum |= 1u << level;
+      DInstr en;
+      memset(&en, 0, sizeof en);
+      en.op = OP_BOOL_END; en.level = level; en.occur = occur; en.flags = scored ? IF_SCORED : 0;
+      en.n = n_req; en.m = n_should; en.r = need;
+      L.instrs.push_back(en);
+      break;
+    }
+    default: fail(QWGPU_EINVALID_ARG, "unknown plan node kind %u", n.kind);
+  }
+}
+
+static inline uint32_t bits_needed64(uint64_t v) { return v == 0 ? 0 : 64 - __builtin_clzll(v); }
+
+static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size_t plan_len) {
+  if (plan_len < sizeof(QwPlanHeader)) fail(QWGPU_EINVALID_ARG, "plan too short");
+  const QwPlanHeader* ph = (const QwPlanHeader*)plan;
+  if (ph->magic != QW_PLAN_MAGIC) fail(QWGPU_EINVALID_ARG, "bad plan magic");
+  size_t need = sizeof(QwPlanHeader) + (size_t)ph->num_nodes * sizeof(QwPlanNode) + (size_t)ph->num_aggs * sizeof(QwAggNode);
+  if (plan_len < need || ph->num_nodes == 0) fail(QWGPU_EINVALID_ARG, "plan truncated");
+  if (ph->max_hits > QW_MAX_TOPK) fail(QWGPU_EUNSUPPORTED, "max_hits + start_offset = %u exceeds the GPU top-K limit %d", ph->max_hits, QW_MAX_TOPK);
+  const QwPlanNode* nodes = (const QwPlanNode*)(plan + sizeof(QwPlanHeader));
+  const QwAggNode* aggs = (const QwAggNode*)(nodes + ph->num_nodes);
+  memset(&L.P, 0, sizeof L.P);
+  L.col_map.assign(sp.view.hdr->num_columns, -1);
+  DSplitPlan& P = L.P;
+  P.data_base = (uint64_t)sp.d_data;
+  P.num_docs = sp.view.hdr->num_docs;
+  P.max_hits = ph->max_hits;
+  P.scoring = ph->scoring;
+  P.sa = ph->search_after;
+  const bool scoring = ph->scoring != 0;
+  if (nodes[0].kind == QW_NODE_BOOL) {
+    lower_node(L, sp, nodes, ph->num_nodes, 0, 0, QW_OCCUR_MUST, scoring);
+  } else {
+    DInstr bg; memset(&bg, 0, sizeof bg); bg.op = OP_BOOL_BEGIN; L.instrs.push_back(bg);
+    L.levels |= 1;
+    lower_node(L, sp, nodes, ph->num_nodes, 0, 0, QW_OCCUR_MUST, scoring);
+    DInstr en; memset(&en, 0, sizeof en); en.op = OP_BOOL_END; en.n = 1; en.flags = scoring ? IF_SCORED : 0; L.instrs.push_back(en);
+  }
+  if (L.instrs.size() > QW_MAX_INSTR) fail(QWGPU_EUNSUPPORTED, "query too large for the GPU program (%zu > %d instructions)", L.instrs.size(), QW_MAX_INSTR);
+  P.n_instr = (uint32_t)L.instrs.size();
+  uint32_t nl = 0;
+  while (L.levels >> nl) nl++;
+  P.n_levels = nl;
+  // fieldnorm / BM25 slots
+  for (int s = 0; s < 2; s++) {
+    P.fn_off[s] = ~0ull;
+    if (L.fn_field[s] >= 0) {
+      const QwImgField& f = sp.view.fields[L.fn_field[s]];
+      P.n_fn_slots = s + 1;
+      P.bm25_tab[s] = (uint64_t)(sp.d_tabs + 256 * L.fn_field[s]);
+      if (f.flags & QW_FIELD_HAS_FIELDNORMS) {
+        P.fn_off[s] = f.fieldnorm_off;
+        L.alg_bytes += std::min<uint64_t>(L.postings, P.num_docs);
+      }
+    }
+  }
+  // sort / key spec (sort_by_from_request, quickwit-search/src/collector.rs:994-1030)
+  DKeySpec& ks = P.key;
+  for (int i = 0; i < 2; i++) {
+    ks.kind[i] = ph->sort[i].kind; ks.order[i] = ph->sort[i].order; ks.col[i] = 0xFFFFFFFFu;
+    if (ph->sort[i].kind == QW_SORT_COLUMN) {
+      if (ph->sort[i].column == 0xFFFFFFFFu) ks.kind[i] = i == 0 ? (uint32_t)QW_SORT_DOCID : (uint32_t)QW_SORT_NONE;  // all None
+      else {
+        uint32_t t = sp.view.columns[ph->sort[i].column].type;
+        if (t == QW_COL_STR) fail(QWGPU_EINVALID_ARG, "Unsupported sort field type `Str`.");
+        ks.col[i] = use_col(L, sp, ph->sort[i].column);
+      }
+    }
+  }
+  if (ks.kind[1] == QW_SORT_DOCID) ks.kind[1] = QW_SORT_NONE;  // _doc as 2nd key extracts None
+  if (ks.kind[0] == QW_SORT_NONE) ks.kind[0] = QW_SORT_DOCID;
+  if (ks.kind[1] == QW_SORT_NONE) ks.order[1] = QW_ORDER_DESC;  // SortByPair::sort_orders default
+  ks.score_scale = 0.f; ks.lin_shr = 0; ks.lin_shl = 0; ks.raw_max = 0;
+  if (ks.kind[0] == QW_SORT_SCORE) {
+    float smax = L.score_max > 1e-30f ? L.score_max : 1.0f;
+    ks.score_scale = 1024.0f / smax;
+  } else if (ks.kind[0] == QW_SORT_COLUMN) {
+    uint32_t bits = L.cols[ks.col[0]].bits;
+    ks.raw_max = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+    if (bits > 10) ks.lin_shr = bits - 10; else ks.lin_shl = 10 - bits;
+  } else {
+    uint32_t bits = bits_needed64(P.num_docs ? P.num_docs - 1 : 0);
+    ks.raw_max = bits == 0 ? 0 : ((1ull << bits) - 1);
+    if (ks.kind[1] != QW_SORT_NONE) ks.lin_shr = 63;  // (None, v2, doc): doc rank must not precede v2
+    else if (bits > 10) ks.lin_shr = bits - 10; else ks.lin_shl = 10 - bits;
+  }
+  // aggregations
+  if (ph->num_aggs > QW_MAX_DAGGS) fail(QWGPU_EUNSUPPORTED, "more than %d aggregation nodes", QW_MAX_DAGGS);
+  std::vector<uint32_t> bases;
+  uint64_t ncells = agg_cell_layout(aggs, ph->num_aggs, &bases);
+  P.n_cells = (uint32_t)ncells;
+  for (uint32_t i = 0; i < ph->num_aggs; i++) {
+    const QwAggNode& a = aggs[i];
+    DAgg d;
+    memset(&d, 0, sizeof d);
+    d.kind = a.kind; d.parent = a.parent; d.first_child = a.first_child; d.num_children = a.num_children;
+    d.col = use_col(L, sp, a.column); d.num_buckets = a.num_buckets; d.has_bounds = a.has_bounds;
+    d.num_ranges = a.num_ranges; d.has_missing = a.has_missing; d.cell_base = bases[i];
+    d.interval = a.interval; d.offset = a.offset; d.bound_min = a.bound_min; d.bound_max = a.bound_max;
+    d.base_pos = a.base_pos;
+    memcpy(d.range_from, a.range_from, sizeof d.range_from);
+    memcpy(d.range_to, a.range_to, sizeof d.range_to);
+    if (a.parent != 0xFFFFFFFFu) {
+      if (a.parent >= ph->num_aggs) fail(QWGPU_EINVALID_ARG, "aggregation parent out of range");
+      uint32_t depth = 1, p = a.parent;
+      while (aggs[p].parent != 0xFFFFFFFFu) { depth++; p = aggs[p].parent; }
+      if (depth > 2 || (depth == 2 && a.kind != QW_AGG_STATS)) fail(QWGPU_EUNSUPPORTED, "aggregation nesting deeper than bucket -> bucket -> metric");
+      if (aggs[a.parent].kind == QW_AGG_STATS) fail(QWGPU_EINVALID_AGG, "metric aggregations cannot have sub-aggregations");
+    }
+    if (a.kind == QW_AGG_RANGE && a.num_ranges > QW_MAX_AGG_RANGES) fail(QWGPU_EUNSUPPORTED, "more than %d ranges", QW_MAX_AGG_RANGES);
+    L.aggs.push_back(d);
+  }
+  P.n_aggs = ph->num_aggs;
+  P.n_cols = (uint32_t)L.cols.size();
+}
+
+// shared-memory arena for a batch (max over the batch's plans)
+static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_ssum, bool scoring,
+                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn, bool hist_or_aggs) {
+  SmemLayout L;
+  memset(&L, 0xFF, sizeof L);
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
+  L.misc = take(64);
+  L.instr = take(std::max(max_instr, 1u) * sizeof(DInstr));
+  L.cols = take(std::max(max_cols, 1u) * sizeof(DCol));
+  L.aggs = take(std::max(max_aggs, 1u) * sizeof(DAgg));
+  for (uint32_t l = 0; l < n_levels; l++) {
+    L.lvl[l].req = take(W / 8);
+    L.lvl[l].shd = take(W / 8);
+    L.lvl[l].nt = take(W / 8);
+    if ((need_cnt >> l) & 1) L.lvl[l].cnt = take(W);
+    if (scoring) L.lvl[l].msum = take(W * 4);
+    if (scoring && ((need_ssum >> l) & 1)) L.lvl[l].ssum = take(W * 4);
+  }
+  L.tmp = take(W / 8);
+  for (uint32_t s = 0; s < n_fn; s++) { L.fn[s] = take(W); L.tab[s] = take(1024); }
+  L.rng = take(QW_MAX_TERMS * 16);
+  L.blktab = take(QW_MAX_TERMS * QW_BLK_TAB * 2);
+  L.blkcnt = take(QW_MAX_TERMS * 4);
+  L.stage = take(QW_STAGE_BYTES);
+  L.hist = take(hist_or_aggs ? QW_SMEM_AGG_CELLS * 4 : 16);
+  L.total = off;
+  return L;
+}
+
+void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
+                    const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats) {
+  const uint32_t n_in = (uint32_t)sp.size();
+  outs.assign(n_in, SplitOutput());
+  CUDA_CHECK(cudaSetDevice(device));
+  // ---- lower every plan; splits whose plan cannot be lowered fail individually ----------------------
+  std::vector<Lowered> low;
+  std::vector<uint32_t> idx;  // position in the caller's arrays
+  low.reserve(n_in);
+  for (uint32_t i = 0; i < n_in; i++) {
+    try {
+      if (!sp[i]) fail(QWGPU_ENOTFOUND, "split not registered");
+      Lowered L;
+      lower_plan(L, *sp[i], plans[i], plan_lens[i]);
+      low.push_back(std::move(L));
+      idx.push_back(i);
+    } catch (const Error& e) {
+      outs[i].status = e.code;
+      outs[i].error = e.what();
+    }
+  }
+  const uint32_t n = (uint32_t)low.size();
+  if (n == 0) return;
+
+  // ---- batch-wide parameters --------------------------------------------------------------------------
+  uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
+  bool scoring = false, any_topk = false, any_aggs = false, smem_aggs = true;
+  uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0;
+  for (auto& L : low) {
+    n_levels = std::max(n_levels, L.P.n_levels);
+    need_cnt |= L.need_cnt; need_ssum |= L.need_ssum;
+    max_instr = std::max(max_instr, L.P.n_instr); max_cols = std::max(max_cols, L.P.n_cols); max_aggs = std::max(max_aggs, L.P.n_aggs);
+    n_fn = std::max(n_fn, L.P.n_fn_slots);
+    scoring |= L.P.scoring != 0; any_topk |= L.P.max_hits > 0; any_aggs |= L.P.n_aggs > 0;
+    if (L.P.n_cells > QW_SMEM_AGG_CELLS) smem_aggs = false;
+    L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
+    tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
+  }
+  uint32_t W = 4096;
+  SmemLayout lay;
+  for (;;) {
+    lay = make_layout(W, n_levels, need_cnt, need_ssum, scoring, max_instr, max_cols, max_aggs, n_fn, true);
+    if ((int)lay.total <= max_smem_optin / 2 || W == 1024) break;  // keep >= 2 blocks per SM
+    W >>= 1;
+  }
+  if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
+
+  // ---- device blob: plans, programs, work maps ----------------------------------------------------------
+  std::vector<uint32_t> fw_all(n + 1), fw_smp(n + 1);
+  uint32_t max_windows = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    low[i].P.num_windows = (low[i].P.num_docs + W - 1) / W;
+    max_windows = std::max(max_windows, low[i].P.num_windows);
+  }
+  uint32_t stride = std::min(16u, std::max(1u, max_windows / 8));
+  fw_all[0] = fw_smp[0] = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t nw = low[i].P.num_windows, phase = stride > 1 ? i % stride : 0;
+    fw_all[i + 1] = fw_all[i] + nw;
+    fw_smp[i + 1] = fw_smp[i] + (nw > phase ? (nw - phase + stride - 1) / stride : 0);
+  }
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
+         o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
+         o_fws = al(o_fwa + (n + 1) * 4), blob_bytes = al(o_fws + (n + 1) * 4);
+  // scratch: thresholds, histograms, candidates
+  size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_cand = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
+         scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
+  // out: per split [hdr 32B][hits][cells]
+  std::vector<size_t> out_off(n + 1);
+  out_off[0] = 0;
+  for (uint32_t i = 0; i < n; i++)
+    out_off[i + 1] = al(out_off[i] + 32 + (size_t)low[i].P.max_hits * sizeof(QwHit) + (size_t)low[i].P.n_cells * sizeof(QwAggCell));
+  size_t out_bytes = out_off[n];
+
+  CallSlot* slot = nullptr;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
+  }
+  if (!slot) {
+    slot = new CallSlot();
+    CUDA_CHECK(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&slot->ev0));
+    CUDA_CHECK(cudaEventCreate(&slot->ev1));
+  }
+  struct Release { Engine* e; CallSlot* s; ~Release() { std::lock_guard<std::mutex> g(e->mu); e->free_slots.push_back(s); } } rel{this, slot};
+  slot->ensure(blob_bytes, scratch_bytes, out_bytes);
+  cudaStream_t st = slot->stream;
+
+  for (uint32_t i = 0; i < n; i++) {
+    DSplitPlan& P = low[i].P;
+    uint8_t* ob = slot->d_out + out_off[i];
+    P.out_num_hits = (uint64_t)ob;            // [0] hits, [1] eligible
+    P.out_nhits = (uint64_t)(ob + 16);
+    P.out_cand_count = (uint64_t)(ob + 20);
+    P.out_hits = (uint64_t)(ob + 32);
+    P.out_cells = (uint64_t)(ob + 32 + (size_t)P.max_hits * sizeof(QwHit));
+    P.out_hist = (uint64_t)(slot->d_scratch + s_hist + (size_t)i * QW_HIST_BINS * 4);
+    P.out_cands = (uint64_t)(slot->d_scratch + s_cand + (size_t)i * QW_CAND_CAP * 24);
+    memcpy(slot->h_blob + o_plans + i * sizeof(DSplitPlan), &P, sizeof P);
+    memcpy(slot->h_blob + o_instr + P.instr_base * sizeof(DInstr), low[i].instrs.data(), P.n_instr * sizeof(DInstr));
+    if (P.n_cols) memcpy(slot->h_blob + o_cols + P.col_base * sizeof(DCol), low[i].cols.data(), P.n_cols * sizeof(DCol));
+    if (P.n_aggs) memcpy(slot->h_blob + o_aggs + P.agg_base * sizeof(DAgg), low[i].aggs.data(), P.n_aggs * sizeof(DAgg));
+  }
+  memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
+  memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
+  CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
+  stats.h2d_bytes += blob_bytes;
+
+  KParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.plans = (const DSplitPlan*)(slot->d_blob + o_plans);
+  kp.instrs = (const DInstr*)(slot->d_blob + o_instr);
+  kp.cols = (const DCol*)(slot->d_blob + o_cols);
+  kp.aggs = (const DAgg*)(slot->d_blob + o_aggs);
+  kp.thresh = (DThresh*)(slot->d_scratch + s_thr);
+  kp.n_splits = n;
+  kp.W = W;
+  kp.smem_aggs = (any_aggs && smem_aggs) ? 1 : 0;
+  kp.sm = lay;
+  int occ = 1;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT>, QW_THREADS, lay.total));
+  occ = std::max(occ, 1);
+  auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix) {
+    KParams q = kp;
+    q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
+    q.total_work = sampled ? fw_smp[n] : fw_all[n];
+    q.stride = sampled ? stride : 1;
+    q.level = level;
+    q.use_prefix = use_prefix;
+    if (q.total_work == 0) return;
+    uint32_t grid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * occ));
+    if (mode == qwk::MODE_HIST) qwk::k_window<qwk::MODE_HIST><<<grid, QW_THREADS, lay.total, st>>>(q);
+    else qwk::k_window<qwk::MODE_COLLECT><<<grid, QW_THREADS, lay.total, st>>>(q);
+    stats.launches++;
+  };
+  const uint32_t sel_smem = 3 * 8 * QW_CAND_CAP;
+  auto run_collect = [&]() {
+    CUDA_CHECK(cudaMemsetAsync(slot->d_out, 0, out_bytes, st));
+    launch_window(qwk::MODE_COLLECT, false, 0, 0);
+    if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans); stats.launches++; }
+    CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    stats.d2h_bytes += out_bytes;
+  };
+  auto verify = [&]() -> bool {
+    for (uint32_t i = 0; i < n; i++) {
+      if (low[i].P.max_hits == 0) continue;
+      const uint8_t* ob = slot->h_out + out_off[i];
+      uint64_t eligible = ((const uint64_t*)ob)[1];
+      uint32_t cand = *(const uint32_t*)(ob + 20);
+      if (cand > QW_CAND_CAP) return false;
+      if (cand < std::min<uint64_t>(low[i].P.max_hits, eligible)) return false;
+    }
+    return true;
+  };
+
+  CUDA_CHECK(cudaEventRecord(slot->ev0, st));
+  CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));  // thresholds + histograms
+  bool ok = true;
+  if (any_topk && stride > 1) {
+    // fast path: threshold from a 1/stride sample of the windows, verified after the collect pass
+    launch_window(qwk::MODE_HIST, true, 0, 0);
+    qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 1, stride);
+    stats.launches++;
+    run_collect();
+    CUDA_CHECK(cudaEventRecord(slot->ev1, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ok = verify();
+    if (!ok) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, slot->ev0, slot->ev1);
+      stats.gpu_time_us += ms * 1000.f;
+      stats.exact_fallbacks++;
+      CUDA_CHECK(cudaEventRecord(slot->ev0, st));
+    }
+  }
+  if (!any_topk) {
+    run_collect();
+    CUDA_CHECK(cudaEventRecord(slot->ev1, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  } else if (stride == 1 || !ok) {
+    // exact radix select over the composite key: one histogram pass per 11-bit digit until the
+    // candidate set of every split fits QW_CAND_CAP (normally a single pass)
+    CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));
+    std::vector<DThresh> th(n);
+    for (uint32_t level = 0; level * QW_DIGIT_BITS < QW_KEY_BITS; level++) {
+      CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
+      launch_window(qwk::MODE_HIST, false, level, level > 0 ? 1 : 0);
+      qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, level, 0, 1);
+      stats.launches++;
+      CUDA_CHECK(cudaMemcpyAsync(th.data(), slot->d_scratch + s_thr, n * sizeof(DThresh), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      bool all_done = true;
+      for (uint32_t i = 0; i < n; i++) if (low[i].P.max_hits && !th[i].done) all_done = false;
+      if (all_done) break;
+    }
+    run_collect();
+    CUDA_CHECK(cudaEventRecord(slot->ev1, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (!verify()) fail(QWGPU_EINTERNAL, "top-K candidate selection failed verification");
+  }
+  CUDA_CHECK(cudaGetLastError());
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, slot->ev0, slot->ev1);
+    stats.gpu_time_us += ms * 1000.f;
+  }
+
+  // ---- unpack ---------------------------------------------------------------------------------------
+  for (uint32_t i = 0; i < n; i++) {
+    SplitOutput& o = outs[idx[i]];
+    const DSplitPlan& P = low[i].P;
+    const uint8_t* ob = slot->h_out + out_off[i];
+    o.num_hits = ((const uint64_t*)ob)[0];
+    uint32_t nh = *(const uint32_t*)(ob + 16);
+    o.hits.assign((const QwHit*)(ob + 32), (const QwHit*)(ob + 32) + nh);
+    if (P.key.kind[0] == QW_SORT_DOCID) for (auto& h : o.hits) { h.flags &= ~1u; h.v1 = 0; }
+    const QwAggCell* c = (const QwAggCell*)(ob + 32 + (size_t)P.max_hits * sizeof(QwHit));
+    o.cells.assign(c, c + P.n_cells);
+    for (auto& cell : o.cells) cell.min_mapped = ~cell.min_mapped;  // device keeps max(~m); see agg_stats
+    o.postings_scored = low[i].postings;
+    // SURVEY.md §8d algorithmic bytes: postings (+ fieldnorms, added at lowering) + column probes
+    uint64_t bytes = low[i].alg_bytes;
+    const SplitDev& s = *sp[idx[i]];
+    auto col_bytes = [&](uint32_t c, uint64_t probes) {
+      const QwImgColumn& ic = s.view.columns[c];
+      uint64_t full = ((uint64_t)ic.num_vals * ic.bits + 7) / 8;
+      return std::min<uint64_t>(probes * ((ic.bits + 7) / 8), full);
+    };
+    uint64_t driver = low[i].min_required_df == ~0ull ? P.num_docs : low[i].min_required_df;
+    for (auto& rc : low[i].range_cols) bytes += col_bytes(rc.first, driver);
+    const QwPlanHeader* ph = (const QwPlanHeader*)plans[idx[i]];
+    for (int k = 0; k < 2; k++)
+      if (ph->sort[k].kind == QW_SORT_COLUMN && ph->sort[k].column != 0xFFFFFFFFu && P.max_hits) bytes += col_bytes(ph->sort[k].column, o.num_hits);
+    const QwAggNode* an = (const QwAggNode*)(plans[idx[i]] + sizeof(QwPlanHeader) + (size_t)ph->num_nodes * sizeof(QwPlanNode));
+    for (uint32_t a = 0; a < ph->num_aggs; a++) if (an[a].column != 0xFFFFFFFFu) bytes += col_bytes(an[a].column, o.num_hits);
+    o.algorithmic_bytes = bytes;
+  }
+}
+
+}  // namespace qw

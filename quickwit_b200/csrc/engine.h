@@ -1,0 +1,67 @@
+// engine.h — host-side engine: split residency in HBM + batched plan execution on the GPU.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace qw {
+
+struct SplitDev {
+  std::string id;
+  std::vector<uint8_t> dir;  // host copy of the image up to data_off (headers, dictionary, strings)
+  ImageView view;            // over `dir` (view.data is NOT valid on the host)
+  uint8_t* d_data = nullptr; // device copy of the data region
+  float* d_tabs = nullptr;   // device float[num_fields][256] BM25 norm tables
+  uint64_t data_len = 0;
+  ~SplitDev();
+};
+
+struct CallSlot;  // per-call stream + scratch (engine.cu)
+
+struct SplitOutput {
+  uint64_t num_hits = 0;
+  std::vector<QwHit> hits;
+  std::vector<QwAggCell> cells;
+  int status = 0;
+  std::string error;
+  uint64_t postings_scored = 0;
+  uint64_t algorithmic_bytes = 0;
+};
+struct BatchStats {
+  float gpu_time_us = 0;
+  uint32_t launches = 0;
+  uint32_t exact_fallbacks = 0;
+  uint64_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+struct Engine {
+  int device = -1;
+  std::mutex mu;
+  std::map<std::string, std::shared_ptr<SplitDev>> splits;
+  std::vector<CallSlot*> free_slots;
+  uint64_t resident = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+
+  explicit Engine(int dev);
+  ~Engine();
+  void register_split(const char* id, const uint8_t* img, uint64_t len);
+  void unregister_split(const char* id);
+  std::shared_ptr<SplitDev> find(const std::string& id);
+  // Runs plan[i] on splits[i]; fills outs[i] (status per split). Throws only on whole-call errors.
+  void search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
+              const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats);
+};
+
+// plan validation helper shared with the compiler: total agg cells + per-node bases
+uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t>* bases);
+
+}  // namespace qw
+
+struct qwgpu_ctx {
+  std::unique_ptr<qw::Engine> engine;  // null for host-only contexts
+};

@@ -61,8 +61,12 @@ struct BTerm {
   uint32_t field;
   std::string bytes;
   uint32_t doc_freq;
+  uint32_t win_shift;
+  uint64_t tf_len = 0;
   std::vector<QwSkip> skips;
+  std::vector<uint32_t> first_docs;  // first doc of each block
   std::vector<uint8_t> data;
+  std::vector<QwWinIdx> widx;
 };
 struct BColumn {
   std::string name;
@@ -124,10 +128,31 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
     s.tf_bits = has_freqs ? (uint8_t)bits_needed(maxtf) : 0;
     s.count = (uint16_t)cnt;
     size_t off = t.data.size();
-    t.data.resize(off + 16u * (s.doc_bits + s.tf_bits));
-    pack_block_4x(deltas, s.doc_bits, t.data.data() + off);
-    pack_block_4x(tfv, s.tf_bits, t.data.data() + off + 16u * s.doc_bits);
+    t.data.resize(off + 16u + 16u * (s.doc_bits + s.tf_bits));
+    memcpy(t.data.data() + off, &s, 16);  // inline header
+    pack_block_4x(deltas, s.doc_bits, t.data.data() + off + 16u);
+    pack_block_4x(tfv, s.tf_bits, t.data.data() + off + 16u + 16u * s.doc_bits);
+    t.first_docs.push_back(docs[start]);
+    t.tf_len += 16u * s.tf_bits;
     prev = s.last_doc;
+  }
+  // window index: granularity 2^win_shift docs, about <= 2 entries per block, never below 4096 docs
+  uint32_t shift = QW_MIN_WIN_SHIFT;
+  while ((((uint64_t)b->num_docs + (1ull << shift) - 1) >> shift) > 2ull * nblocks && shift < 31) shift++;
+  t.win_shift = shift;
+  uint32_t nwin = (uint32_t)(((uint64_t)b->num_docs + (1ull << shift) - 1) >> shift);
+  t.widx.resize(nwin);
+  uint32_t lo = 0;  // first block with last_doc >= window start
+  for (uint32_t j = 0; j < nwin; j++) {
+    uint64_t wstart = (uint64_t)j << shift, wend = wstart + (1ull << shift);
+    while (lo < nblocks && t.skips[lo].last_doc < wstart) lo++;
+    uint32_t hi = lo;  // one past the last block with first_doc < window end
+    while (hi < nblocks && t.first_docs[hi] < wend) hi++;
+    uint32_t sb = lo < nblocks ? t.skips[lo].byte_off : (uint32_t)t.data.size();
+    uint32_t eb = hi < nblocks ? t.skips[hi].byte_off : (uint32_t)t.data.size();
+    if (hi <= lo) eb = sb;
+    t.widx[j].start = sb;
+    t.widx[j].end = eb;
   }
   b->terms.push_back(std::move(t));
 }
@@ -257,6 +282,9 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     o.num_blocks = (uint32_t)t.skips.size();
     o.skip_off = doff; doff = align16(doff + t.skips.size() * sizeof(QwSkip));
     o.data_off = doff; o.data_len = t.data.size(); doff = align16(doff + t.data.size() + 16);
+    o.win_shift = t.win_shift;
+    o.tf_len = t.tf_len;
+    o.widx_off = doff; doff = align16(doff + t.widx.size() * sizeof(QwWinIdx));
   }
   for (uint32_t f = 0; f < nf; f++) { F[f].first_term = 0; F[f].num_terms = 0; }
   for (uint32_t i = 0; i < nt; i++) {
@@ -303,6 +331,7 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     const BTerm& t = b->terms[order[i]];
     memcpy(data + T[i].skip_off, t.skips.data(), t.skips.size() * sizeof(QwSkip));
     if (!t.data.empty()) memcpy(data + T[i].data_off, t.data.data(), t.data.size());
+    if (!t.widx.empty()) memcpy(data + T[i].widx_off, t.widx.data(), t.widx.size() * sizeof(QwWinIdx));
   }
   for (uint32_t c = 0; c < nc; c++) {
     const BColumn& bc = b->columns[c];

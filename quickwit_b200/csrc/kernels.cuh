@@ -1,0 +1,859 @@
+// kernels.cuh — sm_100a kernels of the per-split leaf search hot path.
+//
+// Execution model ("window engine"): a thread block owns one doc-id WINDOW (W <= 4096 docs) of one
+// split and evaluates the whole boolean query over it in shared memory:
+//   1. one dependent load per query term fetches the window-index entry (QwWinIdx) = the exact
+//      byte range of posting blocks overlapping the window; fieldnorm bytes of the window are
+//      staged with 16-byte coalesced loads at the same time;
+//   2. the packed posting bytes of ALL terms are staged with cp.async (16-byte, coalesced);
+//   3. terms are decoded block-per-warp (4-lane-interleaved bit-unpack -> warp-shuffle prefix
+//      scan -> doc ids), BM25 is applied in f32 and accumulated into per-window score arrays in
+//      FIXED clause order (bit-reproducible sums), match sets are shared-memory bitmaps combined
+//      with AND / OR / AND-NOT exactly like tantivy's BooleanWeight;
+//   4. the matched docs of the window are counted, aggregated (bucket counts privatised in shared
+//      memory) and filtered against a per-split top-K threshold; survivors go to a candidate list
+//      that k_select sorts with the reference's total order.
+// This replaces tantivy's doc-at-a-time Scorer/Collector loop (SURVEY.md §3.3 step 10c, §8a rows
+// a3-a12). No tensor cores: the work is integer decode/compare, bound by HBM bandwidth.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace qwk {
+
+struct Key {
+  uint64_t w0, w1, w2;
+};
+
+__device__ __forceinline__ bool key_ge(const Key& a, const Key& b) {
+  if (a.w0 != b.w0) return a.w0 > b.w0;
+  if (a.w1 != b.w1) return a.w1 > b.w1;
+  return a.w2 >= b.w2;
+}
+__device__ __forceinline__ bool key_lt(const Key& a, const Key& b) { return !key_ge(a, b); }
+
+__device__ __forceinline__ Key make_key(uint32_t has1, uint32_t lin1, uint64_t pay1, uint32_t has2,
+                                        uint64_t pay2, uint32_t docp) {
+  Key k;
+  k.w0 = ((uint64_t)has1 << 63) | ((uint64_t)(lin1 & 1023u) << 53) | (pay1 >> 11);
+  k.w1 = (pay1 << 53) | ((uint64_t)has2 << 52) | (pay2 >> 12);
+  k.w2 = (pay2 << 52) | ((uint64_t)docp << 20);
+  return k;
+}
+// 11-bit digit number `level` counted from the most significant bit of the 192-bit key
+__device__ __forceinline__ uint32_t key_digit(const Key& k, uint32_t level) {
+  uint32_t o = level * QW_DIGIT_BITS, word = o >> 6, sh = o & 63;
+  uint64_t hi = word == 0 ? k.w0 : (word == 1 ? k.w1 : k.w2);
+  uint64_t lo = word == 0 ? k.w1 : (word == 1 ? k.w2 : 0ull);
+  uint64_t v = sh ? ((hi << sh) | (lo >> (64 - sh))) : hi;
+  return (uint32_t)(v >> (64 - QW_DIGIT_BITS));
+}
+// do the first `bits` bits of a and b agree?
+__device__ __forceinline__ bool key_prefix_eq(const Key& a, const uint64_t* t, uint32_t bits) {
+  if (bits == 0) return true;
+  uint64_t x0 = a.w0 ^ t[0], x1 = a.w1 ^ t[1], x2 = a.w2 ^ t[2];
+  if (bits <= 64) return (x0 >> (64 - bits)) == 0;
+  if (x0) return false;
+  if (bits <= 128) return (x1 >> (128 - bits)) == 0;
+  if (x1) return false;
+  return (x2 >> (192 - bits)) == 0;
+}
+
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t f64_to_u64_dev(double d) {
+  uint64_t b = (uint64_t)__double_as_longlong(d);
+  return (b & (1ull << 63)) ? ~b : (b ^ (1ull << 63));
+}
+__device__ __forceinline__ double mapped_to_f64(uint32_t type, uint64_t m) {
+  switch (type) {
+    case QW_COL_U64: case QW_COL_BOOL: case QW_COL_STR: return (double)m;
+    case QW_COL_I64: case QW_COL_DATETIME: return (double)(long long)(m ^ (1ull << 63));
+    default: {
+      uint64_t bits = (m & (1ull << 63)) ? (m ^ (1ull << 63)) : ~m;
+      return __longlong_as_double((long long)bits);
+    }
+  }
+}
+
+// ---- columnar reads (tantivy-bitpacker BitUnpacker::get semantics, aligned 64-bit loads) ---------
+__device__ __forceinline__ uint64_t col_raw(const uint8_t* base, const DCol& c, uint64_t idx) {
+  if (c.bits == 0) return 0;
+  const uint64_t* w = (const uint64_t*)(base + c.values_off);
+  uint64_t bitpos = idx * c.bits, wi = bitpos >> 6;
+  uint32_t sh = (uint32_t)(bitpos & 63);
+  uint64_t v = __ldg(w + wi) >> sh;
+  if (sh + c.bits > 64) v |= __ldg(w + wi + 1) << (64 - sh);
+  return c.bits == 64 ? v : (v & ((1ull << c.bits) - 1));
+}
+__device__ __forceinline__ void col_range(const uint8_t* base, const DCol& c, uint32_t d, uint64_t& a, uint64_t& b) {
+  if (c.card == QW_CARD_FULL) { a = d; b = (uint64_t)d + 1; return; }
+  const uint8_t* ix = base + c.index_off;
+  if (c.card == QW_CARD_OPTIONAL) {
+    const uint64_t* present = (const uint64_t*)ix;
+    const uint32_t* rank = (const uint32_t*)(ix + 8ull * c.nwords64);
+    uint64_t word = __ldg(present + (d >> 6));
+    if (!((word >> (d & 63)) & 1)) { a = b = 0; return; }
+    a = __ldg(rank + (d >> 6)) + __popcll(word & ((1ull << (d & 63)) - 1));
+    b = a + 1;
+    return;
+  }
+  const uint32_t* start = (const uint32_t*)ix;
+  a = __ldg(start + d);
+  b = __ldg(start + d + 1);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// SortOrder::compare_opt (quickwit-proto/src/lib.rs:122-140)
+__device__ __forceinline__ int order_cmp(uint32_t order, uint64_t a, uint64_t b) {
+  int c = a < b ? -1 : (a > b ? 1 : 0);
+  return order == QW_ORDER_DESC ? c : -c;
+}
+__device__ __forceinline__ int order_cmp_opt(uint32_t order, bool ha, uint64_t a, bool hb, uint64_t b) {
+  if (ha && hb) return order_cmp(order, a, b);
+  if (ha) return 1;
+  if (hb) return -1;
+  return 0;
+}
+
+// Per-CTA view of the shared-memory arena
+struct Sm {
+  uint8_t* base;
+  const SmemLayout* L;
+  __device__ __forceinline__ uint32_t* u32(uint32_t off) const { return (uint32_t*)(base + off); }
+  __device__ __forceinline__ float* f32(uint32_t off) const { return (float*)(base + off); }
+  __device__ __forceinline__ uint8_t* u8(uint32_t off) const { return base + off; }
+};
+
+struct TermTarget {
+  uint32_t* bits;   // bitmap receiving the term's docs
+  uint8_t* cnt;     // optional per-doc should counter
+  float* score;     // optional score accumulator
+  const uint8_t* fn;  // staged fieldnorm ids of the window (or null)
+  const float* tab;   // BM25 norm table (float[256])
+  float weight;
+  bool has_tf;
+};
+
+// Decode one posting block (header + 4-lane-interleaved bit-packed doc deltas + tfs) with one warp
+// and fold the postings that fall into [ws, we) into the target. `blk` may point to shared or
+// global memory (generic addressing).
+__device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint32_t we, const TermTarget& tg, uint32_t lane) {
+  const uint4 h = *reinterpret_cast<const uint4*>(blk);  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
+  const uint32_t last_doc = h.x, prev = h.y;
+  const uint32_t doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;
+  if (last_doc < ws) return;
+  if (prev != QW_NO_PREV_DOC && prev + 1 >= we) return;
+  const uint4* dp = reinterpret_cast<const uint4*>(blk + 16);
+  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  if (doc_bits) {
+    uint32_t bitpos = lane * doc_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = dp[wi];
+    uint4 B = (sh + doc_bits > 32) ? dp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = doc_bits == 32 ? 0xFFFFFFFFu : ((1u << doc_bits) - 1);
+    v0 = __funnelshift_r(A.x, B.x, sh) & mask;
+    v1 = __funnelshift_r(A.y, B.y, sh) & mask;
+    v2 = __funnelshift_r(A.z, B.z, sh) & mask;
+    v3 = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  // strictly-sorted deltas: doc[i] = doc[i-1] + v[i] + 1
+  uint32_t d0 = v0 + 1, d1 = d0 + v1 + 1, d2 = d1 + v2 + 1, d3 = d2 + v3 + 1;
+  uint32_t incl = d3;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((int)lane >= o) incl += n;
+  }
+  uint32_t basev = prev + (incl - d3);  // mod 2^32 (prev == 0xFFFFFFFF for the first block)
+  uint32_t doc[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
+  uint32_t tf[4] = {1, 1, 1, 1};
+  if (tg.score && tg.has_tf && tf_bits) {
+    const uint4* tp = dp + doc_bits;
+    uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = tp[wi];
+    uint4 B = (sh + tf_bits > 32) ? tp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = tf_bits == 32 ? 0xFFFFFFFFu : ((1u << tf_bits) - 1);
+    tf[0] = __funnelshift_r(A.x, B.x, sh) & mask;
+    tf[1] = __funnelshift_r(A.y, B.y, sh) & mask;
+    tf[2] = __funnelshift_r(A.z, B.z, sh) & mask;
+    tf[3] = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  uint32_t cur_word = 0xFFFFFFFFu, cur_mask = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t idx = lane * 4 + j;
+    if (idx < count && doc[j] >= ws && doc[j] < we) {
+      uint32_t d = doc[j] - ws;
+      uint32_t w = d >> 5;
+      if (w != cur_word) {
+        if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
+        cur_word = w;
+        cur_mask = 0;
+      }
+      cur_mask |= 1u << (d & 31);
+      if (tg.cnt) tg.cnt[d] = (uint8_t)(tg.cnt[d] + 1);
+      if (tg.score) {
+        // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), all f32 round-to-nearest
+        float tff = (float)tf[j];
+        float norm = tg.tab[tg.fn ? tg.fn[d] : 1];
+        float s = __fmul_rn(tg.weight, __fdiv_rn(tff, __fadd_rn(tff, norm)));
+        tg.score[d] = __fadd_rn(tg.score[d], s);
+      }
+    }
+  }
+  if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
+}
+
+// Composite key + eligibility of one matched doc (sort-value extraction:
+// SortingFieldExtractorComponent, quickwit-search/src/collector.rs:139-205)
+struct DocKey {
+  Key key;
+  bool eligible;
+};
+__device__ __forceinline__ DocKey doc_key(const DSplitPlan& P, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
+  const DKeySpec& ks = P.key;
+  uint32_t has1 = 0, has2 = 0, lin = 0;
+  uint64_t v1 = 0, v2 = 0, pay1 = 0, pay2 = 0;
+  const bool desc1 = ks.order[0] == QW_ORDER_DESC;
+  if (ks.kind[0] == QW_SORT_SCORE) {
+    has1 = 1;
+    v1 = f64_to_u64_dev((double)score);
+    uint32_t o = f32_ordered(score);
+    pay1 = (uint64_t)(desc1 ? o : ~o) << 32;
+    float x = __fmul_rn(score, ks.score_scale);
+    uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
+    lin = desc1 ? l : 1023u - l;
+  } else if (ks.kind[0] == QW_SORT_COLUMN && ks.col[0] != 0xFFFFFFFFu) {
+    const DCol& c = cols[ks.col[0]];
+    uint64_t a, b;
+    col_range(base, c, doc, a, b);
+    if (a != b) {
+      has1 = 1;
+      uint64_t raw = col_raw(base, c, a);
+      v1 = c.min_value + c.gcd * raw;
+      pay1 = desc1 ? v1 : ~v1;
+      uint64_t r = desc1 ? raw : ks.raw_max - raw;
+      uint64_t l = (r >> ks.lin_shr) << ks.lin_shl;
+      lin = l > 1023 ? 1023u : (uint32_t)l;
+    }
+  } else {  // doc-id order (also: sort column absent from the split => every value is None)
+    uint32_t r = desc1 ? doc : (uint32_t)ks.raw_max - doc;
+    uint64_t l = ((uint64_t)r >> ks.lin_shr) << ks.lin_shl;
+    lin = l > 1023 ? 1023u : (uint32_t)l;
+  }
+  const bool desc2 = ks.order[1] == QW_ORDER_DESC;
+  if (ks.kind[1] == QW_SORT_SCORE) {
+    has2 = 1;
+    v2 = f64_to_u64_dev((double)score);
+    uint32_t o = f32_ordered(score);
+    pay2 = (uint64_t)(desc2 ? o : ~o) << 32;
+  } else if (ks.kind[1] == QW_SORT_COLUMN && ks.col[1] != 0xFFFFFFFFu) {
+    const DCol& c = cols[ks.col[1]];
+    uint64_t a, b;
+    col_range(base, c, doc, a, b);
+    if (a != b) {
+      has2 = 1;
+      v2 = c.min_value + c.gcd * col_raw(base, c, a);
+      pay2 = desc2 ? v2 : ~v2;
+    }
+  }
+  DocKey out;
+  out.key = make_key(has1, lin, pay1, has2, pay2, desc1 ? doc : ~doc);
+  out.eligible = true;
+  if (P.sa.present) {
+    // GenericQuickwitSegmentTopKCollector::collect_top_k_vals (top_k_collector.rs:663-699)
+    int c = order_cmp_opt(ks.order[0], has1, v1, P.sa.has_v1, P.sa.v1);
+    if (!c) c = order_cmp_opt(ks.order[1], has2, v2, P.sa.has_v2, P.sa.v2);
+    if (P.sa.compare_on_equal) {
+      if (!c) c = P.sa.precomp_order;
+      if (!c) c = order_cmp(ks.order[0], doc, P.sa.doc_id);
+    }
+    out.eligible = c < 0;
+  }
+  return out;
+}
+
+// ---- aggregation collection (dense cells; mirrors oracle agg_collect) -------------------------------
+__device__ __forceinline__ void agg_count(const KParams& p, const Sm& sm, QwAggCell* cells, uint32_t cell) {
+  if (p.smem_aggs) atomicAdd(&sm.u32(sm.L->hist)[cell], 1u);
+  else atomicAdd((unsigned long long*)&cells[cell].count, 1ull);
+}
+__device__ __forceinline__ void agg_stats(const DAgg& g, const DCol& c, const uint8_t* base, QwAggCell* cells, uint32_t cell, uint32_t doc) {
+  uint64_t a, b;
+  col_range(base, c, doc, a, b);
+  QwAggCell* out = &cells[g.cell_base + cell];
+  for (uint64_t i = a; i < b; i++) {
+    uint64_t m = c.min_value + c.gcd * col_raw(base, c, i);
+    atomicAdd((unsigned long long*)&out->count, 1ull);
+    if (c.type == QW_COL_F64) atomicAdd((double*)&out->sum_bits, mapped_to_f64(c.type, m));
+    else atomicAdd((unsigned long long*)&out->sum_bits, (unsigned long long)((c.type == QW_COL_U64 || c.type == QW_COL_BOOL) ? m : (m ^ (1ull << 63))));
+    atomicMax((unsigned long long*)&out->min_mapped, (unsigned long long)~m);  // min kept as max(~m): zero-initialisable
+    atomicMax((unsigned long long*)&out->max_mapped, (unsigned long long)m);
+  }
+}
+// bucket index of value index i for bucket aggregation g; returns false when the value falls in no bucket
+__device__ __forceinline__ bool agg_bucket(const DAgg& g, const DCol& c, const uint8_t* base, uint64_t i, uint32_t r, uint32_t& bucket) {
+  uint64_t raw = col_raw(base, c, i);
+  if (g.kind == QW_AGG_TERMS) { bucket = (uint32_t)raw; return r == 0; }
+  uint64_t m = c.min_value + c.gcd * raw;
+  if (g.kind == QW_AGG_HISTOGRAM) {
+    if (r != 0) return false;
+    double val = mapped_to_f64(c.type, m);
+    if (g.has_bounds && !(val >= g.bound_min && val <= g.bound_max)) return false;
+    double pos = floor(__ddiv_rn(__dsub_rn(val, g.offset), g.interval));
+    long long idx = (long long)pos - g.base_pos;
+    if (idx < 0 || idx >= (long long)g.num_buckets) return false;
+    bucket = (uint32_t)idx;
+    return true;
+  }
+  // RANGE: bucket r = [from, to)
+  bucket = r;
+  return m >= g.range_from[r] && m < g.range_to[r];
+}
+__device__ void agg_collect_doc(const KParams& p, const Sm& sm, const DSplitPlan& P, const DAgg* aggs, const DCol* cols,
+                                const uint8_t* base, QwAggCell* cells, uint32_t doc) {
+  for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
+    const DAgg& g = aggs[gi];
+    if (g.parent != 0xFFFFFFFFu) continue;
+    if (g.kind == QW_AGG_STATS) {
+      if (g.col != 0xFFFFFFFFu) agg_stats(g, cols[g.col], base, cells, 0, doc);
+      continue;
+    }
+    uint64_t a = 0, b = 0;
+    if (g.col != 0xFFFFFFFFu) col_range(base, cols[g.col], doc, a, b);
+    const bool missing = (a == b) && g.kind == QW_AGG_TERMS && g.has_missing;
+    const uint32_t nrep = g.kind == QW_AGG_RANGE ? g.num_ranges : 1;
+    for (uint64_t i = a; i < (missing ? a + 1 : b); i++) {
+      for (uint32_t r = 0; r < nrep; r++) {
+        uint32_t bk;
+        if (missing) bk = g.num_buckets - 1;
+        else if (!agg_bucket(g, cols[g.col], base, i, r, bk)) continue;
+        agg_count(p, sm, cells, g.cell_base + bk);
+        for (uint32_t ci = 0; ci < g.num_children; ci++) {
+          const DAgg& ch = aggs[g.first_child + ci];
+          if (ch.kind == QW_AGG_STATS) {
+            if (ch.col != 0xFFFFFFFFu) agg_stats(ch, cols[ch.col], base, cells, bk, doc);
+            continue;
+          }
+          uint64_t a2 = 0, b2 = 0;
+          if (ch.col != 0xFFFFFFFFu) col_range(base, cols[ch.col], doc, a2, b2);
+          const bool missing2 = (a2 == b2) && ch.kind == QW_AGG_TERMS && ch.has_missing;
+          const uint32_t nrep2 = ch.kind == QW_AGG_RANGE ? ch.num_ranges : 1;
+          for (uint64_t i2 = a2; i2 < (missing2 ? a2 + 1 : b2); i2++) {
+            for (uint32_t r2 = 0; r2 < nrep2; r2++) {
+              uint32_t bk2;
+              if (missing2) bk2 = ch.num_buckets - 1;
+              else if (!agg_bucket(ch, cols[ch.col], base, i2, r2, bk2)) continue;
+              uint32_t cell2 = bk * ch.num_buckets + bk2;
+              agg_count(p, sm, cells, ch.cell_base + cell2);
+              for (uint32_t gc = 0; gc < ch.num_children; gc++) {
+                const DAgg& g3 = aggs[ch.first_child + gc];
+                if (g3.kind == QW_AGG_STATS && g3.col != 0xFFFFFFFFu) agg_stats(g3, cols[g3.col], base, cells, cell2, doc);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+enum { MODE_HIST = 0, MODE_COLLECT = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Sm sm{smem_raw, &p.sm};
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t W = p.W, NW = W >> 5;
+  DInstr* s_instr = (DInstr*)sm.u8(p.sm.instr);
+  DCol* s_cols = (DCol*)sm.u8(p.sm.cols);
+  DAgg* s_aggs = (DAgg*)sm.u8(p.sm.aggs);
+  uint32_t* s_misc = sm.u32(p.sm.misc);  // [0] split, [1] window, [2] scratch counter, [3] eligible counter
+  uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off, instr index
+  uint16_t* s_blktab = (uint16_t*)sm.u8(p.sm.blktab);
+  uint32_t* s_blkcnt = sm.u32(p.sm.blkcnt);
+  uint32_t* s_hist = sm.u32(p.sm.hist);
+  uint8_t* s_stage = sm.u8(p.sm.stage);
+  uint32_t loaded_split = 0xFFFFFFFFu;
+
+  for (uint32_t work = blockIdx.x; work < p.total_work; work += gridDim.x) {
+    // ---- map flat work index -> (split, window) -------------------------------------------------
+    if (tid == 0) {
+      uint32_t lo = 0, hi = p.n_splits;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.first_work + mid) <= work) lo = mid; else hi = mid;
+      }
+      s_misc[0] = lo;
+      uint32_t j = work - __ldg(p.first_work + lo);
+      s_misc[1] = j * p.stride + (p.stride > 1 ? lo % p.stride : 0);
+      s_misc[2] = 0;
+      s_misc[3] = 0;
+    }
+    __syncthreads();
+    const uint32_t split = s_misc[0], window = s_misc[1];
+    const DSplitPlan& P = p.plans[split];
+    if (split != loaded_split) {
+      // (re)load the split's program, columns, aggregations and BM25 tables into shared memory
+      const uint4* src = (const uint4*)(p.instrs + P.instr_base);
+      for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += QW_THREADS) ((uint4*)s_instr)[i] = __ldg(src + i);
+      src = (const uint4*)(p.cols + P.col_base);
+      for (uint32_t i = tid; i < P.n_cols * (sizeof(DCol) / 16); i += QW_THREADS) ((uint4*)s_cols)[i] = __ldg(src + i);
+      src = (const uint4*)(p.aggs + P.agg_base);
+      for (uint32_t i = tid; i < P.n_aggs * (sizeof(DAgg) / 16); i += QW_THREADS) ((uint4*)s_aggs)[i] = __ldg(src + i);
+      for (uint32_t s = 0; s < P.n_fn_slots; s++)
+        for (uint32_t i = tid; i < 256; i += QW_THREADS) sm.f32(p.sm.tab[s])[i] = __ldg((const float*)P.bm25_tab[s] + i);
+      if (MODE == MODE_HIST || p.smem_aggs)
+        for (uint32_t i = tid; i < QW_HIST_BINS * ((MODE == MODE_COLLECT) ? 2 : 1); i += QW_THREADS) s_hist[i] = 0;
+      loaded_split = split;
+      __syncthreads();
+      if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
+      __syncthreads();
+    }
+    const uint8_t* base = (const uint8_t*)P.data_base;
+    const uint32_t ws = window * W;
+    const uint32_t we = min(ws + W, P.num_docs);
+
+    // ---- phase 1: window-index entries + fieldnorm staging --------------------------------------
+    if (tid < P.n_terms) {
+      const DInstr& in = s_instr[s_rng[4 * tid + 3]];
+      uint32_t start = 0, len = 0;
+      if (in.n) {
+        const QwWinIdx* wi = (const QwWinIdx*)(base + in.b);
+        uint2 e = __ldg((const uint2*)(wi + (ws >> in.m)));
+        start = e.x;
+        len = e.y - e.x;
+      }
+      s_rng[4 * tid + 0] = start;
+      s_rng[4 * tid + 1] = len;
+    }
+    for (uint32_t s = 0; s < P.n_fn_slots; s++) {
+      if (P.fn_off[s] == ~0ull) continue;
+      const uint4* src = (const uint4*)(base + P.fn_off[s] + ws);
+      uint4* dst = (uint4*)sm.u8(p.sm.fn[s]);
+      for (uint32_t i = tid; i < (W >> 4); i += QW_THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // ---- phase 2: stage packed posting bytes ------------------------------------------------------
+    if (tid == 0) {
+      uint32_t off = 0;
+      for (uint32_t t = 0; t < P.n_terms; t++) {
+        uint32_t len = s_rng[4 * t + 1];
+        if (len && off + len <= QW_STAGE_BYTES) { s_rng[4 * t + 2] = off; off += len; }
+        else s_rng[4 * t + 2] = 0xFFFFFFFFu;
+      }
+    }
+    __syncthreads();
+    for (uint32_t t = 0; t < P.n_terms; t++) {
+      uint32_t so = s_rng[4 * t + 2];
+      if (so == 0xFFFFFFFFu) continue;
+      const DInstr& in = s_instr[s_rng[4 * t + 3]];
+      const uint8_t* src = base + in.a + s_rng[4 * t + 0];
+      uint32_t n16 = s_rng[4 * t + 1] >> 4;
+      for (uint32_t i = tid; i < n16; i += QW_THREADS) cp_async16(s_stage + so + 16 * i, src + 16 * i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid < P.n_terms) {
+      uint32_t so = s_rng[4 * tid + 2];
+      uint32_t k = 0;
+      if (so != 0xFFFFFFFFu) {
+        uint32_t len = s_rng[4 * tid + 1], pos = 0;
+        while (pos < len && k < QW_BLK_TAB) {
+          s_blktab[tid * QW_BLK_TAB + k++] = (uint16_t)pos;
+          uint32_t bw = *(const uint32_t*)(s_stage + so + pos + 12);
+          pos += 16 + 16 * ((bw & 0xFF) + ((bw >> 8) & 0xFF));
+        }
+        if (pos < len) s_rng[4 * tid + 2] = 0xFFFFFFFFu;  // too many blocks: direct mode
+      }
+      s_blkcnt[tid] = k;
+    }
+    __syncthreads();
+
+    // ---- execute the boolean program ----------------------------------------------------------------
+    uint32_t req_init = 0;  // bit per level, uniform across the block
+    for (uint32_t ip = 0; ip < P.n_instr; ip++) {
+      const DInstr in = s_instr[ip];
+      const SmemLevel& LV = p.sm.lvl[in.level];
+      const bool scored = (in.flags & IF_SCORED) != 0;
+      if (in.op == OP_BOOL_BEGIN) {
+        for (uint32_t i = tid; i < NW; i += QW_THREADS) { sm.u32(LV.shd)[i] = 0; sm.u32(LV.nt)[i] = 0; }
+        if (LV.cnt != 0xFFFFFFFFu) for (uint32_t i = tid; i < (W >> 2); i += QW_THREADS) sm.u32(LV.cnt)[i] = 0;
+        if (LV.msum != 0xFFFFFFFFu) for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(LV.msum)[i] = 0.0f;
+        if (LV.ssum != 0xFFFFFFFFu) for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(LV.ssum)[i] = 0.0f;
+        req_init &= ~(1u << in.level);
+        __syncthreads();
+      } else if (in.op == OP_TERM) {
+        const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
+        TermTarget tg;
+        tg.cnt = nullptr;
+        tg.score = nullptr;
+        if (required) {
+          tg.bits = sm.u32(p.sm.tmp);
+          for (uint32_t i = tid; i < NW; i += QW_THREADS) tg.bits[i] = 0;
+          if (scored) tg.score = sm.f32(LV.msum);
+          __syncthreads();
+        } else if (in.occur == QW_OCCUR_SHOULD) {
+          tg.bits = sm.u32(LV.shd);
+          if (LV.cnt != 0xFFFFFFFFu) tg.cnt = sm.u8(LV.cnt);
+          if (scored) tg.score = sm.f32(LV.ssum);
+        } else {
+          tg.bits = sm.u32(LV.nt);
+        }
+        tg.weight = in.f;
+        tg.has_tf = (in.flags & IF_HAS_TF) != 0;
+        tg.fn = nullptr;
+        tg.tab = nullptr;
+        if (scored) {
+          tg.tab = sm.f32(p.sm.tab[in.r]);
+          if (in.flags & IF_HAS_FN) tg.fn = sm.u8(p.sm.fn[in.r]);
+        }
+        const uint32_t slot = in.t;
+        const uint32_t so = s_rng[4 * slot + 2];
+        if (so != 0xFFFFFFFFu) {
+          const uint32_t nb = s_blkcnt[slot];
+          for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block(s_stage + so + s_blktab[slot * QW_BLK_TAB + k], ws, we, tg, lane);
+        } else if (s_rng[4 * slot + 1]) {
+          // direct mode: locate the first block with last_doc >= ws in the skip list (warp-cooperative
+          // 32-ary search), then decode straight from global memory
+          const QwSkip* skips = (const QwSkip*)(base + in.c);
+          uint32_t lo = 0, hi = in.n;
+          while (hi - lo > 32) {
+            uint32_t step = (hi - lo + 31) >> 5;
+            uint32_t idx = lo + lane * step;
+            bool ok = idx < hi && __ldg(&skips[idx].last_doc) >= ws;
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (m == 0) {
+              uint32_t lastp = lo + ((hi - 1 - lo) / step) * step;
+              lo = lastp + 1;
+            } else {
+              uint32_t f = __ffs(m) - 1;
+              hi = lo + f * step + 1;
+              if (f > 0) lo = lo + (f - 1) * step + 1;
+            }
+          }
+          uint32_t idx = lo + lane;
+          bool ok = idx < hi && __ldg(&skips[idx].last_doc) >= ws;
+          uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+          uint32_t b0 = m ? lo + (__ffs(m) - 1) : in.n;
+          for (uint32_t b = b0 + warp; b < in.n; b += QW_WARPS) {
+            uint4 h = __ldg((const uint4*)&skips[b]);
+            if (h.y != QW_NO_PREV_DOC && h.y + 1 >= we) break;
+            fold_block(base + in.a + h.z, ws, we, tg, lane);
+          }
+        }
+        __syncthreads();
+        if (required) {
+          uint32_t* req = sm.u32(LV.req);
+          const uint32_t* tmp = sm.u32(p.sm.tmp);
+          const bool init = (req_init >> in.level) & 1;
+          for (uint32_t i = tid; i < NW; i += QW_THREADS) req[i] = init ? (req[i] & tmp[i]) : tmp[i];
+          req_init |= 1u << in.level;
+          __syncthreads();
+        }
+      } else if (in.op == OP_RANGE || in.op == OP_EXISTS || in.op == OP_ALL) {
+        const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
+        const bool init = (req_init >> in.level) & 1;
+        const bool gather = required && init;
+        uint32_t* req = sm.u32(LV.req);
+        const bool has_col = in.op == OP_ALL || in.r != 0xFFFFFFFFu;
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+          const uint32_t d = ws + wd * 32 + lane;
+          bool cand = d < we && has_col;
+          if (gather) cand = cand && ((req[wd] >> lane) & 1);
+          bool hit = false;
+          if (cand) {
+            if (in.op == OP_ALL) hit = true;
+            else {
+              const DCol& c = s_cols[in.r];
+              uint64_t a, b;
+              col_range(base, c, d, a, b);
+              if (in.op == OP_EXISTS) hit = a != b;
+              else for (uint64_t i = a; i < b && !hit; i++) {
+                uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
+                hit = mv >= in.a && mv <= in.b;
+              }
+            }
+          }
+          const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
+          const uint32_t di = wd * 32 + lane;
+          if (required) {
+            if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
+            if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], in.f);
+          } else if (in.occur == QW_OCCUR_SHOULD) {
+            if (lane == 0) sm.u32(LV.shd)[wd] |= word;
+            if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
+            if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], in.f);
+          } else {
+            if (lane == 0) sm.u32(LV.nt)[wd] |= word;
+          }
+        }
+        if (required) req_init |= 1u << in.level;
+        __syncthreads();
+      } else if (in.op == OP_BOOL_END) {
+        // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
+        uint32_t* req = sm.u32(LV.req);
+        const uint32_t need = in.r;
+        for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
+          const uint32_t d0 = ws + wd * 32;
+          uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
+          uint32_t r = in.n ? (((req_init >> in.level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
+          uint32_t so;
+          if (need == 0) so = 0xFFFFFFFFu;
+          else if (need == 1) so = sm.u32(LV.shd)[wd];
+          else {
+            so = 0;
+            const uint8_t* cnt = sm.u8(LV.cnt) + wd * 32;
+            for (uint32_t b = 0; b < 32; b++) so |= (cnt[b] >= need ? 1u : 0u) << b;
+          }
+          req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
+        }
+        if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
+          float* ms = sm.f32(LV.msum);
+          const float* ss = sm.f32(LV.ssum);
+          for (uint32_t i = tid; i < W; i += QW_THREADS) ms[i] = __fadd_rn(ms[i], ss[i]);
+        }
+        __syncthreads();
+        if (in.level > 0) {
+          // fold this bool's (bits, score) into the parent level as one clause
+          const SmemLevel& PL = p.sm.lvl[in.level - 1];
+          const uint32_t plevel = in.level - 1;
+          const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
+          const bool pinit = (req_init >> plevel) & 1;
+          for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
+            uint32_t m = req[wd];
+            if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
+            else if (in.occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
+            else sm.u32(PL.nt)[wd] |= m;
+          }
+          if (in.occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || scored)) {
+            for (uint32_t i = tid; i < W; i += QW_THREADS) {
+              if ((req[i >> 5] >> (i & 31)) & 1) {
+                if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
+                if (scored) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], sm.f32(LV.msum)[i]);
+              }
+            }
+          } else if (in.occur == QW_OCCUR_MUST && scored) {
+            for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], sm.f32(LV.msum)[i]);
+          }
+          if (required) req_init |= 1u << plevel;
+          __syncthreads();
+        }
+      }
+    }
+
+    // ---- collect the window's matches ---------------------------------------------------------------
+    const uint32_t* res = sm.u32(p.sm.lvl[0].req);
+    const float* rscore = p.sm.lvl[0].msum != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].msum) : nullptr;
+    const DThresh& T = p.thresh[split];
+    Key thr{T.key[0], T.key[1], T.key[2]};
+    QwAggCell* cells = (QwAggCell*)P.out_cells;
+    uint32_t my_hits = 0, my_elig = 0;
+    for (uint32_t i = tid; i < W; i += QW_THREADS) {
+      if (!((res[i >> 5] >> (i & 31)) & 1)) continue;
+      const uint32_t doc = ws + i;
+      my_hits++;
+      if (P.max_hits) {
+        DocKey dk = doc_key(P, s_cols, base, doc, rscore ? rscore[i] : 0.0f);
+        if (dk.eligible) {
+          my_elig++;
+          if (MODE == MODE_HIST) {
+            if (!p.use_prefix || key_prefix_eq(dk.key, T.key, T.prefix_bits)) atomicAdd(&s_hist[key_digit(dk.key, p.level)], 1u);
+          } else if (key_ge(dk.key, thr)) {
+            uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
+            if (pos < QW_CAND_CAP) {
+              uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
+              c[0] = dk.key.w0; c[1] = dk.key.w1; c[2] = dk.key.w2;
+            }
+          }
+        }
+      }
+      if (MODE == MODE_COLLECT && P.n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
+    }
+    if (MODE == MODE_COLLECT) {
+      // block-reduce the counters, one global atomic per window
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        my_hits += __shfl_down_sync(0xFFFFFFFFu, my_hits, o);
+        my_elig += __shfl_down_sync(0xFFFFFFFFu, my_elig, o);
+      }
+      if (lane == 0) { atomicAdd(&s_misc[2], my_hits); atomicAdd(&s_misc[3], my_elig); }
+    }
+    __syncthreads();
+    if (MODE == MODE_COLLECT) {
+      if (tid == 0) {
+        if (s_misc[2]) atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)s_misc[2]);
+        if (s_misc[3]) atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)s_misc[3]);
+      }
+      if (p.smem_aggs && P.n_aggs) {
+        for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {
+          uint32_t v = s_hist[i];
+          if (v) { atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v); s_hist[i] = 0; }
+        }
+      }
+    } else {
+      uint32_t* gh = (uint32_t*)P.out_hist;
+      for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
+        uint32_t v = s_hist[i];
+        if (v) { atomicAdd(&gh[i], v); s_hist[i] = 0; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Picks the radix digit of the top-K threshold from a split's histogram.
+//   sampled != 0: histogram comes from every `stride`-th window; pick the digit at a conservative
+//                 sample rank `k_sample` (verified afterwards against the true candidate count).
+//   sampled == 0: exact radix-select step at `level` (prefix / above bookkeeping in DThresh).
+__global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* thresh, uint32_t level, uint32_t sampled, uint32_t stride) {
+  __shared__ uint32_t s_part[256];
+  __shared__ uint32_t s_sel[2];
+  const uint32_t split = blockIdx.x, tid = threadIdx.x;
+  const DSplitPlan& P = plans[split];
+  DThresh& T = thresh[split];
+  if (P.max_hits == 0 || (!sampled && T.done)) return;
+  const uint32_t* h = (const uint32_t*)P.out_hist;
+  // thread t owns the 8 bins [2048 - 8(t+1), 2048 - 8t), i.e. thread 0 owns the top bins
+  const uint32_t hi = QW_HIST_BINS - 8 * tid;
+  uint32_t loc[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { loc[j] = h[hi - 1 - j]; sum += loc[j]; }
+  s_part[tid] = sum;
+  if (tid == 0) { s_sel[0] = 0xFFFFFFFFu; s_sel[1] = 0; }
+  __syncthreads();
+  // exclusive prefix over threads (bins above mine)
+  uint32_t above_me = 0;
+  for (uint32_t t = 0; t < tid; t++) above_me += s_part[t];
+  uint32_t K = P.max_hits;
+  uint32_t target, base_above = 0;
+  if (sampled) {
+    // conservative sample rank: 2x the expected sample share of K plus slack
+    target = (2 * K + stride - 1) / stride + 24;
+  } else {
+    base_above = T.above;
+    target = K > base_above ? K - base_above : 1;
+  }
+  // find the largest digit t with suffix(t) >= target
+  uint32_t run = above_me;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    uint32_t before = run;
+    run += loc[j];
+    if (before < target && run >= target) { s_sel[0] = hi - 1 - j; s_sel[1] = before; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t digit = s_sel[0];
+    uint32_t total = 0;
+    for (uint32_t t = 0; t < 256; t++) total += s_part[t];
+    if (digit == 0xFFFFFFFFu) {
+      // fewer than `target` ranked docs: keep everything that matches the current prefix
+      T.done = 1;
+      T.matched = total;
+      if (sampled) { T.key[0] = T.key[1] = T.key[2] = 0; T.prefix_bits = 0; T.above = 0; }
+      return;
+    }
+    uint32_t o = level * QW_DIGIT_BITS, word = o >> 6, sh = o & 63;
+    uint64_t d = (uint64_t)digit << (64 - QW_DIGIT_BITS);
+    if (sampled) { T.key[0] = T.key[1] = T.key[2] = 0; }
+    T.key[word] |= d >> sh;
+    if (sh + QW_DIGIT_BITS > 64 && word < 2) T.key[word + 1] |= d << (64 - sh);
+    T.prefix_bits = o + QW_DIGIT_BITS;
+    if (sampled) { T.above = 0; T.matched = 0; T.done = 1; }
+    else {
+      T.above = base_above + s_sel[1];
+      T.matched = h[digit];
+      T.done = (T.above + T.matched <= QW_CAND_CAP) ? 1 : 0;
+    }
+  }
+}
+
+// Sorts a split's candidates with the reference total order (bitonic sort of the 192-bit keys,
+// descending) and writes the best min(K, n) as QwHit — the harvest step
+// (quickwit-search/src/top_k_collector.rs:404-410, binary_heap.rs:187-193).
+__global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const DSplitPlan& P = plans[blockIdx.x];
+  const uint32_t tid = threadIdx.x;
+  if (P.max_hits == 0) { if (tid == 0) *(uint32_t*)P.out_nhits = 0; return; }
+  uint32_t n = *(const uint32_t*)P.out_cand_count;
+  if (n > QW_CAND_CAP) n = QW_CAND_CAP;  // overflow is detected by the host (cand_count > cap)
+  uint32_t N = 32;
+  while (N < n) N <<= 1;
+  uint64_t* k0 = (uint64_t*)smem_raw;
+  uint64_t* k1 = k0 + N;
+  uint64_t* k2 = k1 + N;
+  const uint64_t* src = (const uint64_t*)P.out_cands;
+  for (uint32_t i = tid; i < N; i += 1024) {
+    if (i < n) { k0[i] = src[3ull * i]; k1[i] = src[3ull * i + 1]; k2[i] = src[3ull * i + 2]; }
+    else { k0[i] = 0; k1[i] = 0; k2[i] = 0; }
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= N; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (N >> 1); i += 1024) {
+        uint32_t pos = 2 * i - (i & (stride - 1));
+        uint32_t q = pos + stride;
+        bool desc = (pos & size) == 0;
+        Key a{k0[pos], k1[pos], k2[pos]}, b{k0[q], k1[q], k2[q]};
+        bool a_lt_b = key_lt(a, b);
+        bool b_lt_a = key_lt(b, a);
+        if (desc ? a_lt_b : b_lt_a) {
+          k0[pos] = b.w0; k1[pos] = b.w1; k2[pos] = b.w2;
+          k0[q] = a.w0; k1[q] = a.w1; k2[q] = a.w2;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t out_n = n < P.max_hits ? n : P.max_hits;
+  QwHit* hits = (QwHit*)P.out_hits;
+  const DKeySpec& ks = P.key;
+  for (uint32_t i = tid; i < out_n; i += 1024) {
+    uint64_t w0 = k0[i], w1 = k1[i], w2 = k2[i];
+    uint32_t has1 = (uint32_t)(w0 >> 63), has2 = (uint32_t)((w1 >> 52) & 1);
+    uint64_t pay1 = (w0 << 11) | (w1 >> 53), pay2 = (w1 << 12) | (w2 >> 52);
+    uint32_t docp = (uint32_t)(w2 >> 20);
+    QwHit hh;
+    hh.doc_id = ks.order[0] == QW_ORDER_DESC ? docp : ~docp;
+    hh.flags = has1 | (has2 << 1);
+    hh.score = 0.0f;
+    hh.reserved = 0;
+    hh.v1 = 0;
+    hh.v2 = 0;
+    if (has1) {
+      if (ks.kind[0] == QW_SORT_SCORE) {
+        uint32_t o = (uint32_t)(pay1 >> 32);
+        if (ks.order[0] != QW_ORDER_DESC) o = ~o;
+        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        hh.score = __uint_as_float(bits);
+        hh.v1 = f64_to_u64_dev((double)hh.score);
+      } else hh.v1 = ks.order[0] == QW_ORDER_DESC ? pay1 : ~pay1;
+    }
+    if (has2) {
+      if (ks.kind[1] == QW_SORT_SCORE) {
+        uint32_t o = (uint32_t)(pay2 >> 32);
+        if (ks.order[1] != QW_ORDER_DESC) o = ~o;
+        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        hh.score = __uint_as_float(bits);
+        hh.v2 = f64_to_u64_dev((double)hh.score);
+      } else hh.v2 = ks.order[1] == QW_ORDER_DESC ? pay2 : ~pay2;
+    }
+    hits[i] = hh;
+  }
+  if (tid == 0) *(uint32_t*)P.out_nhits = out_n;
+}
+
+}  // namespace qwk

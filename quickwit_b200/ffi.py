@@ -30,6 +30,39 @@ PLAN_MAGIC = 0x4E4C5051
 MAX_AGG_RANGES = 16
 
 
+class QwImgHeader(C.Structure):
+    _fields_ = [("magic", C.c_uint64), ("version", C.c_uint32), ("num_docs", C.c_uint32),
+                ("num_fields", C.c_uint32), ("num_terms", C.c_uint32), ("num_columns", C.c_uint32),
+                ("reserved0", C.c_uint32), ("fields_off", C.c_uint64), ("terms_off", C.c_uint64),
+                ("term_bytes_off", C.c_uint64), ("term_bytes_len", C.c_uint64),
+                ("columns_off", C.c_uint64), ("strings_off", C.c_uint64), ("strings_len", C.c_uint64),
+                ("data_off", C.c_uint64), ("data_len", C.c_uint64), ("total_len", C.c_uint64),
+                ("reserved1", C.c_uint64 * 3)]
+
+
+class QwImgField(C.Structure):
+    _fields_ = [("name_off", C.c_uint32), ("name_len", C.c_uint32), ("flags", C.c_uint32),
+                ("tokenizer", C.c_uint32), ("total_num_tokens", C.c_uint64),
+                ("fieldnorm_off", C.c_uint64), ("first_term", C.c_uint32), ("num_terms", C.c_uint32),
+                ("reserved", C.c_uint64)]
+
+
+class QwImgTerm(C.Structure):
+    _fields_ = [("field_id", C.c_uint32), ("bytes_off", C.c_uint32), ("bytes_len", C.c_uint32),
+                ("doc_freq", C.c_uint32), ("num_blocks", C.c_uint32), ("win_shift", C.c_uint32),
+                ("skip_off", C.c_uint64), ("data_off", C.c_uint64), ("data_len", C.c_uint64),
+                ("widx_off", C.c_uint64), ("tf_len", C.c_uint64)]
+
+
+class QwImgColumn(C.Structure):
+    _fields_ = [("name_off", C.c_uint32), ("name_len", C.c_uint32), ("type", C.c_uint32),
+                ("cardinality", C.c_uint32), ("min_value", C.c_uint64), ("max_value", C.c_uint64),
+                ("gcd", C.c_uint64), ("num_vals", C.c_uint64), ("bits", C.c_uint32),
+                ("dict_num_terms", C.c_uint32), ("values_off", C.c_uint64), ("values_len", C.c_uint64),
+                ("index_off", C.c_uint64), ("index_len", C.c_uint64), ("dict_off", C.c_uint64),
+                ("dict_len", C.c_uint64), ("reserved", C.c_uint64)]
+
+
 class QwHit(C.Structure):
     _fields_ = [("v1", C.c_uint64), ("v2", C.c_uint64), ("doc_id", C.c_uint32),
                 ("flags", C.c_uint32), ("score", C.c_float), ("reserved", C.c_uint32)]

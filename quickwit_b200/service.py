@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference interface for this path (Python twin of the Rust shim a
+Quickwit maintainer would write over the C ABI).
+
+Names follow the reference:
+  * `SearcherContext`      — quickwit-search/src/service.rs:405-498 (owns caches; here: HBM residency)
+  * `SearchService.leaf_search(LeafSearchRequest) -> LeafSearchResponse`
+                           — quickwit-search/src/service.rs:81,177-203  (seam A)
+  * `LambdaLeafSearchInvoker.invoke_leaf_search(LeafSearchRequest) -> [LambdaSingleSplitResult]`
+                           — quickwit-search/src/invoker.rs:27-38       (seam B)
+  * `leaf_search_single_split` on a compiled plan (seam C, leaf.rs:498-705 step 10c)
+All of them call straight into libqwgpu.so; nothing here computes results.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+from . import ffi
+from .splitgen import SplitImage
+
+
+class SplitSearchResult:
+    """Fields of the per-split `LeafSearchResponse` before protobuf encoding."""
+
+    def __init__(self, r: ffi.SplitResult):
+        self.num_hits = int(r.num_hits)
+        self.hits: List[Tuple[int, int, int, int, float]] = [
+            (h.doc_id, h.flags, h.v1, h.v2, h.score) for h in (r.hits[i] for i in range(r.num_partial_hits))]
+        self.cells = [(c.count, c.sum_bits, c.min_mapped, c.max_mapped)
+                      for c in (r.agg_cells[i] for i in range(r.num_agg_cells))]
+        self.gpu_time_us = float(r.gpu_time_us)
+        self.num_kernel_launches = int(r.num_kernel_launches)
+        self.postings_scored = int(r.postings_scored)
+        self.algorithmic_bytes = int(r.algorithmic_bytes)
+
+
+class SearcherContext:
+    """Owns one `qwgpu_ctx` (one GPU). device=None gives a host-only context (plan compilation,
+    merging); any search call on it raises QwGpuError(ENODEVICE) — there is no CPU search path."""
+
+    def __init__(self, device: Optional[int] = 0):
+        self._L = ffi.lib()
+        self._ctx = C.c_void_p()
+        ffi.check(self._L.qwgpu_init(-1 if device is None else device, C.byref(self._ctx)))
+
+    def close(self):
+        if self._ctx:
+            self._L.qwgpu_shutdown(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- residency (open_index_with_caches + warmup, leaf.rs:210-251,269-472) --------------------
+    def register_split(self, img: SplitImage, split_id: Optional[str] = None):
+        ffi.check(self._L.qwgpu_split_register(self._ctx, (split_id or img.split_id).encode(), img.ptr, img.nbytes))
+
+    def unregister_split(self, split_id: str):
+        ffi.check(self._L.qwgpu_split_unregister(self._ctx, split_id.encode()))
+
+    def resident_bytes(self) -> int:
+        return int(self._L.qwgpu_resident_bytes(self._ctx))
+
+    # -- seam C -------------------------------------------------------------------------------------
+    def split_search(self, split_ids: Sequence[str], plans: Sequence[bytes]) -> List[SplitSearchResult]:
+        n = len(split_ids)
+        ids = (C.c_char_p * n)(*[s.encode() for s in split_ids])
+        bufs = [C.create_string_buffer(p, len(p)) for p in plans]
+        pp = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+        ln = (C.c_size_t * n)(*[len(p) for p in plans])
+        res = (ffi.SplitResult * n)()
+        status = (C.c_int * n)()
+        ffi.check(self._L.qwgpu_split_search(self._ctx, n, ids, pp, ln, res, status))
+        try:
+            for i in range(n):
+                if status[i] != 0:
+                    raise ffi.QwGpuError(status[i], self._L.qwgpu_last_error().decode("utf-8", "replace"))
+            return [SplitSearchResult(res[i]) for i in range(n)]
+        finally:
+            for i in range(n):
+                self._L.qwgpu_split_result_free(C.byref(res[i]))
+
+    # -- seam A / B -----------------------------------------------------------------------------------
+    def _bytes_call(self, fn, req: bytes) -> bytes:
+        buf = C.create_string_buffer(req, len(req))
+        out, n = C.c_void_p(), C.c_size_t()
+        ffi.check(fn(self._ctx, C.addressof(buf), len(req), C.byref(out), C.byref(n)))
+        return ffi.take_bytes(out, n.value)
+
+    def leaf_search(self, leaf_search_request: bytes) -> bytes:
+        """SearchService::leaf_search: LeafSearchRequest bytes -> LeafSearchResponse bytes."""
+        return self._bytes_call(self._L.qwgpu_leaf_search, leaf_search_request)
+
+    def invoke_leaf_search(self, leaf_search_request: bytes) -> bytes:
+        """LambdaLeafSearchInvoker::invoke_leaf_search -> LambdaSearchResponses bytes."""
+        return self._bytes_call(self._L.qwgpu_invoke_leaf_search, leaf_search_request)
+
+
+def compile_plan(img: SplitImage, search_request_pb: bytes, doc_mapper_json: str, split_id: str = "") -> bytes:
+    """doc_mapper.query + make_collector_for_split for one split (host only)."""
+    L = ffi.lib()
+    buf = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    out, n = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_compile_plan(img.ptr, img.nbytes, (split_id or img.split_id).encode(), C.addressof(buf),
+                                   len(search_request_pb), doc_mapper_json.encode(), C.byref(out), C.byref(n)))
+    return ffi.take_bytes(out, n.value)
+
+
+def merge_leaf_responses(search_request_pb: bytes, responses: Sequence[bytes]) -> bytes:
+    """merge_leaf_responses / QuickwitCollector::merge_fruits (collector.rs:832-974)."""
+    L = ffi.lib()
+    n = len(responses)
+    rb = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    bufs = [C.create_string_buffer(r, max(len(r), 1)) for r in responses]
+    pp = (C.c_void_p * n)(*[C.addressof(b) for b in bufs])
+    ln = (C.c_size_t * n)(*[len(r) for r in responses])
+    out, m = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_merge_leaf_responses(C.addressof(rb), len(search_request_pb), n, pp, ln, C.byref(out), C.byref(m)))
+    return ffi.take_bytes(out, m.value)
+
+
+def finalize_aggregation(aggregation_request_json: str, intermediate: bytes) -> str:
+    """finalize_aggregation (root.rs:1105-1135): intermediate bytes -> final aggregation JSON."""
+    L = ffi.lib()
+    ib = C.create_string_buffer(intermediate, max(len(intermediate), 1))
+    out = C.c_void_p()
+    ffi.check(L.qwgpu_finalize_aggregation(aggregation_request_json.encode(), C.addressof(ib), len(intermediate), C.byref(out)))
+    try:
+        return C.string_at(out).decode()
+    finally:
+        L.qwgpu_buf_free(out)

@@ -46,45 +46,73 @@ class SplitImage:
 
     @property
     def num_docs(self) -> int:
-        return struct.unpack_from("<I", self.array[:16].tobytes(), 12)[0]
+        return self.header().num_docs
 
-    def header(self) -> Dict[str, int]:
-        names = ["magic", "version", "num_docs", "num_fields", "num_terms", "num_columns", "r0",
-                 "fields_off", "terms_off", "term_bytes_off", "term_bytes_len", "columns_off",
-                 "strings_off", "strings_len", "data_off", "data_len", "total_len"]
-        vals = struct.unpack_from("<QIIIIII10Q", self.array[:128].tobytes(), 0)
-        return dict(zip(names, vals))
+    def header(self) -> ffi.QwImgHeader:
+        return ffi.QwImgHeader.from_buffer_copy(self.array[:C.sizeof(ffi.QwImgHeader)].tobytes())
+
+    def _table(self, cls, off: int, n: int):
+        sz = C.sizeof(cls)
+        raw = self.array[off: off + sz * n].tobytes()
+        return [cls.from_buffer_copy(raw[i * sz:(i + 1) * sz]) for i in range(n)]
+
+    def _directory(self):
+        if getattr(self, "_dir", None) is None:
+            h = self.header()
+            strings = self.array[h.strings_off: h.strings_off + h.strings_len].tobytes()
+            tbytes = self.array[h.term_bytes_off: h.term_bytes_off + h.term_bytes_len].tobytes()
+            fields = self._table(ffi.QwImgField, h.fields_off, h.num_fields)
+            terms = self._table(ffi.QwImgTerm, h.terms_off, h.num_terms)
+            cols = self._table(ffi.QwImgColumn, h.columns_off, h.num_columns)
+            self._dir = (h, strings, tbytes, fields, terms, cols)
+        return self._dir
+
+    def field_names(self) -> List[str]:
+        _h, strings, _tb, fields, _t, _c = self._directory()
+        return [strings[f.name_off: f.name_off + f.name_len].decode() for f in fields]
+
+    def column_names(self) -> List[str]:
+        _h, strings, _tb, _f, _t, cols = self._directory()
+        return [strings[c.name_off: c.name_off + c.name_len].decode() for c in cols]
+
+    def columns(self):
+        return self._directory()[5]
+
+    def terms(self):
+        return self._directory()[4]
+
+    def fields(self):
+        return self._directory()[3]
 
     def term_ord(self, field: str, term: bytes | str) -> int:
         """Dictionary lookup (test helper): ord of (field, term) or -1."""
         if isinstance(term, str):
             term = term.encode()
-        h = self.header()
-        raw = self.array.tobytes()
-        for f in range(h["num_fields"]):
-            name_off, name_len, _fl, _tok, _tt, _fo, first, n = struct.unpack_from(
-                "<IIIIQQII", raw, h["fields_off"] + 48 * f)
-            name = raw[h["strings_off"] + name_off: h["strings_off"] + name_off + name_len].decode()
-            if name != field:
-                continue
-            for t in range(first, first + n):
-                _fid, boff, blen = struct.unpack_from("<III", raw, h["terms_off"] + 48 * t)
-                if raw[h["term_bytes_off"] + boff: h["term_bytes_off"] + boff + blen] == term:
-                    return t
+        _h, _s, tbytes, fields, terms, _c = self._directory()
+        names = self.field_names()
+        if field not in names:
+            return -1
+        f = fields[names.index(field)]
+        for t in range(f.first_term, f.first_term + f.num_terms):
+            if tbytes[terms[t].bytes_off: terms[t].bytes_off + terms[t].bytes_len] == term:
+                return t
         return -1
 
     def column_ord(self, name: str) -> int:
-        h = self.header()
-        raw = self.array.tobytes()
-        for c in range(h["num_columns"]):
-            name_off, name_len = struct.unpack_from("<II", raw, h["columns_off"] + 104 * c)
-            if raw[h["strings_off"] + name_off: h["strings_off"] + name_off + name_len].decode() == name:
-                return c
-        return -1
+        names = self.column_names()
+        return names.index(name) if name in names else -1
 
     def doc_freq(self, term_ord: int) -> int:
-        h = self.header()
-        return struct.unpack_from("<I", self.array.tobytes(), h["terms_off"] + 48 * term_ord + 12)[0]
+        return self.terms()[term_ord].doc_freq
+
+    def dictionary(self, column: int) -> List[bytes]:
+        """Sorted term dictionary of a STR column."""
+        h, strings, _tb, _f, _t, cols = self._directory()
+        c = cols[column]
+        n = c.dict_num_terms
+        offs = struct.unpack_from(f"<{n + 1}I", strings, c.dict_off)
+        base = c.dict_off + 4 * (n + 1)
+        return [strings[base + offs[i]: base + offs[i + 1]] for i in range(n)]
 
 
 # ---- value mappings (tantivy MonotonicallyMappableToU64) ---------------------------------------
