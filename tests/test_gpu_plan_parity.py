@@ -23,8 +23,8 @@ def synth(gpu_ctx):
     return imgs
 
 
-def run_both(ctx, img, plan, **kw):
-    got = ctx.split_search([img.split_id], [plan])[0]
+def run_both(sctx, img, plan, **kw):
+    got = sctx.split_search([img.split_id], [plan])[0]
     want = O.split_search(img, plan)
     assert_same(got, want, **kw)
     return got, want
