@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the per-split leaf-search hot path (BASELINE.json configs[1]).
+
+Workload (config.workload = "c2_bm25_or10_top1000"): BM25 10-term OR query, top-1000 by _score,
+over a 100M-doc / 32-split synthetic hdfs-logs-shaped index resident in HBM on each GPU
+(3.125M docs per split; body terms with doc-frequency fractions {20,10,5,5,2,2,1,1,0.5,0.1}%).
+A "step" = one batch of Q = 4 such queries with DISJOINT term sets (the same 32 splits, different
+posting lists), so one step touches Q x postings + the fieldnorm arrays > the 126 MB L2 and the
+next step's data has been evicted by then ("inputs larger than L2").
+
+Metric: docs scored per second = postings visited (sum of the query terms' doc frequencies over all
+splits) / time. `value` uses device time (CUDA events inside libqwgpu around each call's kernel
+sequence, inputs resident in HBM); `e2e` is the wall time of the C-ABI calls (`qwgpu_split_search`:
+host plan bytes in, host result buffers out, H2D/D2H inside). N > 1: one process per GPU, every
+rank owns its own 32 splits (weak scaling), one NCCL all-gather of the fixed-size per-rank partial
+top-K per step stands in for the root merge; time = max over ranks.
+
+`--impl reference`: the reference's CPU algorithm (oracle/qw_oracle.c, a restatement — the real
+quickwit-search + tantivy cannot be built here) on all host cores, one split per
+thread, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRACS = [0.20, 0.10, 0.05, 0.05, 0.02, 0.02, 0.01, 0.01, 0.005, 0.001]
+Q_SETS = 4
+K = 1000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qwgpu", choices=["qwgpu", "reference"])
+    ap.add_argument("--splits", type=int, default=32, help="splits per GPU")
+    ap.add_argument("--docs-per-split", type=int, default=3_125_000)
+    ap.add_argument("--cpu-sample-splits", type=int, default=0, help="splits in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_splits(rank: int, n_splits: int, docs: int, threads: int):
+    from quickwit_b200 import splitgen as S
+
+    def one(i):
+        gid = rank * n_splits + i
+        return S.synth_split(docs, gid, FRACS * Q_SETS, seed=0x5157, ts_start_secs=1_700_000_000 + 86_400 * gid,
+                             split_id=f"bench-{gid:04d}")
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(one, range(n_splits)))
+
+
+def make_plans(imgs):
+    """plans[q][s]: 10-term OR, BM25, top-K by _score desc, for query set q on split s."""
+    from quickwit_b200 import ffi, plan as P
+    plans = []
+    for q in range(Q_SETS):
+        per_split = []
+        for img in imgs:
+            root = P.bool_([P.term(img, "body", f"t{q * 10 + i}", occur=ffi.OCCUR_SHOULD) for i in range(10)])
+            per_split.append(P.make_plan(root, K, [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)]))
+        plans.append(per_split)
+    return plans
+
+
+class RawSearch:
+    """Pre-marshalled arguments for qwgpu_split_search so the timed region is the C call only."""
+
+    def __init__(self, ctx, split_ids, plans):
+        from quickwit_b200 import ffi
+        self.L = ffi.lib()
+        self.ctx = ctx._ctx
+        n = len(split_ids)
+        self.n = n
+        self.ids = (C.c_char_p * n)(*[s.encode() for s in split_ids])
+        self.bufs = [C.create_string_buffer(p, len(p)) for p in plans]
+        self.pp = (C.c_void_p * n)(*[C.addressof(b) for b in self.bufs])
+        self.ln = (C.c_size_t * n)(*[len(p) for p in plans])
+        self.res = (ffi.SplitResult * n)()
+        self.status = (C.c_int * n)()
+        self.plan_bytes = sum(len(p) for p in plans)
+
+    def run(self):
+        rc = self.L.qwgpu_split_search(self.ctx, self.n, self.ids, self.pp, self.ln, self.res, self.status)
+        if rc != 0 or any(self.status[i] for i in range(self.n)):
+            raise RuntimeError(self.L.qwgpu_last_error().decode())
+        r0 = self.res[0]
+        out = dict(gpu_us=r0.gpu_time_us, main_us=r0.main_kernel_us, launches=r0.num_kernel_launches,
+                   fallbacks=r0.exact_fallbacks,
+                   postings=sum(self.res[i].postings_scored for i in range(self.n)),
+                   alg_bytes=sum(self.res[i].algorithmic_bytes for i in range(self.n)),
+                   hits=sum(self.res[i].num_hits for i in range(self.n)),
+                   d2h=sum(32 * self.res[i].num_partial_hits for i in range(self.n)))
+        return out
+
+    def partial(self):
+        """Fixed-size per-rank partial for the all-gather: merged top-K (score bits, split, doc)."""
+        sc = np.concatenate([np.ctypeslib.as_array(C.cast(self.res[i].hits, C.POINTER(C.c_uint64)),
+                                                   shape=(self.res[i].num_partial_hits, 4)) for i in range(self.n)
+                             if self.res[i].num_partial_hits])
+        split = np.concatenate([np.full(self.res[i].num_partial_hits, i, dtype=np.uint64) for i in range(self.n)])
+        order = np.lexsort((sc[:, 2] & 0xFFFFFFFF, split, sc[:, 0]))[::-1][:K]
+        out = np.zeros((K, 3), dtype=np.uint64)
+        out[: len(order), 0] = sc[order, 0]
+        out[: len(order), 1] = split[order]
+        out[: len(order), 2] = sc[order, 2] & 0xFFFFFFFF
+        return out
+
+    def free(self):
+        for i in range(self.n):
+            self.L.qwgpu_split_result_free(C.byref(self.res[i]))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_rate(imgs, plans_q0, threads: int, min_seconds: float = 10.0):
+    """Times the CPU oracle (one split per thread) on a bounded sample; returns postings/s."""
+    from oracle import oracle as O
+    O.lib()
+    n = len(imgs)
+
+    def one(i):
+        r = O.split_search(imgs[i], plans_q0[i])
+        return sum(imgs[i].doc_freq(imgs[i].term_ord("body", f"t{j}")) for j in range(10)), r.num_hits
+    t0 = time.perf_counter()
+    postings = 0
+    rounds = 0
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        while True:
+            for p, _ in ex.map(one, range(n)):
+                postings += p
+            rounds += 1
+            if time.perf_counter() - t0 >= min_seconds or rounds >= 50:
+                break
+    dt = time.perf_counter() - t0
+    return postings / dt, dt, rounds
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "quickwit_b200", "libqwgpu.so")):
+        g.build()
+
+    workload = {"workload": "c2_bm25_or10_top1000", "splits_per_gpu": a.splits, "docs_per_split": a.docs_per_split,
+                "docs_per_gpu": a.splits * a.docs_per_split, "queries_per_step": Q_SETS, "top_k": K,
+                "term_df_fractions": FRACS, "l2": "inputs larger than L2 (disjoint term sets per query in a step)"}
+
+    if a.impl == "reference":
+        # the reference's CPU algorithm on the host cores; rank 0 only
+        if rank != 0:
+            return
+        n_s = a.cpu_sample_splits or min(a.splits, max(4, min(cores, 32)))
+        threads = min(cores, n_s)
+        imgs = build_splits(0, n_s, a.docs_per_split, threads=min(cores, 32))
+        plans = make_plans(imgs)
+        from oracle import oracle as O
+        O.lib()
+
+        def one(args):
+            q, i = args
+            O.split_search(imgs[i], plans[q][i])
+            return sum(imgs[i].doc_freq(imgs[i].term_ord("body", f"t{q * 10 + j}")) for j in range(10))
+        work = [(q, i) for q in range(Q_SETS) for i in range(n_s)]
+        times, postings_step = [], 0
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            for s in range(a.warmup + a.steps):
+                t0 = time.perf_counter()
+                postings_step = sum(ex.map(one, work))
+                dt = time.perf_counter() - t0
+                if s >= a.warmup:
+                    times.append(dt)
+        total = sum(times)
+        value = postings_step * len(times) / total
+        sample = f"{Q_SETS} queries x {n_s} of {a.splits} splits ({n_s * a.docs_per_split} docs) per step, {threads} threads"
+        print(json.dumps({"impl": "reference", "metric": "docs_scored_per_sec", "value": value, "unit": "postings/s",
+                          "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
+                          "data": "synthetic", "config": workload,
+                          "cpu_baseline": {"value": value, "unit": "postings/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": value, "unit": "postings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from quickwit_b200.service import SearcherContext
+
+    t_build = time.perf_counter()
+    imgs = build_splits(rank, a.splits, a.docs_per_split, threads=max(1, min(cores // max(world, 1), 32)))
+    plans = make_plans(imgs)
+    ctx = SearcherContext(local_rank)
+    for img in imgs:
+        ctx.register_split(img)
+    resident = ctx.resident_bytes()
+    ids = [im.split_id for im in imgs]
+    searches = [RawSearch(ctx, ids, plans[q]) for q in range(Q_SETS)]
+    t_build = time.perf_counter() - t_build
+    gather_in = torch.zeros((K, 3), dtype=torch.int64, device="cuda") if world > 1 else None
+    gather_out = torch.zeros((world * K, 3), dtype=torch.int64, device="cuda") if world > 1 else None
+
+    def step():
+        acc = dict(gpu_us=0.0, main_us=0.0, launches=0, postings=0, alg_bytes=0, d2h=0, h2d=0, fallbacks=0)
+        for s in searches:
+            r = s.run()
+            acc["gpu_us"] += r["gpu_us"]
+            acc["main_us"] += r["main_us"]
+            for k in ("launches", "postings", "alg_bytes", "d2h", "fallbacks"):
+                acc[k] += r[k]
+            acc["h2d"] += s.plan_bytes
+            if world > 1:
+                part = torch.from_numpy(s.partial().view(np.int64))
+                gather_in.copy_(part, non_blocking=True)
+                dist.all_gather_into_tensor(gather_out, gather_in)
+            s.free()
+        return acc
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sync()
+    t0 = time.perf_counter()
+    accs = [step() for _ in range(a.steps)]
+    sync()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    gpu_s = sum(x["gpu_us"] for x in accs) * 1e-6
+    main_s = sum(x["main_us"] for x in accs) * 1e-6
+    postings = sum(x["postings"] for x in accs)
+    alg_bytes = sum(x["alg_bytes"] for x in accs)
+    launches = sum(x["launches"] for x in accs)
+    n_main = a.steps * Q_SETS
+    if world > 1:
+        t = torch.tensor([gpu_s, wall, main_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gpu_s, wall, main_s = [float(x) for x in t.tolist()]
+        c = torch.tensor([postings, launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        postings, launches = [int(x) for x in c.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = (alg_bytes / n_main) / (main_s / n_main) / 1e9 if main_s > 0 else 0.0  # rank-0 kernel
+    out = {
+        "metric": "docs_scored_per_sec", "value": postings / gpu_s, "unit": "postings/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": 1e3 * gpu_s / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "config": dict(workload, parallelism=f"splits_x{world}", resident_bytes_per_gpu=resident, build_seconds=round(t_build, 1)),
+        "e2e": {"value": postings / wall, "unit": "postings/s", "ms_per_step": 1e3 * wall / a.steps,
+                "p50_query_latency_ms": 1e3 * wall / (a.steps * Q_SETS),
+                "h2d_bytes_per_step": accs[0]["h2d"], "d2h_bytes_per_step": accs[0]["d2h"]},
+        "gpu_launches": launches,
+        "exact_fallbacks": sum(x["fallbacks"] for x in accs),
+        "roofline": {"bound": "hbm", "kernel": "k_window<COLLECT>", "achieved": achieved, "peak": peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_bytes / n_main, "avg_launch_us": 1e6 * main_s / n_main},
+        "clocks": clocks,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        n_s = a.cpu_sample_splits or min(a.splits, max(4, min(cores, 32)))
+        threads = min(cores, n_s)
+        rate, dt, rounds = cpu_oracle_rate(imgs[:n_s], plans[0][:n_s], threads)
+        out["cpu_baseline"] = {"value": rate, "unit": "postings/s", "cores": threads, "kind": "port",
+                               "sample": f"query set 0 over {n_s} splits x {rounds} rounds ({dt:.1f} s), one split per thread"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

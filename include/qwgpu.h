@@ -99,7 +99,9 @@ typedef struct qwgpu_split_result {
   QwAggCell* agg_cells;      /* malloc'ed; free with qwgpu_buf_free */
   /* measurement: device time of the search kernels of this call (CUDA events), microseconds */
   float gpu_time_us;
+  float main_kernel_us;      /* device time of the dominant kernel (k_window<COLLECT>) of this call */
   uint32_t num_kernel_launches;
+  uint32_t exact_fallbacks;  /* 1 when the sampled top-K threshold failed verification */
   uint64_t postings_scored; /* Σ doc_freq of the plan's terms ("docs scored") */
   uint64_t algorithmic_bytes; /* SURVEY.md §8d numerator for this split/plan */
 } qwgpu_split_result;

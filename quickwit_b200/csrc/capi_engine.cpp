@@ -83,7 +83,9 @@ int qwgpu_split_search(qwgpu_ctx* ctx, uint32_t num_splits, const char* const* s
       memcpy(r.agg_cells, outs[i].cells.data(), outs[i].cells.size() * sizeof(QwAggCell));
     }
     r.gpu_time_us = st.gpu_time_us;
+    r.main_kernel_us = st.main_kernel_us;
     r.num_kernel_launches = st.launches;
+    r.exact_fallbacks = st.exact_fallbacks;
     r.postings_scored = outs[i].postings_scored;
     r.algorithmic_bytes = outs[i].algorithmic_bytes;
   }

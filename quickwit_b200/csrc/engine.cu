@@ -31,7 +31,7 @@ SplitDev::~SplitDev() {
 
 struct CallSlot {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   uint8_t *d_blob = nullptr, *h_blob = nullptr;
   size_t blob_cap = 0;
   uint8_t* d_scratch = nullptr;
@@ -67,6 +67,8 @@ struct CallSlot {
     if (h_out) cudaFreeHost(h_out);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev2) cudaEventDestroy(ev2);
+    if (ev3) cudaEventDestroy(ev3);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -512,6 +514,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&slot->ev0));
     CUDA_CHECK(cudaEventCreate(&slot->ev1));
+    CUDA_CHECK(cudaEventCreate(&slot->ev2));
+    CUDA_CHECK(cudaEventCreate(&slot->ev3));
   }
   struct Release { Engine* e; CallSlot* s; ~Release() { std::lock_guard<std::mutex> g(e->mu); e->free_slots.push_back(s); } } rel{this, slot};
   slot->ensure(blob_bytes, scratch_bytes, out_bytes);
@@ -567,7 +571,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   const uint32_t sel_smem = 3 * 8 * QW_CAND_CAP;
   auto run_collect = [&]() {
     CUDA_CHECK(cudaMemsetAsync(slot->d_out, 0, out_bytes, st));
+    CUDA_CHECK(cudaEventRecord(slot->ev2, st));
     launch_window(qwk::MODE_COLLECT, false, 0, 0);
+    CUDA_CHECK(cudaEventRecord(slot->ev3, st));
     if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans); stats.launches++; }
     CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     stats.d2h_bytes += out_bytes;
@@ -634,6 +640,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     float ms = 0;
     cudaEventElapsedTime(&ms, slot->ev0, slot->ev1);
     stats.gpu_time_us += ms * 1000.f;
+    cudaEventElapsedTime(&ms, slot->ev2, slot->ev3);
+    stats.main_kernel_us = ms * 1000.f;
   }
 
   // ---- unpack ---------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ struct SplitOutput {
 };
 struct BatchStats {
   float gpu_time_us = 0;
+  float main_kernel_us = 0;
   uint32_t launches = 0;
   uint32_t exact_fallbacks = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;

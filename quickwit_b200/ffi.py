@@ -113,7 +113,8 @@ class SplitResult(C.Structure):
     _fields_ = [("num_hits", C.c_uint64), ("num_partial_hits", C.c_uint32),
                 ("num_agg_cells", C.c_uint32), ("hits", C.POINTER(QwHit)),
                 ("agg_cells", C.POINTER(QwAggCell)), ("gpu_time_us", C.c_float),
-                ("num_kernel_launches", C.c_uint32), ("postings_scored", C.c_uint64),
+                ("main_kernel_us", C.c_float), ("num_kernel_launches", C.c_uint32),
+                ("exact_fallbacks", C.c_uint32), ("postings_scored", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64)]
 
 

@@ -29,6 +29,8 @@ class SplitSearchResult:
         self.cells = [(c.count, c.sum_bits, c.min_mapped, c.max_mapped)
                       for c in (r.agg_cells[i] for i in range(r.num_agg_cells))]
         self.gpu_time_us = float(r.gpu_time_us)
+        self.main_kernel_us = float(r.main_kernel_us)
+        self.exact_fallbacks = int(r.exact_fallbacks)
         self.num_kernel_launches = int(r.num_kernel_launches)
         self.postings_scored = int(r.postings_scored)
         self.algorithmic_bytes = int(r.algorithmic_bytes)
