@@ -27,7 +27,7 @@ extern "C" {
 #define QW_BLOCK_LEN 128u                  /* tantivy COMPRESSION_BLOCK_SIZE */
 #define QW_TERMINATED 0x7FFFFFFFu          /* tantivy TERMINATED sentinel (i32::MAX as u32) */
 #define QW_NO_PREV_DOC 0xFFFFFFFFu
-#define QW_MIN_WIN_SHIFT 12u /* evaluation windows are <= 4096 docs and never straddle an index window */
+#define QW_MIN_WIN_SHIFT 12u /* index windows are >= 4096 docs; an evaluation window (<= 8192 docs) spans <= 2 entries */
 
 /* ---------------------------------------------------------------- image ---------------------- */
 

@@ -22,6 +22,7 @@
 
 enum { OP_TERM = 1, OP_RANGE = 2, OP_EXISTS = 3, OP_ALL = 4, OP_BOOL_BEGIN = 5, OP_BOOL_END = 6 };
 enum { IF_SCORED = 1u, IF_HAS_TF = 2u, IF_HAS_FN = 4u };
+#define QW_TFF_ROWS 16 /* tf-factor table: tff[tf][fieldnorm_id] = tf / (tf + norm[id]) for tf < 16 */
 
 struct DInstr {  // 64 bytes
   uint32_t op, level, occur, flags;
@@ -81,7 +82,8 @@ struct DSplitPlan {
   uint32_t max_hits, scoring;
   uint32_t n_fn_slots, n_cells;
   uint64_t fn_off[2];      // data-relative fieldnorm arrays staged per window
-  uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables
+  uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables, followed by the
+                           // float[QW_TFF_ROWS][256] tf-factor table of the same field
   DKeySpec key;
   QwSearchAfter sa;
   uint64_t out_num_hits;   // device address of a uint64 counter
@@ -95,11 +97,12 @@ struct DSplitPlan {
 
 struct SmemLevel {
   uint32_t req, shd, nt, cnt, msum, ssum;  // byte offsets; 0xFFFFFFFF = not allocated
+  uint32_t rsc, pad;                       // result score array of the level (msum, else ssum)
 };
 struct SmemLayout {
   uint32_t instr, cols, aggs;
   SmemLevel lvl[QW_MAX_LEVELS];
-  uint32_t tmp, fn[2], tab[2];
+  uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
   uint32_t rng, blktab, blkcnt, stage, hist, misc;
   uint32_t total;
 };
@@ -114,7 +117,7 @@ struct KParams {
   uint32_t n_splits;
   uint32_t total_work;
   uint32_t stride;   // sampling stride over windows (1 = all)
-  uint32_t W;        // window size in docs (power of two, <= 4096)
+  uint32_t W;        // window size in docs (power of two, <= 8192)
   uint32_t level;    // MODE_HIST: radix level being histogrammed
   uint32_t use_prefix;  // MODE_HIST: restrict to docs whose key matches thresh prefix
   uint32_t smem_aggs;   // 1: aggregation counts privatised in shared memory

@@ -118,11 +118,20 @@ void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
   CUDA_CHECK(cudaMemcpy(sp->d_data, full.data, sp->data_len, cudaMemcpyHostToDevice));
   // Bm25Weight cache per field: K1 * (1 - B + B * fieldnorm(id) / avg)
   uint32_t nf = full.hdr->num_fields;
-  std::vector<float> tabs((size_t)std::max(nf, 1u) * 256);
+  // followed, per field, by the tf-factor table tff[tf][id] = tf / (tf + norm[id]) (tf < 16), built with
+  // the same IEEE f32 ops the kernel would use, so table lookups are bit-identical to dividing
+  const size_t kTab = 256 + QW_TFF_ROWS * 256;
+  std::vector<float> tabs((size_t)std::max(nf, 1u) * kTab);
   for (uint32_t f = 0; f < nf; f++) {
     float avg = (float)full.fields[f].total_num_tokens / (float)full.hdr->num_docs;
+    float* t = tabs.data() + f * kTab;
     for (uint32_t i = 0; i < 256; i++)
-      tabs[f * 256 + i] = BM25_K1 * (1.0f - BM25_B + BM25_B * (float)id_to_fieldnorm((uint8_t)i) / avg);
+      t[i] = BM25_K1 * (1.0f - BM25_B + BM25_B * (float)id_to_fieldnorm((uint8_t)i) / avg);
+    for (uint32_t tf = 0; tf < QW_TFF_ROWS; tf++)
+      for (uint32_t i = 0; i < 256; i++) {
+        volatile float num = (float)tf, den = (float)tf + t[i];
+        t[256 + tf * 256 + i] = num / den;
+      }
   }
   CUDA_CHECK(cudaMalloc(&sp->d_tabs, tabs.size() * sizeof(float)));
   CUDA_CHECK(cudaMemcpy(sp->d_tabs, tabs.data(), tabs.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -168,7 +177,7 @@ struct Lowered {
   std::vector<DCol> cols;
   std::vector<DAgg> aggs;
   std::vector<int> col_map;  // image column -> DCol index
-  uint32_t need_cnt = 0, need_ssum = 0, levels = 0;  // bit per level
+  uint32_t need_cnt = 0, need_ssum = 0, need_msum = 0, levels = 0;  // bit per level
   float score_max = 0.f;
   int fn_field[2] = {-1, -1};
   uint64_t postings = 0, alg_bytes = 0, min_required_df = ~0ull;
@@ -276,12 +285,13 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
       for (uint32_t c : order) {
         const QwPlanNode& cn = child(c);
         uint32_t child_level = cn.kind == QW_NODE_BOOL ? level + 1 : level;
+        if (scored && cn.occur == QW_OCCUR_MUST) L.need_msum |= 1u << level;
+        if (scored && cn.occur == QW_OCCUR_SHOULD) L.need_ssum |= 1u << level;
         lower_node(L, sp, nodes, nn, n.first_child + c, child_level, cn.occur, scored);
       }
       uint32_t msm = n.min_should_match == 0xFFFFFFFFu ? 0 : n.min_should_match;
       uint32_t need = msm > 0 ? msm : (n_req == 0 ? 1 : 0);
       if (need >= 2) L.need_cnt |= 1u << level;
-      if (n_should) L.need_ssum |= 1u << level;
       DInstr en;
       memset(&en, 0, sizeof en);
       en.op = OP_BOOL_END; en.level = level; en.occur = occur; en.flags = scored ? IF_SCORED : 0;
@@ -318,6 +328,7 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
   } else {
     DInstr bg; memset(&bg, 0, sizeof bg); bg.op = OP_BOOL_BEGIN; L.instrs.push_back(bg);
     L.levels |= 1;
+    if (scoring) L.need_msum |= 1;
     lower_node(L, sp, nodes, ph->num_nodes, 0, 0, QW_OCCUR_MUST, scoring);
     DInstr en; memset(&en, 0, sizeof en); en.op = OP_BOOL_END; en.n = 1; en.flags = scoring ? IF_SCORED : 0; L.instrs.push_back(en);
   }
@@ -332,7 +343,7 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
     if (L.fn_field[s] >= 0) {
       const QwImgField& f = sp.view.fields[L.fn_field[s]];
       P.n_fn_slots = s + 1;
-      P.bm25_tab[s] = (uint64_t)(sp.d_tabs + 256 * L.fn_field[s]);
+      P.bm25_tab[s] = (uint64_t)(sp.d_tabs + (size_t)(256 + QW_TFF_ROWS * 256) * L.fn_field[s]);
       if (f.flags & QW_FIELD_HAS_FIELDNORMS) {
         P.fn_off[s] = f.fieldnorm_off;
         L.alg_bytes += std::min<uint64_t>(L.postings, P.num_docs);
@@ -400,8 +411,8 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
 }
 
 // shared-memory arena for a batch (max over the batch's plans)
-static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_ssum, bool scoring,
-                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn, bool hist_or_aggs) {
+static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_msum, uint32_t need_ssum,
+                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn) {
   SmemLayout L;
   memset(&L, 0xFF, sizeof L);
   uint32_t off = 0;
@@ -415,16 +426,17 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
     L.lvl[l].shd = take(W / 8);
     L.lvl[l].nt = take(W / 8);
     if ((need_cnt >> l) & 1) L.lvl[l].cnt = take(W);
-    if (scoring) L.lvl[l].msum = take(W * 4);
-    if (scoring && ((need_ssum >> l) & 1)) L.lvl[l].ssum = take(W * 4);
+    if ((need_msum >> l) & 1) L.lvl[l].msum = take(W * 4);
+    if ((need_ssum >> l) & 1) L.lvl[l].ssum = take(W * 4);
+    L.lvl[l].rsc = L.lvl[l].msum != 0xFFFFFFFFu ? L.lvl[l].msum : L.lvl[l].ssum;
   }
   L.tmp = take(W / 8);
-  for (uint32_t s = 0; s < n_fn; s++) { L.fn[s] = take(W); L.tab[s] = take(1024); }
+  for (uint32_t s = 0; s < n_fn; s++) { L.fn[s] = take(W); L.tab[s] = take((256 + QW_TFF_ROWS * 256) * 4); }
   L.rng = take(QW_MAX_TERMS * 16);
   L.blktab = take(QW_MAX_TERMS * QW_BLK_TAB * 2);
   L.blkcnt = take(QW_MAX_TERMS * 4);
   L.stage = take(QW_STAGE_BYTES);
-  L.hist = take(hist_or_aggs ? QW_SMEM_AGG_CELLS * 4 : 16);
+  L.hist = take(QW_SMEM_AGG_CELLS * 4);
   L.total = off;
   return L;
 }
@@ -454,12 +466,12 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (n == 0) return;
 
   // ---- batch-wide parameters --------------------------------------------------------------------------
-  uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
+  uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, need_msum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
   bool scoring = false, any_topk = false, any_aggs = false, smem_aggs = true;
   uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0;
   for (auto& L : low) {
     n_levels = std::max(n_levels, L.P.n_levels);
-    need_cnt |= L.need_cnt; need_ssum |= L.need_ssum;
+    need_cnt |= L.need_cnt; need_ssum |= L.need_ssum; need_msum |= L.need_msum;
     max_instr = std::max(max_instr, L.P.n_instr); max_cols = std::max(max_cols, L.P.n_cols); max_aggs = std::max(max_aggs, L.P.n_aggs);
     n_fn = std::max(n_fn, L.P.n_fn_slots);
     scoring |= L.P.scoring != 0; any_topk |= L.P.max_hits > 0; any_aggs |= L.P.n_aggs > 0;
@@ -467,13 +479,14 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
     tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
   }
-  uint32_t W = 4096;
+  uint32_t W = 8192;
   SmemLayout lay;
   for (;;) {
-    lay = make_layout(W, n_levels, need_cnt, need_ssum, scoring, max_instr, max_cols, max_aggs, n_fn, true);
-    if ((int)lay.total <= max_smem_optin / 2 || W == 1024) break;  // keep >= 2 blocks per SM
+    lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn);
+    if ((int)lay.total + 1024 <= max_smem_optin / 2 || W == 1024) break;  // keep >= 2 blocks per SM
     W >>= 1;
   }
+  (void)scoring;
   if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
 
   // ---- device blob: plans, programs, work maps ----------------------------------------------------------

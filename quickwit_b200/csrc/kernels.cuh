@@ -136,11 +136,11 @@ struct Sm {
 };
 
 struct TermTarget {
-  uint32_t* bits;   // bitmap receiving the term's docs
-  uint8_t* cnt;     // optional per-doc should counter
-  float* score;     // optional score accumulator
-  const uint8_t* fn;  // staged fieldnorm ids of the window (or null)
-  const float* tab;   // BM25 norm table (float[256])
+  uint32_t* bits;     // bitmap receiving the term's docs
+  uint8_t* cnt;       // optional per-doc should counter
+  float* score;       // optional score accumulator
+  const uint8_t* fn;  // staged fieldnorm ids of the window (or null: constant fieldnorm id 1)
+  const float* tab;   // float[256] BM25 norms followed by float[QW_TFF_ROWS][256] tf factors
   float weight;
   bool has_tf;
 };
@@ -148,6 +148,7 @@ struct TermTarget {
 // Decode one posting block (header + 4-lane-interleaved bit-packed doc deltas + tfs) with one warp
 // and fold the postings that fall into [ws, we) into the target. `blk` may point to shared or
 // global memory (generic addressing).
+template <bool SCORED, bool CNT>
 __device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint32_t we, const TermTarget& tg, uint32_t lane) {
   const uint4 h = *reinterpret_cast<const uint4*>(blk);  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
   const uint32_t last_doc = h.x, prev = h.y;
@@ -174,10 +175,12 @@ __device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint
     uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
     if ((int)lane >= o) incl += n;
   }
-  uint32_t basev = prev + (incl - d3);  // mod 2^32 (prev == 0xFFFFFFFF for the first block)
-  uint32_t doc[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
+  const uint32_t basev = prev + (incl - d3) - ws;  // mod 2^32; window-relative
+  uint32_t rel[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
+  const uint32_t wlen = we - ws;
+  const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;  // postings of this lane that exist
   uint32_t tf[4] = {1, 1, 1, 1};
-  if (tg.score && tg.has_tf && tf_bits) {
+  if (SCORED && tg.has_tf && tf_bits) {
     const uint4* tp = dp + doc_bits;
     uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
     uint4 A = tp[wi];
@@ -191,27 +194,58 @@ __device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint
   uint32_t cur_word = 0xFFFFFFFFu, cur_mask = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    uint32_t idx = lane * 4 + j;
-    if (idx < count && doc[j] >= ws && doc[j] < we) {
-      uint32_t d = doc[j] - ws;
-      uint32_t w = d >> 5;
+    const uint32_t d = rel[j];  // < wlen  <=>  ws <= doc < we (unsigned wrap)
+    if ((uint32_t)j < nvalid && d < wlen) {
+      const uint32_t w = d >> 5;
       if (w != cur_word) {
         if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
         cur_word = w;
         cur_mask = 0;
       }
       cur_mask |= 1u << (d & 31);
-      if (tg.cnt) tg.cnt[d] = (uint8_t)(tg.cnt[d] + 1);
-      if (tg.score) {
-        // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), all f32 round-to-nearest
-        float tff = (float)tf[j];
-        float norm = tg.tab[tg.fn ? tg.fn[d] : 1];
-        float s = __fmul_rn(tg.weight, __fdiv_rn(tff, __fadd_rn(tff, norm)));
-        tg.score[d] = __fadd_rn(tg.score[d], s);
+      if (CNT) tg.cnt[d] = (uint8_t)(tg.cnt[d] + 1);
+      if (SCORED) {
+        // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest.
+        // tf / (tf + norm) comes from a table built with the same IEEE ops for tf < 16.
+        const uint32_t f = tg.fn ? tg.fn[d] : 1u;
+        const uint32_t t = tf[j];
+        float tfn;
+        if (t < QW_TFF_ROWS) tfn = tg.tab[256 + t * 256 + f];
+        else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tg.tab[f])); }
+        tg.score[d] = __fadd_rn(tg.score[d], __fmul_rn(tg.weight, tfn));
       }
     }
   }
   if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
+}
+
+__device__ __forceinline__ void fold_block_dyn(const uint8_t* blk, uint32_t ws, uint32_t we, const TermTarget& tg, uint32_t lane) {
+  if (tg.score) { if (tg.cnt) fold_block<true, true>(blk, ws, we, tg, lane); else fold_block<true, false>(blk, ws, we, tg, lane); }
+  else { if (tg.cnt) fold_block<false, true>(blk, ws, we, tg, lane); else fold_block<false, false>(blk, ws, we, tg, lane); }
+}
+
+// The 11 most significant bits of the composite key ([has1 | lin1]) — enough for the level-0 radix
+// digit and for the cheap threshold pre-filter; avoids building the 192-bit key for every match.
+__device__ __forceinline__ uint32_t key_top11(const DKeySpec& ks, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
+  const bool desc1 = ks.order[0] == QW_ORDER_DESC;
+  if (ks.kind[0] == QW_SORT_SCORE) {
+    float x = __fmul_rn(score, ks.score_scale);
+    uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
+    return 1024u | (desc1 ? l : 1023u - l);
+  }
+  if (ks.kind[0] == QW_SORT_COLUMN && ks.col[0] != 0xFFFFFFFFu) {
+    const DCol& c = cols[ks.col[0]];
+    uint64_t a, b;
+    col_range(base, c, doc, a, b);
+    if (a == b) return 0;
+    uint64_t raw = col_raw(base, c, a);
+    uint64_t r = desc1 ? raw : ks.raw_max - raw;
+    uint64_t l = (r >> ks.lin_shr) << ks.lin_shl;
+    return 1024u | (l > 1023 ? 1023u : (uint32_t)l);
+  }
+  uint32_t r = desc1 ? doc : (uint32_t)ks.raw_max - doc;
+  uint64_t l = ((uint64_t)r >> ks.lin_shr) << ks.lin_shl;
+  return l > 1023 ? 1023u : (uint32_t)l;
 }
 
 // Composite key + eligibility of one matched doc (sort-value extraction:
@@ -370,8 +404,14 @@ __device__ void agg_collect_doc(const KParams& p, const Sm& sm, const DSplitPlan
 
 enum { MODE_HIST = 0, MODE_COLLECT = 1 };
 
+__device__ __forceinline__ void zero_f4(float* p, uint32_t n, uint32_t tid) {
+  float4* q = reinterpret_cast<float4*>(p);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t i = tid; i < (n >> 2); i += QW_THREADS) q[i] = z;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
+__global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Sm sm{smem_raw, &p.sm};
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -379,7 +419,7 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
   DInstr* s_instr = (DInstr*)sm.u8(p.sm.instr);
   DCol* s_cols = (DCol*)sm.u8(p.sm.cols);
   DAgg* s_aggs = (DAgg*)sm.u8(p.sm.aggs);
-  uint32_t* s_misc = sm.u32(p.sm.misc);  // [0] split, [1] window, [2] scratch counter, [3] eligible counter
+  uint32_t* s_misc = sm.u32(p.sm.misc);  // [2] hits counter, [3] eligible counter
   uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off, instr index
   uint16_t* s_blktab = (uint16_t*)sm.u8(p.sm.blktab);
   uint32_t* s_blkcnt = sm.u32(p.sm.blkcnt);
@@ -387,85 +427,95 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
   uint8_t* s_stage = sm.u8(p.sm.stage);
   uint32_t loaded_split = 0xFFFFFFFFu;
 
-  for (uint32_t work = blockIdx.x; work < p.total_work; work += gridDim.x) {
-    // ---- map flat work index -> (split, window) -------------------------------------------------
-    if (tid == 0) {
-      uint32_t lo = 0, hi = p.n_splits;
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(p.first_work + mid) <= work) lo = mid; else hi = mid;
-      }
-      s_misc[0] = lo;
-      uint32_t j = work - __ldg(p.first_work + lo);
-      s_misc[1] = j * p.stride + (p.stride > 1 ? lo % p.stride : 0);
-      s_misc[2] = 0;
-      s_misc[3] = 0;
+  // static contiguous partition of the flat (split, window) work list: a block walks consecutive
+  // windows, so it changes split (and reloads its program) at most a few times
+  const uint32_t per = (p.total_work + gridDim.x - 1) / gridDim.x;
+  const uint32_t w_begin = blockIdx.x * per;
+  const uint32_t w_end = min(w_begin + per, p.total_work);
+  uint32_t split = 0;
+  if (w_begin < w_end) {
+    uint32_t lo = 0, hi = p.n_splits;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(p.first_work + mid) <= w_begin) lo = mid; else hi = mid;
     }
-    __syncthreads();
-    const uint32_t split = s_misc[0], window = s_misc[1];
+    split = lo;
+  }
+
+  for (uint32_t work = w_begin; work < w_end; work++) {
+    while (__ldg(p.first_work + split + 1) <= work) split++;
+    const uint32_t window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
     const DSplitPlan& P = p.plans[split];
     if (split != loaded_split) {
-      // (re)load the split's program, columns, aggregations and BM25 tables into shared memory
+      __syncthreads();  // previous window fully done before its program is overwritten
       const uint4* src = (const uint4*)(p.instrs + P.instr_base);
       for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += QW_THREADS) ((uint4*)s_instr)[i] = __ldg(src + i);
       src = (const uint4*)(p.cols + P.col_base);
       for (uint32_t i = tid; i < P.n_cols * (sizeof(DCol) / 16); i += QW_THREADS) ((uint4*)s_cols)[i] = __ldg(src + i);
       src = (const uint4*)(p.aggs + P.agg_base);
       for (uint32_t i = tid; i < P.n_aggs * (sizeof(DAgg) / 16); i += QW_THREADS) ((uint4*)s_aggs)[i] = __ldg(src + i);
-      for (uint32_t s = 0; s < P.n_fn_slots; s++)
-        for (uint32_t i = tid; i < 256; i += QW_THREADS) sm.f32(p.sm.tab[s])[i] = __ldg((const float*)P.bm25_tab[s] + i);
+      for (uint32_t s = 0; s < P.n_fn_slots; s++) {
+        const uint8_t* tsrc = (const uint8_t*)P.bm25_tab[s];
+        uint8_t* tdst = sm.u8(p.sm.tab[s]);
+        for (uint32_t i = tid; i < (256 + QW_TFF_ROWS * 256) * 4 / 16; i += QW_THREADS) cp_async16(tdst + 16 * i, tsrc + 16 * i);
+      }
       if (MODE == MODE_HIST || p.smem_aggs)
         for (uint32_t i = tid; i < QW_HIST_BINS * ((MODE == MODE_COLLECT) ? 2 : 1); i += QW_THREADS) s_hist[i] = 0;
       loaded_split = split;
+      cp_async_wait_all();
       __syncthreads();
       if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
-      __syncthreads();
     }
     const uint8_t* base = (const uint8_t*)P.data_base;
     const uint32_t ws = window * W;
     const uint32_t we = min(ws + W, P.num_docs);
+    const uint32_t n_terms = P.n_terms, n_instr = P.n_instr, n_fn = P.n_fn_slots;
+    __syncthreads();
 
-    // ---- phase 1: window-index entries + fieldnorm staging --------------------------------------
-    if (tid < P.n_terms) {
+    // ---- phase 1: window-index entries + fieldnorm staging (one round of independent loads) --------
+    if (tid < n_terms) {
       const DInstr& in = s_instr[s_rng[4 * tid + 3]];
       uint32_t start = 0, len = 0;
       if (in.n) {
-        const QwWinIdx* wi = (const QwWinIdx*)(base + in.b);
-        uint2 e = __ldg((const uint2*)(wi + (ws >> in.m)));
-        start = e.x;
-        len = e.y - e.x;
+        const uint2* wi = (const uint2*)(base + in.b);
+        const uint32_t e0 = ws >> in.m, e1 = (we - 1) >> in.m;
+        uint2 a = __ldg(wi + e0);
+        uint2 b = e1 != e0 ? __ldg(wi + e1) : a;
+        start = a.x;
+        len = b.y > a.x ? b.y - a.x : 0;
       }
       s_rng[4 * tid + 0] = start;
       s_rng[4 * tid + 1] = len;
     }
-    for (uint32_t s = 0; s < P.n_fn_slots; s++) {
+    if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
+    for (uint32_t s = 0; s < n_fn; s++) {
       if (P.fn_off[s] == ~0ull) continue;
-      const uint4* src = (const uint4*)(base + P.fn_off[s] + ws);
-      uint4* dst = (uint4*)sm.u8(p.sm.fn[s]);
-      for (uint32_t i = tid; i < (W >> 4); i += QW_THREADS) dst[i] = __ldg(src + i);
+      const uint8_t* src = base + P.fn_off[s] + ws;
+      uint8_t* dst = sm.u8(p.sm.fn[s]);
+      const uint32_t n16 = min(W, (we - ws + 15u) & ~15u) >> 4;  // the array is padded by 16 bytes only
+      for (uint32_t i = tid; i < n16; i += QW_THREADS) cp_async16(dst + 16 * i, src + 16 * i);
     }
     __syncthreads();
-    // ---- phase 2: stage packed posting bytes ------------------------------------------------------
+    // ---- phase 2: stage packed posting bytes (warp per term) ---------------------------------------------
     if (tid == 0) {
       uint32_t off = 0;
-      for (uint32_t t = 0; t < P.n_terms; t++) {
+      for (uint32_t t = 0; t < n_terms; t++) {
         uint32_t len = s_rng[4 * t + 1];
         if (len && off + len <= QW_STAGE_BYTES) { s_rng[4 * t + 2] = off; off += len; }
         else s_rng[4 * t + 2] = 0xFFFFFFFFu;
       }
     }
     __syncthreads();
-    for (uint32_t t = 0; t < P.n_terms; t++) {
-      uint32_t so = s_rng[4 * t + 2];
+    for (uint32_t t = warp; t < n_terms; t += QW_WARPS) {
+      const uint32_t so = s_rng[4 * t + 2];
       if (so == 0xFFFFFFFFu) continue;
-      const DInstr& in = s_instr[s_rng[4 * t + 3]];
-      const uint8_t* src = base + in.a + s_rng[4 * t + 0];
-      uint32_t n16 = s_rng[4 * t + 1] >> 4;
-      for (uint32_t i = tid; i < n16; i += QW_THREADS) cp_async16(s_stage + so + 16 * i, src + 16 * i);
+      const uint8_t* src = base + s_instr[s_rng[4 * t + 3]].a + s_rng[4 * t + 0];
+      const uint32_t n16 = s_rng[4 * t + 1] >> 4;
+      for (uint32_t i = lane; i < n16; i += 32) cp_async16(s_stage + so + 16 * i, src + 16 * i);
     }
     cp_async_wait_all();
     __syncthreads();
-    if (tid < P.n_terms) {
+    if (tid < n_terms) {
       uint32_t so = s_rng[4 * tid + 2];
       uint32_t k = 0;
       if (so != 0xFFFFFFFFu) {
@@ -483,28 +533,30 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
 
     // ---- execute the boolean program ----------------------------------------------------------------
     uint32_t req_init = 0;  // bit per level, uniform across the block
-    for (uint32_t ip = 0; ip < P.n_instr; ip++) {
-      const DInstr in = s_instr[ip];
-      const SmemLevel& LV = p.sm.lvl[in.level];
+    for (uint32_t ip = 0; ip < n_instr; ip++) {
+      const DInstr& in = s_instr[ip];
+      const uint32_t op = in.op, level = in.level, occur = in.occur;
+      const SmemLevel& LV = p.sm.lvl[level];
       const bool scored = (in.flags & IF_SCORED) != 0;
-      if (in.op == OP_BOOL_BEGIN) {
-        for (uint32_t i = tid; i < NW; i += QW_THREADS) { sm.u32(LV.shd)[i] = 0; sm.u32(LV.nt)[i] = 0; }
-        if (LV.cnt != 0xFFFFFFFFu) for (uint32_t i = tid; i < (W >> 2); i += QW_THREADS) sm.u32(LV.cnt)[i] = 0;
-        if (LV.msum != 0xFFFFFFFFu) for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(LV.msum)[i] = 0.0f;
-        if (LV.ssum != 0xFFFFFFFFu) for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(LV.ssum)[i] = 0.0f;
-        req_init &= ~(1u << in.level);
+      if (op == OP_BOOL_BEGIN) {
+        zero_f4((float*)sm.u32(LV.shd), NW, tid);
+        zero_f4((float*)sm.u32(LV.nt), NW, tid);
+        if (LV.cnt != 0xFFFFFFFFu) zero_f4((float*)sm.u32(LV.cnt), W >> 2, tid);
+        if (LV.msum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.msum), W, tid);
+        if (LV.ssum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.ssum), W, tid);
+        req_init &= ~(1u << level);
         __syncthreads();
-      } else if (in.op == OP_TERM) {
-        const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
+      } else if (op == OP_TERM) {
+        const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
         TermTarget tg;
         tg.cnt = nullptr;
         tg.score = nullptr;
         if (required) {
           tg.bits = sm.u32(p.sm.tmp);
-          for (uint32_t i = tid; i < NW; i += QW_THREADS) tg.bits[i] = 0;
+          zero_f4((float*)tg.bits, NW, tid);
           if (scored) tg.score = sm.f32(LV.msum);
           __syncthreads();
-        } else if (in.occur == QW_OCCUR_SHOULD) {
+        } else if (occur == QW_OCCUR_SHOULD) {
           tg.bits = sm.u32(LV.shd);
           if (LV.cnt != 0xFFFFFFFFu) tg.cnt = sm.u8(LV.cnt);
           if (scored) tg.score = sm.f32(LV.ssum);
@@ -523,12 +575,17 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
         const uint32_t so = s_rng[4 * slot + 2];
         if (so != 0xFFFFFFFFu) {
           const uint32_t nb = s_blkcnt[slot];
-          for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block(s_stage + so + s_blktab[slot * QW_BLK_TAB + k], ws, we, tg, lane);
+          const uint16_t* tab = s_blktab + slot * QW_BLK_TAB;
+          const uint8_t* sb = s_stage + so;
+          if (tg.score && !tg.cnt) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false>(sb + tab[k], ws, we, tg, lane); }
+          else if (!tg.score && !tg.cnt) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<false, false>(sb + tab[k], ws, we, tg, lane); }
+          else { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block_dyn(sb + tab[k], ws, we, tg, lane); }
         } else if (s_rng[4 * slot + 1]) {
           // direct mode: locate the first block with last_doc >= ws in the skip list (warp-cooperative
           // 32-ary search), then decode straight from global memory
           const QwSkip* skips = (const QwSkip*)(base + in.c);
-          uint32_t lo = 0, hi = in.n;
+          const uint32_t nblk = in.n;
+          uint32_t lo = 0, hi = nblk;
           while (hi - lo > 32) {
             uint32_t step = (hi - lo + 31) >> 5;
             uint32_t idx = lo + lane * step;
@@ -546,43 +603,51 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
           uint32_t idx = lo + lane;
           bool ok = idx < hi && __ldg(&skips[idx].last_doc) >= ws;
           uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-          uint32_t b0 = m ? lo + (__ffs(m) - 1) : in.n;
-          for (uint32_t b = b0 + warp; b < in.n; b += QW_WARPS) {
+          uint32_t b0 = m ? lo + (__ffs(m) - 1) : nblk;
+          const uint8_t* tdata = base + in.a;
+          for (uint32_t b = b0 + warp; b < nblk; b += QW_WARPS) {
             uint4 h = __ldg((const uint4*)&skips[b]);
             if (h.y != QW_NO_PREV_DOC && h.y + 1 >= we) break;
-            fold_block(base + in.a + h.z, ws, we, tg, lane);
+            fold_block_dyn(tdata + h.z, ws, we, tg, lane);
           }
         }
         __syncthreads();
         if (required) {
           uint32_t* req = sm.u32(LV.req);
           const uint32_t* tmp = sm.u32(p.sm.tmp);
-          const bool init = (req_init >> in.level) & 1;
+          const bool init = (req_init >> level) & 1;
           for (uint32_t i = tid; i < NW; i += QW_THREADS) req[i] = init ? (req[i] & tmp[i]) : tmp[i];
-          req_init |= 1u << in.level;
+          req_init |= 1u << level;
           __syncthreads();
         }
-      } else if (in.op == OP_RANGE || in.op == OP_EXISTS || in.op == OP_ALL) {
-        const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
-        const bool init = (req_init >> in.level) & 1;
+      } else if (op == OP_RANGE || op == OP_EXISTS || op == OP_ALL) {
+        const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
+        const bool init = (req_init >> level) & 1;
         const bool gather = required && init;
         uint32_t* req = sm.u32(LV.req);
-        const bool has_col = in.op == OP_ALL || in.r != 0xFFFFFFFFu;
+        const uint32_t col = in.r;
+        const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
+        const uint64_t lo = in.a, hi = in.b;
+        const float boost = in.f;
         for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t d = ws + wd * 32 + lane;
           bool cand = d < we && has_col;
-          if (gather) cand = cand && ((req[wd] >> lane) & 1);
+          if (gather) {
+            const uint32_t rw = req[wd];
+            if (rw == 0) continue;  // warp-uniform
+            cand = cand && ((rw >> lane) & 1);
+          }
           bool hit = false;
           if (cand) {
-            if (in.op == OP_ALL) hit = true;
+            if (op == OP_ALL) hit = true;
             else {
-              const DCol& c = s_cols[in.r];
+              const DCol& c = s_cols[col];
               uint64_t a, b;
               col_range(base, c, d, a, b);
-              if (in.op == OP_EXISTS) hit = a != b;
+              if (op == OP_EXISTS) hit = a != b;
               else for (uint64_t i = a; i < b && !hit; i++) {
                 uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
-                hit = mv >= in.a && mv <= in.b;
+                hit = mv >= lo && mv <= hi;
               }
             }
           }
@@ -590,25 +655,25 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
           const uint32_t di = wd * 32 + lane;
           if (required) {
             if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
-            if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], in.f);
-          } else if (in.occur == QW_OCCUR_SHOULD) {
+            if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], boost);
+          } else if (occur == QW_OCCUR_SHOULD) {
             if (lane == 0) sm.u32(LV.shd)[wd] |= word;
             if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
-            if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], in.f);
+            if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], boost);
           } else {
             if (lane == 0) sm.u32(LV.nt)[wd] |= word;
           }
         }
-        if (required) req_init |= 1u << in.level;
+        if (required) req_init |= 1u << level;
         __syncthreads();
-      } else if (in.op == OP_BOOL_END) {
+      } else if (op == OP_BOOL_END) {
         // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
         uint32_t* req = sm.u32(LV.req);
-        const uint32_t need = in.r;
+        const uint32_t need = in.r, n_req = in.n;
         for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
           const uint32_t d0 = ws + wd * 32;
           uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
-          uint32_t r = in.n ? (((req_init >> in.level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
+          uint32_t r = n_req ? (((req_init >> level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
           uint32_t so;
           if (need == 0) so = 0xFFFFFFFFu;
           else if (need == 1) so = sm.u32(LV.shd)[wd];
@@ -620,32 +685,37 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
           req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
         }
         if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
-          float* ms = sm.f32(LV.msum);
-          const float* ss = sm.f32(LV.ssum);
-          for (uint32_t i = tid; i < W; i += QW_THREADS) ms[i] = __fadd_rn(ms[i], ss[i]);
+          float4* ms = (float4*)sm.f32(LV.msum);
+          const float4* ss = (const float4*)sm.f32(LV.ssum);
+          for (uint32_t i = tid; i < (W >> 2); i += QW_THREADS) {
+            float4 a = ms[i], b = ss[i];
+            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+            ms[i] = a;
+          }
         }
         __syncthreads();
-        if (in.level > 0) {
+        if (level > 0) {
           // fold this bool's (bits, score) into the parent level as one clause
-          const SmemLevel& PL = p.sm.lvl[in.level - 1];
-          const uint32_t plevel = in.level - 1;
-          const bool required = in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER;
+          const SmemLevel& PL = p.sm.lvl[level - 1];
+          const uint32_t plevel = level - 1;
+          const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
           const bool pinit = (req_init >> plevel) & 1;
+          const float* csc = LV.rsc != 0xFFFFFFFFu ? sm.f32(LV.rsc) : nullptr;
           for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
             uint32_t m = req[wd];
             if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
-            else if (in.occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
+            else if (occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
             else sm.u32(PL.nt)[wd] |= m;
           }
-          if (in.occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || scored)) {
+          if (occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || (scored && csc))) {
             for (uint32_t i = tid; i < W; i += QW_THREADS) {
               if ((req[i >> 5] >> (i & 31)) & 1) {
                 if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
-                if (scored) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], sm.f32(LV.msum)[i]);
+                if (scored && csc) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], csc[i]);
               }
             }
-          } else if (in.occur == QW_OCCUR_MUST && scored) {
-            for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], sm.f32(LV.msum)[i]);
+          } else if (occur == QW_OCCUR_MUST && scored && csc) {
+            for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], csc[i]);
           }
           if (required) req_init |= 1u << plevel;
           __syncthreads();
@@ -655,22 +725,23 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
 
     // ---- collect the window's matches ---------------------------------------------------------------
     const uint32_t* res = sm.u32(p.sm.lvl[0].req);
-    const float* rscore = p.sm.lvl[0].msum != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].msum) : nullptr;
+    const float* rscore = p.sm.lvl[0].rsc != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].rsc) : nullptr;
     const DThresh& T = p.thresh[split];
-    Key thr{T.key[0], T.key[1], T.key[2]};
+    const uint32_t max_hits = P.max_hits, n_aggs = P.n_aggs, sa_present = P.sa.present;
     QwAggCell* cells = (QwAggCell*)P.out_cells;
-    uint32_t my_hits = 0, my_elig = 0;
-    for (uint32_t i = tid; i < W; i += QW_THREADS) {
-      if (!((res[i >> 5] >> (i & 31)) & 1)) continue;
-      const uint32_t doc = ws + i;
-      my_hits++;
-      if (P.max_hits) {
-        DocKey dk = doc_key(P, s_cols, base, doc, rscore ? rscore[i] : 0.0f);
+    if (MODE == MODE_COLLECT) {
+      const Key thr{T.key[0], T.key[1], T.key[2]};
+      const uint32_t thr_top = (uint32_t)(thr.w0 >> 53);
+      const DKeySpec ks = P.key;  // hoisted into registers
+      uint32_t my_hits = 0, my_elig = 0;
+      // hit count: one popc per bitmap word
+      for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
+      auto slow_path = [&](uint32_t i, float sc) {
+        const uint32_t doc = ws + i;
+        DocKey dk = doc_key(P, s_cols, base, doc, sc);
         if (dk.eligible) {
           my_elig++;
-          if (MODE == MODE_HIST) {
-            if (!p.use_prefix || key_prefix_eq(dk.key, T.key, T.prefix_bits)) atomicAdd(&s_hist[key_digit(dk.key, p.level)], 1u);
-          } else if (key_ge(dk.key, thr)) {
+          if (key_ge(dk.key, thr)) {
             uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
             if (pos < QW_CAND_CAP) {
               uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
@@ -678,38 +749,82 @@ __global__ void __launch_bounds__(QW_THREADS) k_window(const KParams p) {
             }
           }
         }
+      };
+      if (max_hits && ks.kind[0] == QW_SORT_SCORE && ks.order[0] == QW_ORDER_DESC && !sa_present && rscore && !n_aggs) {
+        // fast path (BM25 top-K): a float lower bound of the threshold bucket filters 4 docs per lane
+        // per step; only survivors build the 192-bit key. s_lo is conservative (one part in 2^20).
+        float s_lo = -1.0f;
+        if (thr_top >= 1024u) s_lo = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), ks.score_scale), 0.999999f);
+        const float4* sc4 = reinterpret_cast<const float4*>(rscore);
+        for (uint32_t q = tid; q < (W >> 2); q += QW_THREADS) {
+          const uint32_t nib = (res[q >> 3] >> ((q & 7) * 4)) & 0xFu;
+          if (!nib) continue;
+          const float4 v = sc4[q];
+          if ((nib & 1u) && v.x >= s_lo) slow_path(4 * q + 0, v.x);
+          if ((nib & 2u) && v.y >= s_lo) slow_path(4 * q + 1, v.y);
+          if ((nib & 4u) && v.z >= s_lo) slow_path(4 * q + 2, v.z);
+          if ((nib & 8u) && v.w >= s_lo) slow_path(4 * q + 3, v.w);
+        }
+      } else if (max_hits || n_aggs) {
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+          const uint32_t word = res[wd];
+          if (word == 0) continue;  // warp-uniform
+          if (!((word >> lane) & 1)) continue;
+          const uint32_t i = wd * 32 + lane, doc = ws + i;
+          if (max_hits) {
+            const float sc = rscore ? rscore[i] : 0.0f;
+            // cheap pre-filter on the key's first 11 bits; the full 192-bit key is only built for
+            // docs that can reach the threshold (or always, when search_after needs eligibility)
+            if (sa_present || key_top11(ks, s_cols, base, doc, sc) >= thr_top) slow_path(i, sc);
+          }
+          if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
+        }
       }
-      if (MODE == MODE_COLLECT && P.n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
-    }
-    if (MODE == MODE_COLLECT) {
       // block-reduce the counters, one global atomic per window
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        my_hits += __shfl_down_sync(0xFFFFFFFFu, my_hits, o);
         my_elig += __shfl_down_sync(0xFFFFFFFFu, my_elig, o);
+        my_hits += __shfl_down_sync(0xFFFFFFFFu, my_hits, o);
       }
-      if (lane == 0) { atomicAdd(&s_misc[2], my_hits); atomicAdd(&s_misc[3], my_elig); }
-    }
-    __syncthreads();
-    if (MODE == MODE_COLLECT) {
+      if (lane == 0) { if (my_hits) atomicAdd(&s_misc[2], my_hits); if (my_elig) atomicAdd(&s_misc[3], my_elig); }
+      __syncthreads();
       if (tid == 0) {
-        if (s_misc[2]) atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)s_misc[2]);
-        if (s_misc[3]) atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)s_misc[3]);
+        const uint32_t hits = s_misc[2];
+        if (hits) atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)hits);
+        // without search_after every hit is eligible
+        const uint32_t elig = sa_present ? s_misc[3] : (max_hits ? hits : 0);
+        if (elig) atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)elig);
       }
-      if (p.smem_aggs && P.n_aggs) {
+      if (p.smem_aggs && n_aggs) {
         for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {
           uint32_t v = s_hist[i];
           if (v) { atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v); s_hist[i] = 0; }
         }
       }
     } else {
+      if (max_hits) {
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+          const uint32_t word = res[wd];
+          if (word == 0) continue;
+          if (!((word >> lane) & 1)) continue;
+          const uint32_t i = wd * 32 + lane, doc = ws + i;
+          const float sc = rscore ? rscore[i] : 0.0f;
+          if (p.level == 0 && !sa_present) {
+            atomicAdd(&s_hist[key_top11(P.key, s_cols, base, doc, sc)], 1u);
+          } else {
+            DocKey dk = doc_key(P, s_cols, base, doc, sc);
+            if (dk.eligible && (!p.use_prefix || key_prefix_eq(dk.key, T.key, T.prefix_bits)))
+              atomicAdd(&s_hist[key_digit(dk.key, p.level)], 1u);
+          }
+        }
+      }
+      __syncthreads();
       uint32_t* gh = (uint32_t*)P.out_hist;
       for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
         uint32_t v = s_hist[i];
         if (v) { atomicAdd(&gh[i], v); s_hist[i] = 0; }
       }
     }
-    __syncthreads();
   }
 }
 
