@@ -113,6 +113,14 @@ int qwgpu_split_search(qwgpu_ctx* ctx, uint32_t num_splits, const char* const* s
                        qwgpu_split_result* results, int* status);
 void qwgpu_split_result_free(qwgpu_split_result* r);
 
+/* Builds the per-split LeafSearchResponse protobuf (typed sort values, intermediate aggregation
+ * bytes) from a seam-C result: QuickwitSegmentCollector::harvest, collector.rs:564-594. Host only. */
+int qwgpu_build_leaf_response(const uint8_t* img, uint64_t img_len, const char* split_id,
+                              const uint8_t* search_request_pb, size_t search_request_len,
+                              const char* doc_mapper_json, uint64_t num_hits, const QwHit* hits,
+                              uint32_t num_partial_hits, const QwAggCell* cells, uint32_t num_cells,
+                              uint8_t** resp, size_t* resp_len);
+
 /* ---- merge / finalize -------------------------------------------------------------------------- */
 
 /* Merges N LeafSearchResponse protobufs under `search_request_pb` (sort orders, max_hits,

@@ -1,0 +1,482 @@
+// leaf.cpp — the leaf-search surface on top of the GPU engine:
+//   * build_split_response    QuickwitSegmentCollector::harvest + SegmentPartialHit::into_partial_hit
+//                             (quickwit-search/src/collector.rs:493-521,564-594)
+//   * merge_responses         merge_leaf_responses / merge_fruits / IncrementalCollector
+//                             (collector.rs:832-992,1195-1313), SortValue total order
+//                             (quickwit-proto/src/search/mod.rs:137-161), add_leaf_stats (lib.rs:392-425)
+//   * qwgpu_leaf_search       SearchService::leaf_search -> multi_index_leaf_search ->
+//                             single_doc_mapping_leaf_search (service.rs:177-203, leaf.rs:1290-1394,1673-1791)
+//   * qwgpu_invoke_leaf_search LambdaLeafSearchInvoker::invoke_leaf_search (invoker.rs:27-38;
+//                             handler template quickwit-lambda-server/src/handler.rs:55-200)
+//   * partial exchange for the multi-GPU root merge stand-in
+#include <algorithm>
+#include <chrono>
+
+#include "compile.h"
+#include "engine.h"
+
+namespace qw {
+
+// ---- SortValue order (quickwit-proto/src/search/mod.rs:137-161) ----------------------------------------
+static int cmp_i(int64_t a, int64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+static int cmp_u(uint64_t a, uint64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+static int total_cmp(double a, double b) {  // f64::total_cmp
+  int64_t x, y;
+  memcpy(&x, &a, 8);
+  memcpy(&y, &b, 8);
+  x ^= (int64_t)((uint64_t)(x >> 63) >> 1);
+  y ^= (int64_t)((uint64_t)(y >> 63) >> 1);
+  return cmp_i(x, y);
+}
+static int sortvalue_cmp(const pb::SortValue& a, const pb::SortValue& b) {
+  using SV = pb::SortValue;
+  if (a.kind == SV::U64 && b.kind == SV::U64) return cmp_u(a.u, b.u);
+  if (a.kind == SV::I64 && b.kind == SV::I64) return cmp_i(a.i, b.i);
+  if (a.kind == SV::Bool && b.kind == SV::Bool) return cmp_i(a.b, b.b);
+  if (a.kind == SV::U64 && b.kind == SV::I64) { if (a.u > (uint64_t)INT64_MAX) return 1; return cmp_i((int64_t)a.u, b.i); }
+  if (a.kind == SV::F64 && b.kind == SV::F64) return total_cmp(a.f, b.f);
+  if (a.kind == SV::F64 && b.kind == SV::U64) return total_cmp(a.f, (double)b.u);
+  if (a.kind == SV::F64 && b.kind == SV::I64) return total_cmp(a.f, (double)b.i);
+  if (a.kind == SV::Bool) { SV l; l.kind = SV::U64; l.u = a.b; return sortvalue_cmp(l, b); }
+  return -sortvalue_cmp(b, a);
+}
+static int order_cmp_opt_sv(int order, const pb::SortValue* a, const pb::SortValue* b) {
+  if (a && b) { int c = sortvalue_cmp(*a, *b); return order == QW_ORDER_DESC ? c : -c; }
+  if (a) return 1;
+  if (b) return -1;
+  return 0;
+}
+// PartialHitSortingKey::cmp (collector.rs:1130-1153); > 0 when a is better
+static int hit_cmp(int order1, int order2, const pb::PartialHit& a, const pb::PartialHit& b) {
+  auto sv = [](bool has, const pb::SortValue& v) { return has && v.kind != pb::SortValue::None ? &v : nullptr; };
+  int c = order_cmp_opt_sv(order1, sv(a.has_sv1, a.sv1), sv(b.has_sv1, b.sv1));
+  if (c) return c;
+  c = order_cmp_opt_sv(order2, sv(a.has_sv2, a.sv2), sv(b.has_sv2, b.sv2));
+  if (c) return c;
+  // GlobalDocAddress (split, segment_ord, doc_id), quickwit-search/src/lib.rs:107-131
+  int d = a.split_id.compare(b.split_id);
+  d = d < 0 ? -1 : (d > 0 ? 1 : 0);
+  if (!d) d = cmp_u(a.segment_ord, b.segment_ord);
+  if (!d) d = cmp_u(a.doc_id, b.doc_id);
+  return order1 == QW_ORDER_DESC ? d : -d;
+}
+
+static void sort_orders(const pb::SearchRequest& req, int* o1, int* o2) {
+  // sort_by_from_request + SortByPair::sort_orders (collector.rs:66-76,994-1030)
+  *o1 = QW_ORDER_DESC;
+  *o2 = QW_ORDER_DESC;
+  if (req.sort_fields.size() >= 1) *o1 = req.sort_fields[0].sort_order == 0 ? QW_ORDER_ASC : QW_ORDER_DESC;
+  if (req.sort_fields.size() >= 2) *o2 = req.sort_fields[1].sort_order == 0 ? QW_ORDER_ASC : QW_ORDER_DESC;
+}
+
+// convert_u64_ff_val_to_sort_value (collector.rs:183-205)
+static pb::SortValue typed_sort_value(uint32_t kind, int sft, uint64_t v) {
+  pb::SortValue s;
+  if (kind == QW_SORT_SCORE) { s.kind = pb::SortValue::F64; s.f = u64_to_f64(v); return s; }
+  if (kind == QW_SORT_DOCID) { s.kind = pb::SortValue::U64; s.u = v; return s; }
+  switch (sft) {
+    case 0: s.kind = pb::SortValue::U64; s.u = v; break;
+    case 1: case 3: s.kind = pb::SortValue::I64; s.i = u64_to_i64(v); break;
+    case 2: s.kind = pb::SortValue::F64; s.f = u64_to_f64(v); break;
+    default: s.kind = pb::SortValue::Bool; s.b = v != 0; break;
+  }
+  return s;
+}
+
+pb::LeafSearchResponse build_split_response(const CompiledPlan& cp, const ImageView& img, const std::string& split_id,
+                                            uint64_t num_hits, const QwHit* hits, size_t nhits,
+                                            const QwAggCell* cells, size_t ncells) {
+  pb::LeafSearchResponse r;
+  r.num_hits = num_hits;
+  r.num_attempted_splits = 1;
+  r.num_successful_splits = 1;
+  for (size_t i = 0; i < nhits; i++) {
+    pb::PartialHit h;
+    h.split_id = split_id;
+    h.segment_ord = 0;
+    h.doc_id = hits[i].doc_id;
+    if (hits[i].flags & 1) { h.has_sv1 = true; h.sv1 = typed_sort_value(cp.header.sort[0].kind, cp.sort_field_type[0], hits[i].v1); }
+    if (hits[i].flags & 2) { h.has_sv2 = true; h.sv2 = typed_sort_value(cp.header.sort[1].kind, cp.sort_field_type[1], hits[i].v2); }
+    r.partial_hits.push_back(std::move(h));
+  }
+  if (cp.header.num_aggs) r.intermediate_aggregation_result = build_intermediate_aggs(cp, img, cells, ncells);
+  return r;
+}
+
+static void add_split_stats(pb::SplitResourceStats& a, const pb::SplitResourceStats& b) { for (int i = 0; i < 9; i++) a.v[i] += b.v[i]; }
+static uint64_t phase_sum(const pb::SplitResourceStats& s) { return s.v[6] + s.v[8]; }  // warmup + cpu_search
+static void add_leaf_stats(pb::LeafResourceStats& acc, const pb::LeafResourceStats& o) {
+  acc.partial_result_cache_num_splits += o.partial_result_cache_num_splits;
+  acc.partial_result_cache_num_docs += o.partial_result_cache_num_docs;
+  acc.localexec_num_splits += o.localexec_num_splits;
+  acc.localexec_num_docs += o.localexec_num_docs;
+  acc.wall_time_microsecs += o.wall_time_microsecs;
+  for (int i = 0; i < 5; i++) acc.lambda[i] += o.lambda[i];
+  auto min_opt = [](std::optional<uint64_t> a, std::optional<uint64_t> b) { return !a ? b : (!b ? a : std::optional<uint64_t>(std::min(*a, *b))); };
+  acc.min_wait_for_search_permit_microsecs = min_opt(acc.min_wait_for_search_permit_microsecs, o.min_wait_for_search_permit_microsecs);
+  acc.min_wait_for_cpu_pool_microsecs = min_opt(acc.min_wait_for_cpu_pool_microsecs, o.min_wait_for_cpu_pool_microsecs);
+  if (o.split_resources_sum) {
+    if (!acc.split_resources_sum) acc.split_resources_sum = pb::SplitResourceStats();
+    add_split_stats(*acc.split_resources_sum, *o.split_resources_sum);
+  }
+  if (o.split_resources_worst && (!acc.split_resources_worst || phase_sum(*o.split_resources_worst) >= phase_sum(*acc.split_resources_worst)))
+    acc.split_resources_worst = o.split_resources_worst;
+}
+
+pb::LeafSearchResponse merge_responses(const pb::SearchRequest& req, std::vector<pb::LeafSearchResponse> parts) {
+  int o1, o2;
+  sort_orders(req, &o1, &o2);
+  const size_t k = (size_t)(req.start_offset + req.max_hits);
+  pb::LeafSearchResponse m;
+  if (parts.size() == 1) {
+    m = std::move(parts[0]);  // single-response shortcut (collector.rs:922-924)
+  } else {
+    std::vector<std::string> agg_parts;
+    for (auto& p : parts) {
+      if (p.resource_stats) { if (!m.resource_stats) m.resource_stats = pb::LeafResourceStats(); add_leaf_stats(*m.resource_stats, *p.resource_stats); }
+      if (p.intermediate_aggregation_result) agg_parts.push_back(*p.intermediate_aggregation_result);
+      m.num_attempted_splits += p.num_attempted_splits;
+      m.num_successful_splits += p.num_successful_splits;
+      m.num_hits += p.num_hits;
+      for (auto& f : p.failed_splits) m.failed_splits.push_back(f);
+      for (auto& h : p.partial_hits) m.partial_hits.push_back(std::move(h));
+    }
+    if (req.aggregation_request && !req.aggregation_request->empty()) {
+      std::vector<AggReq> reqs = parse_agg_request(*req.aggregation_request);
+      m.intermediate_aggregation_result = merge_intermediate_aggs(reqs, agg_parts);
+    }
+    // top_k_partial_hits (collector.rs:980-992): TopK heap + sorted finalize == sort best-first, keep k
+    std::stable_sort(m.partial_hits.begin(), m.partial_hits.end(), [&](const pb::PartialHit& a, const pb::PartialHit& b) { return hit_cmp(o1, o2, a, b) > 0; });
+    if (m.partial_hits.size() > k) m.partial_hits.resize(k);
+  }
+  // merge_fruits: drop [..start_offset), truncate to max_hits (collector.rs:851-858)
+  size_t drop = std::min<size_t>((size_t)req.start_offset, m.partial_hits.size());
+  m.partial_hits.erase(m.partial_hits.begin(), m.partial_hits.begin() + drop);
+  if (m.partial_hits.size() > req.max_hits) m.partial_hits.resize((size_t)req.max_hits);
+  return m;
+}
+
+// ---- leaf search over the engine -------------------------------------------------------------------------
+struct SplitJob {
+  pb::SplitIdAndFooterOffsets meta;
+  std::shared_ptr<SplitDev> dev;
+  CompiledPlan plan;
+  std::string error;
+  int error_code = 0;
+};
+
+static std::vector<pb::LambdaSingleSplitResult> run_leaf(Engine& eng, const pb::LeafSearchRequest& lr) {
+  using clock = std::chrono::steady_clock;
+  std::vector<SplitJob> jobs;
+  const pb::SearchRequest& sreq = lr.search_request;
+  for (auto& ref : lr.leaf_requests) {
+    if (ref.doc_mapper_ord >= lr.doc_mappers.size()) fail(QWGPU_EINVALID_ARG, "Internal error: doc_mapper_ord out of bounds");
+    DocMapperInfo dm = parse_doc_mapper(lr.doc_mappers[ref.doc_mapper_ord]);
+    for (auto& so : ref.split_offsets) {
+      SplitJob j;
+      j.meta = so;
+      j.dev = eng.find(so.split_id);
+      try {
+        if (!j.dev) fail(QWGPU_ENOTFOUND, "split `%s` is not resident on this GPU", so.split_id.c_str());
+        j.plan = compile_plan(j.dev->view, so.split_id, sreq, dm, &so);
+      } catch (const Error& e) {
+        // malformed queries / aggregations fail the whole request like the reference (service.rs:182-184)
+        if (e.code == QWGPU_EINVALID_QUERY || e.code == QWGPU_EINVALID_AGG || e.code == QWGPU_EINVALID_ARG) throw;
+        j.error = e.what();
+        j.error_code = e.code;
+      }
+      jobs.push_back(std::move(j));
+    }
+  }
+  std::vector<std::shared_ptr<SplitDev>> devs;
+  std::vector<const uint8_t*> plans;
+  std::vector<size_t> lens;
+  std::vector<size_t> which;
+  for (size_t i = 0; i < jobs.size(); i++)
+    if (!jobs[i].error_code) {
+      devs.push_back(jobs[i].dev);
+      plans.push_back((const uint8_t*)jobs[i].plan.bytes.data());
+      lens.push_back(jobs[i].plan.bytes.size());
+      which.push_back(i);
+    }
+  std::vector<SplitOutput> outs;
+  BatchStats st;
+  auto t0 = clock::now();
+  if (!devs.empty()) eng.search(devs, plans, lens, outs, st);
+  uint64_t wall_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t0).count();
+  std::vector<pb::LambdaSingleSplitResult> results(jobs.size());
+  for (size_t i = 0; i < jobs.size(); i++) {
+    results[i].split_id = jobs[i].meta.split_id;
+    if (jobs[i].error_code) { results[i].is_error = true; results[i].error = jobs[i].error; }
+  }
+  for (size_t k = 0; k < which.size(); k++) {
+    size_t i = which[k];
+    SplitOutput& o = outs[k];
+    if (o.status) { results[i].is_error = true; results[i].error = o.error; continue; }
+    pb::LeafSearchResponse r = build_split_response(jobs[i].plan, jobs[i].dev->view, jobs[i].meta.split_id, o.num_hits,
+                                                    o.hits.data(), o.hits.size(), o.cells.data(), o.cells.size());
+    // SplitResourceStats / LeafResourceStats filled like leaf.rs:641-684; cpu_search_microsecs carries
+    // this split's share of the batch's device time
+    pb::SplitResourceStats ss;
+    ss.v[0] = jobs[i].dev->view.hdr->num_docs;
+    ss.v[1] = jobs[i].dev->data_len;
+    ss.v[4] = o.num_hits;
+    ss.v[8] = (uint64_t)(st.gpu_time_us / std::max<size_t>(which.size(), 1));
+    pb::LeafResourceStats ls;
+    ls.localexec_num_splits = 1;
+    ls.localexec_num_docs = ss.v[0];
+    ls.split_resources_sum = ss;
+    ls.split_resources_worst = ss;
+    ls.min_wait_for_search_permit_microsecs = 0;
+    ls.min_wait_for_cpu_pool_microsecs = 0;
+    ls.wall_time_microsecs = wall_us / std::max<size_t>(which.size(), 1);
+    r.resource_stats = ls;
+    results[i].response = std::move(r);
+  }
+  return results;
+}
+
+}  // namespace qw
+
+// ---- C ABI --------------------------------------------------------------------------------------------------
+#define QW_API_BEGIN try {
+#define QW_API_END                                   \
+  }                                                  \
+  catch (const qw::Error& e) {                       \
+    qw::set_last_error(e.what());                    \
+    return e.code;                                   \
+  }                                                  \
+  catch (const std::exception& e) {                  \
+    qw::set_last_error(e.what());                    \
+    return QWGPU_EINTERNAL;                          \
+  }
+
+static void give(const std::string& s, uint8_t** out, size_t* len) {
+  *out = (uint8_t*)malloc(s.size() ? s.size() : 1);
+  if (!*out) qw::fail(QWGPU_EINTERNAL, "out of memory");
+  memcpy(*out, s.data(), s.size());
+  *len = s.size();
+}
+static qw::Engine& engine_of(qwgpu_ctx* ctx) {
+  if (!ctx) qw::fail(QWGPU_EINVALID_ARG, "null context");
+  if (!ctx->engine) qw::fail(QWGPU_ENODEVICE, "host-only context: no CUDA device bound (there is no CPU search path)");
+  return *ctx->engine;
+}
+
+namespace {
+// fixed-size per-rank partial for the single all-gather:
+//   [u64 magic][u64 num_hits][u64 attempted][u64 successful][u32 n_hits][u32 agg_len][u32 n_failed][u32 pad]
+//   n_hits x [u8 kind1, u8 kind2, u16 split_len, u32 doc_id, u64 v1, u64 v2, char split_id[40]]
+//   agg bytes (<= kAggCap)
+const uint64_t kPartMagic = 0x5452415057515157ull;
+const size_t kHitBytes = 64, kAggCap = 1 << 20;
+uint64_t partial_bytes_for(const qw::pb::SearchRequest& r) {
+  size_t k = (size_t)(r.max_hits + r.start_offset);
+  bool aggs = r.aggregation_request && !r.aggregation_request->empty();
+  return 48 + k * kHitBytes + (aggs ? kAggCap : 0);
+}
+}  // namespace
+
+extern "C" {
+
+int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
+  QW_API_BEGIN
+  qw::Engine& eng = engine_of(ctx);
+  qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
+  std::vector<qw::pb::LambdaSingleSplitResult> rs = qw::run_leaf(eng, lr);
+  // IncrementalCollector over the per-split responses (leaf.rs:1778-1785): the merge keeps the leaf's
+  // start_offset = 0 convention (root.rs:1775-1777), so nothing is drained here
+  std::vector<qw::pb::LeafSearchResponse> parts;
+  std::vector<qw::pb::SplitSearchError> failed;
+  for (auto& r : rs) {
+    if (r.is_error) failed.push_back({r.error, r.split_id, true});  // retryable (leaf.rs:1989-2004)
+    else parts.push_back(std::move(r.response));
+  }
+  qw::pb::SearchRequest mreq = lr.search_request;
+  mreq.max_hits += mreq.start_offset;  // keep [0, start_offset + max_hits) at the leaf
+  mreq.start_offset = 0;
+  qw::pb::LeafSearchResponse merged;
+  if (parts.empty()) {
+    if (mreq.aggregation_request && !mreq.aggregation_request->empty())
+      merged.intermediate_aggregation_result = qw::merge_intermediate_aggs(qw::parse_agg_request(*mreq.aggregation_request), {});
+  } else if (parts.size() == 1) {
+    merged = std::move(parts[0]);
+  } else merged = qw::merge_responses(mreq, std::move(parts));
+  for (auto& f : failed) { merged.failed_splits.push_back(f); merged.num_attempted_splits += 1; }
+  give(qw::pb::encode_leaf_search_response(merged), resp, resp_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_invoke_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
+  QW_API_BEGIN
+  qw::Engine& eng = engine_of(ctx);
+  qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
+  give(qw::pb::encode_lambda_responses(qw::run_leaf(eng, lr)), resp, resp_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_compile_plan(const uint8_t* img, uint64_t img_len, const char* split_id, const uint8_t* search_request_pb,
+                       size_t search_request_len, const char* doc_mapper_json, uint8_t** plan, size_t* plan_len) {
+  QW_API_BEGIN
+  qw::ImageView v;
+  v.open(img, img_len);
+  qw::pb::SearchRequest req = qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len));
+  qw::DocMapperInfo dm = qw::parse_doc_mapper(doc_mapper_json ? doc_mapper_json : "");
+  qw::CompiledPlan cp = qw::compile_plan(v, split_id ? split_id : "", req, dm, nullptr);
+  give(cp.bytes, plan, plan_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_build_leaf_response(const uint8_t* img, uint64_t img_len, const char* split_id, const uint8_t* search_request_pb,
+                              size_t search_request_len, const char* doc_mapper_json, uint64_t num_hits, const QwHit* hits,
+                              uint32_t num_partial_hits, const QwAggCell* cells, uint32_t num_cells, uint8_t** resp, size_t* resp_len) {
+  QW_API_BEGIN
+  qw::ImageView v;
+  v.open(img, img_len);
+  qw::pb::SearchRequest req = qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len));
+  qw::DocMapperInfo dm = qw::parse_doc_mapper(doc_mapper_json ? doc_mapper_json : "");
+  qw::CompiledPlan cp = qw::compile_plan(v, split_id ? split_id : "", req, dm, nullptr);
+  qw::pb::LeafSearchResponse r = qw::build_split_response(cp, v, split_id ? split_id : "", num_hits, hits, num_partial_hits, cells, num_cells);
+  give(qw::pb::encode_leaf_search_response(r), resp, resp_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_merge_leaf_responses(const uint8_t* search_request_pb, size_t search_request_len, uint32_t n, const uint8_t* const* resps,
+                               const size_t* resp_lens, uint8_t** merged, size_t* merged_len) {
+  QW_API_BEGIN
+  qw::pb::SearchRequest req = qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len));
+  std::vector<qw::pb::LeafSearchResponse> parts;
+  for (uint32_t i = 0; i < n; i++) parts.push_back(qw::pb::decode_leaf_search_response(resps[i], resp_lens[i]));
+  qw::pb::LeafSearchResponse m;
+  if (parts.empty()) {
+    if (req.aggregation_request && !req.aggregation_request->empty())
+      m.intermediate_aggregation_result = qw::merge_intermediate_aggs(qw::parse_agg_request(*req.aggregation_request), {});
+  } else m = qw::merge_responses(req, std::move(parts));
+  give(qw::pb::encode_leaf_search_response(m), merged, merged_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_finalize_aggregation(const char* aggregation_request_json, const uint8_t* intermediate, size_t intermediate_len, char** json_out) {
+  QW_API_BEGIN
+  std::vector<qw::AggReq> reqs = qw::parse_agg_request(aggregation_request_json ? aggregation_request_json : "{}");
+  std::string js = qw::finalize_aggs_json(reqs, std::string((const char*)intermediate, intermediate_len));
+  *json_out = (char*)malloc(js.size() + 1);
+  if (!*json_out) qw::fail(QWGPU_EINTERNAL, "out of memory");
+  memcpy(*json_out, js.c_str(), js.size() + 1);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_partial_size(const uint8_t* search_request_pb, size_t search_request_len, uint64_t* partial_bytes) {
+  QW_API_BEGIN
+  *partial_bytes = partial_bytes_for(qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len)));
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_response_to_partial(const uint8_t* search_request_pb, size_t search_request_len, const uint8_t* resp, size_t resp_len,
+                              uint8_t* partial, uint64_t partial_bytes) {
+  QW_API_BEGIN
+  qw::pb::SearchRequest req = qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len));
+  if (partial_bytes != partial_bytes_for(req)) qw::fail(QWGPU_EINVALID_ARG, "partial buffer size mismatch");
+  qw::pb::LeafSearchResponse r = qw::pb::decode_leaf_search_response(resp, resp_len);
+  size_t k = (size_t)(req.max_hits + req.start_offset);
+  if (r.partial_hits.size() > k) qw::fail(QWGPU_EINVALID_ARG, "response holds more hits than max_hits + start_offset");
+  memset(partial, 0, partial_bytes);
+  uint64_t hdr[4] = {kPartMagic, r.num_hits, r.num_attempted_splits, r.num_successful_splits};
+  memcpy(partial, hdr, 32);
+  uint32_t meta[4] = {(uint32_t)r.partial_hits.size(), 0, (uint32_t)r.failed_splits.size(), 0};
+  uint8_t* p = partial + 48;
+  for (auto& h : r.partial_hits) {
+    if (h.split_id.size() > 40) qw::fail(QWGPU_EUNSUPPORTED, "split ids longer than 40 bytes do not fit the fixed-size partial");
+    auto pack = [](bool has, const qw::pb::SortValue& v, uint64_t* out) -> uint8_t {
+      if (!has) return 0xFF;
+      switch (v.kind) {
+        case qw::pb::SortValue::U64: *out = v.u; break;
+        case qw::pb::SortValue::I64: *out = (uint64_t)v.i; break;
+        case qw::pb::SortValue::F64: memcpy(out, &v.f, 8); break;
+        case qw::pb::SortValue::Bool: *out = v.b; break;
+        default: *out = 0;
+      }
+      return (uint8_t)v.kind;
+    };
+    uint64_t v1 = 0, v2 = 0;
+    p[0] = pack(h.has_sv1, h.sv1, &v1);
+    p[1] = pack(h.has_sv2, h.sv2, &v2);
+    uint16_t sl = (uint16_t)h.split_id.size();
+    memcpy(p + 2, &sl, 2);
+    memcpy(p + 4, &h.doc_id, 4);
+    memcpy(p + 8, &v1, 8);
+    memcpy(p + 16, &v2, 8);
+    memcpy(p + 24, h.split_id.data(), sl);
+    p += kHitBytes;
+  }
+  if (r.intermediate_aggregation_result) {
+    if (r.intermediate_aggregation_result->size() > kAggCap) qw::fail(QWGPU_EUNSUPPORTED, "intermediate aggregation result exceeds the fixed partial capacity");
+    meta[1] = (uint32_t)r.intermediate_aggregation_result->size();
+    memcpy(partial + 48 + k * kHitBytes, r.intermediate_aggregation_result->data(), meta[1]);
+  }
+  memcpy(partial + 32, meta, 16);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request_len, uint32_t n_ranks, const uint8_t* gathered,
+                         uint64_t partial_bytes, uint8_t** merged, size_t* merged_len) {
+  QW_API_BEGIN
+  qw::pb::SearchRequest req = qw::pb::decode_search_request(qw::pb::Reader(search_request_pb, search_request_len));
+  if (partial_bytes != partial_bytes_for(req)) qw::fail(QWGPU_EINVALID_ARG, "partial buffer size mismatch");
+  size_t k = (size_t)(req.max_hits + req.start_offset);
+  std::vector<qw::pb::LeafSearchResponse> parts;
+  for (uint32_t r = 0; r < n_ranks; r++) {
+    const uint8_t* base = gathered + (size_t)r * partial_bytes;
+    uint64_t hdr[4];
+    uint32_t meta[4];
+    memcpy(hdr, base, 32);
+    memcpy(meta, base + 32, 16);
+    if (hdr[0] != kPartMagic) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial has a bad header", r);
+    qw::pb::LeafSearchResponse lr;
+    lr.num_hits = hdr[1];
+    lr.num_attempted_splits = hdr[2];
+    lr.num_successful_splits = hdr[3];
+    const uint8_t* p = base + 48;
+    for (uint32_t i = 0; i < meta[0]; i++, p += kHitBytes) {
+      qw::pb::PartialHit h;
+      auto unpack = [](uint8_t kind, uint64_t v, bool* has, qw::pb::SortValue* out) {
+        if (kind == 0xFF) { *has = false; return; }
+        *has = true;
+        out->kind = (qw::pb::SortValue::Kind)kind;
+        switch (out->kind) {
+          case qw::pb::SortValue::U64: out->u = v; break;
+          case qw::pb::SortValue::I64: out->i = (int64_t)v; break;
+          case qw::pb::SortValue::F64: memcpy(&out->f, &v, 8); break;
+          case qw::pb::SortValue::Bool: out->b = v != 0; break;
+          default: break;
+        }
+      };
+      uint64_t v1, v2;
+      uint16_t sl;
+      memcpy(&sl, p + 2, 2);
+      memcpy(&h.doc_id, p + 4, 4);
+      memcpy(&v1, p + 8, 8);
+      memcpy(&v2, p + 16, 8);
+      unpack(p[0], v1, &h.has_sv1, &h.sv1);
+      unpack(p[1], v2, &h.has_sv2, &h.sv2);
+      h.split_id.assign((const char*)p + 24, sl);
+      lr.partial_hits.push_back(std::move(h));
+    }
+    if (meta[1]) lr.intermediate_aggregation_result = std::string((const char*)base + 48 + k * kHitBytes, meta[1]);
+    parts.push_back(std::move(lr));
+  }
+  qw::pb::LeafSearchResponse m = qw::merge_responses(req, std::move(parts));
+  give(qw::pb::encode_leaf_search_response(m), merged, merged_len);
+  return 0;
+  QW_API_END
+}
+
+}  // extern "C"

@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
     bind("qwgpu_split_search", [vp, u32, C.POINTER(cp), C.POINTER(vp), C.POINTER(sz),
                                 C.POINTER(SplitResult), C.POINTER(C.c_int)])
     bind("qwgpu_split_result_free", [C.POINTER(SplitResult)], None)
+    bind("qwgpu_build_leaf_response", [vp, u64, cp, vp, sz, cp, u64, vp, u32, vp, u32, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_merge_leaf_responses", [vp, sz, u32, C.POINTER(vp), C.POINTER(sz),
                                         C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_finalize_aggregation", [cp, vp, sz, C.POINTER(vp)])

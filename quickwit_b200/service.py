@@ -134,3 +134,23 @@ def finalize_aggregation(aggregation_request_json: str, intermediate: bytes) -> 
         return C.string_at(out).decode()
     finally:
         L.qwgpu_buf_free(out)
+
+
+def build_leaf_response(img: SplitImage, search_request_pb: bytes, doc_mapper_json: str, num_hits: int,
+                        hits: Sequence[Tuple[int, int, int, int, float]], cells: Sequence[Tuple[int, int, int, int]],
+                        split_id: str = "") -> bytes:
+    """QuickwitSegmentCollector::harvest for a seam-C result: hits are (doc_id, flags, v1, v2, score),
+    cells are (count, sum_bits, min_mapped, max_mapped). Returns LeafSearchResponse bytes."""
+    L = ffi.lib()
+    rb = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    harr = (ffi.QwHit * max(len(hits), 1))()
+    for i, (doc, flags, v1, v2, score) in enumerate(hits):
+        harr[i].doc_id, harr[i].flags, harr[i].v1, harr[i].v2, harr[i].score = doc, flags, v1, v2, score
+    carr = (ffi.QwAggCell * max(len(cells), 1))()
+    for i, (cnt, s, mn, mx) in enumerate(cells):
+        carr[i].count, carr[i].sum_bits, carr[i].min_mapped, carr[i].max_mapped = cnt, s, mn, mx
+    out, n = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_build_leaf_response(img.ptr, img.nbytes, (split_id or img.split_id).encode(), C.addressof(rb),
+                                          len(search_request_pb), doc_mapper_json.encode(), num_hits, harr, len(hits),
+                                          carr, len(cells), C.byref(out), C.byref(n)))
+    return ffi.take_bytes(out, n.value)
