@@ -46,8 +46,10 @@ struct DAgg {
   uint32_t has_missing, cell_base, is_f64, pad;
   double interval, offset, bound_min, bound_max;
   int64_t base_pos;
+  int64_t pad2;  // keeps sizeof(DAgg) a multiple of 16 (copied to shared memory as uint4)
   uint64_t range_from[QW_MAX_AGG_RANGES], range_to[QW_MAX_AGG_RANGES];
 };
+static_assert(sizeof(DInstr) % 16 == 0 && sizeof(DCol) % 16 == 0 && sizeof(DAgg) % 16 == 0, "uint4-copied structs");
 
 // Composite sort key: a 192-bit big-endian bit string, greater = better.
 //   [has1:1][lin1:10][pay1:64][has2:1][pay2:64][doc':32][0:20]

@@ -1,0 +1,136 @@
+"""Seam A / B on the GPU: LeafSearchRequest bytes -> LeafSearchResponse bytes through
+`qwgpu_leaf_search` / `qwgpu_invoke_leaf_search`, compared with the CPU pipeline (oracle + the
+same host code) and with the reference goldens."""
+import json
+
+import numpy as np
+import pytest
+
+from quickwit_b200 import ffi, proto, service, splitgen as S
+from quickwit_b200.proto import ASC, DESC
+from pipeline import MATCH_ALL, bool_, cpu_root_search, cpu_split_response, full_text, leafify, search_request, term
+from test_oracle_goldens import (AGG_MAPPING, AGG_SPLIT1, AGG_SPLIT2, BM25_DOCS, BM25_MAPPING, SORT_DATA, SORT_MAPPING,
+                                 _expected_order)
+
+pytestmark = pytest.mark.gpu
+
+FRACS = [0.2, 0.1, 0.05, 0.05, 0.02, 0.02, 0.01, 0.01, 0.005, 0.001]
+SYNTH_MAPPING = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
+                                    {"name": "severity_text", "type": "text", "tokenizer": "raw", "fast": True},
+                                    {"name": "timestamp", "type": "datetime", "fast": True, "fast_precision": "seconds"},
+                                    {"name": "tenant_id", "type": "u64", "fast": True}], "timestamp_field": "timestamp"}
+
+
+def gpu_root_search(ctx, imgs, query_ast, doc_mapper, **req_kw):
+    """root_search with the GPU leaf: one LeafSearchRequest over all splits, then the root merge."""
+    leaf_pb = search_request(query_ast, **leafify(req_kw))
+    root_pb = search_request(query_ast, **req_kw)
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
+    lreq = proto.enc_leaf_search_request(leaf_pb, offsets, json.dumps(doc_mapper))
+    leaf_resp = ctx.leaf_search(lreq)
+    out = proto.dec_leaf_search_response(service.merge_leaf_responses(root_pb, [leaf_resp]))
+    aggs = req_kw.get("aggs")
+    if aggs is not None:
+        out["aggregations"] = json.loads(service.finalize_aggregation(json.dumps(aggs), out["intermediate_aggregation_result"] or b""))
+    return out, proto.dec_leaf_search_response(leaf_resp)
+
+
+def same(a, b):
+    assert a["num_hits"] == b["num_hits"]
+    assert a["partial_hits"] == b["partial_hits"]
+    assert a.get("aggregations") == b.get("aggregations")
+
+
+@pytest.fixture(scope="module")
+def synth(gpu_ctx):
+    imgs = [S.synth_split(40_000 + 1000 * i, i, FRACS, split_id=f"leaf-{i}", ts_start_secs=1_700_000_000 + 86_400 * i) for i in range(4)]
+    for im in imgs:
+        gpu_ctx.register_split(im)
+    return imgs
+
+
+def test_bm25_golden_through_leaf_search(gpu_ctx):
+    img = S.build_split(BM25_DOCS, BM25_MAPPING, "bm25-gpu")
+    gpu_ctx.register_split(img)
+    f32 = np.float32
+    out, leaf = gpu_root_search(gpu_ctx, [img], term("title", "one"), BM25_MAPPING, max_hits=1000, sort_fields=[("_score", DESC)])
+    assert [(f32(h["sort_value"][1]), h["doc_id"]) for h in out["partial_hits"]] == [(f32(0.1738279), 2), (f32(0.15965714), 1), (f32(0.12343242), 0)]
+    assert leaf["num_attempted_splits"] == 1 and leaf["num_successful_splits"] == 1
+    assert leaf["resource_stats"]["localexec_num_splits"] == 1 and leaf["resource_stats"]["split_resources_sum"]["matched_num_docs"] == 3
+    both = bool_(must=[full_text("title", "one"), full_text("nofreq", "two")])
+    out, _ = gpu_root_search(gpu_ctx, [img], both, BM25_MAPPING, max_hits=1000, sort_fields=[("_score", DESC)])
+    assert [(f32(h["sort_value"][1]), h["doc_id"]) for h in out["partial_hits"]] == [(f32(0.31931427), 1), (f32(0.2972603), 2), (f32(0.24686484), 0)]
+
+
+def test_sort_matrix_through_leaf_search(gpu_ctx):
+    docs = [{k: v for k, v in (("sort1", a), ("sort2", b)) if v is not None} for a, b in SORT_DATA]
+    img = S.build_split(docs, SORT_MAPPING, "sortmatrix-leaf")
+    gpu_ctx.register_split(img)
+    for spec in ([], [("sort1", DESC)], [("sort1", ASC), ("sort2", DESC)], [("sort1", DESC), ("sort2", ASC)]):
+        want = _expected_order(spec)
+        for k in (0, 1, 5, 16):
+            out, _ = gpu_root_search(gpu_ctx, [img], MATCH_ALL, SORT_MAPPING, max_hits=k, sort_fields=spec)
+            assert [h["doc_id"] for h in out["partial_hits"]] == want[:k]
+
+
+def test_config_queries_match_cpu_pipeline(gpu_ctx, synth):
+    or10 = bool_(should=[term("body", f"t{i}") for i in range(10)])
+    cases = [
+        (or10, dict(max_hits=1000, sort_fields=[("_score", DESC)])),                                   # C2
+        (or10, dict(max_hits=20, start_offset=30, sort_fields=[("_score", DESC)])),
+        (bool_(must=[term("body", "t2")]), dict(max_hits=1000, sort_fields=[("timestamp", DESC)],
+                                                start_timestamp=1_700_000_000 + 21_600, end_timestamp=1_700_000_000 + 3 * 86_400 - 21_600)),  # C3
+        (term("severity_text", "ERROR"), dict(max_hits=10)),                                            # C1
+        (MATCH_ALL, dict(max_hits=0, aggs={"by_sev": {"terms": {"field": "severity_text"}},
+                                           "over_time": {"date_histogram": {"field": "timestamp", "fixed_interval": "1h"}}})),  # C4
+        (MATCH_ALL, dict(max_hits=3, sort_fields=[("tenant_id", ASC), ("timestamp", DESC)],
+                         aggs={"by_sev": {"terms": {"field": "severity_text"}, "aggs": {"over_time": {"date_histogram": {"field": "timestamp", "fixed_interval": "6h"}},
+                                                                                          "tenants": {"stats": {"field": "tenant_id"}}}},
+                               "tenants": {"terms": {"field": "tenant_id", "size": 5}}})),
+    ]
+    for ast, kw in cases:
+        got, leaf = gpu_root_search(gpu_ctx, synth, ast, SYNTH_MAPPING, **kw)
+        want = cpu_root_search(synth, ast, SYNTH_MAPPING, **kw)
+        same(got, want)
+        assert leaf["num_successful_splits"] == len(synth) and not leaf["failed_splits"]
+
+
+def test_aggregation_goldens_on_gpu(gpu_ctx):
+    imgs = [S.build_split(AGG_SPLIT1, AGG_MAPPING, "agg-gpu-1"), S.build_split(AGG_SPLIT2, AGG_MAPPING, "agg-gpu-2")]
+    for im in imgs:
+        gpu_ctx.register_split(im)
+    aggs = {"date_histo": {"date_histogram": {"field": "date", "fixed_interval": "30d", "offset": "-4d"},
+                           "aggs": {"response": {"stats": {"field": "response"}}}},
+            "hosts": {"terms": {"field": "host"}}, "tags": {"terms": {"field": "tags"}},
+            "names": {"terms": {"field": "name", "size": 1, "split_size": 1}}}
+    got, _ = gpu_root_search(gpu_ctx, imgs, MATCH_ALL, AGG_MAPPING, max_hits=0, aggs=aggs)
+    a = got["aggregations"]
+    assert [(b["doc_count"], b["key"]) for b in a["date_histo"]["buckets"]] == [(5, 1420070400000.0), (2, 1422662400000.0)]
+    assert a["date_histo"]["buckets"][0]["response"] == {"avg": 85.0, "count": 4, "max": 120.0, "min": 20.0, "sum": 340.0}
+    assert [(b["doc_count"], b["key"]) for b in a["hosts"]["buckets"]] == [(4, "192.168.0.10"), (2, "192.168.0.1"), (1, "192.168.0.11")]
+    assert [(b["doc_count"], b["key"]) for b in a["tags"]["buckets"]] == [(5, "nice"), (2, "cool")]
+    assert a["names"] == {"buckets": [{"doc_count": 2, "key": "Fritz"}], "sum_other_doc_count": 8, "doc_count_error_upper_bound": 2}
+    same(got, cpu_root_search(imgs, MATCH_ALL, AGG_MAPPING, max_hits=0, aggs=aggs))
+
+
+def test_failed_split_is_reported_not_fatal(gpu_ctx, synth):
+    leaf_pb = search_request(term("body", "t0"), max_hits=5)
+    offsets = [proto.enc_split_offsets(synth[0].split_id, synth[0].num_docs), proto.enc_split_offsets("not-resident", 1)]
+    resp = proto.dec_leaf_search_response(gpu_ctx.leaf_search(proto.enc_leaf_search_request(leaf_pb, offsets, json.dumps(SYNTH_MAPPING))))
+    assert resp["num_attempted_splits"] == 2 and resp["num_successful_splits"] == 1
+    assert resp["failed_splits"] == [{"error": "split `not-resident` is not resident on this GPU", "split_id": "not-resident", "retryable_error": True}]
+    assert len(resp["partial_hits"]) == 5
+    with pytest.raises(ffi.QwGpuError) as e:
+        gpu_ctx.leaf_search(proto.enc_leaf_search_request(search_request(term("nope", "x"), max_hits=5), offsets[:1], json.dumps(SYNTH_MAPPING)))
+    assert e.value.code == ffi.EINVALID_QUERY
+
+
+def test_invoke_leaf_search_per_split_results(gpu_ctx, synth):
+    leaf_pb = search_request(bool_(should=[term("body", "t0"), term("body", "t3")]), max_hits=7, sort_fields=[("_score", DESC)])
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in synth] + [proto.enc_split_offsets("ghost", 1)]
+    results = proto.dec_lambda_responses(gpu_ctx.invoke_leaf_search(proto.enc_leaf_search_request(leaf_pb, offsets, json.dumps(SYNTH_MAPPING))))
+    assert [r["split_id"] for r in results] == [im.split_id for im in synth] + ["ghost"]
+    assert results[-1]["error"] and results[-1]["response"] is None
+    for im, r in zip(synth, results):
+        want = proto.dec_leaf_search_response(cpu_split_response(im, leaf_pb, SYNTH_MAPPING))
+        assert r["response"]["num_hits"] == want["num_hits"] and r["response"]["partial_hits"] == want["partial_hits"]
