@@ -178,6 +178,10 @@ typedef struct qwgpu_synth_spec {
 } qwgpu_synth_spec;
 int qwgpu_synth_split(const qwgpu_synth_spec* spec, uint8_t** img, uint64_t* img_len);
 
+/* Bm25Weight of one term: idf(doc_freq, num_docs) * (1 + K1) * boost in f32 (what
+ * qwgpu_compile_plan writes into QwPlanNode.bm25_weight); for hand-built seam-C plans. */
+float qwgpu_bm25_weight(uint64_t doc_freq, uint64_t num_docs, float boost);
+
 /* tantivy fieldnorm <-> id table (tantivy::fieldnorm::{fieldnorm_to_id,id_to_fieldnorm}). */
 uint8_t qwgpu_fieldnorm_to_id(uint32_t fieldnorm);
 uint32_t qwgpu_id_to_fieldnorm(uint8_t id);

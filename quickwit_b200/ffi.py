@@ -189,6 +189,7 @@ def lib() -> C.CDLL:
     bind("qwgpu_imgb_add_column", [vp, cp, u32, u32, vp, u64, vp, vp, vp, u32])
     bind("qwgpu_imgb_finish", [vp, C.POINTER(vp), C.POINTER(u64)])
     bind("qwgpu_synth_split", [C.POINTER(SynthSpec), C.POINTER(vp), C.POINTER(u64)])
+    bind("qwgpu_bm25_weight", [u64, u64, C.c_float], C.c_float)
     bind("qwgpu_fieldnorm_to_id", [u32], C.c_uint8)
     bind("qwgpu_id_to_fieldnorm", [C.c_uint8], u32)
     if missing and not os.environ.get("QWGPU_DEV_PARTIAL"):

@@ -6,7 +6,6 @@ these helpers build the same bytes by hand, which is what the plan-level parity 
 from __future__ import annotations
 
 import ctypes as C
-import math
 import struct
 from typing import List, Optional, Sequence, Tuple
 
@@ -15,15 +14,12 @@ import numpy as np
 from . import ffi
 from .splitgen import SplitImage
 
-K1 = np.float32(1.2)
 
 
 def bm25_weight(doc_freq: int, num_docs: int, boost: float = 1.0) -> float:
-    """tantivy Bm25Weight: idf * (1 + K1) * boost in f32."""
-    x = (np.float32(num_docs - doc_freq) + np.float32(0.5)) / (np.float32(doc_freq) + np.float32(0.5))
-    idf = np.float32(math.log(float(np.float32(1.0) + x)))  # logf; f32 rounding of the f64 log
-    idf = np.log(np.float32(1.0) + x, dtype=np.float32)
-    return float(np.float32(idf * (np.float32(1.0) + K1)) * np.float32(boost))
+    """tantivy Bm25Weight: idf * (1 + K1) * boost in f32 — computed by the
+    C++ host (`qwgpu_bm25_weight`) so hand-built plans carry the exact weights compiled plans do."""
+    return float(ffi.lib().qwgpu_bm25_weight(doc_freq, num_docs, boost))
 
 
 class Node:

@@ -154,3 +154,29 @@ def build_leaf_response(img: SplitImage, search_request_pb: bytes, doc_mapper_js
                                           len(search_request_pb), doc_mapper_json.encode(), num_hits, harr, len(hits),
                                           carr, len(cells), C.byref(out), C.byref(n)))
     return ffi.take_bytes(out, n.value)
+
+
+# ---- multi-GPU partial exchange: one fixed-size all-gather stands in for the root merge
+def partial_size(search_request_pb: bytes) -> int:
+    L = ffi.lib()
+    rb = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    n = C.c_uint64()
+    ffi.check(L.qwgpu_partial_size(C.addressof(rb), len(search_request_pb), C.byref(n)))
+    return int(n.value)
+
+
+def response_to_partial(search_request_pb: bytes, leaf_response: bytes, out_ptr: int, nbytes: int) -> None:
+    """Packs a rank's LeafSearchResponse into the fixed-size partial at `out_ptr` (host memory)."""
+    L = ffi.lib()
+    rb = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    lb = C.create_string_buffer(leaf_response, max(len(leaf_response), 1))
+    ffi.check(L.qwgpu_response_to_partial(C.addressof(rb), len(search_request_pb), C.addressof(lb), len(leaf_response), out_ptr, nbytes))
+
+
+def merge_partials(search_request_pb: bytes, n_ranks: int, gathered_ptr: int, partial_bytes: int) -> bytes:
+    """merge_leaf_responses over the all-gathered partials of every rank -> LeafSearchResponse bytes."""
+    L = ffi.lib()
+    rb = C.create_string_buffer(search_request_pb, len(search_request_pb))
+    out, n = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_merge_partials(C.addressof(rb), len(search_request_pb), n_ranks, gathered_ptr, partial_bytes, C.byref(out), C.byref(n)))
+    return ffi.take_bytes(out, n.value)

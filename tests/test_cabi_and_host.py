@@ -1,0 +1,148 @@
+"""C-ABI surface + host-only logic (no GPU): every symbol declared in include/qwgpu.h is exported,
+the product fails loudly without a device, and the independent Python / C++ protobuf codecs and
+the query compiler agree."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from quickwit_b200 import ffi, plan as P, proto, service, splitgen as S
+from quickwit_b200.proto import ASC, DESC
+from oracle import oracle as O
+from pipeline import MATCH_ALL, bool_, full_text, search_request, term
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "qwgpu.h")).read()
+    names = sorted(set(re.findall(r"\b(qwgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    L = C.CDLL(ffi.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    if os.path.exists("/dev/nvidia0"):
+        pytest.skip("a GPU is present")
+    with pytest.raises(ffi.QwGpuError) as e:
+        service.SearcherContext(0)
+    assert e.value.code == ffi.ENODEVICE
+    ctx = service.SearcherContext(None)  # host-only context
+    img = S.synth_split(2000, 0, [0.1])
+    with pytest.raises(ffi.QwGpuError) as e:
+        ctx.register_split(img)
+    assert e.value.code == ffi.ENODEVICE
+    with pytest.raises(ffi.QwGpuError) as e:
+        ctx.leaf_search(proto.enc_leaf_search_request(search_request(MATCH_ALL, max_hits=1), [], "{}"))
+    assert e.value.code == ffi.ENODEVICE
+
+
+def test_product_does_not_reference_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "quickwit_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "qworacle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_compiled_plan_matches_hand_built_plan():
+    img = S.synth_split(5000, 3, [0.2, 0.1, 0.05], split_id="cp")
+    dm = json.dumps({"field_mappings": [], "timestamp_field": "timestamp"})
+    ast = bool_(should=[term("body", "t0"), term("body", "t1"), term("body", "t2")])
+    got = service.compile_plan(img, search_request(ast, max_hits=10, sort_fields=[("_score", DESC)]), dm)
+    root = P.bool_([P.term(img, "body", f"t{i}", occur=ffi.OCCUR_SHOULD) for i in range(3)])
+    want = P.make_plan(root, 10, [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)])
+    assert got == want
+    # same results through the oracle, including the f32 BM25 weights computed by the C++ host
+    a, b = O.split_search(img, got), O.split_search(img, want)
+    assert a.hits == b.hits and a.num_hits == b.num_hits
+
+
+def test_bool_simplification_rules():
+    """TantivyBoolQuery::simplify (tantivy_query_ast.rs:190-337), observed through compiled plans."""
+    img = S.synth_split(3000, 1, [0.3, 0.2], split_id="simp")
+    dm = "{}"
+    node = lambda pl, i: ffi.QwPlanNode.from_buffer_copy(pl[C.sizeof(ffi.QwPlanHeader) + i * C.sizeof(ffi.QwPlanNode):][:C.sizeof(ffi.QwPlanNode)])
+    nn = lambda pl: ffi.QwPlanHeader.from_buffer_copy(pl[:C.sizeof(ffi.QwPlanHeader)]).num_nodes
+    comp = lambda ast, **kw: service.compile_plan(img, search_request(ast, max_hits=1, **kw), dm)
+    assert node(comp(bool_()), 0).kind == ffi.NODE_ALL                         # empty bool == match_all
+    assert node(comp(bool_(must=[{"type": "match_none"}, term("body", "t0")])), 0).kind == ffi.NODE_NONE
+    pl = comp(bool_(must=[term("body", "t0")]))                                 # single must clause is unwrapped
+    assert nn(pl) == 1 and node(pl, 0).kind == ffi.NODE_TERM
+    pl = comp(bool_(filter=[term("body", "t0")]))                               # a single filter is NOT unwrapped (keeps score 0)
+    assert node(pl, 0).kind == ffi.NODE_BOOL and node(pl, 1).occur == ffi.OCCUR_FILTER
+    pl = comp(bool_(must=[bool_(must=[term("body", "t0")], must_not=[term("body", "t1")])]))  # nested must flattened
+    assert node(pl, 0).kind == ffi.NODE_BOOL and node(pl, 0).num_children == 2
+    pl = comp(bool_(must_not=[term("body", "t0")]))                             # only must_not: match_all is added
+    kinds = sorted(node(pl, i).kind for i in range(1, nn(pl)))
+    assert node(pl, 0).kind == ffi.NODE_BOOL and kinds == [ffi.NODE_TERM, ffi.NODE_ALL]
+    assert node(comp(bool_(should=[], minimum_should_match=1)), 0).kind == ffi.NODE_NONE
+    dm_ts = json.dumps({"timestamp_field": "timestamp", "field_mappings": [{"name": "timestamp", "type": "datetime", "fast": True}]})
+    pl = service.compile_plan(img, search_request(term("body", "t0"), max_hits=1, start_timestamp=1_700_000_010, end_timestamp=1_700_000_020), dm_ts)
+    assert node(pl, 0).kind == ffi.NODE_BOOL and node(pl, 2).kind == ffi.NODE_RANGE and node(pl, 2).occur == ffi.OCCUR_FILTER
+    assert (S.u64_to_i64(node(pl, 2).lo), S.u64_to_i64(node(pl, 2).hi)) == (1_700_000_010 * 10**9, 1_700_000_020 * 10**9 - 1)
+    with pytest.raises(ffi.QwGpuError) as e:
+        comp({"type": "bool", "must": [{"type": "nope"}]})
+    assert e.value.code == ffi.EINVALID_QUERY
+
+
+def test_python_and_cpp_protobuf_codecs_agree():
+    hits = [{"split_id": "s1", "segment_ord": 0, "doc_id": 7, "sort_value": ("f64", 1.5), "sort_value2": ("i64", -3)},
+            {"split_id": "s0", "segment_ord": 0, "doc_id": 9, "sort_value": ("u64", 2**63 + 5)},
+            {"split_id": "s2", "segment_ord": 0, "doc_id": 1, "sort_value": None, "sort_value2": ("bool", True)}]
+    resp = proto.enc_leaf_search_response(42, hits, [("boom", "s9", True)], 3, 2, b"\x00\x01agg")
+    req = proto.enc_search_request("{}", max_hits=10, sort_fields=[("a", DESC), ("b", ASC)])
+    # single-response shortcut: decoded by the C++ codec, re-encoded, decoded by the Python codec
+    out = proto.dec_leaf_search_response(service.merge_leaf_responses(req, [resp]))
+    assert out["num_hits"] == 42 and out["partial_hits"] == hits and out["intermediate_aggregation_result"] == b"\x00\x01agg"
+    assert out["failed_splits"] == [{"error": "boom", "split_id": "s9", "retryable_error": True}]
+    assert (out["num_attempted_splits"], out["num_successful_splits"]) == (3, 2)
+
+
+def test_heterogeneous_sort_value_order():
+    """SortValue::cmp across types (quickwit-proto/src/search/mod.rs:137-161; root.rs:3329-3692)."""
+    mk = lambda i, sv: {"split_id": "s", "segment_ord": 0, "doc_id": i, "sort_value": sv}
+    vals = [("u64", 2**63 + 1), ("i64", -5), ("f64", 2.5), ("u64", 3), ("i64", 2), ("bool", True), ("f64", -7.25), None]
+    parts = [proto.enc_leaf_search_response(1, [mk(i, v)], num_attempted_splits=1, num_successful_splits=1) for i, v in enumerate(vals)]
+    req = lambda o: proto.enc_search_request("{}", max_hits=8, sort_fields=[("f", o)])
+    order = lambda o: [h["doc_id"] for h in proto.dec_leaf_search_response(service.merge_leaf_responses(req(o), parts))["partial_hits"]]
+    assert order(DESC) == [0, 3, 2, 4, 5, 1, 6, 7]   # 2^63+1 > 3 > 2.5 > 2 > true(1) > -5 > -7.25 > None
+    assert order(ASC) == [6, 1, 5, 4, 2, 3, 0, 7]    # None stays last in both directions
+
+
+def test_posting_and_column_format_roundtrip():
+    rng = np.random.default_rng(3)
+    n = 70_000
+    b = S._Builder(n)
+    fid = b.add_field("f", ffi.FIELD_HAS_FREQS, ffi.TOK_RAW, None, n)
+    lists = {}
+    for name, p in (("dense", 0.7), ("mid", 0.03), ("rare", 0.0002), ("all", 1.0), ("one", None)):
+        docs = np.array([n - 1], dtype=np.uint32) if p is None else np.nonzero(rng.random(n) < p)[0].astype(np.uint32)
+        tfs = rng.integers(1, 2000, size=len(docs)).astype(np.uint32)
+        lists[name] = (docs, tfs)
+        b.add_term(fid, name.encode(), docs, tfs)
+    vals = rng.integers(0, 2**40, size=n).astype(np.uint64) * 3 + 11
+    b.add_column("full", ffi.COL_U64, ffi.CARD_FULL, vals, None)
+    some = np.nonzero(rng.random(n) < 0.3)[0].astype(np.uint32)
+    b.add_column("opt", ffi.COL_I64, ffi.CARD_OPTIONAL, np.array([S.i64_to_u64(int(x) - 50) for x in some], dtype=np.uint64), some)
+    wide = rng.integers(0, 2**63, size=n).astype(np.uint64) * 2 + rng.integers(0, 2, size=n).astype(np.uint64)
+    wide[0], wide[1] = 0, 2**64 - 1
+    b.add_column("wide", ffi.COL_U64, ffi.CARD_FULL, wide, None)
+    img = b.finish("fmt")
+    for name, (docs, tfs) in lists.items():
+        d, t = O.decode_postings(img, img.term_ord("f", name), n)
+        assert np.array_equal(d, docs) and np.array_equal(t, tfs), name
+    v, p = O.column_first(img, img.column_ord("full"))
+    assert p.all() and np.array_equal(v, vals)
+    c = img.columns()[img.column_ord("full")]
+    assert c.gcd == 3 and c.min_value == vals.min()
+    v, p = O.column_first(img, img.column_ord("opt"))
+    assert np.array_equal(np.nonzero(p)[0], some) and [S.u64_to_i64(int(x)) for x in v[p][:5]] == [int(x) - 50 for x in some[:5]]
+    assert img.columns()[img.column_ord("wide")].bits == 64
+    v, p = O.column_first(img, img.column_ord("wide"))
+    assert np.array_equal(v, wide)
