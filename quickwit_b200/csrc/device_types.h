@@ -13,6 +13,8 @@
 #define QW_MAX_TERMS 64      /* TERM instructions per plan */
 #define QW_BLK_TAB 48        /* staged blocks per (term, window) before falling back to direct mode */
 #define QW_STAGE_BYTES 16384 /* packed posting bytes staged per window */
+#define QW_MAX_WBLK 256      /* staged blocks per window over all terms */
+#define QW_ENT_BLOCKS 32     /* decoded blocks held at once (one "round"): 32 x 128 entries x 8 B */
 #define QW_HIST_BINS 2048    /* 11-bit radix digits */
 #define QW_DIGIT_BITS 11
 #define QW_KEY_BITS 192
@@ -105,7 +107,7 @@ struct SmemLayout {
   uint32_t instr, cols, aggs;
   SmemLevel lvl[QW_MAX_LEVELS];
   uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
-  uint32_t rng, blktab, blkcnt, stage, hist, misc;
+  uint32_t rng, blkrec, termblk, stage, ent, hist, misc;  // hist aliases ent (dead by collect time)
   uint32_t total;
 };
 

@@ -433,10 +433,11 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.tmp = take(W / 8);
   for (uint32_t s = 0; s < n_fn; s++) { L.fn[s] = take(W); L.tab[s] = take((256 + QW_TFF_ROWS * 256) * 4); }
   L.rng = take(QW_MAX_TERMS * 16);
-  L.blktab = take(QW_MAX_TERMS * QW_BLK_TAB * 2);
-  L.blkcnt = take(QW_MAX_TERMS * 4);
+  L.blkrec = take(QW_MAX_WBLK * 8);
+  L.termblk = take(QW_MAX_TERMS * 8);
   L.stage = take(QW_STAGE_BYTES);
-  L.hist = take(QW_SMEM_AGG_CELLS * 4);
+  L.ent = take(std::max<uint32_t>(QW_ENT_BLOCKS * 128 * 8, QW_SMEM_AGG_CELLS * 4));
+  L.hist = L.ent;
   L.total = off;
   return L;
 }
@@ -479,7 +480,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
     tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
   }
-  uint32_t W = 8192;
+  uint32_t W = 4096;
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn);

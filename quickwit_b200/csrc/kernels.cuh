@@ -22,6 +22,11 @@
 
 namespace qwk {
 
+// The one dynamic shared-memory arena of every kernel in this file. Device functions address it as
+// `qw_smem + offset`, so the compiler emits LDS/STS/ATOMS (32-bit shared addressing) instead of
+// generic loads with 64-bit address arithmetic.
+extern __shared__ __align__(16) uint8_t qw_smem[];
+
 struct Key {
   uint64_t w0, w1, w2;
 };
@@ -128,40 +133,42 @@ __device__ __forceinline__ int order_cmp_opt(uint32_t order, bool ha, uint64_t a
 
 // Per-CTA view of the shared-memory arena
 struct Sm {
-  uint8_t* base;
   const SmemLayout* L;
-  __device__ __forceinline__ uint32_t* u32(uint32_t off) const { return (uint32_t*)(base + off); }
-  __device__ __forceinline__ float* f32(uint32_t off) const { return (float*)(base + off); }
-  __device__ __forceinline__ uint8_t* u8(uint32_t off) const { return base + off; }
+  __device__ __forceinline__ uint32_t* u32(uint32_t off) const { return (uint32_t*)(qw_smem + off); }
+  __device__ __forceinline__ float* f32(uint32_t off) const { return (float*)(qw_smem + off); }
+  __device__ __forceinline__ uint8_t* u8(uint32_t off) const { return qw_smem + off; }
 };
 
 struct TermTarget {
-  uint32_t* bits;     // bitmap receiving the term's docs
-  uint8_t* cnt;       // optional per-doc should counter
-  float* score;       // optional score accumulator
-  const uint8_t* fn;  // staged fieldnorm ids of the window (or null: constant fieldnorm id 1)
-  const float* tab;   // float[256] BM25 norms followed by float[QW_TFF_ROWS][256] tf factors
+  uint32_t bits;   // shared-memory byte offsets (0xFFFFFFFF = absent)
+  uint32_t cnt;
+  uint32_t score;
+  uint32_t fn;     // staged fieldnorm ids of the window (absent: constant fieldnorm id 1)
+  uint32_t tab;    // float[256] BM25 norms followed by float[QW_TFF_ROWS][256] tf factors
   float weight;
   bool has_tf;
 };
 
 // Decode one posting block (header + 4-lane-interleaved bit-packed doc deltas + tfs) with one warp
-// and fold the postings that fall into [ws, we) into the target. `blk` may point to shared or
-// global memory (generic addressing).
-template <bool SCORED, bool CNT>
-__device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint32_t we, const TermTarget& tg, uint32_t lane) {
+// and fold the postings that fall into [ws, we) into the target (all targets live in shared
+// memory). STAGED: the block bytes are in shared memory at qw_smem + blk_off; otherwise `gblk`
+// points to global memory.
+template <bool SCORED, bool CNT, bool STAGED>
+__device__ __forceinline__ void fold_block(uint32_t blk_off, const uint8_t* gblk, uint32_t ws, uint32_t rlo, uint32_t rlen, const TermTarget& tg, uint32_t lane) {
+  const uint8_t* blk = STAGED ? (qw_smem + blk_off) : gblk;
   const uint4 h = *reinterpret_cast<const uint4*>(blk);  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
   const uint32_t last_doc = h.x, prev = h.y;
   const uint32_t doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;
-  if (last_doc < ws) return;
-  if (prev != QW_NO_PREV_DOC && prev + 1 >= we) return;
+  // accepted docs: ws + rlo <= doc < ws + rlo + rlen (targets are indexed by doc - ws)
+  if (last_doc < ws + rlo) return;
+  if (prev != QW_NO_PREV_DOC && prev + 1 >= ws + rlo + rlen) return;
   const uint4* dp = reinterpret_cast<const uint4*>(blk + 16);
   uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
   if (doc_bits) {
     uint32_t bitpos = lane * doc_bits, wi = bitpos >> 5, sh = bitpos & 31;
     uint4 A = dp[wi];
     uint4 B = (sh + doc_bits > 32) ? dp[wi + 1] : make_uint4(0, 0, 0, 0);
-    uint32_t mask = doc_bits == 32 ? 0xFFFFFFFFu : ((1u << doc_bits) - 1);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - doc_bits);
     v0 = __funnelshift_r(A.x, B.x, sh) & mask;
     v1 = __funnelshift_r(A.y, B.y, sh) & mask;
     v2 = __funnelshift_r(A.z, B.z, sh) & mask;
@@ -177,7 +184,6 @@ __device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint
   }
   const uint32_t basev = prev + (incl - d3) - ws;  // mod 2^32; window-relative
   uint32_t rel[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
-  const uint32_t wlen = we - ws;
   const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;  // postings of this lane that exist
   uint32_t tf[4] = {1, 1, 1, 1};
   if (SCORED && tg.has_tf && tf_bits) {
@@ -185,43 +191,51 @@ __device__ __forceinline__ void fold_block(const uint8_t* blk, uint32_t ws, uint
     uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
     uint4 A = tp[wi];
     uint4 B = (sh + tf_bits > 32) ? tp[wi + 1] : make_uint4(0, 0, 0, 0);
-    uint32_t mask = tf_bits == 32 ? 0xFFFFFFFFu : ((1u << tf_bits) - 1);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - tf_bits);
     tf[0] = __funnelshift_r(A.x, B.x, sh) & mask;
     tf[1] = __funnelshift_r(A.y, B.y, sh) & mask;
     tf[2] = __funnelshift_r(A.z, B.z, sh) & mask;
     tf[3] = __funnelshift_r(A.w, B.w, sh) & mask;
   }
+  uint32_t* bits = reinterpret_cast<uint32_t*>(qw_smem + tg.bits);
+  float* score = reinterpret_cast<float*>(qw_smem + tg.score);
+  const float* tab = reinterpret_cast<const float*>(qw_smem + tg.tab);
+  const uint8_t* fn = qw_smem + tg.fn;
+  uint8_t* cnt = qw_smem + tg.cnt;
+  const bool has_fn = tg.fn != 0xFFFFFFFFu;
   uint32_t cur_word = 0xFFFFFFFFu, cur_mask = 0;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint32_t d = rel[j];  // < wlen  <=>  ws <= doc < we (unsigned wrap)
-    if ((uint32_t)j < nvalid && d < wlen) {
+    const uint32_t d = rel[j];  // doc - ws (unsigned wrap for docs before the window)
+    if ((uint32_t)j < nvalid && d - rlo < rlen) {
       const uint32_t w = d >> 5;
       if (w != cur_word) {
-        if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
+        if (cur_mask) atomicOr(&bits[cur_word], cur_mask);
         cur_word = w;
         cur_mask = 0;
       }
       cur_mask |= 1u << (d & 31);
-      if (CNT) tg.cnt[d] = (uint8_t)(tg.cnt[d] + 1);
+      if (CNT) cnt[d] = (uint8_t)(cnt[d] + 1);
       if (SCORED) {
         // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest.
         // tf / (tf + norm) comes from a table built with the same IEEE ops for tf < 16.
-        const uint32_t f = tg.fn ? tg.fn[d] : 1u;
+        const uint32_t f = has_fn ? fn[d] : 1u;
         const uint32_t t = tf[j];
         float tfn;
-        if (t < QW_TFF_ROWS) tfn = tg.tab[256 + t * 256 + f];
-        else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tg.tab[f])); }
-        tg.score[d] = __fadd_rn(tg.score[d], __fmul_rn(tg.weight, tfn));
+        if (t < QW_TFF_ROWS) tfn = tab[256 + t * 256 + f];
+        else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tab[f])); }
+        score[d] = __fadd_rn(score[d], __fmul_rn(tg.weight, tfn));
       }
     }
   }
-  if (cur_mask) atomicOr(&tg.bits[cur_word], cur_mask);
+  if (cur_mask) atomicOr(&bits[cur_word], cur_mask);
 }
 
-__device__ __forceinline__ void fold_block_dyn(const uint8_t* blk, uint32_t ws, uint32_t we, const TermTarget& tg, uint32_t lane) {
-  if (tg.score) { if (tg.cnt) fold_block<true, true>(blk, ws, we, tg, lane); else fold_block<true, false>(blk, ws, we, tg, lane); }
-  else { if (tg.cnt) fold_block<false, true>(blk, ws, we, tg, lane); else fold_block<false, false>(blk, ws, we, tg, lane); }
+template <bool STAGED>
+__device__ __forceinline__ void fold_block_dyn(uint32_t blk_off, const uint8_t* gblk, uint32_t ws, uint32_t rlo, uint32_t rlen, const TermTarget& tg, uint32_t lane) {
+  const bool sc = tg.score != 0xFFFFFFFFu, cn = tg.cnt != 0xFFFFFFFFu;
+  if (sc) { if (cn) fold_block<true, true, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); else fold_block<true, false, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); }
+  else { if (cn) fold_block<false, true, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); else fold_block<false, false, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); }
 }
 
 // The 11 most significant bits of the composite key ([has1 | lin1]) — enough for the level-0 radix
@@ -404,50 +418,139 @@ __device__ void agg_collect_doc(const KParams& p, const Sm& sm, const DSplitPlan
 
 enum { MODE_HIST = 0, MODE_COLLECT = 1 };
 
-__device__ __forceinline__ void zero_f4(float* p, uint32_t n, uint32_t tid) {
-  float4* q = reinterpret_cast<float4*>(p);
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (uint32_t i = tid; i < (n >> 2); i += QW_THREADS) q[i] = z;
+// ---- warp-private helpers (each warp owns the doc sub-range [lo, lo + S) of the window) ------------
+__device__ __forceinline__ void wzero_u32(uint32_t* p, uint32_t first, uint32_t n, uint32_t lane) {
+  for (uint32_t i = lane; i < n; i += 32) p[first + i] = 0;
 }
 
+struct BlkRec {  // one staged posting block of the window
+  uint16_t soff;  // byte offset of the block inside the stage area
+  uint16_t lo;    // lower bound of its first doc, window-relative, clamped to [0, W]
+  uint16_t hi;    // last doc, window-relative, clamped to [0, W-1] (0xFFFF: entirely before the window)
+  uint8_t slot;   // term slot
+  uint8_t pad;
+};
+
+// Phase X: decode one staged posting block with one warp into 128 entries {rel doc, score}.
+// Entries outside the window (or past the block's count) get rel doc 0xFFFFFFFF.
+__device__ __forceinline__ void decode_block_entries(uint32_t blk_off, uint32_t ws, uint32_t wlen, bool scored, bool has_tf,
+                                                     uint32_t fn_off, uint32_t tab_off, float weight, uint2* out, uint32_t lane) {
+  const uint8_t* blk = qw_smem + blk_off;
+  const uint4 h = *reinterpret_cast<const uint4*>(blk);
+  const uint32_t prev = h.y;
+  const uint32_t doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;
+  const uint4* dp = reinterpret_cast<const uint4*>(blk + 16);
+  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  if (doc_bits) {
+    uint32_t bitpos = lane * doc_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = dp[wi];
+    uint4 B = (sh + doc_bits > 32) ? dp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - doc_bits);
+    v0 = __funnelshift_r(A.x, B.x, sh) & mask;
+    v1 = __funnelshift_r(A.y, B.y, sh) & mask;
+    v2 = __funnelshift_r(A.z, B.z, sh) & mask;
+    v3 = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  uint32_t d0 = v0 + 1, d1 = d0 + v1 + 1, d2 = d1 + v2 + 1, d3 = d2 + v3 + 1;
+  uint32_t incl = d3;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((int)lane >= o) incl += n;
+  }
+  const uint32_t basev = prev + (incl - d3) - ws;
+  uint32_t rel[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
+  const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;
+  uint32_t tf[4] = {1, 1, 1, 1};
+  if (scored && has_tf && tf_bits) {
+    const uint4* tp = dp + doc_bits;
+    uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = tp[wi];
+    uint4 B = (sh + tf_bits > 32) ? tp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - tf_bits);
+    tf[0] = __funnelshift_r(A.x, B.x, sh) & mask;
+    tf[1] = __funnelshift_r(A.y, B.y, sh) & mask;
+    tf[2] = __funnelshift_r(A.z, B.z, sh) & mask;
+    tf[3] = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  const float* tab = reinterpret_cast<const float*>(qw_smem + tab_off);
+  const uint8_t* fn = qw_smem + fn_off;
+  const bool has_fn = fn_off != 0xFFFFFFFFu;
+  // independent chains for the 4 postings of this lane: all fieldnorm loads, then all table loads
+  uint32_t f[4];
+  bool in[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    in[j] = (uint32_t)j < nvalid && rel[j] < wlen;
+    f[j] = (scored && has_fn && in[j]) ? fn[rel[j]] : 1u;
+  }
+  float sc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (scored) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (!in[j]) continue;
+      // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest; the
+      // quotient comes from a table built with the same IEEE ops for tf < 16
+      const uint32_t t = tf[j];
+      float tfn;
+      if (t < QW_TFF_ROWS) tfn = tab[256 + t * 256 + f[j]];
+      else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tab[f[j]])); }
+      sc[j] = __fmul_rn(weight, tfn);
+    }
+  }
+  // entry i of the block lives at out[i]; lane holds entries 4*lane .. 4*lane+3 (two 16-byte stores)
+  uint4* o4 = reinterpret_cast<uint4*>(out + 4 * lane);
+  o4[0] = make_uint4(in[0] ? rel[0] : 0xFFFFFFFFu, __float_as_uint(sc[0]), in[1] ? rel[1] : 0xFFFFFFFFu, __float_as_uint(sc[1]));
+  o4[1] = make_uint4(in[2] ? rel[2] : 0xFFFFFFFFu, __float_as_uint(sc[2]), in[3] ? rel[3] : 0xFFFFFFFFu, __float_as_uint(sc[3]));
+}
+
+
+
+// The window engine, v4: "decode once in parallel, then evaluate per warp without block barriers".
+//   phase 1-3  index entries, fieldnorm + posting staging (cp.async), block table   [block barriers]
+//   phase X    every staged posting block of every term is decoded by some warp into an entry list
+//   phase Y    each warp interprets the boolean program for ITS doc sub-range (W/8 docs): posting
+//              entries are applied clause by clause in plan order (fixed f32 summation order),
+//              bitmaps/score slices are warp-private, so only __syncwarp separates clauses
+//   collect    each warp counts / filters / aggregates its own sub-range
 template <int MODE>
 __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  Sm sm{smem_raw, &p.sm};
+  Sm sm{&p.sm};
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t W = p.W, NW = W >> 5;
+  const uint32_t S = W / QW_WARPS, SW = S >> 5;      // docs / bitmap words per warp
+  const uint32_t lo = warp * S, wlo = warp * SW;      // this warp's sub-range (window-relative)
   DInstr* s_instr = (DInstr*)sm.u8(p.sm.instr);
   DCol* s_cols = (DCol*)sm.u8(p.sm.cols);
   DAgg* s_aggs = (DAgg*)sm.u8(p.sm.aggs);
-  uint32_t* s_misc = sm.u32(p.sm.misc);  // [2] hits counter, [3] eligible counter
+  uint32_t* s_misc = sm.u32(p.sm.misc);  // [0] total staged blocks, [2] hits, [3] eligible
   uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off, instr index
-  uint16_t* s_blktab = (uint16_t*)sm.u8(p.sm.blktab);
-  uint32_t* s_blkcnt = sm.u32(p.sm.blkcnt);
+  BlkRec* s_blk = (BlkRec*)sm.u8(p.sm.blkrec);
+  uint32_t* s_tblk = sm.u32(p.sm.termblk);  // per term slot: first global block, block count
   uint32_t* s_hist = sm.u32(p.sm.hist);
   uint8_t* s_stage = sm.u8(p.sm.stage);
+  uint2* s_ent = (uint2*)sm.u8(p.sm.ent);
   uint32_t loaded_split = 0xFFFFFFFFu;
 
-  // static contiguous partition of the flat (split, window) work list: a block walks consecutive
-  // windows, so it changes split (and reloads its program) at most a few times
   const uint32_t per = (p.total_work + gridDim.x - 1) / gridDim.x;
   const uint32_t w_begin = blockIdx.x * per;
   const uint32_t w_end = min(w_begin + per, p.total_work);
   uint32_t split = 0;
   if (w_begin < w_end) {
-    uint32_t lo = 0, hi = p.n_splits;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(p.first_work + mid) <= w_begin) lo = mid; else hi = mid;
+    uint32_t a = 0, b = p.n_splits;
+    while (b - a > 1) {
+      uint32_t mid = (a + b) >> 1;
+      if (__ldg(p.first_work + mid) <= w_begin) a = mid; else b = mid;
     }
-    split = lo;
+    split = a;
   }
 
   for (uint32_t work = w_begin; work < w_end; work++) {
     while (__ldg(p.first_work + split + 1) <= work) split++;
     const uint32_t window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
     const DSplitPlan& P = p.plans[split];
+    __syncthreads();  // previous window fully finished (stage / entries / program are reused)
     if (split != loaded_split) {
-      __syncthreads();  // previous window fully done before its program is overwritten
       const uint4* src = (const uint4*)(p.instrs + P.instr_base);
       for (uint32_t i = tid; i < P.n_instr * (sizeof(DInstr) / 16); i += QW_THREADS) ((uint4*)s_instr)[i] = __ldg(src + i);
       src = (const uint4*)(p.cols + P.col_base);
@@ -459,18 +562,17 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
         uint8_t* tdst = sm.u8(p.sm.tab[s]);
         for (uint32_t i = tid; i < (256 + QW_TFF_ROWS * 256) * 4 / 16; i += QW_THREADS) cp_async16(tdst + 16 * i, tsrc + 16 * i);
       }
-      if (MODE == MODE_HIST || p.smem_aggs)
-        for (uint32_t i = tid; i < QW_HIST_BINS * ((MODE == MODE_COLLECT) ? 2 : 1); i += QW_THREADS) s_hist[i] = 0;
       loaded_split = split;
       cp_async_wait_all();
       __syncthreads();
       if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
+      __syncthreads();
     }
     const uint8_t* base = (const uint8_t*)P.data_base;
     const uint32_t ws = window * W;
     const uint32_t we = min(ws + W, P.num_docs);
+    const uint32_t wlen = we - ws;
     const uint32_t n_terms = P.n_terms, n_instr = P.n_instr, n_fn = P.n_fn_slots;
-    __syncthreads();
 
     // ---- phase 1: window-index entries + fieldnorm staging (one round of independent loads) --------
     if (tid < n_terms) {
@@ -492,7 +594,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       if (P.fn_off[s] == ~0ull) continue;
       const uint8_t* src = base + P.fn_off[s] + ws;
       uint8_t* dst = sm.u8(p.sm.fn[s]);
-      const uint32_t n16 = min(W, (we - ws + 15u) & ~15u) >> 4;  // the array is padded by 16 bytes only
+      const uint32_t n16 = min(W, (wlen + 15u) & ~15u) >> 4;  // the array is padded by 16 bytes only
       for (uint32_t i = tid; i < n16; i += QW_THREADS) cp_async16(dst + 16 * i, src + 16 * i);
     }
     __syncthreads();
@@ -515,227 +617,302 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
     }
     cp_async_wait_all();
     __syncthreads();
+    // ---- phase 3: block table. One thread per term counts its blocks, thread 0 assigns global block
+    // numbers, then the same threads write one BlkRec per block -------------------------------------------
+    uint32_t my_nb = 0;
     if (tid < n_terms) {
-      uint32_t so = s_rng[4 * tid + 2];
-      uint32_t k = 0;
+      const uint32_t so = s_rng[4 * tid + 2];
       if (so != 0xFFFFFFFFu) {
-        uint32_t len = s_rng[4 * tid + 1], pos = 0;
-        while (pos < len && k < QW_BLK_TAB) {
-          s_blktab[tid * QW_BLK_TAB + k++] = (uint16_t)pos;
+        const uint32_t len = s_rng[4 * tid + 1];
+        uint32_t pos = 0;
+        while (pos < len && my_nb <= QW_BLK_TAB) {
           uint32_t bw = *(const uint32_t*)(s_stage + so + pos + 12);
           pos += 16 + 16 * ((bw & 0xFF) + ((bw >> 8) & 0xFF));
+          my_nb++;
         }
-        if (pos < len) s_rng[4 * tid + 2] = 0xFFFFFFFFu;  // too many blocks: direct mode
+        if (my_nb > QW_BLK_TAB) { my_nb = 0; s_rng[4 * tid + 2] = 0xFFFFFFFFu; }  // too many blocks: direct mode
       }
-      s_blkcnt[tid] = k;
+      s_tblk[2 * tid + 1] = my_nb;
     }
     __syncthreads();
+    if (tid == 0) {
+      uint32_t g = 0;
+      for (uint32_t t = 0; t < n_terms; t++) {
+        uint32_t nb = s_tblk[2 * t + 1];
+        if (g + nb > QW_MAX_WBLK) { nb = 0; s_tblk[2 * t + 1] = 0; s_rng[4 * t + 2] = 0xFFFFFFFFu; }
+        s_tblk[2 * t] = g;
+        g += nb;
+      }
+      s_misc[0] = g;
+    }
+    __syncthreads();
+    if (tid < n_terms && s_tblk[2 * tid + 1]) {
+      const uint32_t so = s_rng[4 * tid + 2], nb = s_tblk[2 * tid + 1], g0 = s_tblk[2 * tid];
+      uint32_t pos = 0;
+      for (uint32_t k = 0; k < nb; k++) {
+        const uint4 h = *(const uint4*)(s_stage + so + pos);
+        BlkRec r;
+        r.soff = (uint16_t)(so + pos);
+        r.slot = (uint8_t)tid;
+        r.pad = 0;
+        const uint32_t first_lb = h.y + 1;  // lower bound of the first doc (0 when h.y == 0xFFFFFFFF)
+        r.lo = (uint16_t)(first_lb <= ws ? 0u : min(first_lb - ws, W));
+        r.hi = (uint16_t)(h.x < ws ? 0xFFFFu : min(h.x - ws, W - 1));
+        if (h.x < ws || first_lb >= we) { r.lo = (uint16_t)W; r.hi = 0; }  // no overlap: lo > hi
+        s_blk[g0 + k] = r;
+        pos += 16 + 16 * ((h.w & 0xFF) + ((h.w >> 8) & 0xFF));
+      }
+    }
+    __syncthreads();
+    const uint32_t total_blocks = s_misc[0];
 
-    // ---- execute the boolean program ----------------------------------------------------------------
-    uint32_t req_init = 0;  // bit per level, uniform across the block
-    for (uint32_t ip = 0; ip < n_instr; ip++) {
-      const DInstr& in = s_instr[ip];
-      const uint32_t op = in.op, level = in.level, occur = in.occur;
-      const SmemLevel& LV = p.sm.lvl[level];
-      const bool scored = (in.flags & IF_SCORED) != 0;
-      if (op == OP_BOOL_BEGIN) {
-        zero_f4((float*)sm.u32(LV.shd), NW, tid);
-        zero_f4((float*)sm.u32(LV.nt), NW, tid);
-        if (LV.cnt != 0xFFFFFFFFu) zero_f4((float*)sm.u32(LV.cnt), W >> 2, tid);
-        if (LV.msum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.msum), W, tid);
-        if (LV.ssum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.ssum), W, tid);
-        req_init &= ~(1u << level);
-        __syncthreads();
-      } else if (op == OP_TERM) {
-        const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
-        TermTarget tg;
-        tg.cnt = nullptr;
-        tg.score = nullptr;
-        if (required) {
-          tg.bits = sm.u32(p.sm.tmp);
-          zero_f4((float*)tg.bits, NW, tid);
-          if (scored) tg.score = sm.f32(LV.msum);
-          __syncthreads();
-        } else if (occur == QW_OCCUR_SHOULD) {
-          tg.bits = sm.u32(LV.shd);
-          if (LV.cnt != 0xFFFFFFFFu) tg.cnt = sm.u8(LV.cnt);
-          if (scored) tg.score = sm.f32(LV.ssum);
-        } else {
-          tg.bits = sm.u32(LV.nt);
-        }
-        tg.weight = in.f;
-        tg.has_tf = (in.flags & IF_HAS_TF) != 0;
-        tg.fn = nullptr;
-        tg.tab = nullptr;
-        if (scored) {
-          tg.tab = sm.f32(p.sm.tab[in.r]);
-          if (in.flags & IF_HAS_FN) tg.fn = sm.u8(p.sm.fn[in.r]);
-        }
-        const uint32_t slot = in.t;
-        const uint32_t so = s_rng[4 * slot + 2];
-        if (so != 0xFFFFFFFFu) {
-          const uint32_t nb = s_blkcnt[slot];
-          const uint16_t* tab = s_blktab + slot * QW_BLK_TAB;
-          const uint8_t* sb = s_stage + so;
-          if (tg.score && !tg.cnt) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false>(sb + tab[k], ws, we, tg, lane); }
-          else if (!tg.score && !tg.cnt) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<false, false>(sb + tab[k], ws, we, tg, lane); }
-          else { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block_dyn(sb + tab[k], ws, we, tg, lane); }
-        } else if (s_rng[4 * slot + 1]) {
-          // direct mode: locate the first block with last_doc >= ws in the skip list (warp-cooperative
-          // 32-ary search), then decode straight from global memory
-          const QwSkip* skips = (const QwSkip*)(base + in.c);
-          const uint32_t nblk = in.n;
-          uint32_t lo = 0, hi = nblk;
-          while (hi - lo > 32) {
-            uint32_t step = (hi - lo + 31) >> 5;
-            uint32_t idx = lo + lane * step;
-            bool ok = idx < hi && __ldg(&skips[idx].last_doc) >= ws;
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (m == 0) {
-              uint32_t lastp = lo + ((hi - 1 - lo) / step) * step;
-              lo = lastp + 1;
-            } else {
-              uint32_t f = __ffs(m) - 1;
-              hi = lo + f * step + 1;
-              if (f > 0) lo = lo + (f - 1) * step + 1;
-            }
-          }
-          uint32_t idx = lo + lane;
-          bool ok = idx < hi && __ldg(&skips[idx].last_doc) >= ws;
-          uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-          uint32_t b0 = m ? lo + (__ffs(m) - 1) : nblk;
-          const uint8_t* tdata = base + in.a;
-          for (uint32_t b = b0 + warp; b < nblk; b += QW_WARPS) {
-            uint4 h = __ldg((const uint4*)&skips[b]);
-            if (h.y != QW_NO_PREV_DOC && h.y + 1 >= we) break;
-            fold_block_dyn(tdata + h.z, ws, we, tg, lane);
-          }
-        }
-        __syncthreads();
-        if (required) {
-          uint32_t* req = sm.u32(LV.req);
-          const uint32_t* tmp = sm.u32(p.sm.tmp);
-          const bool init = (req_init >> level) & 1;
-          for (uint32_t i = tid; i < NW; i += QW_THREADS) req[i] = init ? (req[i] & tmp[i]) : tmp[i];
-          req_init |= 1u << level;
-          __syncthreads();
-        }
-      } else if (op == OP_RANGE || op == OP_EXISTS || op == OP_ALL) {
-        const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
-        const bool init = (req_init >> level) & 1;
-        const bool gather = required && init;
-        uint32_t* req = sm.u32(LV.req);
-        const uint32_t col = in.r;
-        const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
-        const uint64_t lo = in.a, hi = in.b;
-        const float boost = in.f;
-        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
-          const uint32_t d = ws + wd * 32 + lane;
-          bool cand = d < we && has_col;
-          if (gather) {
-            const uint32_t rw = req[wd];
-            if (rw == 0) continue;  // warp-uniform
-            cand = cand && ((rw >> lane) & 1);
-          }
-          bool hit = false;
-          if (cand) {
-            if (op == OP_ALL) hit = true;
-            else {
-              const DCol& c = s_cols[col];
-              uint64_t a, b;
-              col_range(base, c, d, a, b);
-              if (op == OP_EXISTS) hit = a != b;
-              else for (uint64_t i = a; i < b && !hit; i++) {
-                uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
-                hit = mv >= lo && mv <= hi;
-              }
-            }
-          }
-          const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
-          const uint32_t di = wd * 32 + lane;
-          if (required) {
-            if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
-            if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], boost);
-          } else if (occur == QW_OCCUR_SHOULD) {
-            if (lane == 0) sm.u32(LV.shd)[wd] |= word;
-            if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
-            if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], boost);
-          } else {
-            if (lane == 0) sm.u32(LV.nt)[wd] |= word;
-          }
-        }
-        if (required) req_init |= 1u << level;
-        __syncthreads();
-      } else if (op == OP_BOOL_END) {
-        // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
-        uint32_t* req = sm.u32(LV.req);
-        const uint32_t need = in.r, n_req = in.n;
-        for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
-          const uint32_t d0 = ws + wd * 32;
-          uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
-          uint32_t r = n_req ? (((req_init >> level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
-          uint32_t so;
-          if (need == 0) so = 0xFFFFFFFFu;
-          else if (need == 1) so = sm.u32(LV.shd)[wd];
-          else {
-            so = 0;
-            const uint8_t* cnt = sm.u8(LV.cnt) + wd * 32;
-            for (uint32_t b = 0; b < 32; b++) so |= (cnt[b] >= need ? 1u : 0u) << b;
-          }
-          req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
-        }
-        if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
-          float4* ms = (float4*)sm.f32(LV.msum);
-          const float4* ss = (const float4*)sm.f32(LV.ssum);
-          for (uint32_t i = tid; i < (W >> 2); i += QW_THREADS) {
-            float4 a = ms[i], b = ss[i];
-            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
-            ms[i] = a;
-          }
-        }
-        __syncthreads();
-        if (level > 0) {
-          // fold this bool's (bits, score) into the parent level as one clause
-          const SmemLevel& PL = p.sm.lvl[level - 1];
-          const uint32_t plevel = level - 1;
+    // ---- rounds of (phase X: parallel decode) + (phase Y: per-warp program) ------------------------------
+    uint32_t ip = 0;             // program counter of this warp (uniform across the block by construction)
+    uint32_t req_init = 0;       // bit per level
+    bool term_open = false;      // a required TERM clause spans rounds: tmp bits already cleared
+    for (uint32_t rb = 0; rb == 0 || rb < total_blocks; rb += QW_ENT_BLOCKS) {
+      const uint32_t re = min(rb + QW_ENT_BLOCKS, total_blocks);
+      if (rb) __syncthreads();  // every warp is done reading the previous round's entries
+      for (uint32_t b = rb + warp; b < re; b += QW_WARPS) {
+        const BlkRec r = s_blk[b];
+        uint2* out = s_ent + (size_t)(b - rb) * 128;
+        if (r.lo > r.hi) continue;  // no overlap with the window: phase Y never reads its entries
+        const DInstr& in = s_instr[s_rng[4 * r.slot + 3]];
+        const bool scored = (in.flags & IF_SCORED) != 0;
+        decode_block_entries(p.sm.stage + r.soff, ws, wlen, scored, (in.flags & IF_HAS_TF) != 0,
+                             (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu, scored ? p.sm.tab[in.r] : 0u, in.f, out, lane);
+      }
+      __syncthreads();
+
+      // phase Y: run the program as far as this round's entries allow
+      bool stop = false;
+      while (ip < n_instr && !stop) {
+        const DInstr& in = s_instr[ip];
+        const uint32_t op = in.op, level = in.level, occur = in.occur;
+        const SmemLevel& LV = p.sm.lvl[level];
+        const bool scored = (in.flags & IF_SCORED) != 0;
+        if (op == OP_BOOL_BEGIN) {
+          wzero_u32(sm.u32(LV.shd), wlo, SW, lane);
+          wzero_u32(sm.u32(LV.nt), wlo, SW, lane);
+          if (LV.cnt != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.cnt), lo >> 2, S >> 2, lane);
+          if (LV.msum != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.msum), lo, S, lane);
+          if (LV.ssum != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.ssum), lo, S, lane);
+          req_init &= ~(1u << level);
+          __syncwarp();
+          ip++;
+        } else if (op == OP_TERM) {
           const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
-          const bool pinit = (req_init >> plevel) & 1;
-          const float* csc = LV.rsc != 0xFFFFFFFFu ? sm.f32(LV.rsc) : nullptr;
-          for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
-            uint32_t m = req[wd];
-            if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
-            else if (occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
-            else sm.u32(PL.nt)[wd] |= m;
-          }
-          if (occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || (scored && csc))) {
-            for (uint32_t i = tid; i < W; i += QW_THREADS) {
-              if ((req[i >> 5] >> (i & 31)) & 1) {
-                if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
-                if (scored && csc) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], csc[i]);
+          const uint32_t slot = in.t;
+          uint32_t* bits;
+          float* score = nullptr;
+          uint8_t* cnt = nullptr;
+          if (required) {
+            bits = sm.u32(p.sm.tmp);
+            if (!term_open) { wzero_u32(bits, wlo, SW, lane); __syncwarp(); }
+            if (scored) score = sm.f32(LV.msum);
+          } else if (occur == QW_OCCUR_SHOULD) {
+            bits = sm.u32(LV.shd);
+            if (LV.cnt != 0xFFFFFFFFu) cnt = sm.u8(LV.cnt);
+            if (scored) score = sm.f32(LV.ssum);
+          } else bits = sm.u32(LV.nt);
+          bool finished = true;
+          if (s_rng[4 * slot + 2] != 0xFFFFFFFFu) {
+            const uint32_t g0 = s_tblk[2 * slot], nb = s_tblk[2 * slot + 1];
+            const uint32_t b0 = max(g0, rb), b1 = min(g0 + nb, re);
+            for (uint32_t kb = b0; kb < b1; kb += 32) {
+              const uint32_t b = kb + lane;
+              bool ok = false;
+              if (b < b1) { const BlkRec r = s_blk[b]; ok = r.lo <= r.hi && (uint32_t)r.hi >= lo && (uint32_t)r.lo < lo + S; }
+              uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+              while (m) {
+                const uint32_t bb = kb + __ffs(m) - 1;
+                m &= m - 1;
+                const uint2* e = s_ent + (size_t)(bb - rb) * 128;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                  const uint2 v = e[c * 32 + lane];
+                  const uint32_t d = v.x;
+                  if (d - lo < S) {  // also rejects the invalid marker
+                    atomicOr(&bits[d >> 5], 1u << (d & 31));
+                    if (cnt) cnt[d] = (uint8_t)(cnt[d] + 1);
+                    if (score) score[d] = __fadd_rn(score[d], __uint_as_float(v.y));
+                  }
+                }
               }
             }
-          } else if (occur == QW_OCCUR_MUST && scored && csc) {
-            for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], csc[i]);
+            if (g0 + nb > re) finished = false;  // the rest of this term is decoded in the next round
+          } else if (s_rng[4 * slot + 1]) {
+            // direct mode (range not staged): this warp decodes the blocks overlapping its own sub-range
+            // straight from global memory
+            TermTarget tg;
+            tg.bits = required ? p.sm.tmp : (occur == QW_OCCUR_SHOULD ? LV.shd : LV.nt);
+            tg.cnt = (occur == QW_OCCUR_SHOULD) ? LV.cnt : 0xFFFFFFFFu;
+            tg.score = !scored ? 0xFFFFFFFFu : (required ? LV.msum : LV.ssum);
+            tg.weight = in.f;
+            tg.has_tf = (in.flags & IF_HAS_TF) != 0;
+            tg.fn = (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu;
+            tg.tab = scored ? p.sm.tab[in.r] : 0u;
+            const uint32_t sub_ws = ws + lo, sub_we = min(ws + lo + S, we);
+            if (sub_ws < sub_we) {
+              const QwSkip* skips = (const QwSkip*)(base + in.c);
+              const uint32_t nblk = in.n;
+              uint32_t a = 0, b = nblk;
+              while (b - a > 32) {
+                uint32_t step = (b - a + 31) >> 5;
+                uint32_t idx = a + lane * step;
+                bool ok = idx < b && __ldg(&skips[idx].last_doc) >= sub_ws;
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+                if (m == 0) a = a + ((b - 1 - a) / step) * step + 1;
+                else { uint32_t f = __ffs(m) - 1; b = a + f * step + 1; if (f > 0) a = a + (f - 1) * step + 1; }
+              }
+              uint32_t idx = a + lane;
+              bool ok = idx < b && __ldg(&skips[idx].last_doc) >= sub_ws;
+              uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+              const uint32_t bfirst = m ? a + (__ffs(m) - 1) : nblk;
+              const uint8_t* tdata = base + in.a;
+              for (uint32_t bb = bfirst; bb < nblk; bb++) {
+                uint4 h = __ldg((const uint4*)&skips[bb]);
+                if (h.y != QW_NO_PREV_DOC && h.y + 1 >= sub_we) break;
+                fold_block_dyn<false>(0, tdata + h.z, ws, lo, sub_we - sub_ws, tg, lane);
+              }
+            }
           }
-          if (required) req_init |= 1u << plevel;
-          __syncthreads();
+          __syncwarp();
+          if (!finished) { term_open = required; stop = true; break; }
+          term_open = false;
+          if (required) {
+            uint32_t* req = sm.u32(LV.req);
+            const uint32_t* tmp = sm.u32(p.sm.tmp);
+            const bool init = (req_init >> level) & 1;
+            for (uint32_t i = lane; i < SW; i += 32) req[wlo + i] = init ? (req[wlo + i] & tmp[wlo + i]) : tmp[wlo + i];
+            req_init |= 1u << level;
+            __syncwarp();
+          }
+          ip++;
+        } else if (op == OP_RANGE || op == OP_EXISTS || op == OP_ALL) {
+          const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
+          const bool init = (req_init >> level) & 1;
+          const bool gather = required && init;
+          uint32_t* req = sm.u32(LV.req);
+          const uint32_t col = in.r;
+          const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
+          const uint64_t rlo = in.a, rhi = in.b;
+          const float boost = in.f;
+          for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
+            const uint32_t d = ws + wd * 32 + lane;
+            bool cand = d < we && has_col;
+            if (gather) {
+              const uint32_t rw = req[wd];
+              if (rw == 0) continue;  // warp-uniform
+              cand = cand && ((rw >> lane) & 1);
+            }
+            bool hit = false;
+            if (cand) {
+              if (op == OP_ALL) hit = true;
+              else {
+                const DCol& c = s_cols[col];
+                uint64_t a, b;
+                col_range(base, c, d, a, b);
+                if (op == OP_EXISTS) hit = a != b;
+                else for (uint64_t i = a; i < b && !hit; i++) {
+                  uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
+                  hit = mv >= rlo && mv <= rhi;
+                }
+              }
+            }
+            const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
+            const uint32_t di = wd * 32 + lane;
+            if (required) {
+              if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
+              if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], boost);
+            } else if (occur == QW_OCCUR_SHOULD) {
+              if (lane == 0) sm.u32(LV.shd)[wd] |= word;
+              if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
+              if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], boost);
+            } else {
+              if (lane == 0) sm.u32(LV.nt)[wd] |= word;
+            }
+          }
+          if (required) req_init |= 1u << level;
+          __syncwarp();
+          ip++;
+        } else {  // OP_BOOL_END
+          // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
+          uint32_t* req = sm.u32(LV.req);
+          const uint32_t need = in.r, n_req = in.n;
+          for (uint32_t i = lane; i < SW; i += 32) {
+            const uint32_t wd = wlo + i;
+            const uint32_t d0 = ws + wd * 32;
+            uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
+            uint32_t r = n_req ? (((req_init >> level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
+            uint32_t so;
+            if (need == 0) so = 0xFFFFFFFFu;
+            else if (need == 1) so = sm.u32(LV.shd)[wd];
+            else {
+              so = 0;
+              const uint8_t* cnt = sm.u8(LV.cnt) + wd * 32;
+              for (uint32_t b = 0; b < 32; b++) so |= (cnt[b] >= need ? 1u : 0u) << b;
+            }
+            req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
+          }
+          if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
+            float* ms = sm.f32(LV.msum) + lo;
+            const float* ss = sm.f32(LV.ssum) + lo;
+            for (uint32_t i = lane; i < S; i += 32) ms[i] = __fadd_rn(ms[i], ss[i]);
+          }
+          __syncwarp();
+          if (level > 0) {
+            // fold this bool's (bits, score) into the parent level as one clause
+            const SmemLevel& PL = p.sm.lvl[level - 1];
+            const uint32_t plevel = level - 1;
+            const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
+            const bool pinit = (req_init >> plevel) & 1;
+            const float* csc = LV.rsc != 0xFFFFFFFFu ? sm.f32(LV.rsc) : nullptr;
+            for (uint32_t i = lane; i < SW; i += 32) {
+              const uint32_t wd = wlo + i;
+              uint32_t m = req[wd];
+              if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
+              else if (occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
+              else sm.u32(PL.nt)[wd] |= m;
+            }
+            if (occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || (scored && csc))) {
+              for (uint32_t i = lo + lane; i < lo + S; i += 32) {
+                if ((req[i >> 5] >> (i & 31)) & 1) {
+                  if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
+                  if (scored && csc) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], csc[i]);
+                }
+              }
+            } else if (occur == QW_OCCUR_MUST && scored && csc) {
+              for (uint32_t i = lo + lane; i < lo + S; i += 32) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], csc[i]);
+            }
+            if (required) req_init |= 1u << plevel;
+            __syncwarp();
+          }
+          ip++;
         }
       }
     }
 
-    // ---- collect the window's matches ---------------------------------------------------------------
+    // ---- collect this warp's sub-range -----------------------------------------------------------------
     const uint32_t* res = sm.u32(p.sm.lvl[0].req);
     const float* rscore = p.sm.lvl[0].rsc != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].rsc) : nullptr;
     const DThresh& T = p.thresh[split];
     const uint32_t max_hits = P.max_hits, n_aggs = P.n_aggs, sa_present = P.sa.present;
     QwAggCell* cells = (QwAggCell*)P.out_cells;
+    const bool use_hist = MODE == MODE_HIST || (p.smem_aggs && n_aggs);
+    if (use_hist) {
+      // the histogram / privatised aggregation counters alias the entry area: wait until every warp is
+      // done with the entries, then clear
+      __syncthreads();
+      for (uint32_t i = tid; i < (MODE == MODE_HIST ? QW_HIST_BINS : P.n_cells); i += QW_THREADS) s_hist[i] = 0;
+      __syncthreads();
+    }
     if (MODE == MODE_COLLECT) {
       const Key thr{T.key[0], T.key[1], T.key[2]};
       const uint32_t thr_top = (uint32_t)(thr.w0 >> 53);
-      const DKeySpec ks = P.key;  // hoisted into registers
+      const DKeySpec ks = P.key;
       uint32_t my_hits = 0, my_elig = 0;
-      // hit count: one popc per bitmap word
-      for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
+      for (uint32_t i = lane; i < SW; i += 32) my_hits += __popc(res[wlo + i]);
       auto slow_path = [&](uint32_t i, float sc) {
         const uint32_t doc = ws + i;
         DocKey dk = doc_key(P, s_cols, base, doc, sc);
@@ -756,7 +933,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
         float s_lo = -1.0f;
         if (thr_top >= 1024u) s_lo = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), ks.score_scale), 0.999999f);
         const float4* sc4 = reinterpret_cast<const float4*>(rscore);
-        for (uint32_t q = tid; q < (W >> 2); q += QW_THREADS) {
+        for (uint32_t q = (lo >> 2) + lane; q < ((lo + S) >> 2); q += 32) {
           const uint32_t nib = (res[q >> 3] >> ((q & 7) * 4)) & 0xFu;
           if (!nib) continue;
           const float4 v = sc4[q];
@@ -766,7 +943,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
           if ((nib & 8u) && v.w >= s_lo) slow_path(4 * q + 3, v.w);
         }
       } else if (max_hits || n_aggs) {
-        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+        for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
           const uint32_t word = res[wd];
           if (word == 0) continue;  // warp-uniform
           if (!((word >> lane) & 1)) continue;
@@ -780,7 +957,6 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
           if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
         }
       }
-      // block-reduce the counters, one global atomic per window
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         my_elig += __shfl_down_sync(0xFFFFFFFFu, my_elig, o);
@@ -798,12 +974,12 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       if (p.smem_aggs && n_aggs) {
         for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {
           uint32_t v = s_hist[i];
-          if (v) { atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v); s_hist[i] = 0; }
+          if (v) atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v);
         }
       }
     } else {
       if (max_hits) {
-        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+        for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
           const uint32_t word = res[wd];
           if (word == 0) continue;
           if (!((word >> lane) & 1)) continue;
@@ -822,7 +998,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       uint32_t* gh = (uint32_t*)P.out_hist;
       for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
         uint32_t v = s_hist[i];
-        if (v) { atomicAdd(&gh[i], v); s_hist[i] = 0; }
+        if (v) atomicAdd(&gh[i], v);
       }
     }
   }
@@ -899,7 +1075,7 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
 // descending) and writes the best min(K, n) as QwHit — the harvest step
 // (quickwit-search/src/top_k_collector.rs:404-410, binary_heap.rs:187-193).
 __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem_raw = qw_smem;
   const DSplitPlan& P = plans[blockIdx.x];
   const uint32_t tid = threadIdx.x;
   if (P.max_hits == 0) { if (tid == 0) *(uint32_t*)P.out_nhits = 0; return; }
