@@ -4,16 +4,21 @@
 
 #include "../../include/qwgpu_format.h"
 
+#ifndef QW_THREADS
 #define QW_THREADS 256
+#endif
+#ifndef QW_MIN_BLOCKS_PER_SM
+#define QW_MIN_BLOCKS_PER_SM (QW_THREADS <= 256 ? 2 : 1)
+#endif
 #define QW_WARPS (QW_THREADS / 32)
 #define QW_MAX_INSTR 96
 #define QW_MAX_DCOLS 16
 #define QW_MAX_DAGGS 8
 #define QW_MAX_LEVELS QW_MAX_PLAN_DEPTH
 #define QW_MAX_TERMS 64      /* TERM instructions per plan */
-#define QW_BLK_TAB 48        /* staged blocks per (term, window) before falling back to direct mode */
+#define QW_BLK_TAB 160       /* staged blocks per (term, window) before falling back to direct mode */
 #define QW_STAGE_BYTES 16384 /* packed posting bytes staged per window */
-#define QW_MAX_WBLK 256      /* staged blocks per window over all terms */
+#define QW_MAX_WBLK 512      /* staged blocks per window over all terms */
 #define QW_ENT_BLOCKS 32     /* decoded blocks held at once (one "round"): 32 x 128 entries x 8 B */
 #define QW_HIST_BINS 2048    /* 11-bit radix digits */
 #define QW_DIGIT_BITS 11
@@ -23,7 +28,7 @@
 #define QW_SMEM_AGG_CELLS 4096
 
 enum { OP_TERM = 1, OP_RANGE = 2, OP_EXISTS = 3, OP_ALL = 4, OP_BOOL_BEGIN = 5, OP_BOOL_END = 6 };
-enum { IF_SCORED = 1u, IF_HAS_TF = 2u, IF_HAS_FN = 4u };
+enum { IF_SCORED = 1u, IF_HAS_TF = 2u, IF_HAS_FN = 4u, IF_BITS_FROM_SCORE = 8u };
 #define QW_TFF_ROWS 16 /* tf-factor table: tff[tf][fieldnorm_id] = tf / (tf + norm[id]) for tf < 16 */
 
 struct DInstr {  // 64 bytes
@@ -125,6 +130,6 @@ struct KParams {
   uint32_t level;    // MODE_HIST: radix level being histogrammed
   uint32_t use_prefix;  // MODE_HIST: restrict to docs whose key matches thresh prefix
   uint32_t smem_aggs;   // 1: aggregation counts privatised in shared memory
-  uint32_t pad;
+  uint32_t stage_bytes; // capacity of the posting staging area
   SmemLayout sm;
 };

@@ -260,6 +260,7 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
       memset(&bg, 0, sizeof bg);
       bg.op = OP_BOOL_BEGIN; bg.level = level;
       L.instrs.push_back(bg);
+      const size_t first_instr = L.instrs.size();
       L.levels |= 1u << level;
       uint32_t n_req = 0, n_should = 0;
       if (n.first_child + n.num_children > nn) fail(QWGPU_EINVALID_ARG, "plan children out of range");
@@ -292,9 +293,21 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
       uint32_t msm = n.min_should_match == 0xFFFFFFFFu ? 0 : n.min_should_match;
       uint32_t need = msm > 0 ? msm : (n_req == 0 ? 1 : 0);
       if (need >= 2) L.need_cnt |= 1u << level;
+      // Scored should-TERMs with a strictly positive weight contribute > 0 to ssum for every matching
+      // doc, so their bitmap is (ssum > 0): skip the per-posting bit set and rebuild it at BOOL_END.
+      bool any_from_score = false;
+      if (need < 2 && scored) {
+        for (size_t ii = first_instr; ii < L.instrs.size(); ii++) {
+          DInstr& ci = L.instrs[ii];
+          if (ci.op == OP_TERM && ci.level == level && ci.occur == QW_OCCUR_SHOULD && (ci.flags & IF_SCORED) && ci.f >= 1e-20f && ci.f < 1e30f) {
+            ci.flags |= IF_BITS_FROM_SCORE;
+            any_from_score = true;
+          }
+        }
+      }
       DInstr en;
       memset(&en, 0, sizeof en);
-      en.op = OP_BOOL_END; en.level = level; en.occur = occur; en.flags = scored ? IF_SCORED : 0;
+      en.op = OP_BOOL_END; en.level = level; en.occur = occur; en.flags = (scored ? IF_SCORED : 0) | (any_from_score ? IF_BITS_FROM_SCORE : 0);
       en.n = n_req; en.m = n_should; en.r = need;
       L.instrs.push_back(en);
       break;
@@ -411,6 +424,11 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
 }
 
 // shared-memory arena for a batch (max over the batch's plans)
+static uint32_t stage_bytes_for(uint32_t W) {
+  if (const char* e = getenv("QWGPU_STAGE")) return (uint32_t)atoi(e) & ~15u;
+  return std::max<uint32_t>(8192, std::min<uint32_t>(W * 2, 49152));
+}
+
 static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_msum, uint32_t need_ssum,
                               uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn) {
   SmemLayout L;
@@ -431,13 +449,13 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
     L.lvl[l].rsc = L.lvl[l].msum != 0xFFFFFFFFu ? L.lvl[l].msum : L.lvl[l].ssum;
   }
   L.tmp = take(W / 8);
-  for (uint32_t s = 0; s < n_fn; s++) { L.fn[s] = take(W); L.tab[s] = take((256 + QW_TFF_ROWS * 256) * 4); }
+  for (uint32_t s = 0; s < n_fn; s++) L.fn[s] = take(W);  // BM25 tables stay in global memory (L1-resident)
   L.rng = take(QW_MAX_TERMS * 16);
   L.blkrec = take(QW_MAX_WBLK * 8);
   L.termblk = take(QW_MAX_TERMS * 8);
-  L.stage = take(QW_STAGE_BYTES);
-  L.ent = take(std::max<uint32_t>(QW_ENT_BLOCKS * 128 * 8, QW_SMEM_AGG_CELLS * 4));
-  L.hist = L.ent;
+  L.stage = take(stage_bytes_for(W));
+  L.ent = L.stage;
+  L.hist = L.stage;  // histogram / privatised aggregation counters reuse the staging area at collect time
   L.total = off;
   return L;
 }
@@ -469,6 +487,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // ---- batch-wide parameters --------------------------------------------------------------------------
   uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, need_msum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
   bool scoring = false, any_topk = false, any_aggs = false, smem_aggs = true;
+  uint32_t max_cells = 0;
   uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0;
   for (auto& L : low) {
     n_levels = std::max(n_levels, L.P.n_levels);
@@ -476,15 +495,18 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     max_instr = std::max(max_instr, L.P.n_instr); max_cols = std::max(max_cols, L.P.n_cols); max_aggs = std::max(max_aggs, L.P.n_aggs);
     n_fn = std::max(n_fn, L.P.n_fn_slots);
     scoring |= L.P.scoring != 0; any_topk |= L.P.max_hits > 0; any_aggs |= L.P.n_aggs > 0;
-    if (L.P.n_cells > QW_SMEM_AGG_CELLS) smem_aggs = false;
+    max_cells = std::max(max_cells, L.P.n_cells);
     L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
     tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
   }
-  uint32_t W = 4096;
+  // window size: as large as shared memory allows for the configured blocks/SM (per-window fixed
+  // costs — staging, program interpretation, barriers — amortise over more postings)
+  uint32_t W = QW_THREADS <= 256 ? 8192 : 32768;
+  if (const char* e = getenv("QWGPU_W")) W = (uint32_t)atoi(e);
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn);
-    if ((int)lay.total + 1024 <= max_smem_optin / 2 || W == 1024) break;  // keep >= 2 blocks per SM
+    if ((int)lay.total + 1024 <= max_smem_optin / QW_MIN_BLOCKS_PER_SM || W == 1024) break;
     W >>= 1;
   }
   (void)scoring;
@@ -564,6 +586,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   kp.thresh = (DThresh*)(slot->d_scratch + s_thr);
   kp.n_splits = n;
   kp.W = W;
+  kp.stage_bytes = stage_bytes_for(W);
+  // privatised aggregation counters (and the radix histogram, 8 KB) live in the staging area
+  if (max_cells * 4 > kp.stage_bytes || max_cells > QW_SMEM_AGG_CELLS) smem_aggs = false;
   kp.smem_aggs = (any_aggs && smem_aggs) ? 1 : 0;
   kp.sm = lay;
   int occ = 1;

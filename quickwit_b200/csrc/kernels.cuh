@@ -144,7 +144,7 @@ struct TermTarget {
   uint32_t cnt;
   uint32_t score;
   uint32_t fn;     // staged fieldnorm ids of the window (absent: constant fieldnorm id 1)
-  uint32_t tab;    // float[256] BM25 norms followed by float[QW_TFF_ROWS][256] tf factors
+  const float* gtab;  // global: float[256] BM25 norms then float[QW_TFF_ROWS][256] tf factors (read via L1)
   float weight;
   bool has_tf;
 };
@@ -153,7 +153,7 @@ struct TermTarget {
 // and fold the postings that fall into [ws, we) into the target (all targets live in shared
 // memory). STAGED: the block bytes are in shared memory at qw_smem + blk_off; otherwise `gblk`
 // points to global memory.
-template <bool SCORED, bool CNT, bool STAGED>
+template <bool SCORED, bool CNT, bool STAGED, bool BITS = true>
 __device__ __forceinline__ void fold_block(uint32_t blk_off, const uint8_t* gblk, uint32_t ws, uint32_t rlo, uint32_t rlen, const TermTarget& tg, uint32_t lane) {
   const uint8_t* blk = STAGED ? (qw_smem + blk_off) : gblk;
   const uint4 h = *reinterpret_cast<const uint4*>(blk);  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
@@ -199,36 +199,57 @@ __device__ __forceinline__ void fold_block(uint32_t blk_off, const uint8_t* gblk
   }
   uint32_t* bits = reinterpret_cast<uint32_t*>(qw_smem + tg.bits);
   float* score = reinterpret_cast<float*>(qw_smem + tg.score);
-  const float* tab = reinterpret_cast<const float*>(qw_smem + tg.tab);
+  const float* tab = tg.gtab;
   const uint8_t* fn = qw_smem + tg.fn;
   uint8_t* cnt = qw_smem + tg.cnt;
   const bool has_fn = tg.fn != 0xFFFFFFFFu;
-  uint32_t cur_word = 0xFFFFFFFFu, cur_mask = 0;
+  // The 4 postings of a lane are independent (distinct docs): issue all loads of a stage before
+  // consuming them so the shared-memory latencies overlap (fieldnorm -> table -> score RMW).
+  bool in[4];
+  uint32_t f[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const uint32_t d = rel[j];  // doc - ws (unsigned wrap for docs before the window)
-    if ((uint32_t)j < nvalid && d - rlo < rlen) {
-      const uint32_t w = d >> 5;
+    in[j] = (uint32_t)j < nvalid && rel[j] - rlo < rlen;  // rel = doc - ws (unsigned wrap before the window)
+    f[j] = (SCORED && has_fn && in[j]) ? fn[rel[j]] : 1u;
+  }
+  if (SCORED) {
+    float tfn[4], old[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest; the
+      // quotient comes from a table built with the same IEEE ops for tf < 16
+      const uint32_t t = tf[j];
+      tfn[j] = 0.0f;
+      old[j] = 0.0f;
+      if (in[j]) {
+        if (t < QW_TFF_ROWS) tfn[j] = __ldg(tab + 256 + t * 256 + f[j]);
+        else { float tff = (float)t; tfn[j] = __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + f[j]))); }
+        old[j] = score[rel[j]];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (in[j]) score[rel[j]] = __fadd_rn(old[j], __fmul_rn(tg.weight, tfn[j]));
+  }
+  if (CNT) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (in[j]) cnt[rel[j]] = (uint8_t)(cnt[rel[j]] + 1);
+  }
+  if (BITS) {
+    uint32_t cur_word = 0xFFFFFFFFu, cur_mask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (!in[j]) continue;
+      const uint32_t w = rel[j] >> 5;
       if (w != cur_word) {
         if (cur_mask) atomicOr(&bits[cur_word], cur_mask);
         cur_word = w;
         cur_mask = 0;
       }
-      cur_mask |= 1u << (d & 31);
-      if (CNT) cnt[d] = (uint8_t)(cnt[d] + 1);
-      if (SCORED) {
-        // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest.
-        // tf / (tf + norm) comes from a table built with the same IEEE ops for tf < 16.
-        const uint32_t f = has_fn ? fn[d] : 1u;
-        const uint32_t t = tf[j];
-        float tfn;
-        if (t < QW_TFF_ROWS) tfn = tab[256 + t * 256 + f];
-        else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tab[f])); }
-        score[d] = __fadd_rn(score[d], __fmul_rn(tg.weight, tfn));
-      }
+      cur_mask |= 1u << (rel[j] & 31);
     }
+    if (cur_mask) atomicOr(&bits[cur_word], cur_mask);
   }
-  if (cur_mask) atomicOr(&bits[cur_word], cur_mask);
 }
 
 template <bool STAGED>
@@ -423,6 +444,12 @@ __device__ __forceinline__ void wzero_u32(uint32_t* p, uint32_t first, uint32_t 
   for (uint32_t i = lane; i < n; i += 32) p[first + i] = 0;
 }
 
+__device__ __forceinline__ void zero_f4(float* p, uint32_t n, uint32_t tid) {
+  float4* q = reinterpret_cast<float4*>(p);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t i = tid; i < (n >> 2); i += QW_THREADS) q[i] = z;
+}
+
 struct BlkRec {  // one staged posting block of the window
   uint16_t soff;  // byte offset of the block inside the stage area
   uint16_t lo;    // lower bound of its first doc, window-relative, clamped to [0, W]
@@ -431,90 +458,10 @@ struct BlkRec {  // one staged posting block of the window
   uint8_t pad;
 };
 
-// Phase X: decode one staged posting block with one warp into 128 entries {rel doc, score}.
-// Entries outside the window (or past the block's count) get rel doc 0xFFFFFFFF.
-__device__ __forceinline__ void decode_block_entries(uint32_t blk_off, uint32_t ws, uint32_t wlen, bool scored, bool has_tf,
-                                                     uint32_t fn_off, uint32_t tab_off, float weight, uint2* out, uint32_t lane) {
-  const uint8_t* blk = qw_smem + blk_off;
-  const uint4 h = *reinterpret_cast<const uint4*>(blk);
-  const uint32_t prev = h.y;
-  const uint32_t doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;
-  const uint4* dp = reinterpret_cast<const uint4*>(blk + 16);
-  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-  if (doc_bits) {
-    uint32_t bitpos = lane * doc_bits, wi = bitpos >> 5, sh = bitpos & 31;
-    uint4 A = dp[wi];
-    uint4 B = (sh + doc_bits > 32) ? dp[wi + 1] : make_uint4(0, 0, 0, 0);
-    uint32_t mask = 0xFFFFFFFFu >> (32 - doc_bits);
-    v0 = __funnelshift_r(A.x, B.x, sh) & mask;
-    v1 = __funnelshift_r(A.y, B.y, sh) & mask;
-    v2 = __funnelshift_r(A.z, B.z, sh) & mask;
-    v3 = __funnelshift_r(A.w, B.w, sh) & mask;
-  }
-  uint32_t d0 = v0 + 1, d1 = d0 + v1 + 1, d2 = d1 + v2 + 1, d3 = d2 + v3 + 1;
-  uint32_t incl = d3;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if ((int)lane >= o) incl += n;
-  }
-  const uint32_t basev = prev + (incl - d3) - ws;
-  uint32_t rel[4] = {basev + d0, basev + d1, basev + d2, basev + d3};
-  const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;
-  uint32_t tf[4] = {1, 1, 1, 1};
-  if (scored && has_tf && tf_bits) {
-    const uint4* tp = dp + doc_bits;
-    uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
-    uint4 A = tp[wi];
-    uint4 B = (sh + tf_bits > 32) ? tp[wi + 1] : make_uint4(0, 0, 0, 0);
-    uint32_t mask = 0xFFFFFFFFu >> (32 - tf_bits);
-    tf[0] = __funnelshift_r(A.x, B.x, sh) & mask;
-    tf[1] = __funnelshift_r(A.y, B.y, sh) & mask;
-    tf[2] = __funnelshift_r(A.z, B.z, sh) & mask;
-    tf[3] = __funnelshift_r(A.w, B.w, sh) & mask;
-  }
-  const float* tab = reinterpret_cast<const float*>(qw_smem + tab_off);
-  const uint8_t* fn = qw_smem + fn_off;
-  const bool has_fn = fn_off != 0xFFFFFFFFu;
-  // independent chains for the 4 postings of this lane: all fieldnorm loads, then all table loads
-  uint32_t f[4];
-  bool in[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    in[j] = (uint32_t)j < nvalid && rel[j] < wlen;
-    f[j] = (scored && has_fn && in[j]) ? fn[rel[j]] : 1u;
-  }
-  float sc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (scored) {
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (!in[j]) continue;
-      // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest; the
-      // quotient comes from a table built with the same IEEE ops for tf < 16
-      const uint32_t t = tf[j];
-      float tfn;
-      if (t < QW_TFF_ROWS) tfn = tab[256 + t * 256 + f[j]];
-      else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, tab[f[j]])); }
-      sc[j] = __fmul_rn(weight, tfn);
-    }
-  }
-  // entry i of the block lives at out[i]; lane holds entries 4*lane .. 4*lane+3 (two 16-byte stores)
-  uint4* o4 = reinterpret_cast<uint4*>(out + 4 * lane);
-  o4[0] = make_uint4(in[0] ? rel[0] : 0xFFFFFFFFu, __float_as_uint(sc[0]), in[1] ? rel[1] : 0xFFFFFFFFu, __float_as_uint(sc[1]));
-  o4[1] = make_uint4(in[2] ? rel[2] : 0xFFFFFFFFu, __float_as_uint(sc[2]), in[3] ? rel[3] : 0xFFFFFFFFu, __float_as_uint(sc[3]));
-}
-
-
-
-// The window engine, v4: "decode once in parallel, then evaluate per warp without block barriers".
-//   phase 1-3  index entries, fieldnorm + posting staging (cp.async), block table   [block barriers]
-//   phase X    every staged posting block of every term is decoded by some warp into an entry list
-//   phase Y    each warp interprets the boolean program for ITS doc sub-range (W/8 docs): posting
-//              entries are applied clause by clause in plan order (fixed f32 summation order),
-//              bitmaps/score slices are warp-private, so only __syncwarp separates clauses
-//   collect    each warp counts / filters / aggregates its own sub-range
+// The window engine (see the file header): phases 1-3 stage the window's bytes and build the block
+// table, then the boolean program runs block-wide, then the matches are collected.
 template <int MODE>
-__global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
+__global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(const KParams p) {
   Sm sm{&p.sm};
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t W = p.W, NW = W >> 5;
@@ -557,13 +504,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       for (uint32_t i = tid; i < P.n_cols * (sizeof(DCol) / 16); i += QW_THREADS) ((uint4*)s_cols)[i] = __ldg(src + i);
       src = (const uint4*)(p.aggs + P.agg_base);
       for (uint32_t i = tid; i < P.n_aggs * (sizeof(DAgg) / 16); i += QW_THREADS) ((uint4*)s_aggs)[i] = __ldg(src + i);
-      for (uint32_t s = 0; s < P.n_fn_slots; s++) {
-        const uint8_t* tsrc = (const uint8_t*)P.bm25_tab[s];
-        uint8_t* tdst = sm.u8(p.sm.tab[s]);
-        for (uint32_t i = tid; i < (256 + QW_TFF_ROWS * 256) * 4 / 16; i += QW_THREADS) cp_async16(tdst + 16 * i, tsrc + 16 * i);
-      }
       loaded_split = split;
-      cp_async_wait_all();
       __syncthreads();
       if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
       __syncthreads();
@@ -603,7 +544,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       uint32_t off = 0;
       for (uint32_t t = 0; t < n_terms; t++) {
         uint32_t len = s_rng[4 * t + 1];
-        if (len && off + len <= QW_STAGE_BYTES) { s_rng[4 * t + 2] = off; off += len; }
+        if (len && off + len <= p.stage_bytes) { s_rng[4 * t + 2] = off; off += len; }
         else s_rng[4 * t + 2] = 0xFFFFFFFFu;
       }
     }
@@ -666,253 +607,224 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
     __syncthreads();
     const uint32_t total_blocks = s_misc[0];
 
-    // ---- rounds of (phase X: parallel decode) + (phase Y: per-warp program) ------------------------------
-    uint32_t ip = 0;             // program counter of this warp (uniform across the block by construction)
-    uint32_t req_init = 0;       // bit per level
-    bool term_open = false;      // a required TERM clause spans rounds: tmp bits already cleared
-    for (uint32_t rb = 0; rb == 0 || rb < total_blocks; rb += QW_ENT_BLOCKS) {
-      const uint32_t re = min(rb + QW_ENT_BLOCKS, total_blocks);
-      if (rb) __syncthreads();  // every warp is done reading the previous round's entries
-      for (uint32_t b = rb + warp; b < re; b += QW_WARPS) {
-        const BlkRec r = s_blk[b];
-        uint2* out = s_ent + (size_t)(b - rb) * 128;
-        if (r.lo > r.hi) continue;  // no overlap with the window: phase Y never reads its entries
-        const DInstr& in = s_instr[s_rng[4 * r.slot + 3]];
-        const bool scored = (in.flags & IF_SCORED) != 0;
-        decode_block_entries(p.sm.stage + r.soff, ws, wlen, scored, (in.flags & IF_HAS_TF) != 0,
-                             (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu, scored ? p.sm.tab[in.r] : 0u, in.f, out, lane);
-      }
-      __syncthreads();
-
-      // phase Y: run the program as far as this round's entries allow
-      bool stop = false;
-      while (ip < n_instr && !stop) {
+    // ---- execute the boolean program (block-wide; one barrier per clause keeps the f32 order fixed) ----
+    // A TERM clause folds its staged posting blocks directly into the level's bitmaps / score array,
+    // one block per warp per step (fold_block); clauses whose range was not staged decode from global
+    // memory (direct mode).
+    uint32_t ip = 0;
+    uint32_t req_init = 0;  // bit per level, uniform across the block
+    {
+      while (ip < n_instr) {
         const DInstr& in = s_instr[ip];
         const uint32_t op = in.op, level = in.level, occur = in.occur;
         const SmemLevel& LV = p.sm.lvl[level];
         const bool scored = (in.flags & IF_SCORED) != 0;
         if (op == OP_BOOL_BEGIN) {
-          wzero_u32(sm.u32(LV.shd), wlo, SW, lane);
-          wzero_u32(sm.u32(LV.nt), wlo, SW, lane);
-          if (LV.cnt != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.cnt), lo >> 2, S >> 2, lane);
-          if (LV.msum != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.msum), lo, S, lane);
-          if (LV.ssum != 0xFFFFFFFFu) wzero_u32(sm.u32(LV.ssum), lo, S, lane);
+          zero_f4((float*)sm.u32(LV.shd), NW, tid);
+          zero_f4((float*)sm.u32(LV.nt), NW, tid);
+          if (LV.cnt != 0xFFFFFFFFu) zero_f4((float*)sm.u32(LV.cnt), W >> 2, tid);
+          if (LV.msum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.msum), W, tid);
+          if (LV.ssum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.ssum), W, tid);
           req_init &= ~(1u << level);
-          __syncwarp();
+          __syncthreads();
           ip++;
         } else if (op == OP_TERM) {
           const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
           const uint32_t slot = in.t;
-          uint32_t* bits;
-          float* score = nullptr;
-          uint8_t* cnt = nullptr;
+          const bool from_score = (in.flags & IF_BITS_FROM_SCORE) != 0;  // bitmap derived at BOOL_END
+          TermTarget tg;
+          tg.cnt = 0xFFFFFFFFu;
+          tg.score = 0xFFFFFFFFu;
           if (required) {
-            bits = sm.u32(p.sm.tmp);
-            if (!term_open) { wzero_u32(bits, wlo, SW, lane); __syncwarp(); }
-            if (scored) score = sm.f32(LV.msum);
+            tg.bits = p.sm.tmp;
+            zero_f4((float*)sm.u32(p.sm.tmp), NW, tid);
+            if (scored) tg.score = LV.msum;
+            __syncthreads();
           } else if (occur == QW_OCCUR_SHOULD) {
-            bits = sm.u32(LV.shd);
-            if (LV.cnt != 0xFFFFFFFFu) cnt = sm.u8(LV.cnt);
-            if (scored) score = sm.f32(LV.ssum);
-          } else bits = sm.u32(LV.nt);
-          bool finished = true;
+            tg.bits = LV.shd;
+            tg.cnt = LV.cnt;
+            if (scored) tg.score = LV.ssum;
+          } else tg.bits = LV.nt;
+          tg.weight = in.f;
+          tg.has_tf = (in.flags & IF_HAS_TF) != 0;
+          tg.fn = (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu;
+          tg.gtab = scored ? (const float*)P.bm25_tab[in.r] : nullptr;
           if (s_rng[4 * slot + 2] != 0xFFFFFFFFu) {
             const uint32_t g0 = s_tblk[2 * slot], nb = s_tblk[2 * slot + 1];
-            const uint32_t b0 = max(g0, rb), b1 = min(g0 + nb, re);
-            for (uint32_t kb = b0; kb < b1; kb += 32) {
-              const uint32_t b = kb + lane;
-              bool ok = false;
-              if (b < b1) { const BlkRec r = s_blk[b]; ok = r.lo <= r.hi && (uint32_t)r.hi >= lo && (uint32_t)r.lo < lo + S; }
-              uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-              while (m) {
-                const uint32_t bb = kb + __ffs(m) - 1;
-                m &= m - 1;
-                const uint2* e = s_ent + (size_t)(bb - rb) * 128;
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                  const uint2 v = e[c * 32 + lane];
-                  const uint32_t d = v.x;
-                  if (d - lo < S) {  // also rejects the invalid marker
-                    atomicOr(&bits[d >> 5], 1u << (d & 31));
-                    if (cnt) cnt[d] = (uint8_t)(cnt[d] + 1);
-                    if (score) score[d] = __fadd_rn(score[d], __uint_as_float(v.y));
-                  }
-                }
-              }
-            }
-            if (g0 + nb > re) finished = false;  // the rest of this term is decoded in the next round
+            const bool sc = tg.score != 0xFFFFFFFFu, cn = tg.cnt != 0xFFFFFFFFu;
+            if (sc && !cn && from_score) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false, true, false>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane); }
+            else if (sc && !cn) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false, true, true>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane); }
+            else if (!sc && !cn) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<false, false, true, true>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane); }
+            else { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block_dyn<true>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane); }
           } else if (s_rng[4 * slot + 1]) {
-            // direct mode (range not staged): this warp decodes the blocks overlapping its own sub-range
-            // straight from global memory
-            TermTarget tg;
-            tg.bits = required ? p.sm.tmp : (occur == QW_OCCUR_SHOULD ? LV.shd : LV.nt);
-            tg.cnt = (occur == QW_OCCUR_SHOULD) ? LV.cnt : 0xFFFFFFFFu;
-            tg.score = !scored ? 0xFFFFFFFFu : (required ? LV.msum : LV.ssum);
-            tg.weight = in.f;
-            tg.has_tf = (in.flags & IF_HAS_TF) != 0;
-            tg.fn = (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu;
-            tg.tab = scored ? p.sm.tab[in.r] : 0u;
-            const uint32_t sub_ws = ws + lo, sub_we = min(ws + lo + S, we);
-            if (sub_ws < sub_we) {
-              const QwSkip* skips = (const QwSkip*)(base + in.c);
-              const uint32_t nblk = in.n;
-              uint32_t a = 0, b = nblk;
-              while (b - a > 32) {
-                uint32_t step = (b - a + 31) >> 5;
-                uint32_t idx = a + lane * step;
-                bool ok = idx < b && __ldg(&skips[idx].last_doc) >= sub_ws;
-                uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-                if (m == 0) a = a + ((b - 1 - a) / step) * step + 1;
-                else { uint32_t f = __ffs(m) - 1; b = a + f * step + 1; if (f > 0) a = a + (f - 1) * step + 1; }
-              }
-              uint32_t idx = a + lane;
-              bool ok = idx < b && __ldg(&skips[idx].last_doc) >= sub_ws;
+            // direct mode (range not staged): warps decode whole blocks straight from global memory
+            const QwSkip* skips = (const QwSkip*)(base + in.c);
+            const uint32_t nblk = in.n;
+            uint32_t a = 0, b = nblk;
+            while (b - a > 32) {
+              uint32_t step = (b - a + 31) >> 5;
+              uint32_t idx = a + lane * step;
+              bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
               uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-              const uint32_t bfirst = m ? a + (__ffs(m) - 1) : nblk;
-              const uint8_t* tdata = base + in.a;
-              for (uint32_t bb = bfirst; bb < nblk; bb++) {
-                uint4 h = __ldg((const uint4*)&skips[bb]);
-                if (h.y != QW_NO_PREV_DOC && h.y + 1 >= sub_we) break;
-                fold_block_dyn<false>(0, tdata + h.z, ws, lo, sub_we - sub_ws, tg, lane);
-              }
+              if (m == 0) a = a + ((b - 1 - a) / step) * step + 1;
+              else { uint32_t f = __ffs(m) - 1; b = a + f * step + 1; if (f > 0) a = a + (f - 1) * step + 1; }
+            }
+            uint32_t idx = a + lane;
+            bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+            const uint32_t bfirst = m ? a + (__ffs(m) - 1) : nblk;
+            const uint8_t* tdata = base + in.a;
+            for (uint32_t bb = bfirst + warp; bb < nblk; bb += QW_WARPS) {
+              uint4 h = __ldg((const uint4*)&skips[bb]);
+              if (h.y != QW_NO_PREV_DOC && h.y + 1 >= we) break;
+              fold_block_dyn<false>(0, tdata + h.z, ws, 0, wlen, tg, lane);
             }
           }
-          __syncwarp();
-          if (!finished) { term_open = required; stop = true; break; }
-          term_open = false;
+          __syncthreads();
           if (required) {
             uint32_t* req = sm.u32(LV.req);
             const uint32_t* tmp = sm.u32(p.sm.tmp);
             const bool init = (req_init >> level) & 1;
-            for (uint32_t i = lane; i < SW; i += 32) req[wlo + i] = init ? (req[wlo + i] & tmp[wlo + i]) : tmp[wlo + i];
+            for (uint32_t i = tid; i < NW; i += QW_THREADS) req[i] = init ? (req[i] & tmp[i]) : tmp[i];
             req_init |= 1u << level;
-            __syncwarp();
+            __syncthreads();
           }
           ip++;
-        } else if (op == OP_RANGE || op == OP_EXISTS || op == OP_ALL) {
-          const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
-          const bool init = (req_init >> level) & 1;
-          const bool gather = required && init;
-          uint32_t* req = sm.u32(LV.req);
-          const uint32_t col = in.r;
-          const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
-          const uint64_t rlo = in.a, rhi = in.b;
-          const float boost = in.f;
-          for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
-            const uint32_t d = ws + wd * 32 + lane;
-            bool cand = d < we && has_col;
-            if (gather) {
-              const uint32_t rw = req[wd];
-              if (rw == 0) continue;  // warp-uniform
-              cand = cand && ((rw >> lane) & 1);
-            }
-            bool hit = false;
-            if (cand) {
-              if (op == OP_ALL) hit = true;
-              else {
-                const DCol& c = s_cols[col];
-                uint64_t a, b;
-                col_range(base, c, d, a, b);
-                if (op == OP_EXISTS) hit = a != b;
-                else for (uint64_t i = a; i < b && !hit; i++) {
-                  uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
-                  hit = mv >= rlo && mv <= rhi;
-                }
-              }
-            }
-            const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
-            const uint32_t di = wd * 32 + lane;
-            if (required) {
-              if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
-              if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], boost);
-            } else if (occur == QW_OCCUR_SHOULD) {
-              if (lane == 0) sm.u32(LV.shd)[wd] |= word;
-              if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
-              if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], boost);
-            } else {
-              if (lane == 0) sm.u32(LV.nt)[wd] |= word;
-            }
+      } else if (op == OP_RANGE || op == OP_EXISTS || op == OP_ALL) {
+        const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
+        const bool init = (req_init >> level) & 1;
+        const bool gather = required && init;
+        uint32_t* req = sm.u32(LV.req);
+        const uint32_t col = in.r;
+        const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
+        const uint64_t lo = in.a, hi = in.b;
+        const float boost = in.f;
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+          const uint32_t d = ws + wd * 32 + lane;
+          bool cand = d < we && has_col;
+          if (gather) {
+            const uint32_t rw = req[wd];
+            if (rw == 0) continue;  // warp-uniform
+            cand = cand && ((rw >> lane) & 1);
           }
-          if (required) req_init |= 1u << level;
-          __syncwarp();
-          ip++;
-        } else {  // OP_BOOL_END
-          // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
-          uint32_t* req = sm.u32(LV.req);
-          const uint32_t need = in.r, n_req = in.n;
-          for (uint32_t i = lane; i < SW; i += 32) {
-            const uint32_t wd = wlo + i;
-            const uint32_t d0 = ws + wd * 32;
-            uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
-            uint32_t r = n_req ? (((req_init >> level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
-            uint32_t so;
-            if (need == 0) so = 0xFFFFFFFFu;
-            else if (need == 1) so = sm.u32(LV.shd)[wd];
+          bool hit = false;
+          if (cand) {
+            if (op == OP_ALL) hit = true;
             else {
-              so = 0;
-              const uint8_t* cnt = sm.u8(LV.cnt) + wd * 32;
-              for (uint32_t b = 0; b < 32; b++) so |= (cnt[b] >= need ? 1u : 0u) << b;
-            }
-            req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
-          }
-          if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
-            float* ms = sm.f32(LV.msum) + lo;
-            const float* ss = sm.f32(LV.ssum) + lo;
-            for (uint32_t i = lane; i < S; i += 32) ms[i] = __fadd_rn(ms[i], ss[i]);
-          }
-          __syncwarp();
-          if (level > 0) {
-            // fold this bool's (bits, score) into the parent level as one clause
-            const SmemLevel& PL = p.sm.lvl[level - 1];
-            const uint32_t plevel = level - 1;
-            const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
-            const bool pinit = (req_init >> plevel) & 1;
-            const float* csc = LV.rsc != 0xFFFFFFFFu ? sm.f32(LV.rsc) : nullptr;
-            for (uint32_t i = lane; i < SW; i += 32) {
-              const uint32_t wd = wlo + i;
-              uint32_t m = req[wd];
-              if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
-              else if (occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
-              else sm.u32(PL.nt)[wd] |= m;
-            }
-            if (occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || (scored && csc))) {
-              for (uint32_t i = lo + lane; i < lo + S; i += 32) {
-                if ((req[i >> 5] >> (i & 31)) & 1) {
-                  if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
-                  if (scored && csc) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], csc[i]);
-                }
+              const DCol& c = s_cols[col];
+              uint64_t a, b;
+              col_range(base, c, d, a, b);
+              if (op == OP_EXISTS) hit = a != b;
+              else for (uint64_t i = a; i < b && !hit; i++) {
+                uint64_t mv = c.min_value + c.gcd * col_raw(base, c, i);
+                hit = mv >= lo && mv <= hi;
               }
-            } else if (occur == QW_OCCUR_MUST && scored && csc) {
-              for (uint32_t i = lo + lane; i < lo + S; i += 32) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], csc[i]);
             }
-            if (required) req_init |= 1u << plevel;
-            __syncwarp();
           }
-          ip++;
+          const uint32_t word = __ballot_sync(0xFFFFFFFFu, hit);
+          const uint32_t di = wd * 32 + lane;
+          if (required) {
+            if (lane == 0) req[wd] = init ? (req[wd] & word) : word;
+            if (hit && scored) sm.f32(LV.msum)[di] = __fadd_rn(sm.f32(LV.msum)[di], boost);
+          } else if (occur == QW_OCCUR_SHOULD) {
+            if (lane == 0) sm.u32(LV.shd)[wd] |= word;
+            if (hit && LV.cnt != 0xFFFFFFFFu) sm.u8(LV.cnt)[di]++;
+            if (hit && scored) sm.f32(LV.ssum)[di] = __fadd_rn(sm.f32(LV.ssum)[di], boost);
+          } else {
+            if (lane == 0) sm.u32(LV.nt)[wd] |= word;
+          }
         }
+        if (required) req_init |= 1u << level;
+        __syncthreads();
+        ip++;
+      } else if (op == OP_BOOL_END) {
+        // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
+        uint32_t* req = sm.u32(LV.req);
+        const uint32_t need = in.r, n_req = in.n;
+        if (in.flags & IF_BITS_FROM_SCORE) {
+          // every contribution of the flagged should-terms is > 0, so "matched some of them" == (ssum > 0)
+          const float* ss = sm.f32(LV.ssum);
+          uint32_t* shd = sm.u32(LV.shd);
+          for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, ss[wd * 32 + lane] > 0.0f);
+            if (lane == 0) shd[wd] |= m;
+          }
+          __syncthreads();
+        }
+        for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
+          const uint32_t d0 = ws + wd * 32;
+          uint32_t valid = d0 >= we ? 0u : (we - d0 >= 32 ? 0xFFFFFFFFu : ((1u << (we - d0)) - 1));
+          uint32_t r = n_req ? (((req_init >> level) & 1) ? req[wd] : 0u) : 0xFFFFFFFFu;
+          uint32_t so;
+          if (need == 0) so = 0xFFFFFFFFu;
+          else if (need == 1) so = sm.u32(LV.shd)[wd];
+          else {
+            so = 0;
+            const uint8_t* cnt = sm.u8(LV.cnt) + wd * 32;
+            for (uint32_t b = 0; b < 32; b++) so |= (cnt[b] >= need ? 1u : 0u) << b;
+          }
+          req[wd] = r & so & ~sm.u32(LV.nt)[wd] & valid;
+        }
+        if (LV.msum != 0xFFFFFFFFu && LV.ssum != 0xFFFFFFFFu) {
+          float4* ms = (float4*)sm.f32(LV.msum);
+          const float4* ss = (const float4*)sm.f32(LV.ssum);
+          for (uint32_t i = tid; i < (W >> 2); i += QW_THREADS) {
+            float4 a = ms[i], b = ss[i];
+            a.x = __fadd_rn(a.x, b.x); a.y = __fadd_rn(a.y, b.y); a.z = __fadd_rn(a.z, b.z); a.w = __fadd_rn(a.w, b.w);
+            ms[i] = a;
+          }
+        }
+        __syncthreads();
+        if (level > 0) {
+          // fold this bool's (bits, score) into the parent level as one clause
+          const SmemLevel& PL = p.sm.lvl[level - 1];
+          const uint32_t plevel = level - 1;
+          const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
+          const bool pinit = (req_init >> plevel) & 1;
+          const float* csc = LV.rsc != 0xFFFFFFFFu ? sm.f32(LV.rsc) : nullptr;
+          for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) {
+            uint32_t m = req[wd];
+            if (required) sm.u32(PL.req)[wd] = pinit ? (sm.u32(PL.req)[wd] & m) : m;
+            else if (occur == QW_OCCUR_SHOULD) sm.u32(PL.shd)[wd] |= m;
+            else sm.u32(PL.nt)[wd] |= m;
+          }
+          if (occur == QW_OCCUR_SHOULD && (PL.cnt != 0xFFFFFFFFu || (scored && csc))) {
+            for (uint32_t i = tid; i < W; i += QW_THREADS) {
+              if ((req[i >> 5] >> (i & 31)) & 1) {
+                if (PL.cnt != 0xFFFFFFFFu) sm.u8(PL.cnt)[i]++;
+                if (scored && csc) sm.f32(PL.ssum)[i] = __fadd_rn(sm.f32(PL.ssum)[i], csc[i]);
+              }
+            }
+          } else if (occur == QW_OCCUR_MUST && scored && csc) {
+            for (uint32_t i = tid; i < W; i += QW_THREADS) sm.f32(PL.msum)[i] = __fadd_rn(sm.f32(PL.msum)[i], csc[i]);
+          }
+          if (required) req_init |= 1u << plevel;
+          __syncthreads();
+        }
+        ip++;
       }
+      }  // while ip
     }
 
-    // ---- collect this warp's sub-range -----------------------------------------------------------------
+
+    // ---- collect the window's matches ---------------------------------------------------------------
     const uint32_t* res = sm.u32(p.sm.lvl[0].req);
     const float* rscore = p.sm.lvl[0].rsc != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].rsc) : nullptr;
     const DThresh& T = p.thresh[split];
     const uint32_t max_hits = P.max_hits, n_aggs = P.n_aggs, sa_present = P.sa.present;
     QwAggCell* cells = (QwAggCell*)P.out_cells;
-    const bool use_hist = MODE == MODE_HIST || (p.smem_aggs && n_aggs);
-    if (use_hist) {
-      // the histogram / privatised aggregation counters alias the entry area: wait until every warp is
-      // done with the entries, then clear
-      __syncthreads();
-      for (uint32_t i = tid; i < (MODE == MODE_HIST ? QW_HIST_BINS : P.n_cells); i += QW_THREADS) s_hist[i] = 0;
+    if (MODE == MODE_HIST || (p.smem_aggs && n_aggs)) {
+      // the histogram / privatised aggregation counters alias the (now dead) entry area
+      for (uint32_t i = tid; i < (MODE == MODE_HIST ? (uint32_t)QW_HIST_BINS : P.n_cells); i += QW_THREADS) s_hist[i] = 0;
       __syncthreads();
     }
     if (MODE == MODE_COLLECT) {
       const Key thr{T.key[0], T.key[1], T.key[2]};
       const uint32_t thr_top = (uint32_t)(thr.w0 >> 53);
-      const DKeySpec ks = P.key;
+      const DKeySpec ks = P.key;  // hoisted into registers
       uint32_t my_hits = 0, my_elig = 0;
-      for (uint32_t i = lane; i < SW; i += 32) my_hits += __popc(res[wlo + i]);
+      // hit count: one popc per bitmap word
+      for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
       auto slow_path = [&](uint32_t i, float sc) {
         const uint32_t doc = ws + i;
         DocKey dk = doc_key(P, s_cols, base, doc, sc);
@@ -933,7 +845,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
         float s_lo = -1.0f;
         if (thr_top >= 1024u) s_lo = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), ks.score_scale), 0.999999f);
         const float4* sc4 = reinterpret_cast<const float4*>(rscore);
-        for (uint32_t q = (lo >> 2) + lane; q < ((lo + S) >> 2); q += 32) {
+        for (uint32_t q = tid; q < (W >> 2); q += QW_THREADS) {
           const uint32_t nib = (res[q >> 3] >> ((q & 7) * 4)) & 0xFu;
           if (!nib) continue;
           const float4 v = sc4[q];
@@ -943,7 +855,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
           if ((nib & 8u) && v.w >= s_lo) slow_path(4 * q + 3, v.w);
         }
       } else if (max_hits || n_aggs) {
-        for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t word = res[wd];
           if (word == 0) continue;  // warp-uniform
           if (!((word >> lane) & 1)) continue;
@@ -957,6 +869,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
           if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
         }
       }
+      // block-reduce the counters, one global atomic per window
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         my_elig += __shfl_down_sync(0xFFFFFFFFu, my_elig, o);
@@ -974,12 +887,12 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       if (p.smem_aggs && n_aggs) {
         for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {
           uint32_t v = s_hist[i];
-          if (v) atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v);
+          if (v) { atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v); s_hist[i] = 0; }
         }
       }
     } else {
       if (max_hits) {
-        for (uint32_t wd = wlo; wd < wlo + SW; wd++) {
+        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t word = res[wd];
           if (word == 0) continue;
           if (!((word >> lane) & 1)) continue;
@@ -998,7 +911,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_window(const KParams p) {
       uint32_t* gh = (uint32_t*)P.out_hist;
       for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
         uint32_t v = s_hist[i];
-        if (v) atomicAdd(&gh[i], v);
+        if (v) { atomicAdd(&gh[i], v); s_hist[i] = 0; }
       }
     }
   }
