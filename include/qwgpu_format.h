@@ -83,7 +83,8 @@ typedef struct QwImgTerm {
  * This is what lets a GPU thread block that owns a doc-id window fetch exactly the posting bytes
  * it needs with ONE dependent load instead of a binary search over the skip list. */
 typedef struct QwWinIdx {
-  uint32_t start, end;
+  uint32_t start, end;             /* byte range inside QwImgTerm data */
+  uint32_t first_block, end_block; /* the same blocks as ordinals into the skip list */
 } QwWinIdx;
 
 /* One skip entry per posting block; 16 bytes = one coalesced 128-bit load.

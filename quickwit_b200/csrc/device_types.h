@@ -5,10 +5,10 @@
 #include "../../include/qwgpu_format.h"
 
 #ifndef QW_THREADS
-#define QW_THREADS 256
+#define QW_THREADS 512
 #endif
 #ifndef QW_MIN_BLOCKS_PER_SM
-#define QW_MIN_BLOCKS_PER_SM (QW_THREADS <= 256 ? 2 : 1)
+#define QW_MIN_BLOCKS_PER_SM 2
 #endif
 #define QW_WARPS (QW_THREADS / 32)
 #define QW_MAX_INSTR 96
@@ -90,6 +90,7 @@ struct DSplitPlan {
   uint32_t n_terms, n_levels;
   uint32_t max_hits, scoring;
   uint32_t n_fn_slots, n_cells;
+  uint32_t fused_score_root, pad0;  // root bool is a pure OR of positive-weight scored terms
   uint64_t fn_off[2];      // data-relative fieldnorm arrays staged per window
   uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables, followed by the
                            // float[QW_TFF_ROWS][256] tf-factor table of the same field

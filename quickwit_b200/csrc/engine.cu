@@ -345,6 +345,17 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
     lower_node(L, sp, nodes, ph->num_nodes, 0, 0, QW_OCCUR_MUST, scoring);
     DInstr en; memset(&en, 0, sizeof en); en.op = OP_BOOL_END; en.n = 1; en.flags = scoring ? IF_SCORED : 0; L.instrs.push_back(en);
   }
+  {
+    // root bool == pure OR of positive-weight scored terms (the BM25 top-K shape): the collect pass can
+    // take matches, hit count and the next window's zeroed accumulator straight from the score array
+    const DInstr& last = L.instrs.back();
+    bool pure = last.op == OP_BOOL_END && last.level == 0 && (last.flags & IF_BITS_FROM_SCORE) && last.n == 0 && last.r == 1;
+    for (const DInstr& in : L.instrs) {
+      if (in.op == OP_BOOL_BEGIN || in.op == OP_BOOL_END) { if (in.level != 0) pure = false; continue; }
+      if (!(in.op == OP_TERM && in.occur == QW_OCCUR_SHOULD && (in.flags & IF_BITS_FROM_SCORE))) pure = false;
+    }
+    L.P.fused_score_root = pure ? 1 : 0;
+  }
   if (L.instrs.size() > QW_MAX_INSTR) fail(QWGPU_EUNSUPPORTED, "query too large for the GPU program (%zu > %d instructions)", L.instrs.size(), QW_MAX_INSTR);
   P.n_instr = (uint32_t)L.instrs.size();
   uint32_t nl = 0;
@@ -426,7 +437,7 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
 // shared-memory arena for a batch (max over the batch's plans)
 static uint32_t stage_bytes_for(uint32_t W) {
   if (const char* e = getenv("QWGPU_STAGE")) return (uint32_t)atoi(e) & ~15u;
-  return std::max<uint32_t>(8192, std::min<uint32_t>(W * 2, 49152));
+  return std::min<uint32_t>(std::max<uint32_t>(W, 8192), 24576);
 }
 
 static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_msum, uint32_t need_ssum,
@@ -435,7 +446,7 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   memset(&L, 0xFF, sizeof L);
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
-  L.misc = take(64);
+  L.misc = take(32 + 4 * QW_MAX_TERMS);
   L.instr = take(std::max(max_instr, 1u) * sizeof(DInstr));
   L.cols = take(std::max(max_cols, 1u) * sizeof(DCol));
   L.aggs = take(std::max(max_aggs, 1u) * sizeof(DAgg));
@@ -501,7 +512,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   }
   // window size: as large as shared memory allows for the configured blocks/SM (per-window fixed
   // costs — staging, program interpretation, barriers — amortise over more postings)
-  uint32_t W = QW_THREADS <= 256 ? 8192 : 32768;
+  uint32_t W = 32768;
   if (const char* e = getenv("QWGPU_W")) W = (uint32_t)atoi(e);
   SmemLayout lay;
   for (;;) {

@@ -153,6 +153,8 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
     if (hi <= lo) eb = sb;
     t.widx[j].start = sb;
     t.widx[j].end = eb;
+    t.widx[j].first_block = lo;
+    t.widx[j].end_block = hi > lo ? hi : lo;
   }
   b->terms.push_back(std::move(t));
 }

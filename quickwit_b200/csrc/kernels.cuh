@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
   uint8_t* s_stage = sm.u8(p.sm.stage);
   uint2* s_ent = (uint2*)sm.u8(p.sm.ent);
   uint32_t loaded_split = 0xFFFFFFFFu;
+  bool ssum_clean = false;  // level-0 should-score array is all zero (left so by a fused collect)
 
   const uint32_t per = (p.total_work + gridDim.x - 1) / gridDim.x;
   const uint32_t w_begin = blockIdx.x * per;
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       src = (const uint4*)(p.aggs + P.agg_base);
       for (uint32_t i = tid; i < P.n_aggs * (sizeof(DAgg) / 16); i += QW_THREADS) ((uint4*)s_aggs)[i] = __ldg(src + i);
       loaded_split = split;
+      ssum_clean = false;
       __syncthreads();
       if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
       __syncthreads();
@@ -518,17 +520,21 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     // ---- phase 1: window-index entries + fieldnorm staging (one round of independent loads) --------
     if (tid < n_terms) {
       const DInstr& in = s_instr[s_rng[4 * tid + 3]];
-      uint32_t start = 0, len = 0;
+      uint32_t start = 0, len = 0, fb = 0, nb = 0;
       if (in.n) {
-        const uint2* wi = (const uint2*)(base + in.b);
+        const uint4* wi = (const uint4*)(base + in.b);
         const uint32_t e0 = ws >> in.m, e1 = (we - 1) >> in.m;
-        uint2 a = __ldg(wi + e0);
-        uint2 b = e1 != e0 ? __ldg(wi + e1) : a;
+        uint4 a = __ldg(wi + e0);
+        uint4 b = e1 != e0 ? __ldg(wi + e1) : a;
         start = a.x;
         len = b.y > a.x ? b.y - a.x : 0;
+        fb = a.z;
+        nb = (len && b.w > a.z) ? b.w - a.z : 0;
       }
       s_rng[4 * tid + 0] = start;
       s_rng[4 * tid + 1] = len;
+      s_tblk[2 * tid] = fb;        // first block ordinal (rewritten to the global block base below)
+      s_tblk[2 * tid + 1] = nb;
     }
     if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
     for (uint32_t s = 0; s < n_fn; s++) {
@@ -539,73 +545,53 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       for (uint32_t i = tid; i < n16; i += QW_THREADS) cp_async16(dst + 16 * i, src + 16 * i);
     }
     __syncthreads();
-    // ---- phase 2: stage packed posting bytes (warp per term) ---------------------------------------------
+    // ---- phase 2: stage offsets + global block numbering (one thread), then, in ONE round of loads,
+    // cp.async the packed posting bytes and read the skip entries that describe each staged block ------
     if (tid == 0) {
-      uint32_t off = 0;
+      uint32_t off = 0, g = 0;
       for (uint32_t t = 0; t < n_terms; t++) {
-        uint32_t len = s_rng[4 * t + 1];
-        if (len && off + len <= p.stage_bytes) { s_rng[4 * t + 2] = off; off += len; }
-        else s_rng[4 * t + 2] = 0xFFFFFFFFu;
+        const uint32_t len = s_rng[4 * t + 1], nb = s_tblk[2 * t + 1];
+        if (len && off + len <= p.stage_bytes && nb <= QW_BLK_TAB && g + nb <= QW_MAX_WBLK) {
+          s_rng[4 * t + 2] = off;
+          off += len;
+          s_misc[8 + t] = g;  // global block base of term slot t
+          g += nb;
+        } else {
+          s_rng[4 * t + 2] = 0xFFFFFFFFu;  // direct mode (or nothing to do)
+          s_misc[8 + t] = g;
+        }
       }
+      s_misc[0] = g;
     }
     __syncthreads();
     for (uint32_t t = warp; t < n_terms; t += QW_WARPS) {
       const uint32_t so = s_rng[4 * t + 2];
       if (so == 0xFFFFFFFFu) continue;
-      const uint8_t* src = base + s_instr[s_rng[4 * t + 3]].a + s_rng[4 * t + 0];
+      const DInstr& in = s_instr[s_rng[4 * t + 3]];
+      const uint32_t start = s_rng[4 * t + 0];
+      const uint8_t* src = base + in.a + start;
       const uint32_t n16 = s_rng[4 * t + 1] >> 4;
       for (uint32_t i = lane; i < n16; i += 32) cp_async16(s_stage + so + 16 * i, src + 16 * i);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    // ---- phase 3: block table. One thread per term counts its blocks, thread 0 assigns global block
-    // numbers, then the same threads write one BlkRec per block -------------------------------------------
-    uint32_t my_nb = 0;
-    if (tid < n_terms) {
-      const uint32_t so = s_rng[4 * tid + 2];
-      if (so != 0xFFFFFFFFu) {
-        const uint32_t len = s_rng[4 * tid + 1];
-        uint32_t pos = 0;
-        while (pos < len && my_nb <= QW_BLK_TAB) {
-          uint32_t bw = *(const uint32_t*)(s_stage + so + pos + 12);
-          pos += 16 + 16 * ((bw & 0xFF) + ((bw >> 8) & 0xFF));
-          my_nb++;
-        }
-        if (my_nb > QW_BLK_TAB) { my_nb = 0; s_rng[4 * tid + 2] = 0xFFFFFFFFu; }  // too many blocks: direct mode
-      }
-      s_tblk[2 * tid + 1] = my_nb;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t g = 0;
-      for (uint32_t t = 0; t < n_terms; t++) {
-        uint32_t nb = s_tblk[2 * t + 1];
-        if (g + nb > QW_MAX_WBLK) { nb = 0; s_tblk[2 * t + 1] = 0; s_rng[4 * t + 2] = 0xFFFFFFFFu; }
-        s_tblk[2 * t] = g;
-        g += nb;
-      }
-      s_misc[0] = g;
-    }
-    __syncthreads();
-    if (tid < n_terms && s_tblk[2 * tid + 1]) {
-      const uint32_t so = s_rng[4 * tid + 2], nb = s_tblk[2 * tid + 1], g0 = s_tblk[2 * tid];
-      uint32_t pos = 0;
-      for (uint32_t k = 0; k < nb; k++) {
-        const uint4 h = *(const uint4*)(s_stage + so + pos);
+      // block records straight from the skip list (coalesced 16-byte entries)
+      const uint4* skips = (const uint4*)(base + in.c) + s_tblk[2 * t];
+      const uint32_t nb = s_tblk[2 * t + 1], g0 = s_misc[8 + t];
+      for (uint32_t k = lane; k < nb; k += 32) {
+        const uint4 h = __ldg(skips + k);  // last_doc, prev_last_doc, byte_off, widths/count
         BlkRec r;
-        r.soff = (uint16_t)(so + pos);
-        r.slot = (uint8_t)tid;
+        r.soff = (uint16_t)(so + (h.z - start));
+        r.slot = (uint8_t)t;
         r.pad = 0;
         const uint32_t first_lb = h.y + 1;  // lower bound of the first doc (0 when h.y == 0xFFFFFFFF)
         r.lo = (uint16_t)(first_lb <= ws ? 0u : min(first_lb - ws, W));
         r.hi = (uint16_t)(h.x < ws ? 0xFFFFu : min(h.x - ws, W - 1));
         if (h.x < ws || first_lb >= we) { r.lo = (uint16_t)W; r.hi = 0; }  // no overlap: lo > hi
         s_blk[g0 + k] = r;
-        pos += 16 + 16 * ((h.w & 0xFF) + ((h.w >> 8) & 0xFF));
       }
     }
+    cp_async_wait_all();
     __syncthreads();
-    const uint32_t total_blocks = s_misc[0];
+    if (tid < n_terms) s_tblk[2 * tid] = s_misc[8 + tid];  // from here on: global block base
+    __syncthreads();
 
     // ---- execute the boolean program (block-wide; one barrier per clause keeps the f32 order fixed) ----
     // A TERM clause folds its staged posting blocks directly into the level's bitmaps / score array,
@@ -613,6 +599,10 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     // memory (direct mode).
     uint32_t ip = 0;
     uint32_t req_init = 0;  // bit per level, uniform across the block
+    // fused BM25 shape (COLLECT pass only): matches / hit count come from the score array, which the
+    // collect loop also re-zeroes for the next window of the same split plan
+    const bool fused = MODE == MODE_COLLECT && P.fused_score_root && P.max_hits && !P.sa.present && !P.n_aggs &&
+                       P.key.kind[0] == QW_SORT_SCORE && P.key.order[0] == QW_ORDER_DESC;
     {
       while (ip < n_instr) {
         const DInstr& in = s_instr[ip];
@@ -624,7 +614,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           zero_f4((float*)sm.u32(LV.nt), NW, tid);
           if (LV.cnt != 0xFFFFFFFFu) zero_f4((float*)sm.u32(LV.cnt), W >> 2, tid);
           if (LV.msum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.msum), W, tid);
-          if (LV.ssum != 0xFFFFFFFFu) zero_f4(sm.f32(LV.ssum), W, tid);
+          if (LV.ssum != 0xFFFFFFFFu && !(fused && level == 0 && ssum_clean)) zero_f4(sm.f32(LV.ssum), W, tid);
           req_init &= ~(1u << level);
           __syncthreads();
           ip++;
@@ -741,7 +731,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         // BooleanWeight combination: all required AND NOT any excluded AND >= r should clauses
         uint32_t* req = sm.u32(LV.req);
         const uint32_t need = in.r, n_req = in.n;
-        if (in.flags & IF_BITS_FROM_SCORE) {
+        if ((in.flags & IF_BITS_FROM_SCORE) && !(fused && level == 0)) {
           // every contribution of the flagged should-terms is > 0, so "matched some of them" == (ssum > 0)
           const float* ss = sm.f32(LV.ssum);
           uint32_t* shd = sm.u32(LV.shd);
@@ -824,7 +814,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       const DKeySpec ks = P.key;  // hoisted into registers
       uint32_t my_hits = 0, my_elig = 0;
       // hit count: one popc per bitmap word
-      for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
+      if (!fused) for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
       auto slow_path = [&](uint32_t i, float sc) {
         const uint32_t doc = ws + i;
         DocKey dk = doc_key(P, s_cols, base, doc, sc);
@@ -839,7 +829,24 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           }
         }
       };
-      if (max_hits && ks.kind[0] == QW_SORT_SCORE && ks.order[0] == QW_ORDER_DESC && !sa_present && rscore && !n_aggs) {
+      if (fused) {
+        // fused BM25 pass: one sweep over the score array counts the matches (score > 0), filters them
+        // against the float lower bound of the threshold bucket and clears the array for the next window
+        float s_lo = -1.0f;
+        if (thr_top >= 1024u) s_lo = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), ks.score_scale), 0.999999f);
+        float4* sc4 = reinterpret_cast<float4*>(sm.f32(p.sm.lvl[0].ssum));
+        my_hits = 0;
+        for (uint32_t q = tid; q < (W >> 2); q += QW_THREADS) {
+          const float4 v = sc4[q];
+          sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          my_hits += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
+          if (v.x > 0.0f && v.x >= s_lo) slow_path(4 * q + 0, v.x);
+          if (v.y > 0.0f && v.y >= s_lo) slow_path(4 * q + 1, v.y);
+          if (v.z > 0.0f && v.z >= s_lo) slow_path(4 * q + 2, v.z);
+          if (v.w > 0.0f && v.w >= s_lo) slow_path(4 * q + 3, v.w);
+        }
+        ssum_clean = true;
+      } else if (max_hits && ks.kind[0] == QW_SORT_SCORE && ks.order[0] == QW_ORDER_DESC && !sa_present && rscore && !n_aggs) {
         // fast path (BM25 top-K): a float lower bound of the threshold bucket filters 4 docs per lane
         // per step; only survivors build the 192-bit key. s_lo is conservative (one part in 2^20).
         float s_lo = -1.0f;
