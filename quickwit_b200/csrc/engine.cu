@@ -87,7 +87,7 @@ Engine::Engine(int dev) : device(dev) {
   max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * QW_CAND_CAP));
 }
 
 Engine::~Engine() {
@@ -618,7 +618,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     else qwk::k_window<qwk::MODE_COLLECT><<<grid, QW_THREADS, lay.total, st>>>(q);
     stats.launches++;
   };
-  const uint32_t sel_smem = 3 * 8 * QW_CAND_CAP;
+  const uint32_t sel_smem = 3 * 8 * QW_CAND_CAP;  // [all first words | 3 x QW_SEL_MAX survivors] or 3 x all (degenerate ties)
   auto run_collect = [&]() {
     CUDA_CHECK(cudaMemsetAsync(slot->d_out, 0, out_bytes, st));
     CUDA_CHECK(cudaEventRecord(slot->ev2, st));

@@ -991,25 +991,96 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
   }
 }
 
-// Sorts a split's candidates with the reference total order (bitonic sort of the 192-bit keys,
-// descending) and writes the best min(K, n) as QwHit — the harvest step
-// (quickwit-search/src/top_k_collector.rs:404-410, binary_heap.rs:187-193).
+// Harvest (quickwit-search/src/top_k_collector.rs:404-410, binary_heap.rs:187-193): the best
+// min(K, n) candidates of a split, best first, decoded back to QwHit.
+//   1. exact radix select (8-bit digits, MSB first) of the K-th largest first key word;
+//   2. compaction of the candidates >= that word (all ties kept) — normally ~K of the ~2-3K candidates;
+//   3. bitonic sort of the survivors with the full 192-bit comparison (the reference total order).
+#define QW_SEL_MAX 2048  /* survivors sorted in shared memory; more ties than this => sort everything */
 __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
-  uint8_t* smem_raw = qw_smem;
   const DSplitPlan& P = plans[blockIdx.x];
   const uint32_t tid = threadIdx.x;
   if (P.max_hits == 0) { if (tid == 0) *(uint32_t*)P.out_nhits = 0; return; }
   uint32_t n = *(const uint32_t*)P.out_cand_count;
   if (n > QW_CAND_CAP) n = QW_CAND_CAP;  // overflow is detected by the host (cand_count > cap)
-  uint32_t N = 32;
-  while (N < n) N <<= 1;
-  uint64_t* k0 = (uint64_t*)smem_raw;
-  uint64_t* k1 = k0 + N;
-  uint64_t* k2 = k1 + N;
+  const uint32_t K = P.max_hits;
   const uint64_t* src = (const uint64_t*)P.out_cands;
-  for (uint32_t i = tid; i < N; i += 1024) {
-    if (i < n) { k0[i] = src[3ull * i]; k1[i] = src[3ull * i + 1]; k2[i] = src[3ull * i + 2]; }
-    else { k0[i] = 0; k1[i] = 0; k2[i] = 0; }
+  // shared memory: all first words [QW_CAND_CAP], then the compacted survivors (3 x sort capacity)
+  uint64_t* a0 = (uint64_t*)qw_smem;
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_sel[3];  // [0] digit, [1] count above digit, [2] survivor counter
+  for (uint32_t i = tid; i < n; i += 1024) a0[i] = src[3ull * i];
+  if (tid == 0) s_sel[2] = 0;
+  __syncthreads();
+  uint64_t thr = 0;  // keep candidates with w0 >= thr
+  if (n > K) {
+    uint64_t prefix = 0;
+    uint32_t need = K;  // rank of the wanted element among those matching the prefix
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const uint64_t himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+      for (uint32_t i = tid; i < n; i += 1024) {
+        const uint64_t v = a0[i];
+        if ((v & himask) == prefix) atomicAdd(&s_hist[(uint32_t)(v >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // lane owns 8 bins, top bins first: lane 0 -> bins 255..248
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { loc[j] = s_hist[255 - (tid * 8 + j)]; sum += loc[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)tid >= o) incl += t; }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t before = run;
+          run += loc[j];
+          if (before < need && run >= need) { s_sel[0] = 255 - (tid * 8 + j); s_sel[1] = before; }
+        }
+      }
+      __syncthreads();
+      prefix |= (uint64_t)s_sel[0] << shift;
+      need -= s_sel[1];
+      __syncthreads();
+    }
+    thr = prefix;  // the exact K-th largest first word
+  }
+  // count survivors; too many ties on the first word => sort every candidate instead
+  uint32_t mine = 0;
+  for (uint32_t i = tid; i < n; i += 1024) mine += a0[i] >= thr;
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_sel[2], mine);
+  __syncthreads();
+  uint32_t m = s_sel[2];
+  const bool all = m > QW_SEL_MAX;
+  __syncthreads();
+  uint64_t *k0, *k1, *k2;
+  uint32_t N = 32;
+  if (all) {
+    // degenerate: keys live interleaved [w0 | w1 | w2] over the whole candidate set
+    m = n;
+    while (N < m) N <<= 1;
+    k0 = a0; k1 = k0 + N; k2 = k1 + N;
+    for (uint32_t i = tid; i < N; i += 1024) {
+      if (i < n) { k0[i] = src[3ull * i]; k1[i] = src[3ull * i + 1]; k2[i] = src[3ull * i + 2]; }
+      else { k0[i] = 0; k1[i] = 0; k2[i] = 0; }
+    }
+  } else {
+    while (N < m) N <<= 1;
+    k0 = a0 + QW_CAND_CAP; k1 = k0 + QW_SEL_MAX; k2 = k1 + QW_SEL_MAX;
+    if (tid == 0) s_sel[2] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += 1024) {
+      const uint64_t v = a0[i];
+      if (v >= thr) {
+        const uint32_t pos = atomicAdd(&s_sel[2], 1u);
+        k0[pos] = v; k1[pos] = src[3ull * i + 1]; k2[pos] = src[3ull * i + 2];
+      }
+    }
+    for (uint32_t i = m + tid; i < N; i += 1024) { k0[i] = 0; k1[i] = 0; k2[i] = 0; }
   }
   __syncthreads();
   for (uint32_t size = 2; size <= N; size <<= 1) {
@@ -1029,7 +1100,7 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
       __syncthreads();
     }
   }
-  const uint32_t out_n = n < P.max_hits ? n : P.max_hits;
+  const uint32_t out_n = m < K ? m : K;
   QwHit* hits = (QwHit*)P.out_hits;
   const DKeySpec& ks = P.key;
   for (uint32_t i = tid; i < out_n; i += 1024) {
