@@ -9,11 +9,16 @@ posting lists), so one step touches Q x postings + the fieldnorm arrays > the 12
 next step's data has been evicted by then ("inputs larger than L2").
 
 Metric: docs scored per second = postings visited (sum of the query terms' doc frequencies over all
-splits) / time. `value` uses device time (CUDA events inside libqwgpu around each call's kernel
-sequence, inputs resident in HBM); `e2e` is the wall time of the C-ABI calls (`qwgpu_split_search`:
-host plan bytes in, host result buffers out, H2D/D2H inside). N > 1: one process per GPU, every
-rank owns its own 32 splits (weak scaling), one NCCL all-gather of the fixed-size per-rank partial
-top-K per step stands in for the root merge; time = max over ranks.
+splits) / time. Two timed regions of K steps each (same queries, W warm-up steps before each):
+  * `value`: seam C (`qwgpu_split_search`, compiled plans) — device time from CUDA events recorded inside
+    libqwgpu on the launching stream around each call's kernel sequence; split data resident in HBM;
+  * `e2e`: the reference-facing call `SearchService::leaf_search` = `qwgpu_leaf_search`: host
+    LeafSearchRequest protobuf bytes in (QueryAst JSON), host LeafSearchResponse bytes out — request
+    decode, plan compilation, H2D of the plans, kernels, D2H of the hits, leaf merge and protobuf
+    encoding all inside the wall-clock region.
+N > 1: one process per GPU, every rank owns its own 32 splits (weak scaling); in the e2e region ONE
+NCCL all-gather of the fixed-size per-rank partial (top-K + counters) per query stands in for the root
+merge (`qwgpu_response_to_partial` / `qwgpu_merge_partials`); times are the max over ranks.
 
 `--impl reference`: the reference's CPU algorithm (oracle/qw_oracle.c, a restatement — the real
 quickwit-search + tantivy cannot be built here) on all host cores, one split per
@@ -255,9 +260,21 @@ def main():
     resident = ctx.resident_bytes()
     ids = [im.split_id for im in imgs]
     searches = [RawSearch(ctx, ids, plans[q]) for q in range(Q_SETS)]
+    # the same queries as LeafSearchRequest protobufs (QueryAst JSON), for the e2e region
+    from quickwit_b200 import proto, service
+    doc_mapper = json.dumps({"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
+                                                {"name": "timestamp", "type": "datetime", "fast": True}], "timestamp_field": "timestamp"})
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
+    sreqs = [proto.enc_search_request(json.dumps({"type": "bool", "should": [{"type": "term", "field": "body", "value": f"t{q * 10 + i}"} for i in range(10)]}),
+                                      max_hits=K, sort_fields=[("_score", 1)]) for q in range(Q_SETS)]
+    lreqs = [proto.enc_leaf_search_request(sr, offsets, doc_mapper) for sr in sreqs]
     t_build = time.perf_counter() - t_build
-    gather_in = torch.zeros((K, 3), dtype=torch.int64, device="cuda") if world > 1 else None
-    gather_out = torch.zeros((world * K, 3), dtype=torch.int64, device="cuda") if world > 1 else None
+    part_bytes = service.partial_size(sreqs[0]) if world > 1 else 0
+    if world > 1:
+        part_host = torch.zeros(part_bytes, dtype=torch.uint8).pin_memory()
+        part_dev = torch.zeros(part_bytes, dtype=torch.uint8, device="cuda")
+        gath_dev = torch.zeros(world * part_bytes, dtype=torch.uint8, device="cuda")
+        gath_host = torch.zeros(world * part_bytes, dtype=torch.uint8).pin_memory()
 
     def step():
         acc = dict(gpu_us=0.0, main_us=0.0, launches=0, postings=0, alg_bytes=0, d2h=0, h2d=0, fallbacks=0)
@@ -268,12 +285,21 @@ def main():
             for k in ("launches", "postings", "alg_bytes", "d2h", "fallbacks"):
                 acc[k] += r[k]
             acc["h2d"] += s.plan_bytes
-            if world > 1:
-                part = torch.from_numpy(s.partial().view(np.int64))
-                gather_in.copy_(part, non_blocking=True)
-                dist.all_gather_into_tensor(gather_out, gather_in)
             s.free()
         return acc
+
+    last = {}
+
+    def step_e2e():
+        for q in range(Q_SETS):
+            resp = ctx.leaf_search(lreqs[q])
+            if world > 1:
+                service.response_to_partial(sreqs[q], resp, part_host.data_ptr(), part_bytes)
+                part_dev.copy_(part_host, non_blocking=True)
+                dist.all_gather_into_tensor(gath_dev, part_dev)   # the single collective of the data path
+                gath_host.copy_(gath_dev)
+                resp = service.merge_partials(sreqs[q], world, gath_host.data_ptr(), part_bytes)
+            last[q] = resp
 
     def sync():
         torch.cuda.synchronize()
@@ -290,8 +316,18 @@ def main():
     t0 = time.perf_counter()
     accs = [step() for _ in range(a.steps)]
     sync()
+    wall_c = time.perf_counter() - t0
+    for _ in range(max(a.warmup, 3)):
+        step_e2e()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    sync()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    hits0 = proto.dec_leaf_search_response(last[0])
+    assert len(hits0["partial_hits"]) == K and hits0["num_hits"] > 0
 
     gpu_s = sum(x["gpu_us"] for x in accs) * 1e-6
     main_s = sum(x["main_us"] for x in accs) * 1e-6
@@ -299,10 +335,11 @@ def main():
     alg_bytes = sum(x["alg_bytes"] for x in accs)
     launches = sum(x["launches"] for x in accs)
     n_main = a.steps * Q_SETS
+    postings_rank0 = postings
     if world > 1:
-        t = torch.tensor([gpu_s, wall, main_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([gpu_s, wall, main_s, wall_c], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gpu_s, wall, main_s = [float(x) for x in t.tolist()]
+        gpu_s, wall, main_s, wall_c = [float(x) for x in t.tolist()]
         c = torch.tensor([postings, launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         postings, launches = [int(x) for x in c.tolist()]
@@ -323,9 +360,11 @@ def main():
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": 1e3 * gpu_s / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
         "config": dict(workload, parallelism=f"splits_x{world}", resident_bytes_per_gpu=resident, build_seconds=round(t_build, 1)),
-        "e2e": {"value": postings / wall, "unit": "postings/s", "ms_per_step": 1e3 * wall / a.steps,
-                "p50_query_latency_ms": 1e3 * wall / (a.steps * Q_SETS),
-                "h2d_bytes_per_step": accs[0]["h2d"], "d2h_bytes_per_step": accs[0]["d2h"]},
+        "e2e": {"value": postings / wall, "unit": "postings/s", "api": "qwgpu_leaf_search (LeafSearchRequest -> LeafSearchResponse bytes)",
+                "ms_per_step": 1e3 * wall / a.steps, "mean_query_latency_ms": 1e3 * wall / (a.steps * Q_SETS),
+                "h2d_bytes_per_step": accs[0]["h2d"] + sum(len(x) for x in lreqs),
+                "d2h_bytes_per_step": Q_SETS * a.splits * (32 + 32 * K),
+                "seam_c_wall_value": postings / wall_c},
         "gpu_launches": launches,
         "exact_fallbacks": sum(x["fallbacks"] for x in accs),
         "roofline": {"bound": "hbm", "kernel": "k_window<COLLECT>", "achieved": achieved, "peak": peak,

@@ -63,8 +63,10 @@ struct CompiledPlan {
   std::vector<AggReq> agg_request;
   std::vector<AggBinding> agg_bindings;  // parallel to the plan's QwAggNode[]; point into agg_request
 };
+// `parsed_ast`: the request's query_ast already parsed (one parse per leaf request, not per split)
 CompiledPlan compile_plan(const ImageView& img, const std::string& split_id, const pb::SearchRequest& req,
-                          const DocMapperInfo& dm, const pb::SplitIdAndFooterOffsets* split_meta);
+                          const DocMapperInfo& dm, const pb::SplitIdAndFooterOffsets* split_meta,
+                          const Json* parsed_ast = nullptr);
 
 // ---- intermediate aggregation results (role of tantivy's IntermediateAggregationResults; our own
 // postcard-style byte layout — the reference layout is a tantivy-internal struct, SURVEY.md §7 hard

@@ -165,10 +165,18 @@ struct SplitJob {
   int error_code = 0;
 };
 
-static std::vector<pb::LambdaSingleSplitResult> run_leaf(Engine& eng, const pb::LeafSearchRequest& lr) {
-  using clock = std::chrono::steady_clock;
+struct LeafRun {
   std::vector<SplitJob> jobs;
+  std::vector<size_t> which;      // jobs[which[k]] <-> outs[k]
+  std::vector<SplitOutput> outs;
+  BatchStats st;
+  uint64_t wall_us = 0;
+};
+
+static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run) {
+  using clock = std::chrono::steady_clock;
   const pb::SearchRequest& sreq = lr.search_request;
+  Json ast = parse_json(sreq.query_ast, QWGPU_EINVALID_QUERY);  // once per request
   for (auto& ref : lr.leaf_requests) {
     if (ref.doc_mapper_ord >= lr.doc_mappers.size()) fail(QWGPU_EINVALID_ARG, "Internal error: doc_mapper_ord out of bounds");
     DocMapperInfo dm = parse_doc_mapper(lr.doc_mappers[ref.doc_mapper_ord]);
@@ -178,62 +186,143 @@ static std::vector<pb::LambdaSingleSplitResult> run_leaf(Engine& eng, const pb::
       j.dev = eng.find(so.split_id);
       try {
         if (!j.dev) fail(QWGPU_ENOTFOUND, "split `%s` is not resident on this GPU", so.split_id.c_str());
-        j.plan = compile_plan(j.dev->view, so.split_id, sreq, dm, &so);
+        j.plan = compile_plan(j.dev->view, so.split_id, sreq, dm, &so, &ast);
       } catch (const Error& e) {
         // malformed queries / aggregations fail the whole request like the reference (service.rs:182-184)
         if (e.code == QWGPU_EINVALID_QUERY || e.code == QWGPU_EINVALID_AGG || e.code == QWGPU_EINVALID_ARG) throw;
         j.error = e.what();
         j.error_code = e.code;
       }
-      jobs.push_back(std::move(j));
+      run.jobs.push_back(std::move(j));
     }
   }
   std::vector<std::shared_ptr<SplitDev>> devs;
   std::vector<const uint8_t*> plans;
   std::vector<size_t> lens;
-  std::vector<size_t> which;
-  for (size_t i = 0; i < jobs.size(); i++)
-    if (!jobs[i].error_code) {
-      devs.push_back(jobs[i].dev);
-      plans.push_back((const uint8_t*)jobs[i].plan.bytes.data());
-      lens.push_back(jobs[i].plan.bytes.size());
-      which.push_back(i);
+  for (size_t i = 0; i < run.jobs.size(); i++)
+    if (!run.jobs[i].error_code) {
+      devs.push_back(run.jobs[i].dev);
+      plans.push_back((const uint8_t*)run.jobs[i].plan.bytes.data());
+      lens.push_back(run.jobs[i].plan.bytes.size());
+      run.which.push_back(i);
     }
-  std::vector<SplitOutput> outs;
-  BatchStats st;
   auto t0 = clock::now();
-  if (!devs.empty()) eng.search(devs, plans, lens, outs, st);
-  uint64_t wall_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t0).count();
-  std::vector<pb::LambdaSingleSplitResult> results(jobs.size());
-  for (size_t i = 0; i < jobs.size(); i++) {
-    results[i].split_id = jobs[i].meta.split_id;
-    if (jobs[i].error_code) { results[i].is_error = true; results[i].error = jobs[i].error; }
+  if (!devs.empty()) eng.search(devs, plans, lens, run.outs, run.st);
+  run.wall_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t0).count();
+}
+
+// SplitResourceStats / LeafResourceStats filled like leaf.rs:641-684; cpu_search_microsecs carries the
+// split's share of the batch's device time
+static pb::LeafResourceStats split_stats(const LeafRun& run, size_t k) {
+  const SplitJob& j = run.jobs[run.which[k]];
+  const size_t n = std::max<size_t>(run.which.size(), 1);
+  pb::SplitResourceStats ss;
+  ss.v[0] = j.dev->view.hdr->num_docs;
+  ss.v[1] = j.dev->data_len;
+  ss.v[4] = run.outs[k].num_hits;
+  ss.v[8] = (uint64_t)(run.st.gpu_time_us / n);
+  pb::LeafResourceStats ls;
+  ls.localexec_num_splits = 1;
+  ls.localexec_num_docs = ss.v[0];
+  ls.split_resources_sum = ss;
+  ls.split_resources_worst = ss;
+  ls.min_wait_for_search_permit_microsecs = 0;
+  ls.min_wait_for_cpu_pool_microsecs = 0;
+  ls.wall_time_microsecs = run.wall_us / n;
+  return ls;
+}
+
+static std::vector<pb::LambdaSingleSplitResult> run_leaf(Engine& eng, const pb::LeafSearchRequest& lr) {
+  LeafRun run;
+  run_leaf_raw(eng, lr, run);
+  std::vector<pb::LambdaSingleSplitResult> results(run.jobs.size());
+  for (size_t i = 0; i < run.jobs.size(); i++) {
+    results[i].split_id = run.jobs[i].meta.split_id;
+    if (run.jobs[i].error_code) { results[i].is_error = true; results[i].error = run.jobs[i].error; }
   }
-  for (size_t k = 0; k < which.size(); k++) {
-    size_t i = which[k];
-    SplitOutput& o = outs[k];
+  for (size_t k = 0; k < run.which.size(); k++) {
+    size_t i = run.which[k];
+    SplitOutput& o = run.outs[k];
     if (o.status) { results[i].is_error = true; results[i].error = o.error; continue; }
-    pb::LeafSearchResponse r = build_split_response(jobs[i].plan, jobs[i].dev->view, jobs[i].meta.split_id, o.num_hits,
+    pb::LeafSearchResponse r = build_split_response(run.jobs[i].plan, run.jobs[i].dev->view, run.jobs[i].meta.split_id, o.num_hits,
                                                     o.hits.data(), o.hits.size(), o.cells.data(), o.cells.size());
-    // SplitResourceStats / LeafResourceStats filled like leaf.rs:641-684; cpu_search_microsecs carries
-    // this split's share of the batch's device time
-    pb::SplitResourceStats ss;
-    ss.v[0] = jobs[i].dev->view.hdr->num_docs;
-    ss.v[1] = jobs[i].dev->data_len;
-    ss.v[4] = o.num_hits;
-    ss.v[8] = (uint64_t)(st.gpu_time_us / std::max<size_t>(which.size(), 1));
-    pb::LeafResourceStats ls;
-    ls.localexec_num_splits = 1;
-    ls.localexec_num_docs = ss.v[0];
-    ls.split_resources_sum = ss;
-    ls.split_resources_worst = ss;
-    ls.min_wait_for_search_permit_microsecs = 0;
-    ls.min_wait_for_cpu_pool_microsecs = 0;
-    ls.wall_time_microsecs = wall_us / std::max<size_t>(which.size(), 1);
-    r.resource_stats = ls;
+    r.resource_stats = split_stats(run, k);
     results[i].response = std::move(r);
   }
   return results;
+}
+
+// Leaf-level merge (IncrementalCollector, collector.rs:1195-1313) done on the device-format hits: the
+// per-split lists are already sorted best-first, so a k-way heap merge in the u64 fast-field space
+// (order-preserving per sort-field type) yields the leaf's top (max_hits + start_offset) without
+// materialising every split's PartialHits. Falls back to the generic path when the sort-field types
+// differ across splits.
+static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, LeafRun& run) {
+  pb::LeafSearchResponse m;
+  const size_t n = run.which.size();
+  int o1, o2;
+  sort_orders(sreq, &o1, &o2);
+  const size_t k = (size_t)(sreq.max_hits + sreq.start_offset);
+  // rank of every split id (tie-break uses the split id string order)
+  std::vector<size_t> by_id(n);
+  for (size_t i = 0; i < n; i++) by_id[i] = i;
+  std::sort(by_id.begin(), by_id.end(), [&](size_t a, size_t b) { return run.jobs[run.which[a]].meta.split_id < run.jobs[run.which[b]].meta.split_id; });
+  std::vector<uint32_t> rank(n);
+  for (size_t r = 0; r < n; r++) rank[by_id[r]] = (uint32_t)r;
+  const CompiledPlan& p0 = run.jobs[run.which[0]].plan;
+  // sort-field type of each key: taken from a split that actually has the column (splits without it
+  // only produce None values)
+  int sft[2] = {p0.sort_field_type[0], p0.sort_field_type[1]};
+  for (int i = 0; i < 2; i++)
+    for (size_t s2 = 0; s2 < n; s2++) {
+      const CompiledPlan& pp = run.jobs[run.which[s2]].plan;
+      if (pp.header.sort[i].kind == QW_SORT_COLUMN && pp.header.sort[i].column != 0xFFFFFFFFu) { sft[i] = pp.sort_field_type[i]; break; }
+    }
+  auto better = [&](size_t sa, const QwHit& a, size_t sb, const QwHit& b) {  // a strictly better than b
+    auto cmp_opt = [](int order, bool ha, uint64_t x, bool hb, uint64_t y) {
+      if (ha && hb) { int c = x < y ? -1 : (x > y ? 1 : 0); return order == QW_ORDER_DESC ? c : -c; }
+      return ha ? 1 : (hb ? -1 : 0);
+    };
+    int c = cmp_opt(o1, a.flags & 1, a.v1, b.flags & 1, b.v1);
+    if (!c) c = cmp_opt(o2, (a.flags >> 1) & 1, a.v2, (b.flags >> 1) & 1, b.v2);
+    if (!c) { int d = rank[sa] < rank[sb] ? -1 : (rank[sa] > rank[sb] ? 1 : (a.doc_id < b.doc_id ? -1 : (a.doc_id > b.doc_id ? 1 : 0))); c = o1 == QW_ORDER_DESC ? d : -d; }
+    return c > 0;
+  };
+  std::vector<size_t> pos(n, 0), heap;
+  auto heap_less = [&](size_t x, size_t y) { return better(y, run.outs[y].hits[pos[y]], x, run.outs[x].hits[pos[x]]); };  // max-heap on "better"
+  std::vector<std::string> agg_parts;
+  pb::LeafResourceStats stats_acc;
+  bool any_stats = false;
+  for (size_t s = 0; s < n; s++) {
+    SplitOutput& o = run.outs[s];
+    m.num_hits += o.num_hits;
+    m.num_attempted_splits += 1;
+    m.num_successful_splits += 1;
+    if (!o.hits.empty()) heap.push_back(s);
+    const SplitJob& j = run.jobs[run.which[s]];
+    if (j.plan.header.num_aggs) agg_parts.push_back(build_intermediate_aggs(j.plan, j.dev->view, o.cells.data(), o.cells.size()));
+    add_leaf_stats(stats_acc, split_stats(run, s));
+    any_stats = true;
+  }
+  std::make_heap(heap.begin(), heap.end(), heap_less);
+  while (!heap.empty() && m.partial_hits.size() < k) {
+    std::pop_heap(heap.begin(), heap.end(), heap_less);
+    size_t s = heap.back();
+    const SplitJob& j = run.jobs[run.which[s]];
+    const QwHit& h = run.outs[s].hits[pos[s]];
+    pb::PartialHit ph;
+    ph.split_id = j.meta.split_id;
+    ph.doc_id = h.doc_id;
+    if (h.flags & 1) { ph.has_sv1 = true; ph.sv1 = typed_sort_value(p0.header.sort[0].kind, sft[0], h.v1); }
+    if (h.flags & 2) { ph.has_sv2 = true; ph.sv2 = typed_sort_value(p0.header.sort[1].kind, sft[1], h.v2); }
+    m.partial_hits.push_back(std::move(ph));
+    if (++pos[s] < run.outs[s].hits.size()) std::push_heap(heap.begin(), heap.end(), heap_less);
+    else heap.pop_back();
+  }
+  if (sreq.aggregation_request && !sreq.aggregation_request->empty())
+    m.intermediate_aggregation_result = merge_intermediate_aggs(p0.agg_request, agg_parts);
+  if (any_stats) m.resource_stats = stats_acc;
+  return m;
 }
 
 }  // namespace qw
@@ -283,25 +372,50 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
   qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
-  std::vector<qw::pb::LambdaSingleSplitResult> rs = qw::run_leaf(eng, lr);
-  // IncrementalCollector over the per-split responses (leaf.rs:1778-1785): the merge keeps the leaf's
-  // start_offset = 0 convention (root.rs:1775-1777), so nothing is drained here
-  std::vector<qw::pb::LeafSearchResponse> parts;
-  std::vector<qw::pb::SplitSearchError> failed;
-  for (auto& r : rs) {
-    if (r.is_error) failed.push_back({r.error, r.split_id, true});  // retryable (leaf.rs:1989-2004)
-    else parts.push_back(std::move(r.response));
-  }
+  qw::LeafRun run;
+  qw::run_leaf_raw(eng, lr, run);
+  // the leaf keeps [0, start_offset + max_hits) (root.rs:1775-1777): nothing is drained here
   qw::pb::SearchRequest mreq = lr.search_request;
-  mreq.max_hits += mreq.start_offset;  // keep [0, start_offset + max_hits) at the leaf
+  mreq.max_hits += mreq.start_offset;
   mreq.start_offset = 0;
+  std::vector<qw::pb::SplitSearchError> failed;
+  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, true});  // retryable (leaf.rs:1989-2004)
+  // drop splits whose search failed on the device from the merge set
+  {
+    std::vector<size_t> w2;
+    std::vector<qw::SplitOutput> o2;
+    for (size_t k = 0; k < run.which.size(); k++) {
+      if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, true});
+      else { w2.push_back(run.which[k]); o2.push_back(std::move(run.outs[k])); }
+    }
+    run.which.swap(w2);
+    run.outs.swap(o2);
+  }
+  bool same_types = true;
+  for (size_t k = 1; k < run.which.size(); k++) {
+    const qw::CompiledPlan &a = run.jobs[run.which[0]].plan, &b = run.jobs[run.which[k]].plan;
+    for (int i = 0; i < 2; i++)
+      if (a.header.sort[i].kind != b.header.sort[i].kind || (a.header.sort[i].kind == QW_SORT_COLUMN && a.sort_field_type[i] != b.sort_field_type[i] &&
+                                                              a.header.sort[i].column != 0xFFFFFFFFu && b.header.sort[i].column != 0xFFFFFFFFu))
+        same_types = false;
+  }
   qw::pb::LeafSearchResponse merged;
-  if (parts.empty()) {
+  if (run.which.empty()) {
     if (mreq.aggregation_request && !mreq.aggregation_request->empty())
       merged.intermediate_aggregation_result = qw::merge_intermediate_aggs(qw::parse_agg_request(*mreq.aggregation_request), {});
-  } else if (parts.size() == 1) {
-    merged = std::move(parts[0]);
-  } else merged = qw::merge_responses(mreq, std::move(parts));
+  } else if (same_types) {
+    merged = qw::leaf_merge_fast(mreq, run);
+  } else {
+    std::vector<qw::pb::LeafSearchResponse> parts;
+    for (size_t k = 0; k < run.which.size(); k++) {
+      const qw::SplitJob& j = run.jobs[run.which[k]];
+      qw::SplitOutput& o = run.outs[k];
+      qw::pb::LeafSearchResponse r = qw::build_split_response(j.plan, j.dev->view, j.meta.split_id, o.num_hits, o.hits.data(), o.hits.size(), o.cells.data(), o.cells.size());
+      r.resource_stats = qw::split_stats(run, k);
+      parts.push_back(std::move(r));
+    }
+    merged = parts.size() == 1 ? std::move(parts[0]) : qw::merge_responses(mreq, std::move(parts));
+  }
   for (auto& f : failed) { merged.failed_splits.push_back(f); merged.num_attempted_splits += 1; }
   give(qw::pb::encode_leaf_search_response(merged), resp, resp_len);
   return 0;

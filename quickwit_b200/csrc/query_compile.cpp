@@ -595,13 +595,14 @@ static bool convert_to_u64_ff_val(const pb::SortValue& sv, uint32_t kind, int sf
 }
 
 CompiledPlan compile_plan(const ImageView& img, const std::string& split_id, const pb::SearchRequest& req_in,
-                          const DocMapperInfo& dm, const pb::SplitIdAndFooterOffsets* split_meta) {
+                          const DocMapperInfo& dm, const pb::SplitIdAndFooterOffsets* split_meta, const Json* parsed_ast) {
   pb::SearchRequest req = req_in;
   // rewrite_request (leaf.rs:712-729)
   if (req.max_hits == 0 && req.start_offset == 0) req.sort_fields.clear();
   Ctx cx{img, dm};
-  Json ast = parse_json(req.query_ast, QWGPU_EINVALID_QUERY);
-  TQ root = build(cx, ast, 0);
+  Json local_ast;
+  if (!parsed_ast) { local_ast = parse_json(req.query_ast, QWGPU_EINVALID_QUERY); parsed_ast = &local_ast; }
+  TQ root = build(cx, *parsed_ast, 0);
   // [start_timestamp, end_timestamp) folded into the AST as a filter on the timestamp field
   // (remove_redundant_timestamp_range, leaf.rs:841-946); the clause is skipped when the split's own
   // time range already lies inside the bounds
