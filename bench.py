@@ -44,6 +44,10 @@ sys.path.insert(0, ROOT)
 FRACS = [0.20, 0.10, 0.05, 0.05, 0.02, 0.02, 0.01, 0.01, 0.005, 0.001]
 Q_SETS = 4
 K = 1000
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_window<COLLECT> launch on this workload, from
+# the `ncu --set full` capture summarised in profiles/r1_summary.md (170.8 MB + 4.2 MB). A constant of
+# the workload + build, not measured live (ncu cannot run inside the timed bench).
+NCU_TRAFFIC_BYTES = 175.0e6
 
 
 def parse_args():
@@ -369,7 +373,7 @@ def main():
         "exact_fallbacks": sum(x["fallbacks"] for x in accs),
         "roofline": {"bound": "hbm", "kernel": "k_window<COLLECT>", "achieved": achieved, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (a.splits, a.docs_per_split) == (32, 3_125_000) else None,
                      "algorithmic_bytes_per_launch": alg_bytes / n_main, "avg_launch_us": 1e6 * main_s / n_main},
         "clocks": clocks,
     }
