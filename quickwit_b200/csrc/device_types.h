@@ -1,5 +1,6 @@
 // device_types.h — structures shared by the host engine (engine.cu host half) and the kernels.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/qwgpu_format.h"
@@ -58,20 +59,28 @@ struct DAgg {
 };
 static_assert(sizeof(DInstr) % 16 == 0 && sizeof(DCol) % 16 == 0 && sizeof(DAgg) % 16 == 0, "uint4-copied structs");
 
-// Composite sort key: a 192-bit big-endian bit string, greater = better.
-//   [has1:1][lin1:10][pay1:64][has2:1][pay2:64][doc':32][0:20]
-// lin1 is a value-linear 10-bit bucket of the first sort value (so the first radix digit already
-// discriminates well), pay* are order-preserving payloads (complemented for ascending order) and
-// doc' is the doc id (complemented when the first order is ascending): exactly the total order of
-// SegmentPartialHitSortingKey (quickwit-search/src/collector.rs:1082-1112).
-struct DKeySpec {
+// Composite sort key: a big-endian bit string of at most 192 bits, greater = better, packed from the
+// most significant bit with no padding between fields:
+//   [has1:1][r1:rbits0] [has2:1][r2:rbits1] [doc':doc_bits]
+// r_i is the RANK of sort value i: the column's bit-packed raw value (raw_max - raw for ascending
+// order), or for _score a value-linear 10-bit bucket followed by the order-preserving f32 bits (42
+// bits as first key, 32 as second). A field that cannot discriminate (doc-id sort, column absent from
+// the split) contributes no bits at all. doc' is the doc id (complemented within doc_bits when the
+// first order is ascending). This is exactly the total order of SegmentPartialHitSortingKey
+// (quickwit-search/src/collector.rs:1082-1112), None last; because the fields are only as wide as
+// the split's data needs, every 11-bit radix digit of the key discriminates.
+struct alignas(16) DKeySpec {
   uint32_t kind[2], order[2], col[2];
+  uint32_t rbits[2];     // width of r_i
+  uint32_t hasbit[2];    // 1: a has-value bit precedes r_i
+  uint32_t doc_bits, total_bits;
+  uint32_t top_mode;     // how the first 11 key bits are derived cheaply (QW_TOP_*)
   float score_scale;     // SCORE: lin = min(1023, (uint)(score * scale))
-  uint32_t lin_shr;      // COLUMN/DOCID: lin = min(1023, (r' >> shr) << shl)
-  uint32_t lin_shl;
-  uint32_t pad;
-  uint64_t raw_max;      // r' = order == DESC ? raw : raw_max - raw
+  uint64_t raw_max[2];   // r_i = order == DESC ? raw : raw_max - raw
+  uint64_t pad;          // sizeof % 16 == 0: copied to shared memory as uint4
 };
+static_assert(sizeof(DKeySpec) % 16 == 0, "uint4-copied struct");
+enum { QW_TOP_FULL = 0, QW_TOP_SCORE = 1, QW_TOP_COLUMN = 2, QW_TOP_DOC = 3 };
 
 struct DThresh {  // per split, device-resident, written by k_pick
   uint64_t key[3];       // candidates are docs with composite key >= key
@@ -105,15 +114,18 @@ struct DSplitPlan {
   uint64_t out_nhits;      // device address of uint32 (hits written by k_select)
 };
 
+static_assert(offsetof(DSplitPlan, key) % 16 == 0 && sizeof(DSplitPlan) % 16 == 0, "DKeySpec is read as uint4");
+
 struct SmemLevel {
   uint32_t req, shd, nt, cnt, msum, ssum;  // byte offsets; 0xFFFFFFFF = not allocated
   uint32_t rsc, pad;                       // result score array of the level (msum, else ssum)
 };
 struct SmemLayout {
-  uint32_t instr, cols, aggs;
+  uint32_t instr, cols, aggs, key;
   SmemLevel lvl[QW_MAX_LEVELS];
   uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
   uint32_t rng, blkrec, termblk, stage, ent, hist, misc;  // hist aliases ent (dead by collect time)
+  uint32_t l0hist;  // COLLECT pass: exact level-0 digit histogram of the window's matches (0xFFFFFFFF: not recorded)
   uint32_t total;
 };
 
@@ -132,5 +144,13 @@ struct KParams {
   uint32_t use_prefix;  // MODE_HIST: restrict to docs whose key matches thresh prefix
   uint32_t smem_aggs;   // 1: aggregation counts privatised in shared memory
   uint32_t stage_bytes; // capacity of the posting staging area
+  // second-chance top-K (engine.cu): a COLLECT pass may record the exact level-0 histogram and each
+  // window's best level-0 digit; refinement passes then skip verified splits and windows that cannot
+  // hold a candidate, and only emit candidates (hit counts / aggregations are already final)
+  uint32_t rec_l0;        // COLLECT: record out_hist + wmax
+  uint32_t refine;        // 1: skip splits with split_state == 0 and windows with wmax < threshold digit
+  uint32_t cands_only;    // COLLECT: emit candidates only
+  uint16_t* wmax;         // per flat window: 1 + best level-0 digit among its matches (0: no match)
+  const uint32_t* split_state;  // per split: 1 = needs refinement
   SmemLayout sm;
 };

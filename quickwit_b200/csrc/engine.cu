@@ -5,6 +5,7 @@
 // Replaces, for one leaf request: open_index_with_caches + warmup (quickwit-search/src/leaf.rs:
 // 210-251,269-472) at register time, and searcher.search(&query,&collector) (leaf.rs:637) per call.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 
 #include "engine.h"
@@ -85,8 +86,9 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
   sm_count = prop.multiProcessorCount;
   max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * QW_CAND_CAP));
 }
 
@@ -390,20 +392,29 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
   if (ks.kind[1] == QW_SORT_DOCID) ks.kind[1] = QW_SORT_NONE;  // _doc as 2nd key extracts None
   if (ks.kind[0] == QW_SORT_NONE) ks.kind[0] = QW_SORT_DOCID;
   if (ks.kind[1] == QW_SORT_NONE) ks.order[1] = QW_ORDER_DESC;  // SortByPair::sort_orders default
-  ks.score_scale = 0.f; ks.lin_shr = 0; ks.lin_shl = 0; ks.raw_max = 0;
+  ks.score_scale = 0.f;
+  ks.doc_bits = bits_needed64(P.num_docs ? P.num_docs - 1 : 0);
+  ks.total_bits = ks.doc_bits;
+  for (int i = 0; i < 2; i++) {
+    ks.rbits[i] = 0; ks.hasbit[i] = 0; ks.raw_max[i] = 0;
+    if (ks.kind[i] == QW_SORT_SCORE) {
+      ks.hasbit[i] = 1;
+      ks.rbits[i] = i == 0 ? 42 : 32;  // [lin:10 |] order-preserving f32 bits
+    } else if (ks.kind[i] == QW_SORT_COLUMN) {
+      const uint32_t bits = L.cols[ks.col[i]].bits;
+      ks.hasbit[i] = 1;
+      ks.rbits[i] = bits;
+      ks.raw_max[i] = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+    }
+    ks.total_bits += ks.hasbit[i] + ks.rbits[i];
+  }
   if (ks.kind[0] == QW_SORT_SCORE) {
     float smax = L.score_max > 1e-30f ? L.score_max : 1.0f;
     ks.score_scale = 1024.0f / smax;
-  } else if (ks.kind[0] == QW_SORT_COLUMN) {
-    uint32_t bits = L.cols[ks.col[0]].bits;
-    ks.raw_max = bits == 64 ? ~0ull : ((1ull << bits) - 1);
-    if (bits > 10) ks.lin_shr = bits - 10; else ks.lin_shl = 10 - bits;
-  } else {
-    uint32_t bits = bits_needed64(P.num_docs ? P.num_docs - 1 : 0);
-    ks.raw_max = bits == 0 ? 0 : ((1ull << bits) - 1);
-    if (ks.kind[1] != QW_SORT_NONE) ks.lin_shr = 63;  // (None, v2, doc): doc rank must not precede v2
-    else if (bits > 10) ks.lin_shr = bits - 10; else ks.lin_shl = 10 - bits;
-  }
+    ks.top_mode = QW_TOP_SCORE;
+  } else if (ks.kind[0] == QW_SORT_COLUMN && ks.rbits[0] >= 10) ks.top_mode = QW_TOP_COLUMN;
+  else if (ks.kind[0] == QW_SORT_DOCID && ks.kind[1] == QW_SORT_NONE && ks.doc_bits >= 11) ks.top_mode = QW_TOP_DOC;
+  else ks.top_mode = QW_TOP_FULL;
   // aggregations
   if (ph->num_aggs > QW_MAX_DAGGS) fail(QWGPU_EUNSUPPORTED, "more than %d aggregation nodes", QW_MAX_DAGGS);
   std::vector<uint32_t> bases;
@@ -441,7 +452,7 @@ static uint32_t stage_bytes_for(uint32_t W) {
 }
 
 static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_msum, uint32_t need_ssum,
-                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn) {
+                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn, bool rec_l0) {
   SmemLayout L;
   memset(&L, 0xFF, sizeof L);
   uint32_t off = 0;
@@ -450,6 +461,7 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.instr = take(std::max(max_instr, 1u) * sizeof(DInstr));
   L.cols = take(std::max(max_cols, 1u) * sizeof(DCol));
   L.aggs = take(std::max(max_aggs, 1u) * sizeof(DAgg));
+  L.key = take(sizeof(DKeySpec));
   for (uint32_t l = 0; l < n_levels; l++) {
     L.lvl[l].req = take(W / 8);
     L.lvl[l].shd = take(W / 8);
@@ -467,6 +479,7 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.stage = take(stage_bytes_for(W));
   L.ent = L.stage;
   L.hist = L.stage;  // histogram / privatised aggregation counters reuse the staging area at collect time
+  if (rec_l0) L.l0hist = take(QW_HIST_BINS * 4);
   L.total = off;
   return L;
 }
@@ -475,6 +488,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
                     const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats) {
   const uint32_t n_in = (uint32_t)sp.size();
   outs.assign(n_in, SplitOutput());
+  static const bool trace = getenv("QWGPU_TRACE") != nullptr;  // host phase timings on stderr
+  using tclock = std::chrono::steady_clock;
+  const auto t_begin = tclock::now();
   CUDA_CHECK(cudaSetDevice(device));
   // ---- lower every plan; splits whose plan cannot be lowered fail individually ----------------------
   std::vector<Lowered> low;
@@ -494,13 +510,25 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   }
   const uint32_t n = (uint32_t)low.size();
   if (n == 0) return;
+  const auto t_lowered = tclock::now();
 
   // ---- batch-wide parameters --------------------------------------------------------------------------
   uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, need_msum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
   bool scoring = false, any_topk = false, any_aggs = false, smem_aggs = true;
-  uint32_t max_cells = 0;
+  uint32_t max_cells = 0, max_key_bits = 0;
   uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0;
+  // second-chance top-K: when no plan ranks by _score first, the collect pass also records the exact
+  // level-0 histogram and every window's best digit, so that a failed sampled threshold is repaired
+  // by a candidates-only pass over the few windows that can hold candidates
+  bool rec_l0 = true;
+  // every plan has the BM25 top-K shape => the specialised UNION instantiation of the collect kernel
+  bool all_union = true;
   for (auto& L : low) {
+    if (!(L.P.fused_score_root && L.P.max_hits && !L.P.sa.present && !L.P.n_aggs && L.P.key.kind[0] == QW_SORT_SCORE &&
+          L.P.key.order[0] == QW_ORDER_DESC))
+      all_union = false;
+    if (L.P.max_hits && L.P.key.kind[0] == QW_SORT_SCORE) rec_l0 = false;
+    max_key_bits = std::max(max_key_bits, L.P.key.total_bits);
     n_levels = std::max(n_levels, L.P.n_levels);
     need_cnt |= L.need_cnt; need_ssum |= L.need_ssum; need_msum |= L.need_msum;
     max_instr = std::max(max_instr, L.P.n_instr); max_cols = std::max(max_cols, L.P.n_cols); max_aggs = std::max(max_aggs, L.P.n_aggs);
@@ -510,13 +538,14 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
     tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
   }
+  rec_l0 = rec_l0 && any_topk;
   // window size: as large as shared memory allows for the configured blocks/SM (per-window fixed
   // costs — staging, program interpretation, barriers — amortise over more postings)
   uint32_t W = 32768;
   if (const char* e = getenv("QWGPU_W")) W = (uint32_t)atoi(e);
   SmemLayout lay;
   for (;;) {
-    lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn);
+    lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0);
     if ((int)lay.total + 1024 <= max_smem_optin / QW_MIN_BLOCKS_PER_SM || W == 1024) break;
     W >>= 1;
   }
@@ -542,7 +571,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
          o_fws = al(o_fwa + (n + 1) * 4), blob_bytes = al(o_fws + (n + 1) * 4);
   // scratch: thresholds, histograms, candidates
-  size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_cand = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
+  size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
+         s_wmax = al(s_state + (size_t)n * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
          scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
@@ -602,53 +632,67 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (max_cells * 4 > kp.stage_bytes || max_cells > QW_SMEM_AGG_CELLS) smem_aggs = false;
   kp.smem_aggs = (any_aggs && smem_aggs) ? 1 : 0;
   kp.sm = lay;
+  kp.wmax = (uint16_t*)(slot->d_scratch + s_wmax);
+  kp.split_state = (const uint32_t*)(slot->d_scratch + s_state);
   int occ = 1;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT>, QW_THREADS, lay.total));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT, false>, QW_THREADS, lay.total));
   occ = std::max(occ, 1);
-  auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix) {
+  enum { F_REC = 1, F_REFINE = 2, F_CANDS_ONLY = 4 };
+  auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix, uint32_t flags) {
     KParams q = kp;
     q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
     q.total_work = sampled ? fw_smp[n] : fw_all[n];
     q.stride = sampled ? stride : 1;
     q.level = level;
     q.use_prefix = use_prefix;
+    q.rec_l0 = (flags & F_REC) ? 1 : 0;
+    q.refine = (flags & F_REFINE) ? 1 : 0;
+    q.cands_only = (flags & F_CANDS_ONLY) ? 1 : 0;
     if (q.total_work == 0) return;
     uint32_t grid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * occ));
-    if (mode == qwk::MODE_HIST) qwk::k_window<qwk::MODE_HIST><<<grid, QW_THREADS, lay.total, st>>>(q);
-    else qwk::k_window<qwk::MODE_COLLECT><<<grid, QW_THREADS, lay.total, st>>>(q);
+    if (mode == qwk::MODE_HIST) qwk::k_window<qwk::MODE_HIST, false><<<grid, QW_THREADS, lay.total, st>>>(q);
+    else if (all_union) qwk::k_window<qwk::MODE_COLLECT, true><<<grid, QW_THREADS, lay.total, st>>>(q);
+    else qwk::k_window<qwk::MODE_COLLECT, false><<<grid, QW_THREADS, lay.total, st>>>(q);
     stats.launches++;
   };
   const uint32_t sel_smem = 3 * 8 * QW_CAND_CAP;  // [all first words | 3 x QW_SEL_MAX survivors] or 3 x all (degenerate ties)
-  auto run_collect = [&]() {
-    CUDA_CHECK(cudaMemsetAsync(slot->d_out, 0, out_bytes, st));
+  auto run_collect = [&](uint32_t flags) {
+    if (!(flags & F_CANDS_ONLY)) CUDA_CHECK(cudaMemsetAsync(slot->d_out, 0, out_bytes, st));
     CUDA_CHECK(cudaEventRecord(slot->ev2, st));
-    launch_window(qwk::MODE_COLLECT, false, 0, 0);
+    launch_window(qwk::MODE_COLLECT, false, 0, 0, flags);
     CUDA_CHECK(cudaEventRecord(slot->ev3, st));
-    if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans); stats.launches++; }
+    if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans, kp.cols); stats.launches++; }
     CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     stats.d2h_bytes += out_bytes;
   };
+  // a split's candidate set is good when it holds at least min(K, eligible) and did not overflow
+  std::vector<uint32_t> state(n, 0);
   auto verify = [&]() -> bool {
+    bool all = true;
     for (uint32_t i = 0; i < n; i++) {
+      state[i] = 0;
       if (low[i].P.max_hits == 0) continue;
       const uint8_t* ob = slot->h_out + out_off[i];
       uint64_t eligible = ((const uint64_t*)ob)[1];
       uint32_t cand = *(const uint32_t*)(ob + 20);
-      if (cand > QW_CAND_CAP) return false;
-      if (cand < std::min<uint64_t>(low[i].P.max_hits, eligible)) return false;
+      if (cand > QW_CAND_CAP || cand < std::min<uint64_t>(low[i].P.max_hits, eligible)) { state[i] = 1; all = false; }
     }
-    return true;
+    return all;
   };
 
+  const auto t_staged = tclock::now();
   CUDA_CHECK(cudaEventRecord(slot->ev0, st));
-  CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));  // thresholds + histograms
+  CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));  // thresholds, histograms, refinement state
   bool ok = true;
+  float main_ms = 0;
+  auto add_main = [&]() { float ms = 0; cudaEventElapsedTime(&ms, slot->ev2, slot->ev3); main_ms += ms; };
   if (any_topk && stride > 1) {
     // fast path: threshold from a 1/stride sample of the windows, verified after the collect pass
-    launch_window(qwk::MODE_HIST, true, 0, 0);
-    qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 1, stride);
+    launch_window(qwk::MODE_HIST, true, 0, 0, 0);
+    qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 1, stride, nullptr);
     stats.launches++;
-    run_collect();
+    if (rec_l0) CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
+    run_collect(rec_l0 ? F_REC : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     ok = verify();
@@ -656,31 +700,50 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       float ms = 0;
       cudaEventElapsedTime(&ms, slot->ev0, slot->ev1);
       stats.gpu_time_us += ms * 1000.f;
+      add_main();
       stats.exact_fallbacks++;
       CUDA_CHECK(cudaEventRecord(slot->ev0, st));
     }
   }
   if (!any_topk) {
-    run_collect();
+    run_collect(0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
   } else if (stride == 1 || !ok) {
     // exact radix select over the composite key: one histogram pass per 11-bit digit until the
-    // candidate set of every split fits QW_CAND_CAP (normally a single pass)
-    CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));
+    // candidate set of every split fits QW_CAND_CAP. After a failed sampled threshold with the
+    // level-0 histogram on record (refine), level 0 needs no pass at all, only the failing splits are
+    // revisited, and windows whose best digit is below the threshold digit are skipped.
+    const bool refine = !ok && rec_l0;
+    const uint32_t* d_state = refine ? kp.split_state : nullptr;
     std::vector<DThresh> th(n);
-    for (uint32_t level = 0; level * QW_DIGIT_BITS < QW_KEY_BITS; level++) {
-      CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
-      launch_window(qwk::MODE_HIST, false, level, level > 0 ? 1 : 0);
-      qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, level, 0, 1);
+    auto all_done = [&]() {
+      for (uint32_t i = 0; i < n; i++) if (low[i].P.max_hits && (!refine || state[i]) && !th[i].done) return false;
+      return true;
+    };
+    uint32_t level = 0;
+    bool done = false;
+    if (refine) {
+      CUDA_CHECK(cudaMemcpyAsync(slot->d_scratch + s_state, state.data(), n * 4, cudaMemcpyHostToDevice, st));
+      qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 0, 1, d_state);
       stats.launches++;
       CUDA_CHECK(cudaMemcpyAsync(th.data(), slot->d_scratch + s_thr, n * sizeof(DThresh), cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
-      bool all_done = true;
-      for (uint32_t i = 0; i < n; i++) if (low[i].P.max_hits && !th[i].done) all_done = false;
-      if (all_done) break;
+      done = all_done();
+      level = 1;
+    } else {
+      CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));
     }
-    run_collect();
+    for (; !done && level * QW_DIGIT_BITS < std::max(max_key_bits, 1u); level++) {
+      CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
+      launch_window(qwk::MODE_HIST, false, level, level > 0 ? 1 : 0, refine ? F_REFINE : 0);
+      qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, level, 0, 1, d_state);
+      stats.launches++;
+      CUDA_CHECK(cudaMemcpyAsync(th.data(), slot->d_scratch + s_thr, n * sizeof(DThresh), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      done = all_done();
+    }
+    run_collect(refine ? (F_REFINE | F_CANDS_ONLY) : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (!verify()) fail(QWGPU_EINTERNAL, "top-K candidate selection failed verification");
@@ -690,10 +753,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     float ms = 0;
     cudaEventElapsedTime(&ms, slot->ev0, slot->ev1);
     stats.gpu_time_us += ms * 1000.f;
-    cudaEventElapsedTime(&ms, slot->ev2, slot->ev3);
-    stats.main_kernel_us = ms * 1000.f;
+    add_main();
+    stats.main_kernel_us = main_ms * 1000.f;
   }
 
+  const auto t_searched = tclock::now();
   // ---- unpack ---------------------------------------------------------------------------------------
   for (uint32_t i = 0; i < n; i++) {
     SplitOutput& o = outs[idx[i]];
@@ -723,6 +787,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     const QwAggNode* an = (const QwAggNode*)(plans[idx[i]] + sizeof(QwPlanHeader) + (size_t)ph->num_nodes * sizeof(QwPlanNode));
     for (uint32_t a = 0; a < ph->num_aggs; a++) if (an[a].column != 0xFFFFFFFFu) bytes += col_bytes(an[a].column, o.num_hits);
     o.algorithmic_bytes = bytes;
+  }
+  if (trace) {
+    auto us = [](tclock::time_point a, tclock::time_point b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    fprintf(stderr, "[qwgpu] search: lower %ld us, stage %ld us, launch+wait %ld us (device %.0f us), unpack %ld us\n", us(t_begin, t_lowered),
+            us(t_lowered, t_staged), us(t_staged, t_searched), stats.gpu_time_us, us(t_searched, tclock::now()));
   }
 }
 

@@ -38,13 +38,23 @@ __device__ __forceinline__ bool key_ge(const Key& a, const Key& b) {
 }
 __device__ __forceinline__ bool key_lt(const Key& a, const Key& b) { return !key_ge(a, b); }
 
-__device__ __forceinline__ Key make_key(uint32_t has1, uint32_t lin1, uint64_t pay1, uint32_t has2,
-                                        uint64_t pay2, uint32_t docp) {
-  Key k;
-  k.w0 = ((uint64_t)has1 << 63) | ((uint64_t)(lin1 & 1023u) << 53) | (pay1 >> 11);
-  k.w1 = (pay1 << 53) | ((uint64_t)has2 << 52) | (pay2 >> 12);
-  k.w2 = (pay2 << 52) | ((uint64_t)docp << 20);
-  return k;
+// ORs the low `nbits` bits of v (v < 2^nbits) into the key at bit position `pos`, counted from the
+// most significant bit of the 192-bit string
+__device__ __forceinline__ void key_put(Key& k, uint32_t pos, uint64_t v, uint32_t nbits) {
+  if (nbits == 0) return;
+  const uint32_t sh = 192u - pos - nbits, w = sh >> 6, s = sh & 63u;
+  const uint64_t lo = v << s, hi = s ? v >> (64u - s) : 0ull;
+  if (w == 0) { k.w2 |= lo; k.w1 |= hi; }
+  else if (w == 1) { k.w1 |= lo; k.w0 |= hi; }
+  else k.w0 |= lo;
+}
+__device__ __forceinline__ uint64_t key_get(const Key& k, uint32_t pos, uint32_t nbits) {
+  if (nbits == 0) return 0;
+  const uint32_t sh = 192u - pos - nbits, w = sh >> 6, s = sh & 63u;
+  const uint64_t lo = w == 0 ? k.w2 : (w == 1 ? k.w1 : k.w0);
+  const uint64_t hi = w == 0 ? k.w1 : (w == 1 ? k.w0 : 0ull);
+  const uint64_t v = s ? ((lo >> s) | (hi << (64u - s))) : lo;
+  return nbits >= 64 ? v : (v & ((1ull << nbits) - 1));
 }
 // 11-bit digit number `level` counted from the most significant bit of the 192-bit key
 __device__ __forceinline__ uint32_t key_digit(const Key& k, uint32_t level) {
@@ -259,90 +269,58 @@ __device__ __forceinline__ void fold_block_dyn(uint32_t blk_off, const uint8_t* 
   else { if (cn) fold_block<false, true, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); else fold_block<false, false, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); }
 }
 
-// The 11 most significant bits of the composite key ([has1 | lin1]) — enough for the level-0 radix
-// digit and for the cheap threshold pre-filter; avoids building the 192-bit key for every match.
-__device__ __forceinline__ uint32_t key_top11(const DKeySpec& ks, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
-  const bool desc1 = ks.order[0] == QW_ORDER_DESC;
-  if (ks.kind[0] == QW_SORT_SCORE) {
-    float x = __fmul_rn(score, ks.score_scale);
-    uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
-    return 1024u | (desc1 ? l : 1023u - l);
-  }
-  if (ks.kind[0] == QW_SORT_COLUMN && ks.col[0] != 0xFFFFFFFFu) {
-    const DCol& c = cols[ks.col[0]];
-    uint64_t a, b;
-    col_range(base, c, doc, a, b);
-    if (a == b) return 0;
-    uint64_t raw = col_raw(base, c, a);
-    uint64_t r = desc1 ? raw : ks.raw_max - raw;
-    uint64_t l = (r >> ks.lin_shr) << ks.lin_shl;
-    return 1024u | (l > 1023 ? 1023u : (uint32_t)l);
-  }
-  uint32_t r = desc1 ? doc : (uint32_t)ks.raw_max - doc;
-  uint64_t l = ((uint64_t)r >> ks.lin_shr) << ks.lin_shl;
-  return l > 1023 ? 1023u : (uint32_t)l;
-}
-
 // Composite key + eligibility of one matched doc (sort-value extraction:
 // SortingFieldExtractorComponent, quickwit-search/src/collector.rs:139-205)
 struct DocKey {
   Key key;
   bool eligible;
 };
-__device__ __forceinline__ DocKey doc_key(const DSplitPlan& P, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
-  const DKeySpec& ks = P.key;
-  uint32_t has1 = 0, has2 = 0, lin = 0;
-  uint64_t v1 = 0, v2 = 0, pay1 = 0, pay2 = 0;
+__device__ __forceinline__ uint32_t score_lin(const DKeySpec& ks, float score, bool desc) {
+  const float x = __fmul_rn(score, ks.score_scale);
+  const uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
+  return desc ? l : 1023u - l;
+}
+__device__ __forceinline__ DocKey doc_key(const DSplitPlan& P, const DKeySpec& ks, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
+  uint32_t has[2] = {0, 0};
+  uint64_t v[2] = {0, 0}, r[2] = {0, 0};
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const bool desc = ks.order[i] == QW_ORDER_DESC;
+    if (ks.kind[i] == QW_SORT_SCORE) {
+      has[i] = 1;
+      v[i] = f64_to_u64_dev((double)score);
+      const uint32_t o = f32_ordered(score);
+      r[i] = desc ? o : ~o;
+      if (i == 0) r[i] |= (uint64_t)score_lin(ks, score, desc) << 32;
+    } else if (ks.kind[i] == QW_SORT_COLUMN && ks.col[i] != 0xFFFFFFFFu) {
+      const DCol& c = cols[ks.col[i]];
+      uint64_t a, b;
+      col_range(base, c, doc, a, b);
+      if (a != b) {
+        has[i] = 1;
+        const uint64_t raw = col_raw(base, c, a);
+        v[i] = c.min_value + c.gcd * raw;
+        r[i] = desc ? raw : ks.raw_max[i] - raw;
+      }
+    }  // doc-id order / column absent from the split: the field contributes no key bits
+  }
   const bool desc1 = ks.order[0] == QW_ORDER_DESC;
-  if (ks.kind[0] == QW_SORT_SCORE) {
-    has1 = 1;
-    v1 = f64_to_u64_dev((double)score);
-    uint32_t o = f32_ordered(score);
-    pay1 = (uint64_t)(desc1 ? o : ~o) << 32;
-    float x = __fmul_rn(score, ks.score_scale);
-    uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
-    lin = desc1 ? l : 1023u - l;
-  } else if (ks.kind[0] == QW_SORT_COLUMN && ks.col[0] != 0xFFFFFFFFu) {
-    const DCol& c = cols[ks.col[0]];
-    uint64_t a, b;
-    col_range(base, c, doc, a, b);
-    if (a != b) {
-      has1 = 1;
-      uint64_t raw = col_raw(base, c, a);
-      v1 = c.min_value + c.gcd * raw;
-      pay1 = desc1 ? v1 : ~v1;
-      uint64_t r = desc1 ? raw : ks.raw_max - raw;
-      uint64_t l = (r >> ks.lin_shr) << ks.lin_shl;
-      lin = l > 1023 ? 1023u : (uint32_t)l;
-    }
-  } else {  // doc-id order (also: sort column absent from the split => every value is None)
-    uint32_t r = desc1 ? doc : (uint32_t)ks.raw_max - doc;
-    uint64_t l = ((uint64_t)r >> ks.lin_shr) << ks.lin_shl;
-    lin = l > 1023 ? 1023u : (uint32_t)l;
-  }
-  const bool desc2 = ks.order[1] == QW_ORDER_DESC;
-  if (ks.kind[1] == QW_SORT_SCORE) {
-    has2 = 1;
-    v2 = f64_to_u64_dev((double)score);
-    uint32_t o = f32_ordered(score);
-    pay2 = (uint64_t)(desc2 ? o : ~o) << 32;
-  } else if (ks.kind[1] == QW_SORT_COLUMN && ks.col[1] != 0xFFFFFFFFu) {
-    const DCol& c = cols[ks.col[1]];
-    uint64_t a, b;
-    col_range(base, c, doc, a, b);
-    if (a != b) {
-      has2 = 1;
-      v2 = c.min_value + c.gcd * col_raw(base, c, a);
-      pay2 = desc2 ? v2 : ~v2;
-    }
-  }
+  const uint32_t docmask = ks.doc_bits >= 32 ? 0xFFFFFFFFu : ((1u << ks.doc_bits) - 1);
   DocKey out;
-  out.key = make_key(has1, lin, pay1, has2, pay2, desc1 ? doc : ~doc);
+  out.key = Key{0, 0, 0};
+  uint32_t pos = 0;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    if (ks.hasbit[i]) { key_put(out.key, pos, has[i], 1); pos++; }
+    key_put(out.key, pos, r[i], ks.rbits[i]);
+    pos += ks.rbits[i];
+  }
+  key_put(out.key, pos, desc1 ? doc : docmask - doc, ks.doc_bits);
   out.eligible = true;
   if (P.sa.present) {
     // GenericQuickwitSegmentTopKCollector::collect_top_k_vals (top_k_collector.rs:663-699)
-    int c = order_cmp_opt(ks.order[0], has1, v1, P.sa.has_v1, P.sa.v1);
-    if (!c) c = order_cmp_opt(ks.order[1], has2, v2, P.sa.has_v2, P.sa.v2);
+    int c = order_cmp_opt(ks.order[0], has[0], v[0], P.sa.has_v1, P.sa.v1);
+    if (!c) c = order_cmp_opt(ks.order[1], has[1], v[1], P.sa.has_v2, P.sa.v2);
     if (P.sa.compare_on_equal) {
       if (!c) c = P.sa.precomp_order;
       if (!c) c = order_cmp(ks.order[0], doc, P.sa.doc_id);
@@ -352,22 +330,93 @@ __device__ __forceinline__ DocKey doc_key(const DSplitPlan& P, const DCol* cols,
   return out;
 }
 
-// ---- aggregation collection (dense cells; mirrors oracle agg_collect) -------------------------------
-__device__ __forceinline__ void agg_count(const KParams& p, const Sm& sm, QwAggCell* cells, uint32_t cell) {
-  if (p.smem_aggs) atomicAdd(&sm.u32(sm.L->hist)[cell], 1u);
-  else atomicAdd((unsigned long long*)&cells[cell].count, 1ull);
+// The 11 most significant bits of the composite key — the level-0 radix digit and the cheap
+// threshold pre-filter — without building the whole key when the first field is wide enough.
+__device__ __forceinline__ uint32_t key_top11(const DSplitPlan& P, const DKeySpec& ks, const DCol* cols, const uint8_t* base, uint32_t doc, float score) {
+  const bool desc1 = ks.order[0] == QW_ORDER_DESC;
+  if (ks.top_mode == QW_TOP_SCORE) return 1024u | score_lin(ks, score, desc1);
+  if (ks.top_mode == QW_TOP_COLUMN) {
+    const DCol& c = cols[ks.col[0]];
+    uint64_t a, b;
+    col_range(base, c, doc, a, b);
+    if (a == b) return 0;
+    const uint64_t raw = col_raw(base, c, a);
+    return 1024u | (uint32_t)((desc1 ? raw : ks.raw_max[0] - raw) >> (ks.rbits[0] - 10));
+  }
+  if (ks.top_mode == QW_TOP_DOC) {
+    const uint32_t docmask = ks.doc_bits >= 32 ? 0xFFFFFFFFu : ((1u << ks.doc_bits) - 1);
+    return (desc1 ? doc : docmask - doc) >> (ks.doc_bits - 11);
+  }
+  return (uint32_t)(doc_key(P, ks, cols, base, doc, score).key.w0 >> 53);
 }
-__device__ __forceinline__ void agg_stats(const DAgg& g, const DCol& c, const uint8_t* base, QwAggCell* cells, uint32_t cell, uint32_t doc) {
-  uint64_t a, b;
-  col_range(base, c, doc, a, b);
-  QwAggCell* out = &cells[g.cell_base + cell];
-  for (uint64_t i = a; i < b; i++) {
-    uint64_t m = c.min_value + c.gcd * col_raw(base, c, i);
-    atomicAdd((unsigned long long*)&out->count, 1ull);
-    if (c.type == QW_COL_F64) atomicAdd((double*)&out->sum_bits, mapped_to_f64(c.type, m));
-    else atomicAdd((unsigned long long*)&out->sum_bits, (unsigned long long)((c.type == QW_COL_U64 || c.type == QW_COL_BOOL) ? m : (m ^ (1ull << 63))));
-    atomicMax((unsigned long long*)&out->min_mapped, (unsigned long long)~m);  // min kept as max(~m): zero-initialisable
-    atomicMax((unsigned long long*)&out->max_mapped, (unsigned long long)m);
+
+// ---- aggregation collection (dense cells; mirrors oracle agg_collect) -------------------------------
+// All 32 lanes of a warp call these together (`on` = this lane holds a matched doc): lanes that hit
+// the same cell are combined with match_any before touching the counter, because time-ordered log
+// data sends whole warps to the same histogram / terms bucket and same-address atomics serialise.
+#define QW_FULL 0xFFFFFFFFu
+__device__ __forceinline__ void warp_count(uint32_t* ctr, uint32_t idx, bool on, uint32_t lane) {
+  const uint32_t peers = __match_any_sync(QW_FULL, on ? idx : 0xFFFFFFFFu);
+  if (on && (uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(&ctr[idx], (uint32_t)__popc(peers));
+}
+// Same contract, cheaper when the counted lanes usually agree (histogram digits of time-ordered keys):
+// one broadcast + ballot decides between a single aggregated atomic and plain per-lane atomics.
+__device__ __forceinline__ void warp_count_uniform(uint32_t* ctr, uint32_t idx, bool on, uint32_t lane) {
+  const uint32_t m = __ballot_sync(QW_FULL, on);
+  if (m == 0) return;
+  const uint32_t lead = __ffs(m) - 1;
+  const uint32_t same = __ballot_sync(QW_FULL, on && idx == __shfl_sync(QW_FULL, idx, lead));
+  if (same == m) { if (lane == lead) atomicAdd(&ctr[idx], (uint32_t)__popc(m)); }
+  else if (on) atomicAdd(&ctr[idx], 1u);
+}
+__device__ __forceinline__ void agg_count(const KParams& p, const Sm& sm, QwAggCell* cells, uint32_t cell, bool on, uint32_t lane) {
+  const uint32_t peers = __match_any_sync(QW_FULL, on ? cell : 0xFFFFFFFFu);
+  if (on && (uint32_t)(__ffs(peers) - 1) == lane) {
+    if (p.smem_aggs) atomicAdd(&sm.u32(sm.L->hist)[cell], (uint32_t)__popc(peers));
+    else atomicAdd((unsigned long long*)&cells[cell].count, (unsigned long long)__popc(peers));
+  }
+}
+__device__ __forceinline__ void agg_stats(const DAgg& g, const DCol& c, const uint8_t* base, QwAggCell* cells, uint32_t cell, uint32_t doc, bool on, uint32_t lane) {
+  uint64_t a = 0, b = 0;
+  if (on) col_range(base, c, doc, a, b);
+  const uint32_t nv = (uint32_t)(b - a);
+  const uint32_t maxv = __reduce_max_sync(QW_FULL, nv);
+  const bool is_f64 = c.type == QW_COL_F64;
+  const bool plain = c.type == QW_COL_U64 || c.type == QW_COL_BOOL;
+  for (uint32_t k = 0; k < maxv; k++) {
+    const bool ok = k < nv;
+    const uint32_t okmask = __ballot_sync(QW_FULL, ok);
+    uint64_t m = 0;
+    if (ok) m = c.min_value + c.gcd * col_raw(base, c, a + k);
+    const uint32_t peers = __match_any_sync(QW_FULL, ok ? cell : 0xFFFFFFFFu);
+    QwAggCell* out = &cells[g.cell_base + cell];
+    if (__all_sync(QW_FULL, !ok || peers == okmask)) {
+      // the whole warp feeds one cell: butterfly-reduce, one lane issues the four atomics
+      unsigned long long isum = ok ? (plain ? m : (m ^ (1ull << 63))) : 0ull;
+      double dsum = (ok && is_f64) ? mapped_to_f64(c.type, m) : 0.0;
+      unsigned long long nmin = ok ? ~m : 0ull, vmax = ok ? m : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        isum += __shfl_xor_sync(QW_FULL, isum, o);
+        if (is_f64) dsum += __shfl_xor_sync(QW_FULL, dsum, o);
+        const unsigned long long x = __shfl_xor_sync(QW_FULL, nmin, o), y = __shfl_xor_sync(QW_FULL, vmax, o);
+        nmin = x > nmin ? x : nmin;
+        vmax = y > vmax ? y : vmax;
+      }
+      if (ok && (uint32_t)(__ffs(okmask) - 1) == lane) {
+        atomicAdd((unsigned long long*)&out->count, (unsigned long long)__popc(okmask));
+        if (is_f64) atomicAdd((double*)&out->sum_bits, dsum);
+        else atomicAdd((unsigned long long*)&out->sum_bits, isum);
+        atomicMax((unsigned long long*)&out->min_mapped, nmin);  // min kept as max(~m): zero-initialisable
+        atomicMax((unsigned long long*)&out->max_mapped, vmax);
+      }
+    } else if (ok) {
+      atomicAdd((unsigned long long*)&out->count, 1ull);
+      if (is_f64) atomicAdd((double*)&out->sum_bits, mapped_to_f64(c.type, m));
+      else atomicAdd((unsigned long long*)&out->sum_bits, (unsigned long long)(plain ? m : (m ^ (1ull << 63))));
+      atomicMax((unsigned long long*)&out->min_mapped, (unsigned long long)~m);
+      atomicMax((unsigned long long*)&out->max_mapped, (unsigned long long)m);
+    }
   }
 }
 // bucket index of value index i for bucket aggregation g; returns false when the value falls in no bucket
@@ -389,45 +438,61 @@ __device__ __forceinline__ bool agg_bucket(const DAgg& g, const DCol& c, const u
   bucket = r;
   return m >= g.range_from[r] && m < g.range_to[r];
 }
+// value-index range of `doc` in bucket aggregation g's column (one pseudo value for a `missing` bucket)
+__device__ __forceinline__ uint32_t agg_values(const DAgg& g, const DCol* cols, const uint8_t* base, uint32_t doc, bool on, uint64_t& a, bool& missing) {
+  uint64_t b = 0;
+  a = 0;
+  if (on && g.col != 0xFFFFFFFFu) col_range(base, cols[g.col], doc, a, b);
+  missing = on && (a == b) && g.kind == QW_AGG_TERMS && g.has_missing;
+  return on ? (missing ? 1u : (uint32_t)(b - a)) : 0u;
+}
 __device__ void agg_collect_doc(const KParams& p, const Sm& sm, const DSplitPlan& P, const DAgg* aggs, const DCol* cols,
-                                const uint8_t* base, QwAggCell* cells, uint32_t doc) {
+                                const uint8_t* base, QwAggCell* cells, uint32_t doc, bool on, uint32_t lane) {
   for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
     const DAgg& g = aggs[gi];
     if (g.parent != 0xFFFFFFFFu) continue;
     if (g.kind == QW_AGG_STATS) {
-      if (g.col != 0xFFFFFFFFu) agg_stats(g, cols[g.col], base, cells, 0, doc);
+      if (g.col != 0xFFFFFFFFu) agg_stats(g, cols[g.col], base, cells, 0, doc, on, lane);
       continue;
     }
-    uint64_t a = 0, b = 0;
-    if (g.col != 0xFFFFFFFFu) col_range(base, cols[g.col], doc, a, b);
-    const bool missing = (a == b) && g.kind == QW_AGG_TERMS && g.has_missing;
+    uint64_t a;
+    bool missing;
+    const uint32_t nv = agg_values(g, cols, base, doc, on, a, missing);
+    const uint32_t maxv = __reduce_max_sync(QW_FULL, nv);
     const uint32_t nrep = g.kind == QW_AGG_RANGE ? g.num_ranges : 1;
-    for (uint64_t i = a; i < (missing ? a + 1 : b); i++) {
+    for (uint32_t k = 0; k < maxv; k++) {
       for (uint32_t r = 0; r < nrep; r++) {
-        uint32_t bk;
-        if (missing) bk = g.num_buckets - 1;
-        else if (!agg_bucket(g, cols[g.col], base, i, r, bk)) continue;
-        agg_count(p, sm, cells, g.cell_base + bk);
+        bool ok = k < nv;
+        uint32_t bk = 0;
+        if (ok) {
+          if (missing) bk = g.num_buckets - 1;
+          else ok = agg_bucket(g, cols[g.col], base, a + k, r, bk);
+        }
+        agg_count(p, sm, cells, g.cell_base + bk, ok, lane);
         for (uint32_t ci = 0; ci < g.num_children; ci++) {
           const DAgg& ch = aggs[g.first_child + ci];
           if (ch.kind == QW_AGG_STATS) {
-            if (ch.col != 0xFFFFFFFFu) agg_stats(ch, cols[ch.col], base, cells, bk, doc);
+            if (ch.col != 0xFFFFFFFFu) agg_stats(ch, cols[ch.col], base, cells, bk, doc, ok, lane);
             continue;
           }
-          uint64_t a2 = 0, b2 = 0;
-          if (ch.col != 0xFFFFFFFFu) col_range(base, cols[ch.col], doc, a2, b2);
-          const bool missing2 = (a2 == b2) && ch.kind == QW_AGG_TERMS && ch.has_missing;
+          uint64_t a2;
+          bool missing2;
+          const uint32_t nv2 = agg_values(ch, cols, base, doc, ok, a2, missing2);
+          const uint32_t maxv2 = __reduce_max_sync(QW_FULL, nv2);
           const uint32_t nrep2 = ch.kind == QW_AGG_RANGE ? ch.num_ranges : 1;
-          for (uint64_t i2 = a2; i2 < (missing2 ? a2 + 1 : b2); i2++) {
+          for (uint32_t k2 = 0; k2 < maxv2; k2++) {
             for (uint32_t r2 = 0; r2 < nrep2; r2++) {
-              uint32_t bk2;
-              if (missing2) bk2 = ch.num_buckets - 1;
-              else if (!agg_bucket(ch, cols[ch.col], base, i2, r2, bk2)) continue;
-              uint32_t cell2 = bk * ch.num_buckets + bk2;
-              agg_count(p, sm, cells, ch.cell_base + cell2);
+              bool ok2 = k2 < nv2;
+              uint32_t bk2 = 0;
+              if (ok2) {
+                if (missing2) bk2 = ch.num_buckets - 1;
+                else ok2 = agg_bucket(ch, cols[ch.col], base, a2 + k2, r2, bk2);
+              }
+              const uint32_t cell2 = bk * ch.num_buckets + bk2;
+              agg_count(p, sm, cells, ch.cell_base + cell2, ok2, lane);
               for (uint32_t gc = 0; gc < ch.num_children; gc++) {
                 const DAgg& g3 = aggs[ch.first_child + gc];
-                if (g3.kind == QW_AGG_STATS && g3.col != 0xFFFFFFFFu) agg_stats(g3, cols[g3.col], base, cells, cell2, doc);
+                if (g3.kind == QW_AGG_STATS && g3.col != 0xFFFFFFFFu) agg_stats(g3, cols[g3.col], base, cells, cell2, doc, ok2, lane);
               }
             }
           }
@@ -450,6 +515,24 @@ __device__ __forceinline__ void zero_f4(float* p, uint32_t n, uint32_t tid) {
   for (uint32_t i = tid; i < (n >> 2); i += QW_THREADS) q[i] = z;
 }
 
+// Warp-cooperative 32-ary search of a term's skip list: ordinal of the first block whose last doc
+// is >= ws (nblk when there is none). All lanes return the same value.
+__device__ __forceinline__ uint32_t first_block_ge(const QwSkip* skips, uint32_t nblk, uint32_t ws, uint32_t lane) {
+  uint32_t a = 0, b = nblk;
+  while (b - a > 32) {
+    uint32_t step = (b - a + 31) >> 5;
+    uint32_t idx = a + lane * step;
+    bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+    if (m == 0) a = a + ((b - 1 - a) / step) * step + 1;
+    else { uint32_t f = __ffs(m) - 1; b = a + f * step + 1; if (f > 0) a = a + (f - 1) * step + 1; }
+  }
+  uint32_t idx = a + lane;
+  bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+  return m ? a + (__ffs(m) - 1) : nblk;
+}
+
 struct BlkRec {  // one staged posting block of the window
   uint16_t soff;  // byte offset of the block inside the stage area
   uint16_t lo;    // lower bound of its first doc, window-relative, clamped to [0, W]
@@ -460,7 +543,13 @@ struct BlkRec {  // one staged posting block of the window
 
 // The window engine (see the file header): phases 1-3 stage the window's bytes and build the block
 // table, then the boolean program runs block-wide, then the matches are collected.
-template <int MODE>
+//
+// UNION = true is the specialised instantiation for the BM25 top-K shape (every plan of the batch is
+// a pure OR of positive-weight scored terms ranked by _score desc, no search_after, no aggregations;
+// see lower_plan): the program degenerates to "zero the accumulator, fold every term", matches and
+// the hit count come from the score array in the fused collect sweep, and none of the bitmap
+// machinery is compiled in. The host launches it only when the whole batch qualifies.
+template <int MODE, bool UNION>
 __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(const KParams p) {
   Sm sm{&p.sm};
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,6 +559,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
   DInstr* s_instr = (DInstr*)sm.u8(p.sm.instr);
   DCol* s_cols = (DCol*)sm.u8(p.sm.cols);
   DAgg* s_aggs = (DAgg*)sm.u8(p.sm.aggs);
+  const DKeySpec& ks = *(const DKeySpec*)sm.u8(p.sm.key);  // the current split's key spec (shared-memory copy)
   uint32_t* s_misc = sm.u32(p.sm.misc);  // [0] total staged blocks, [2] hits, [3] eligible
   uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off, instr index
   BlkRec* s_blk = (BlkRec*)sm.u8(p.sm.blkrec);
@@ -496,6 +586,12 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
   for (uint32_t work = w_begin; work < w_end; work++) {
     while (__ldg(p.first_work + split + 1) <= work) split++;
     const uint32_t window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
+    if (p.refine) {
+      // second-chance passes: verified splits are final, and a window whose best level-0 digit is
+      // below the threshold digit cannot hold a candidate (block-uniform tests)
+      if (__ldg(p.split_state + split) == 0) continue;
+      if ((uint32_t)p.wmax[work] < (uint32_t)(p.thresh[split].key[0] >> 53) + 1u) continue;
+    }
     const DSplitPlan& P = p.plans[split];
     __syncthreads();  // previous window fully finished (stage / entries / program are reused)
     if (split != loaded_split) {
@@ -505,6 +601,8 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       for (uint32_t i = tid; i < P.n_cols * (sizeof(DCol) / 16); i += QW_THREADS) ((uint4*)s_cols)[i] = __ldg(src + i);
       src = (const uint4*)(p.aggs + P.agg_base);
       for (uint32_t i = tid; i < P.n_aggs * (sizeof(DAgg) / 16); i += QW_THREADS) ((uint4*)s_aggs)[i] = __ldg(src + i);
+      src = (const uint4*)&P.key;
+      if (tid < sizeof(DKeySpec) / 16) ((uint4*)sm.u8(p.sm.key))[tid] = __ldg(src + tid);
       loaded_split = split;
       ssum_clean = false;
       __syncthreads();
@@ -601,15 +699,45 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     uint32_t req_init = 0;  // bit per level, uniform across the block
     // fused BM25 shape (COLLECT pass only): matches / hit count come from the score array, which the
     // collect loop also re-zeroes for the next window of the same split plan
-    const bool fused = MODE == MODE_COLLECT && P.fused_score_root && P.max_hits && !P.sa.present && !P.n_aggs &&
-                       P.key.kind[0] == QW_SORT_SCORE && P.key.order[0] == QW_ORDER_DESC;
+    constexpr bool fused = UNION;
     {
       while (ip < n_instr) {
         const DInstr& in = s_instr[ip];
         const uint32_t op = in.op, level = in.level, occur = in.occur;
         const SmemLevel& LV = p.sm.lvl[level];
         const bool scored = (in.flags & IF_SCORED) != 0;
-        if (op == OP_BOOL_BEGIN) {
+        if (UNION && op == OP_BOOL_BEGIN) {
+          if (!ssum_clean) zero_f4(sm.f32(LV.ssum), W, tid);
+          __syncthreads();
+          ip++;
+        } else if (UNION && op == OP_BOOL_END) {
+          ip++;
+        } else if (UNION) {  // OP_TERM, should + scored, bitmap implied by the score
+          const uint32_t slot = in.t;
+          TermTarget tg;
+          tg.bits = 0xFFFFFFFFu;
+          tg.cnt = 0xFFFFFFFFu;
+          tg.score = LV.ssum;
+          tg.weight = in.f;
+          tg.has_tf = (in.flags & IF_HAS_TF) != 0;
+          tg.fn = (in.flags & IF_HAS_FN) ? p.sm.fn[in.r] : 0xFFFFFFFFu;
+          tg.gtab = (const float*)P.bm25_tab[in.r];
+          if (s_rng[4 * slot + 2] != 0xFFFFFFFFu) {
+            const uint32_t g0 = s_tblk[2 * slot], nb = s_tblk[2 * slot + 1];
+            for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false, true, false>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane);
+          } else if (s_rng[4 * slot + 1]) {
+            const QwSkip* skips = (const QwSkip*)(base + in.c);
+            const uint32_t bfirst = first_block_ge(skips, in.n, ws, lane);
+            const uint8_t* tdata = base + in.a;
+            for (uint32_t bb = bfirst + warp; bb < in.n; bb += QW_WARPS) {
+              uint4 h = __ldg((const uint4*)&skips[bb]);
+              if (h.y != QW_NO_PREV_DOC && h.y + 1 >= we) break;
+              fold_block<true, false, false, false>(0, tdata + h.z, ws, 0, wlen, tg, lane);
+            }
+          }
+          __syncthreads();
+          ip++;
+        } else if (op == OP_BOOL_BEGIN) {
           zero_f4((float*)sm.u32(LV.shd), NW, tid);
           zero_f4((float*)sm.u32(LV.nt), NW, tid);
           if (LV.cnt != 0xFFFFFFFFu) zero_f4((float*)sm.u32(LV.cnt), W >> 2, tid);
@@ -650,19 +778,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
             // direct mode (range not staged): warps decode whole blocks straight from global memory
             const QwSkip* skips = (const QwSkip*)(base + in.c);
             const uint32_t nblk = in.n;
-            uint32_t a = 0, b = nblk;
-            while (b - a > 32) {
-              uint32_t step = (b - a + 31) >> 5;
-              uint32_t idx = a + lane * step;
-              bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
-              uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-              if (m == 0) a = a + ((b - 1 - a) / step) * step + 1;
-              else { uint32_t f = __ffs(m) - 1; b = a + f * step + 1; if (f > 0) a = a + (f - 1) * step + 1; }
-            }
-            uint32_t idx = a + lane;
-            bool ok = idx < b && __ldg(&skips[idx].last_doc) >= ws;
-            uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-            const uint32_t bfirst = m ? a + (__ffs(m) - 1) : nblk;
+            const uint32_t bfirst = first_block_ge(skips, nblk, ws, lane);
             const uint8_t* tdata = base + in.a;
             for (uint32_t bb = bfirst + warp; bb < nblk; bb += QW_WARPS) {
               uint4 h = __ldg((const uint4*)&skips[bb]);
@@ -801,32 +917,36 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     const uint32_t* res = sm.u32(p.sm.lvl[0].req);
     const float* rscore = p.sm.lvl[0].rsc != 0xFFFFFFFFu ? sm.f32(p.sm.lvl[0].rsc) : nullptr;
     const DThresh& T = p.thresh[split];
-    const uint32_t max_hits = P.max_hits, n_aggs = P.n_aggs, sa_present = P.sa.present;
+    const uint32_t max_hits = P.max_hits, sa_present = P.sa.present;
+    const uint32_t n_aggs = (MODE == MODE_COLLECT && p.cands_only) ? 0u : P.n_aggs;
     QwAggCell* cells = (QwAggCell*)P.out_cells;
-    if (MODE == MODE_HIST || (p.smem_aggs && n_aggs)) {
-      // the histogram / privatised aggregation counters alias the (now dead) entry area
+    const bool rec = MODE == MODE_COLLECT && p.rec_l0 && max_hits && !fused;
+    uint32_t* s_l0 = sm.u32(p.sm.l0hist);
+    if (MODE == MODE_HIST || (p.smem_aggs && n_aggs) || rec) {
+      // the histogram / privatised aggregation counters alias the (now dead) staging area
       for (uint32_t i = tid; i < (MODE == MODE_HIST ? (uint32_t)QW_HIST_BINS : P.n_cells); i += QW_THREADS) s_hist[i] = 0;
+      if (rec) for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) s_l0[i] = 0;
+      if (tid == 0) s_misc[4] = 0;
       __syncthreads();
     }
     if (MODE == MODE_COLLECT) {
       const Key thr{T.key[0], T.key[1], T.key[2]};
       const uint32_t thr_top = (uint32_t)(thr.w0 >> 53);
-      const DKeySpec ks = P.key;  // hoisted into registers
-      uint32_t my_hits = 0, my_elig = 0;
+      uint32_t my_hits = 0, my_elig = 0, my_top = 0;
       // hit count: one popc per bitmap word
-      if (!fused) for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
+      if (!fused && !p.cands_only) for (uint32_t wd = tid; wd < NW; wd += QW_THREADS) my_hits += __popc(res[wd]);
+      auto emit = [&](const Key& k) {
+        const uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
+        if (pos < QW_CAND_CAP) {
+          uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
+          c[0] = k.w0; c[1] = k.w1; c[2] = k.w2;
+        }
+      };
       auto slow_path = [&](uint32_t i, float sc) {
-        const uint32_t doc = ws + i;
-        DocKey dk = doc_key(P, s_cols, base, doc, sc);
+        DocKey dk = doc_key(P, ks, s_cols, base, ws + i, sc);
         if (dk.eligible) {
           my_elig++;
-          if (key_ge(dk.key, thr)) {
-            uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
-            if (pos < QW_CAND_CAP) {
-              uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
-              c[0] = dk.key.w0; c[1] = dk.key.w1; c[2] = dk.key.w2;
-            }
-          }
+          if (key_ge(dk.key, thr)) emit(dk.key);
         }
       };
       if (fused) {
@@ -845,10 +965,11 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           if (v.z > 0.0f && v.z >= s_lo) slow_path(4 * q + 2, v.z);
           if (v.w > 0.0f && v.w >= s_lo) slow_path(4 * q + 3, v.w);
         }
+        if (p.cands_only) my_hits = 0;
         ssum_clean = true;
-      } else if (max_hits && ks.kind[0] == QW_SORT_SCORE && ks.order[0] == QW_ORDER_DESC && !sa_present && rscore && !n_aggs) {
+      } else if (max_hits && ks.kind[0] == QW_SORT_SCORE && ks.order[0] == QW_ORDER_DESC && !sa_present && rscore && !n_aggs && !rec) {
         // fast path (BM25 top-K): a float lower bound of the threshold bucket filters 4 docs per lane
-        // per step; only survivors build the 192-bit key. s_lo is conservative (one part in 2^20).
+        // per step; only survivors build the composite key. s_lo is conservative (one part in 2^20).
         float s_lo = -1.0f;
         if (thr_top >= 1024u) s_lo = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), ks.score_scale), 0.999999f);
         const float4* sc4 = reinterpret_cast<const float4*>(rscore);
@@ -862,19 +983,44 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           if ((nib & 8u) && v.w >= s_lo) slow_path(4 * q + 3, v.w);
         }
       } else if (max_hits || n_aggs) {
+        // generic path, warp-converged: lane = doc of a 32-doc bitmap word
         for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t word = res[wd];
           if (word == 0) continue;  // warp-uniform
-          if (!((word >> lane) & 1)) continue;
+          const bool on = (word >> lane) & 1;
           const uint32_t i = wd * 32 + lane, doc = ws + i;
           if (max_hits) {
-            const float sc = rscore ? rscore[i] : 0.0f;
-            // cheap pre-filter on the key's first 11 bits; the full 192-bit key is only built for
-            // docs that can reach the threshold (or always, when search_after needs eligibility)
-            if (sa_present || key_top11(ks, s_cols, base, doc, sc) >= thr_top) slow_path(i, sc);
+            const float sc = (on && rscore) ? rscore[i] : 0.0f;
+            uint32_t top = 0;
+            bool ranked = false;  // eligible for the top-K (search_after may exclude matches)
+            if (on) {
+              if (sa_present) {
+                const DocKey dk = doc_key(P, ks, s_cols, base, doc, sc);
+                if (dk.eligible) {
+                  ranked = true;
+                  my_elig++;
+                  top = (uint32_t)(dk.key.w0 >> 53);
+                  if (key_ge(dk.key, thr)) emit(dk.key);
+                }
+              } else {
+                // cheap pre-filter on the key's first 11 bits; the composite key is only built for docs
+                // that can reach the threshold
+                ranked = true;
+                top = key_top11(P, ks, s_cols, base, doc, sc);
+                if (top >= thr_top) {
+                  const DocKey dk = doc_key(P, ks, s_cols, base, doc, sc);
+                  if (key_ge(dk.key, thr)) emit(dk.key);
+                }
+              }
+            }
+            if (rec) {
+              warp_count_uniform(s_l0, top, ranked, lane);
+              if (ranked) my_top = max(my_top, top + 1);
+            }
           }
-          if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc);
+          if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc, on, lane);
         }
+        if (!sa_present) my_elig = 0;
       }
       // block-reduce the counters, one global atomic per window
 #pragma unroll
@@ -882,14 +1028,20 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         my_elig += __shfl_down_sync(0xFFFFFFFFu, my_elig, o);
         my_hits += __shfl_down_sync(0xFFFFFFFFu, my_hits, o);
       }
-      if (lane == 0) { if (my_hits) atomicAdd(&s_misc[2], my_hits); if (my_elig) atomicAdd(&s_misc[3], my_elig); }
+      if (rec) my_top = __reduce_max_sync(0xFFFFFFFFu, my_top);
+      if (lane == 0) {
+        if (my_hits) atomicAdd(&s_misc[2], my_hits);
+        if (my_elig) atomicAdd(&s_misc[3], my_elig);
+        if (rec && my_top) atomicMax(&s_misc[4], my_top);
+      }
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 && !p.cands_only) {
         const uint32_t hits = s_misc[2];
         if (hits) atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)hits);
         // without search_after every hit is eligible
         const uint32_t elig = sa_present ? s_misc[3] : (max_hits ? hits : 0);
         if (elig) atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)elig);
+        if (rec) p.wmax[work] = (uint16_t)s_misc[4];
       }
       if (p.smem_aggs && n_aggs) {
         for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {
@@ -897,21 +1049,34 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           if (v) { atomicAdd((unsigned long long*)&cells[i].count, (unsigned long long)v); s_hist[i] = 0; }
         }
       }
+      if (rec) {
+        uint32_t* gh = (uint32_t*)P.out_hist;
+        for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
+          const uint32_t v = s_l0[i];
+          if (v) atomicAdd(&gh[i], v);
+        }
+      }
     } else {
       if (max_hits) {
         for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t word = res[wd];
           if (word == 0) continue;
-          if (!((word >> lane) & 1)) continue;
+          const bool on = (word >> lane) & 1;
           const uint32_t i = wd * 32 + lane, doc = ws + i;
-          const float sc = rscore ? rscore[i] : 0.0f;
-          if (p.level == 0 && !sa_present) {
-            atomicAdd(&s_hist[key_top11(P.key, s_cols, base, doc, sc)], 1u);
-          } else {
-            DocKey dk = doc_key(P, s_cols, base, doc, sc);
-            if (dk.eligible && (!p.use_prefix || key_prefix_eq(dk.key, T.key, T.prefix_bits)))
-              atomicAdd(&s_hist[key_digit(dk.key, p.level)], 1u);
+          const float sc = (on && rscore) ? rscore[i] : 0.0f;
+          uint32_t digit = 0;
+          bool ranked = false;
+          if (on) {
+            if (p.level == 0 && !sa_present) {
+              digit = key_top11(P, ks, s_cols, base, doc, sc);
+              ranked = true;
+            } else {
+              const DocKey dk = doc_key(P, ks, s_cols, base, doc, sc);
+              ranked = dk.eligible && (!p.use_prefix || key_prefix_eq(dk.key, T.key, T.prefix_bits));
+              digit = key_digit(dk.key, p.level);
+            }
           }
+          warp_count_uniform(s_hist, digit, ranked, lane);
         }
       }
       __syncthreads();
@@ -928,13 +1093,18 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
 //   sampled != 0: histogram comes from every `stride`-th window; pick the digit at a conservative
 //                 sample rank `k_sample` (verified afterwards against the true candidate count).
 //   sampled == 0: exact radix-select step at `level` (prefix / above bookkeeping in DThresh).
-__global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* thresh, uint32_t level, uint32_t sampled, uint32_t stride) {
+//   split_state != null: only splits flagged for refinement are touched, and their candidate
+//                 counters are reset for the candidates-only collect pass that follows.
+__global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* thresh, uint32_t level, uint32_t sampled, uint32_t stride,
+                                              const uint32_t* split_state) {
   __shared__ uint32_t s_part[256];
   __shared__ uint32_t s_sel[2];
   const uint32_t split = blockIdx.x, tid = threadIdx.x;
   const DSplitPlan& P = plans[split];
   DThresh& T = thresh[split];
-  if (P.max_hits == 0 || (!sampled && T.done)) return;
+  if (P.max_hits == 0 || (split_state && split_state[split] == 0)) return;
+  if (split_state && tid == 0) *(uint32_t*)P.out_cand_count = 0;
+  if (!sampled && level > 0 && T.done) return;
   const uint32_t* h = (const uint32_t*)P.out_hist;
   // thread t owns the 8 bins [2048 - 8(t+1), 2048 - 8t), i.e. thread 0 owns the top bins
   const uint32_t hi = QW_HIST_BINS - 8 * tid;
@@ -953,7 +1123,7 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
     // conservative sample rank: 2x the expected sample share of K plus slack
     target = (2 * K + stride - 1) / stride + 24;
   } else {
-    base_above = T.above;
+    base_above = level == 0 ? 0u : T.above;
     target = K > base_above ? K - base_above : 1;
   }
   // find the largest digit t with suffix(t) >= target
@@ -973,12 +1143,12 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
       // fewer than `target` ranked docs: keep everything that matches the current prefix
       T.done = 1;
       T.matched = total;
-      if (sampled) { T.key[0] = T.key[1] = T.key[2] = 0; T.prefix_bits = 0; T.above = 0; }
+      if (sampled || level == 0) { T.key[0] = T.key[1] = T.key[2] = 0; T.prefix_bits = 0; T.above = 0; }
       return;
     }
     uint32_t o = level * QW_DIGIT_BITS, word = o >> 6, sh = o & 63;
     uint64_t d = (uint64_t)digit << (64 - QW_DIGIT_BITS);
-    if (sampled) { T.key[0] = T.key[1] = T.key[2] = 0; }
+    if (sampled || level == 0) { T.key[0] = T.key[1] = T.key[2] = 0; }
     T.key[word] |= d >> sh;
     if (sh + QW_DIGIT_BITS > 64 && word < 2) T.key[word + 1] |= d << (64 - sh);
     T.prefix_bits = o + QW_DIGIT_BITS;
@@ -997,7 +1167,7 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
 //   2. compaction of the candidates >= that word (all ties kept) — normally ~K of the ~2-3K candidates;
 //   3. bitonic sort of the survivors with the full 192-bit comparison (the reference total order).
 #define QW_SEL_MAX 2048  /* survivors sorted in shared memory; more ties than this => sort everything */
-__global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
+__global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const DCol* all_cols) {
   const DSplitPlan& P = plans[blockIdx.x];
   const uint32_t tid = threadIdx.x;
   if (P.max_hits == 0) { if (tid == 0) *(uint32_t*)P.out_nhits = 0; return; }
@@ -1103,36 +1273,43 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans) {
   const uint32_t out_n = m < K ? m : K;
   QwHit* hits = (QwHit*)P.out_hits;
   const DKeySpec& ks = P.key;
+  const DCol* cols = all_cols + P.col_base;
+  const uint32_t docmask = ks.doc_bits >= 32 ? 0xFFFFFFFFu : ((1u << ks.doc_bits) - 1);
   for (uint32_t i = tid; i < out_n; i += 1024) {
-    uint64_t w0 = k0[i], w1 = k1[i], w2 = k2[i];
-    uint32_t has1 = (uint32_t)(w0 >> 63), has2 = (uint32_t)((w1 >> 52) & 1);
-    uint64_t pay1 = (w0 << 11) | (w1 >> 53), pay2 = (w1 << 12) | (w2 >> 52);
-    uint32_t docp = (uint32_t)(w2 >> 20);
+    const Key k{k0[i], k1[i], k2[i]};
+    uint32_t pos = 0, has[2];
+    uint64_t r[2];
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      has[f] = ks.hasbit[f] ? (uint32_t)key_get(k, pos, 1) : 0u;
+      pos += ks.hasbit[f];
+      r[f] = key_get(k, pos, ks.rbits[f]);
+      pos += ks.rbits[f];
+    }
+    const uint32_t docr = (uint32_t)key_get(k, pos, ks.doc_bits);
     QwHit hh;
-    hh.doc_id = ks.order[0] == QW_ORDER_DESC ? docp : ~docp;
-    hh.flags = has1 | (has2 << 1);
+    hh.doc_id = ks.order[0] == QW_ORDER_DESC ? docr : docmask - docr;
+    hh.flags = has[0] | (has[1] << 1);
     hh.score = 0.0f;
     hh.reserved = 0;
-    hh.v1 = 0;
-    hh.v2 = 0;
-    if (has1) {
-      if (ks.kind[0] == QW_SORT_SCORE) {
-        uint32_t o = (uint32_t)(pay1 >> 32);
-        if (ks.order[0] != QW_ORDER_DESC) o = ~o;
-        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    uint64_t v[2] = {0, 0};
+#pragma unroll
+    for (int f = 0; f < 2; f++) {
+      if (!has[f]) continue;
+      const bool desc = ks.order[f] == QW_ORDER_DESC;
+      if (ks.kind[f] == QW_SORT_SCORE) {
+        uint32_t o = (uint32_t)r[f];
+        if (!desc) o = ~o;
+        const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
         hh.score = __uint_as_float(bits);
-        hh.v1 = f64_to_u64_dev((double)hh.score);
-      } else hh.v1 = ks.order[0] == QW_ORDER_DESC ? pay1 : ~pay1;
+        v[f] = f64_to_u64_dev((double)hh.score);
+      } else {
+        const DCol& c = cols[ks.col[f]];
+        v[f] = c.min_value + c.gcd * (desc ? r[f] : ks.raw_max[f] - r[f]);
+      }
     }
-    if (has2) {
-      if (ks.kind[1] == QW_SORT_SCORE) {
-        uint32_t o = (uint32_t)(pay2 >> 32);
-        if (ks.order[1] != QW_ORDER_DESC) o = ~o;
-        uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-        hh.score = __uint_as_float(bits);
-        hh.v2 = f64_to_u64_dev((double)hh.score);
-      } else hh.v2 = ks.order[1] == QW_ORDER_DESC ? pay2 : ~pay2;
-    }
+    hh.v1 = v[0];
+    hh.v2 = v[1];
     hits[i] = hh;
   }
   if (tid == 0) *(uint32_t*)P.out_nhits = out_n;

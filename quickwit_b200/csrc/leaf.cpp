@@ -176,6 +176,7 @@ struct LeafRun {
 static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run) {
   using clock = std::chrono::steady_clock;
   const pb::SearchRequest& sreq = lr.search_request;
+  const auto t_compile = clock::now();
   Json ast = parse_json(sreq.query_ast, QWGPU_EINVALID_QUERY);  // once per request
   for (auto& ref : lr.leaf_requests) {
     if (ref.doc_mapper_ord >= lr.doc_mappers.size()) fail(QWGPU_EINVALID_ARG, "Internal error: doc_mapper_ord out of bounds");
@@ -207,6 +208,8 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
       run.which.push_back(i);
     }
   auto t0 = clock::now();
+  if (getenv("QWGPU_TRACE"))
+    fprintf(stderr, "[qwgpu] compile: %ld us for %zu splits\n", (long)std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_compile).count(), run.jobs.size());
   if (!devs.empty()) eng.search(devs, plans, lens, run.outs, run.st);
   run.wall_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t0).count();
 }
@@ -371,9 +374,15 @@ extern "C" {
 int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
+  // QWGPU_TRACE=1: per-phase host timings of this call on stderr (diagnostics only)
+  static const bool trace = getenv("QWGPU_TRACE") != nullptr;
+  using tclock = std::chrono::steady_clock;
+  auto t_start = tclock::now();
   qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
+  auto t_dec = tclock::now();
   qw::LeafRun run;
   qw::run_leaf_raw(eng, lr, run);
+  auto t_run = tclock::now();
   // the leaf keeps [0, start_offset + max_hits) (root.rs:1775-1777): nothing is drained here
   qw::pb::SearchRequest mreq = lr.search_request;
   mreq.max_hits += mreq.start_offset;
@@ -417,7 +426,13 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
     merged = parts.size() == 1 ? std::move(parts[0]) : qw::merge_responses(mreq, std::move(parts));
   }
   for (auto& f : failed) { merged.failed_splits.push_back(f); merged.num_attempted_splits += 1; }
+  auto t_merge = tclock::now();
   give(qw::pb::encode_leaf_search_response(merged), resp, resp_len);
+  if (trace) {
+    auto us = [](tclock::time_point a, tclock::time_point b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };
+    fprintf(stderr, "[qwgpu] leaf_search: decode %ld us, compile+search %ld us (engine wall %lu us, device %.0f us, %u launches), merge %ld us, encode %ld us\n",
+            us(t_start, t_dec), us(t_dec, t_run), (unsigned long)run.wall_us, run.st.gpu_time_us, run.st.launches, us(t_run, t_merge), us(t_merge, tclock::now()));
+  }
   return 0;
   QW_API_END
 }

@@ -60,6 +60,8 @@ def main():
     ap.add_argument("--docs-per-split", type=int, default=3_125_000)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--cpu-splits", type=int, default=8)
+    ap.add_argument("--only", default="", help="run only configs whose name starts with this prefix (e.g. C4)")
+    ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "configs.json"))
     a = ap.parse_args()
     import torch
@@ -77,6 +79,8 @@ def main():
     offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
     rows = []
     for name, ast, kw in configs(a.splits):
+        if a.only and not name.startswith(a.only + " "):
+            continue
         kw = dict(kw)
         aggs = kw.pop("aggs", None)
         sreq = proto.enc_search_request(json.dumps(ast), aggregation_request=json.dumps(aggs) if aggs else None, **kw)
@@ -101,11 +105,13 @@ def main():
         ns = min(a.cpu_splits, a.splits)
         def one(i):
             return O.split_search(imgs[i], plans[i]).num_hits
-        with ThreadPoolExecutor(max_workers=ns) as ex:
-            list(ex.map(one, range(ns)))
-            t0 = time.perf_counter()
-            list(ex.map(one, range(ns)))
-            cpu = time.perf_counter() - t0
+        cpu = 0.0
+        if not a.no_oracle:
+            with ThreadPoolExecutor(max_workers=ns) as ex:
+                list(ex.map(one, range(ns)))
+                t0 = time.perf_counter()
+                list(ex.map(one, range(ns)))
+                cpu = time.perf_counter() - t0
         docs = a.splits * a.docs_per_split
         row = {"config": name, "num_hits": dec["num_hits"], "partial_hits": len(dec["partial_hits"]),
                "device_us": gpu_us / a.reps, "k_window_collect_us": main_us / a.reps, "launches": r["launches"],
