@@ -365,7 +365,8 @@ __device__ __forceinline__ void warp_count_uniform(uint32_t* ctr, uint32_t idx, 
   const uint32_t m = __ballot_sync(QW_FULL, on);
   if (m == 0) return;
   const uint32_t lead = __ffs(m) - 1;
-  const uint32_t same = __ballot_sync(QW_FULL, on && idx == __shfl_sync(QW_FULL, idx, lead));
+  const uint32_t lead_idx = __shfl_sync(QW_FULL, idx, lead);  // (outside the &&: every lane must take part)
+  const uint32_t same = __ballot_sync(QW_FULL, on && idx == lead_idx);
   if (same == m) { if (lane == lead) atomicAdd(&ctr[idx], (uint32_t)__popc(m)); }
   else if (on) atomicAdd(&ctr[idx], 1u);
 }
