@@ -77,7 +77,8 @@ struct alignas(16) DKeySpec {
   uint32_t top_mode;     // how the first 11 key bits are derived cheaply (QW_TOP_*)
   float score_scale;     // SCORE: lin = min(1023, (uint)(score * scale))
   uint64_t raw_max[2];   // r_i = order == DESC ? raw : raw_max - raw
-  uint64_t pad;          // sizeof % 16 == 0: copied to shared memory as uint4
+  // total_bits <= 64 (the usual case): the key is w0 = OR of (field << shift), shifts precomputed
+  uint32_t narrow, sh_has[2], sh_r[2], sh_doc;
 };
 static_assert(sizeof(DKeySpec) % 16 == 0, "uint4-copied struct");
 enum { QW_TOP_FULL = 0, QW_TOP_SCORE = 1, QW_TOP_COLUMN = 2, QW_TOP_DOC = 3 };
@@ -121,7 +122,7 @@ struct SmemLevel {
   uint32_t rsc, pad;                       // result score array of the level (msum, else ssum)
 };
 struct SmemLayout {
-  uint32_t instr, cols, aggs, key;
+  uint32_t instr, cols, aggs, key, hitq;  // hitq: per-warp compacted hit queues of the generic collect
   SmemLevel lvl[QW_MAX_LEVELS];
   uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
   uint32_t rng, blkrec, termblk, stage, ent, hist, misc;  // hist aliases ent (dead by collect time)

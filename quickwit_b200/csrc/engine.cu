@@ -408,6 +408,18 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
     }
     ks.total_bits += ks.hasbit[i] + ks.rbits[i];
   }
+  ks.narrow = ks.total_bits <= 64 ? 1 : 0;
+  {
+    uint32_t pos = 0;
+    for (int i = 0; i < 2; i++) {
+      ks.sh_has[i] = ks.hasbit[i] ? 64 - pos - 1 : 0;
+      pos += ks.hasbit[i];
+      ks.sh_r[i] = (ks.narrow && ks.rbits[i]) ? 64 - pos - ks.rbits[i] : 0;
+      pos += ks.rbits[i];
+    }
+    ks.sh_doc = (ks.narrow && ks.doc_bits) ? 64 - pos - ks.doc_bits : 0;
+    if (!ks.narrow) ks.sh_has[0] = ks.sh_has[1] = 0;
+  }
   if (ks.kind[0] == QW_SORT_SCORE) {
     float smax = L.score_max > 1e-30f ? L.score_max : 1.0f;
     ks.score_scale = 1024.0f / smax;
@@ -457,11 +469,12 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   memset(&L, 0xFF, sizeof L);
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
-  L.misc = take(32 + 4 * QW_MAX_TERMS);
+  L.misc = take(32 + 4 * QW_MAX_TERMS + QW_MAX_TERMS);  // counters, per-term block bases, per-term instruction index
   L.instr = take(std::max(max_instr, 1u) * sizeof(DInstr));
   L.cols = take(std::max(max_cols, 1u) * sizeof(DCol));
   L.aggs = take(std::max(max_aggs, 1u) * sizeof(DAgg));
   L.key = take(sizeof(DKeySpec));
+
   for (uint32_t l = 0; l < n_levels; l++) {
     L.lvl[l].req = take(W / 8);
     L.lvl[l].shd = take(W / 8);
@@ -474,6 +487,7 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.tmp = take(W / 8);
   for (uint32_t s = 0; s < n_fn; s++) L.fn[s] = take(W);  // BM25 tables stay in global memory (L1-resident)
   L.rng = take(QW_MAX_TERMS * 16);
+  L.hitq = L.rng;  // the collect-time hit queues alias rng / blkrec / termblk (contiguous, dead after the program)
   L.blkrec = take(QW_MAX_WBLK * 8);
   L.termblk = take(QW_MAX_TERMS * 8);
   L.stage = take(stage_bytes_for(W));

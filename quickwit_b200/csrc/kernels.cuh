@@ -308,14 +308,22 @@ __device__ __forceinline__ DocKey doc_key(const DSplitPlan& P, const DKeySpec& k
   const uint32_t docmask = ks.doc_bits >= 32 ? 0xFFFFFFFFu : ((1u << ks.doc_bits) - 1);
   DocKey out;
   out.key = Key{0, 0, 0};
-  uint32_t pos = 0;
+  const uint32_t docr = desc1 ? doc : docmask - doc;
+  if (ks.narrow) {
+    // fields that are absent have width 0 and value 0, so their (zero) shift is harmless
+    out.key.w0 = ((uint64_t)(has[0] & ks.hasbit[0]) << ks.sh_has[0]) | (r[0] << ks.sh_r[0]) |
+                 ((uint64_t)(has[1] & ks.hasbit[1]) << ks.sh_has[1]) | (r[1] << ks.sh_r[1]) |
+                 ((uint64_t)(ks.doc_bits ? docr : 0u) << ks.sh_doc);
+  } else {
+    uint32_t pos = 0;
 #pragma unroll
-  for (int i = 0; i < 2; i++) {
-    if (ks.hasbit[i]) { key_put(out.key, pos, has[i], 1); pos++; }
-    key_put(out.key, pos, r[i], ks.rbits[i]);
-    pos += ks.rbits[i];
+    for (int i = 0; i < 2; i++) {
+      if (ks.hasbit[i]) { key_put(out.key, pos, has[i], 1); pos++; }
+      key_put(out.key, pos, r[i], ks.rbits[i]);
+      pos += ks.rbits[i];
+    }
+    key_put(out.key, pos, docr, ks.doc_bits);
   }
-  key_put(out.key, pos, desc1 ? doc : docmask - doc, ks.doc_bits);
   out.eligible = true;
   if (P.sa.present) {
     // GenericQuickwitSegmentTopKCollector::collect_top_k_vals (top_k_collector.rs:663-699)
@@ -516,6 +524,56 @@ __device__ __forceinline__ void zero_f4(float* p, uint32_t n, uint32_t tid) {
   for (uint32_t i = tid; i < (n >> 2); i += QW_THREADS) q[i] = z;
 }
 
+// Runs body(i, on) over the set bits of a window bitmap with FULL warps: each warp compacts the hits of
+// its share of the bitmap (8 words = 256 docs per step) into a small shared-memory queue and calls the
+// body on 32 hits at a time — sparse result sets (a few hits per 32-doc word) would otherwise spend a
+// whole warp iteration per word with one or two active lanes. The body always runs converged (all 32
+// lanes, `on` false for padding lanes), so it may use warp collectives.
+// The queues alias the per-window term tables (rng / blkrec / termblk), which are dead once the
+// program has run.
+#define QW_HITQ_WORDS 4
+#define QW_HITQ_CAP (32 + 32 * QW_HITQ_WORDS)
+static_assert(QW_WARPS * QW_HITQ_CAP * 2 <= QW_MAX_TERMS * 16 + QW_MAX_WBLK * 8 + QW_MAX_TERMS * 8, "hit queues must fit the aliased term tables");
+static_assert(QW_MAX_INSTR <= 255, "s_tinstr holds instruction indices as bytes");
+template <class F>
+__device__ __forceinline__ void warp_for_hits(const uint32_t* res, uint32_t NW, uint32_t warp, uint32_t lane, uint16_t* q, F&& body) {
+  uint32_t cnt = 0;  // queued hits (warp-uniform)
+  for (uint32_t w0 = warp * QW_HITQ_WORDS; w0 < NW; w0 += QW_WARPS * QW_HITQ_WORDS) {
+    uint32_t word = (lane < QW_HITQ_WORDS && w0 + lane < NW) ? res[w0 + lane] : 0u;
+    const uint32_t c = __popc(word);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < QW_HITQ_WORDS; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, QW_HITQ_WORDS - 1);
+    if (total == 0) continue;
+    uint32_t off = cnt + incl - c;
+    const uint32_t first = (w0 + lane) * 32;
+    while (word) {
+      q[off++] = (uint16_t)(first + __ffs(word) - 1);
+      word &= word - 1;
+    }
+    __syncwarp();
+    cnt += total;
+    uint32_t done = 0;
+    while (cnt - done >= 32) {
+      body((uint32_t)q[done + lane], true);
+      done += 32;
+    }
+    if (done) {
+      const uint32_t rem = cnt - done;
+      const uint16_t v = lane < rem ? q[done + lane] : (uint16_t)0;
+      __syncwarp();
+      if (lane < rem) q[lane] = v;
+      cnt = rem;
+    }
+    __syncwarp();
+  }
+  if (cnt) body(lane < cnt ? (uint32_t)q[lane] : 0u, lane < cnt);
+}
+
 // Warp-cooperative 32-ary search of a term's skip list: ordinal of the first block whose last doc
 // is >= ws (nblk when there is none). All lanes return the same value.
 __device__ __forceinline__ uint32_t first_block_ge(const QwSkip* skips, uint32_t nblk, uint32_t ws, uint32_t lane) {
@@ -561,8 +619,10 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
   DCol* s_cols = (DCol*)sm.u8(p.sm.cols);
   DAgg* s_aggs = (DAgg*)sm.u8(p.sm.aggs);
   const DKeySpec& ks = *(const DKeySpec*)sm.u8(p.sm.key);  // the current split's key spec (shared-memory copy)
+  uint16_t* s_hitq = (uint16_t*)sm.u8(p.sm.hitq) + (threadIdx.x >> 5) * QW_HITQ_CAP;  // this warp's hit queue
   uint32_t* s_misc = sm.u32(p.sm.misc);  // [0] total staged blocks, [2] hits, [3] eligible
-  uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off, instr index
+  uint32_t* s_rng = sm.u32(p.sm.rng);    // per term slot: start, len, stage_off (per window)
+  uint8_t* s_tinstr = sm.u8(p.sm.misc) + 32 + 4 * QW_MAX_TERMS;  // per term slot: its TERM instruction (per split)
   BlkRec* s_blk = (BlkRec*)sm.u8(p.sm.blkrec);
   uint32_t* s_tblk = sm.u32(p.sm.termblk);  // per term slot: first global block, block count
   uint32_t* s_hist = sm.u32(p.sm.hist);
@@ -607,7 +667,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       loaded_split = split;
       ssum_clean = false;
       __syncthreads();
-      if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_rng[4 * s_instr[tid].t + 3] = tid;
+      if (tid < P.n_instr && s_instr[tid].op == OP_TERM) s_tinstr[s_instr[tid].t] = (uint8_t)tid;  // term slot -> instruction (kept per split)
       __syncthreads();
     }
     const uint8_t* base = (const uint8_t*)P.data_base;
@@ -618,7 +678,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
 
     // ---- phase 1: window-index entries + fieldnorm staging (one round of independent loads) --------
     if (tid < n_terms) {
-      const DInstr& in = s_instr[s_rng[4 * tid + 3]];
+      const DInstr& in = s_instr[s_tinstr[tid]];
       uint32_t start = 0, len = 0, fb = 0, nb = 0;
       if (in.n) {
         const uint4* wi = (const uint4*)(base + in.b);
@@ -666,7 +726,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     for (uint32_t t = warp; t < n_terms; t += QW_WARPS) {
       const uint32_t so = s_rng[4 * t + 2];
       if (so == 0xFFFFFFFFu) continue;
-      const DInstr& in = s_instr[s_rng[4 * t + 3]];
+      const DInstr& in = s_instr[s_tinstr[t]];
       const uint32_t start = s_rng[4 * t + 0];
       const uint8_t* src = base + in.a + start;
       const uint32_t n16 = s_rng[4 * t + 1] >> 4;
@@ -984,12 +1044,9 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           if ((nib & 8u) && v.w >= s_lo) slow_path(4 * q + 3, v.w);
         }
       } else if (max_hits || n_aggs) {
-        // generic path, warp-converged: lane = doc of a 32-doc bitmap word
-        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
-          const uint32_t word = res[wd];
-          if (word == 0) continue;  // warp-uniform
-          const bool on = (word >> lane) & 1;
-          const uint32_t i = wd * 32 + lane, doc = ws + i;
+        // generic path, warp-converged over compacted hits: lane = one matched doc
+        warp_for_hits(res, NW, warp, lane, s_hitq, [&](uint32_t i, bool on) {
+          const uint32_t doc = ws + i;
           if (max_hits) {
             const float sc = (on && rscore) ? rscore[i] : 0.0f;
             uint32_t top = 0;
@@ -1020,7 +1077,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
             }
           }
           if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc, on, lane);
-        }
+        });
         if (!sa_present) my_elig = 0;
       }
       // block-reduce the counters, one global atomic per window
@@ -1059,11 +1116,8 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       }
     } else {
       if (max_hits) {
-        for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
-          const uint32_t word = res[wd];
-          if (word == 0) continue;
-          const bool on = (word >> lane) & 1;
-          const uint32_t i = wd * 32 + lane, doc = ws + i;
+        warp_for_hits(res, NW, warp, lane, s_hitq, [&](uint32_t i, bool on) {
+          const uint32_t doc = ws + i;
           const float sc = (on && rscore) ? rscore[i] : 0.0f;
           uint32_t digit = 0;
           bool ranked = false;
@@ -1078,7 +1132,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
             }
           }
           warp_count_uniform(s_hist, digit, ranked, lane);
-        }
+        });
       }
       __syncthreads();
       uint32_t* gh = (uint32_t*)P.out_hist;
