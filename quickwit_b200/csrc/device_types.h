@@ -54,7 +54,13 @@ struct DAgg {
   uint32_t has_missing, cell_base, is_f64, pad;
   double interval, offset, bound_min, bound_max;
   int64_t base_pos;
-  int64_t pad2;  // keeps sizeof(DAgg) a multiple of 16 (copied to shared memory as uint4)
+  // fast path (flat bucket aggregations over single-valued columns, see lower_plan): histogram
+  // buckets are found in RAW space — bounds[k] = smallest bit-packed raw value that falls into
+  // bucket >= k (k = 0..num_buckets), computed on the host with the reference f64 formula, so the
+  // device needs no f64 arithmetic and stays bit-exact
+  uint64_t bounds;       // device address of uint64[num_buckets + 1] (HISTOGRAM only)
+  float inv_step;        // ~ num_buckets / (bounds[nb] - bounds[0]): first guess of the bucket
+  uint32_t pad3[3];      // keeps sizeof(DAgg) a multiple of 16 (copied to shared memory as uint4)
   uint64_t range_from[QW_MAX_AGG_RANGES], range_to[QW_MAX_AGG_RANGES];
 };
 static_assert(sizeof(DInstr) % 16 == 0 && sizeof(DCol) % 16 == 0 && sizeof(DAgg) % 16 == 0, "uint4-copied structs");
@@ -100,7 +106,8 @@ struct DSplitPlan {
   uint32_t n_terms, n_levels;
   uint32_t max_hits, scoring;
   uint32_t n_fn_slots, n_cells;
-  uint32_t fused_score_root, pad0;  // root bool is a pure OR of positive-weight scored terms
+  uint32_t fused_score_root;  // root bool is a pure OR of positive-weight scored terms
+  uint32_t fast_aggs;         // every aggregation is a flat bucket aggregation over a single-valued column
   uint64_t fn_off[2];      // data-relative fieldnorm arrays staged per window
   uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables, followed by the
                            // float[QW_TFF_ROWS][256] tf-factor table of the same field
@@ -123,6 +130,7 @@ struct SmemLevel {
 };
 struct SmemLayout {
   uint32_t instr, cols, aggs, key, hitq;  // hitq: per-warp compacted hit queues of the generic collect
+  uint32_t rangeq;  // per-warp queues of required RANGE / EXISTS clauses (0xFFFFFFFF: probe per bitmap word)
   SmemLevel lvl[QW_MAX_LEVELS];
   uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
   uint32_t rng, blkrec, termblk, stage, ent, hist, misc;  // hist aliases ent (dead by collect time)

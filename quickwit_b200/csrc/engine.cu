@@ -173,10 +173,21 @@ uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t
 }
 
 // ---- lowering: QwPlan tree -> window-engine program ----------------------------------------------
+// kernels.cuh mapped_to_f64 on the host (tantivy MonotonicallyMappableToU64 inverses, as f64)
+static double mapped_to_f64_host(uint32_t type, uint64_t m) {
+  switch (type) {
+    case QW_COL_U64: case QW_COL_BOOL: case QW_COL_STR: return (double)m;
+    case QW_COL_I64: case QW_COL_DATETIME: return (double)(int64_t)(m ^ (1ull << 63));
+    default: return u64_to_f64(m);
+  }
+}
+
 struct Lowered {
   DSplitPlan P;
   std::vector<DInstr> instrs;
   std::vector<DCol> cols;
+  std::vector<uint64_t> bounds;  // raw-space histogram boundary tables of the fast aggregation path
+  uint32_t bounds_base = 0;      // position of `bounds` in the batch's table region
   std::vector<DAgg> aggs;
   std::vector<int> col_map;  // image column -> DCol index
   uint32_t need_cnt = 0, need_ssum = 0, need_msum = 0, levels = 0;  // bit per level
@@ -455,6 +466,53 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
   }
   P.n_aggs = ph->num_aggs;
   P.n_cols = (uint32_t)L.cols.size();
+  // fast aggregation path: flat (no nesting) TERMS / HISTOGRAM nodes over always-present single-valued
+  // columns. Histogram buckets are located through a raw-space boundary table built here with the
+  // reference formula (agg_bucket in kernels.cuh == tantivy's ((val - offset) / interval).floor()),
+  // which is monotone in the raw value.
+  bool fast = ph->num_aggs > 0;
+  for (const DAgg& d : L.aggs)
+    if (d.parent != 0xFFFFFFFFu || d.num_children || (d.kind != QW_AGG_TERMS && d.kind != QW_AGG_HISTOGRAM) || d.col == 0xFFFFFFFFu ||
+        L.cols[d.col].card != QW_CARD_FULL || d.num_buckets > QW_SMEM_AGG_CELLS || d.num_buckets == 0)
+      fast = false;
+  if (fast) {
+    for (DAgg& d : L.aggs) {
+      if (d.kind != QW_AGG_HISTOGRAM) continue;
+      const DCol& c = L.cols[d.col];
+      const uint64_t raw_end = c.bits >= 64 ? ~0ull : (1ull << c.bits);  // raws are < raw_end (bits == 64: <= ~0)
+      const uint32_t nb = d.num_buckets;
+      // g(raw): bucket index clamped to [-1, nb]; monotone non-decreasing in raw
+      auto g = [&](uint64_t raw) -> int64_t {
+        const unsigned __int128 wide = (unsigned __int128)c.gcd * raw + c.min_value;  // saturate beyond the column's range
+        const double val = mapped_to_f64_host(c.type, wide > (unsigned __int128)~0ull ? ~0ull : (uint64_t)wide);
+        if (d.has_bounds) {
+          if (!(val >= d.bound_min)) return -1;
+          if (!(val <= d.bound_max)) return (int64_t)nb;
+        }
+        const double pos = std::floor((val - d.offset) / d.interval);
+        if (!(pos >= -9.0e18)) return -1;
+        if (!(pos <= 9.0e18)) return (int64_t)nb;
+        const int64_t idx = (int64_t)pos - d.base_pos;
+        return idx < 0 ? -1 : (idx >= (int64_t)nb ? (int64_t)nb : idx);
+      };
+      d.bounds = L.bounds.size();  // index for now; turned into a device address when the blob is laid out
+      uint64_t lo = 0;
+      for (uint32_t k = 0; k <= nb; k++) {
+        // smallest raw in [lo, raw_end] with g(raw) >= k (raw_end when there is none)
+        uint64_t a = lo, b = raw_end;
+        if (c.bits >= 64 && g(~0ull) < (int64_t)k) a = b = ~0ull;  // (2^64 is not representable: saturate)
+        while (a < b) {
+          const uint64_t mid = a + (b - a) / 2;
+          if (g(mid) >= (int64_t)k) b = mid; else a = mid + 1;
+        }
+        L.bounds.push_back(a);
+        lo = a;
+      }
+      const uint64_t b0 = L.bounds[d.bounds], bn = L.bounds[d.bounds + nb];
+      d.inv_step = bn > b0 ? (float)((double)nb / (double)(bn - b0)) : 0.0f;
+    }
+  }
+  P.fast_aggs = fast ? 1 : 0;
 }
 
 // shared-memory arena for a batch (max over the batch's plans)
@@ -464,7 +522,7 @@ static uint32_t stage_bytes_for(uint32_t W) {
 }
 
 static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, uint32_t need_msum, uint32_t need_ssum,
-                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn, bool rec_l0) {
+                              uint32_t max_instr, uint32_t max_cols, uint32_t max_aggs, uint32_t n_fn, bool rec_l0, bool rangeq) {
   SmemLayout L;
   memset(&L, 0xFF, sizeof L);
   uint32_t off = 0;
@@ -494,6 +552,7 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.ent = L.stage;
   L.hist = L.stage;  // histogram / privatised aggregation counters reuse the staging area at collect time
   if (rec_l0) L.l0hist = take(QW_HIST_BINS * 4);
+  if (rangeq) L.rangeq = take(QW_WARPS * (32 + 32 * 4) * 2);  // QW_WARPS x QW_HITQ_CAP uint16 (kernels.cuh)
   L.total = off;
   return L;
 }
@@ -530,11 +589,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   uint32_t n_levels = 1, need_cnt = 0, need_ssum = 0, need_msum = 0, max_instr = 0, max_cols = 0, max_aggs = 0, n_fn = 0;
   bool scoring = false, any_topk = false, any_aggs = false, smem_aggs = true;
   uint32_t max_cells = 0, max_key_bits = 0;
-  uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0;
+  uint32_t tot_instr = 0, tot_cols = 0, tot_aggs = 0, tot_bounds = 0;
   // second-chance top-K: when no plan ranks by _score first, the collect pass also records the exact
   // level-0 histogram and every window's best digit, so that a failed sampled threshold is repaired
   // by a candidates-only pass over the few windows that can hold candidates
-  bool rec_l0 = true;
+  bool rec_l0 = true, rangeq = false;
   // every plan has the BM25 top-K shape => the specialised UNION instantiation of the collect kernel
   bool all_union = true;
   for (auto& L : low) {
@@ -543,6 +602,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       all_union = false;
     if (L.P.max_hits && L.P.key.kind[0] == QW_SORT_SCORE) rec_l0 = false;
     max_key_bits = std::max(max_key_bits, L.P.key.total_bits);
+    for (const DInstr& in : L.instrs)
+      if ((in.op == OP_RANGE || in.op == OP_EXISTS) && (in.occur == QW_OCCUR_MUST || in.occur == QW_OCCUR_FILTER)) rangeq = true;
     n_levels = std::max(n_levels, L.P.n_levels);
     need_cnt |= L.need_cnt; need_ssum |= L.need_ssum; need_msum |= L.need_msum;
     max_instr = std::max(max_instr, L.P.n_instr); max_cols = std::max(max_cols, L.P.n_cols); max_aggs = std::max(max_aggs, L.P.n_aggs);
@@ -550,7 +611,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     scoring |= L.P.scoring != 0; any_topk |= L.P.max_hits > 0; any_aggs |= L.P.n_aggs > 0;
     max_cells = std::max(max_cells, L.P.n_cells);
     L.P.instr_base = tot_instr; L.P.col_base = tot_cols; L.P.agg_base = tot_aggs;
-    tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs;
+    L.bounds_base = tot_bounds;
+    tot_instr += L.P.n_instr; tot_cols += L.P.n_cols; tot_aggs += L.P.n_aggs; tot_bounds += (uint32_t)L.bounds.size();
   }
   rec_l0 = rec_l0 && any_topk;
   // window size: as large as shared memory allows for the configured blocks/SM (per-window fixed
@@ -559,7 +621,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (const char* e = getenv("QWGPU_W")) W = (uint32_t)atoi(e);
   SmemLayout lay;
   for (;;) {
-    lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0);
+    lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);
     if ((int)lay.total + 1024 <= max_smem_optin / QW_MIN_BLOCKS_PER_SM || W == 1024) break;
     W >>= 1;
   }
@@ -583,7 +645,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
-         o_fws = al(o_fwa + (n + 1) * 4), blob_bytes = al(o_fws + (n + 1) * 4);
+         o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), blob_bytes = al(o_bounds + (size_t)tot_bounds * 8);
   // scratch: thresholds, histograms, candidates
   size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
          s_wmax = al(s_state + (size_t)n * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
@@ -625,7 +687,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     memcpy(slot->h_blob + o_plans + i * sizeof(DSplitPlan), &P, sizeof P);
     memcpy(slot->h_blob + o_instr + P.instr_base * sizeof(DInstr), low[i].instrs.data(), P.n_instr * sizeof(DInstr));
     if (P.n_cols) memcpy(slot->h_blob + o_cols + P.col_base * sizeof(DCol), low[i].cols.data(), P.n_cols * sizeof(DCol));
+    if (P.fast_aggs)
+      for (DAgg& d : low[i].aggs)
+        if (d.kind == QW_AGG_HISTOGRAM) d.bounds = (uint64_t)(slot->d_blob + o_bounds) + (low[i].bounds_base + d.bounds) * 8;
     if (P.n_aggs) memcpy(slot->h_blob + o_aggs + P.agg_base * sizeof(DAgg), low[i].aggs.data(), P.n_aggs * sizeof(DAgg));
+    if (!low[i].bounds.empty()) memcpy(slot->h_blob + o_bounds + (size_t)low[i].bounds_base * 8, low[i].bounds.data(), low[i].bounds.size() * 8);
   }
   memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);

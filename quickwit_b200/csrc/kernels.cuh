@@ -378,6 +378,47 @@ __device__ __forceinline__ void warp_count_uniform(uint32_t* ctr, uint32_t idx, 
   if (same == m) { if (lane == lead) atomicAdd(&ctr[idx], (uint32_t)__popc(m)); }
   else if (on) atomicAdd(&ctr[idx], 1u);
 }
+// Same contract for counters with a handful of distinct targets per warp (terms buckets of a
+// low-cardinality column): up to four leader-broadcast rounds, stragglers fall back to plain atomics.
+__device__ __forceinline__ void warp_count_few(uint32_t* ctr, uint32_t idx, bool on, uint32_t lane) {
+  uint32_t rem = __ballot_sync(QW_FULL, on);
+#pragma unroll 1
+  for (int r = 0; r < 4 && rem; r++) {
+    const uint32_t lead = __ffs(rem) - 1;
+    const uint32_t lead_idx = __shfl_sync(QW_FULL, idx, lead);
+    const uint32_t same = __ballot_sync(QW_FULL, on && idx == lead_idx) & rem;
+    if (lane == lead) atomicAdd(&ctr[lead_idx], (uint32_t)__popc(same));
+    rem &= ~same;
+  }
+  if ((rem >> lane) & 1) atomicAdd(&ctr[idx], 1u);
+}
+// Fast aggregation path (DSplitPlan::fast_aggs): flat TERMS / HISTOGRAM nodes over single-valued
+// columns, counts privatised in shared memory. A histogram bucket is found in raw space through the
+// host-built boundary table (DAgg::bounds) — no f64 arithmetic, bit-exact by construction.
+__device__ __forceinline__ void agg_collect_fast(const Sm& sm, const DSplitPlan& P, const DAgg* aggs, const DCol* cols,
+                                                 const uint8_t* base, uint32_t doc, bool on, uint32_t lane) {
+  uint32_t* ctr = sm.u32(sm.L->hist);
+  for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
+    const DAgg& g = aggs[gi];
+    const uint64_t raw = on ? col_raw(base, cols[g.col], doc) : 0ull;
+    bool ok = on;
+    uint32_t bk = (uint32_t)raw;
+    if (g.kind == QW_AGG_HISTOGRAM) {
+      const uint64_t* B = (const uint64_t*)g.bounds;
+      const uint32_t nb = g.num_buckets;
+      const uint64_t b0 = __ldg(B), bn = __ldg(B + nb);
+      ok = on && raw >= b0 && raw < bn;
+      bk = 0;
+      if (ok) {
+        const float f = __fmul_rn((float)(raw - b0), g.inv_step);
+        bk = f >= (float)(nb - 1) ? nb - 1 : (uint32_t)f;
+        while (raw < __ldg(B + bk)) bk--;
+        while (raw >= __ldg(B + bk + 1)) bk++;
+      }
+    }
+    warp_count_few(ctr, g.cell_base + bk, ok, lane);
+  }
+}
 __device__ __forceinline__ void agg_count(const KParams& p, const Sm& sm, QwAggCell* cells, uint32_t cell, bool on, uint32_t lane) {
   const uint32_t peers = __match_any_sync(QW_FULL, on ? cell : 0xFFFFFFFFu);
   if (on && (uint32_t)(__ffs(peers) - 1) == lane) {
@@ -549,6 +590,15 @@ __device__ __forceinline__ void warp_for_hits(const uint32_t* res, uint32_t NW, 
     }
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, QW_HITQ_WORDS - 1);
     if (total == 0) continue;
+    if (total >= 24 * QW_HITQ_WORDS) {
+      // dense stretch: lanes map straight to docs, no compaction
+#pragma unroll
+      for (int k = 0; k < QW_HITQ_WORDS; k++) {
+        const uint32_t wk = __shfl_sync(0xFFFFFFFFu, word, k);
+        if (wk) body((w0 + k) * 32 + lane, (wk >> lane) & 1);
+      }
+      continue;
+    }
     uint32_t off = cnt + incl - c;
     const uint32_t first = (w0 + lane) * 32;
     while (word) {
@@ -866,6 +916,26 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         const bool has_col = op == OP_ALL || col != 0xFFFFFFFFu;
         const uint64_t lo = in.a, hi = in.b;
         const float boost = in.f;
+        if (gather && op != OP_ALL && p.sm.rangeq != 0xFFFFFFFFu) {
+          // required clause over an already narrowed candidate set: probe only the surviving docs,
+          // 32 per warp step (compacted), and clear the bits of those that fail
+          uint16_t* rq = (uint16_t*)sm.u8(p.sm.rangeq) + warp * QW_HITQ_CAP;
+          warp_for_hits(req, NW, warp, lane, rq, [&](uint32_t i, bool on) {
+            bool hit = false;
+            if (on && has_col) {
+              const DCol& c = s_cols[col];
+              uint64_t a, b;
+              col_range(base, c, ws + i, a, b);
+              if (op == OP_EXISTS) hit = a != b;
+              else for (uint64_t k = a; k < b && !hit; k++) {
+                uint64_t mv = c.min_value + c.gcd * col_raw(base, c, k);
+                hit = mv >= lo && mv <= hi;
+              }
+            }
+            if (on && !hit) atomicAnd(&req[i >> 5], ~(1u << (i & 31)));
+            if (hit && scored) sm.f32(LV.msum)[i] = __fadd_rn(sm.f32(LV.msum)[i], boost);
+          });
+        } else
         for (uint32_t wd = warp; wd < NW; wd += QW_WARPS) {
           const uint32_t d = ws + wd * 32 + lane;
           bool cand = d < we && has_col;
@@ -982,6 +1052,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     const uint32_t n_aggs = (MODE == MODE_COLLECT && p.cands_only) ? 0u : P.n_aggs;
     QwAggCell* cells = (QwAggCell*)P.out_cells;
     const bool rec = MODE == MODE_COLLECT && p.rec_l0 && max_hits && !fused;
+    const bool fast_aggs = P.fast_aggs && p.smem_aggs;
     uint32_t* s_l0 = sm.u32(p.sm.l0hist);
     if (MODE == MODE_HIST || (p.smem_aggs && n_aggs) || rec) {
       // the histogram / privatised aggregation counters alias the (now dead) staging area
@@ -1076,7 +1147,10 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
               if (ranked) my_top = max(my_top, top + 1);
             }
           }
-          if (n_aggs) agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc, on, lane);
+          if (n_aggs) {
+            if (fast_aggs) agg_collect_fast(sm, P, s_aggs, s_cols, base, doc, on, lane);
+            else agg_collect_doc(p, sm, P, s_aggs, s_cols, base, cells, doc, on, lane);
+          }
         });
         if (!sa_present) my_elig = 0;
       }
