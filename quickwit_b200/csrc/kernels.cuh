@@ -578,35 +578,9 @@ static_assert(QW_WARPS * QW_HITQ_CAP * 2 <= QW_MAX_TERMS * 16 + QW_MAX_WBLK * 8 
 static_assert(QW_MAX_INSTR <= 255, "s_tinstr holds instruction indices as bytes");
 template <class F>
 __device__ __forceinline__ void warp_for_hits(const uint32_t* res, uint32_t NW, uint32_t warp, uint32_t lane, uint16_t* q, F&& body) {
-  uint32_t cnt = 0;  // queued hits (warp-uniform)
-  for (uint32_t w0 = warp * QW_HITQ_WORDS; w0 < NW; w0 += QW_WARPS * QW_HITQ_WORDS) {
-    uint32_t word = (lane < QW_HITQ_WORDS && w0 + lane < NW) ? res[w0 + lane] : 0u;
-    const uint32_t c = __popc(word);
-    uint32_t incl = c;
-#pragma unroll
-    for (int o = 1; o < QW_HITQ_WORDS; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if ((int)lane >= o) incl += t;
-    }
-    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, QW_HITQ_WORDS - 1);
-    if (total == 0) continue;
-    if (total >= 24 * QW_HITQ_WORDS) {
-      // dense stretch: lanes map straight to docs, no compaction
-#pragma unroll
-      for (int k = 0; k < QW_HITQ_WORDS; k++) {
-        const uint32_t wk = __shfl_sync(0xFFFFFFFFu, word, k);
-        if (wk) body((w0 + k) * 32 + lane, (wk >> lane) & 1);
-      }
-      continue;
-    }
-    uint32_t off = cnt + incl - c;
-    const uint32_t first = (w0 + lane) * 32;
-    while (word) {
-      q[off++] = (uint16_t)(first + __ffs(word) - 1);
-      word &= word - 1;
-    }
-    __syncwarp();
-    cnt += total;
+  uint32_t cnt = 0;  // queued hits (warp-uniform, < 32 between steps)
+  // drain full batches of 32 from the queue, move the remainder to the front
+  auto drain = [&]() {
     uint32_t done = 0;
     while (cnt - done >= 32) {
       body((uint32_t)q[done + lane], true);
@@ -620,6 +594,64 @@ __device__ __forceinline__ void warp_for_hits(const uint32_t* res, uint32_t NW, 
       cnt = rem;
     }
     __syncwarp();
+  };
+  // a super-step covers 32 bitmap words (1024 docs), one word per lane
+  for (uint32_t s0 = warp * 32; s0 < NW; s0 += QW_WARPS * 32) {
+    uint32_t word = s0 + lane < NW ? res[s0 + lane] : 0u;
+    const uint32_t c = __popc(word);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if ((int)lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0) continue;
+    if (total <= 32 * QW_HITQ_WORDS) {
+      // sparse: every lane extracts the hits of its own word; the queue has room for all of them
+      uint32_t off = cnt + incl - c;
+      const uint32_t first = (s0 + lane) * 32;
+      while (word) {
+        q[off++] = (uint16_t)(first + __ffs(word) - 1);
+        word &= word - 1;
+      }
+      __syncwarp();
+      cnt += total;
+      drain();
+      continue;
+    }
+    // denser: QW_HITQ_WORDS words at a time
+    for (uint32_t g = 0; g < 32; g += QW_HITQ_WORDS) {
+      uint32_t wg = __shfl_sync(0xFFFFFFFFu, word, g + (lane & (QW_HITQ_WORDS - 1)));
+      if (lane >= QW_HITQ_WORDS) wg = 0;
+      const uint32_t cg = __popc(wg);
+      uint32_t ig = cg;
+#pragma unroll
+      for (int o = 1; o < QW_HITQ_WORDS; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ig, o);
+        if ((int)lane >= o) ig += t;
+      }
+      const uint32_t tg = __shfl_sync(0xFFFFFFFFu, ig, QW_HITQ_WORDS - 1);
+      if (tg == 0) continue;
+      if (tg >= 24 * QW_HITQ_WORDS) {
+        // dense stretch: lanes map straight to docs, no compaction
+#pragma unroll
+        for (int k = 0; k < QW_HITQ_WORDS; k++) {
+          const uint32_t wk = __shfl_sync(0xFFFFFFFFu, wg, k);
+          if (wk) body((s0 + g + k) * 32 + lane, (wk >> lane) & 1);
+        }
+        continue;
+      }
+      uint32_t off = cnt + ig - cg;
+      const uint32_t first = (s0 + g + lane) * 32;
+      while (wg) {
+        q[off++] = (uint16_t)(first + __ffs(wg) - 1);
+        wg &= wg - 1;
+      }
+      __syncwarp();
+      cnt += tg;
+      drain();
+    }
   }
   if (cnt) body(lane < cnt ? (uint32_t)q[lane] : 0u, lane < cnt);
 }
