@@ -1221,7 +1221,20 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         }
       }
     } else {
-      if (max_hits) {
+      if (UNION) {
+        // level-0 histogram of a BM25 union straight from the score array (digit = [1 | lin:10]);
+        // the sweep also clears the array for the next window
+        float4* sc4 = reinterpret_cast<float4*>(sm.f32(p.sm.lvl[0].ssum));
+        for (uint32_t q = tid; q < (W >> 2); q += QW_THREADS) {
+          const float4 v = sc4[q];
+          sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (v.x > 0.0f) atomicAdd(&s_hist[1024u | score_lin(ks, v.x, true)], 1u);
+          if (v.y > 0.0f) atomicAdd(&s_hist[1024u | score_lin(ks, v.y, true)], 1u);
+          if (v.z > 0.0f) atomicAdd(&s_hist[1024u | score_lin(ks, v.z, true)], 1u);
+          if (v.w > 0.0f) atomicAdd(&s_hist[1024u | score_lin(ks, v.w, true)], 1u);
+        }
+        ssum_clean = true;
+      } else if (max_hits) {
         warp_for_hits(res, NW, warp, lane, s_hitq, [&](uint32_t i, bool on) {
           const uint32_t doc = ws + i;
           const float sc = (on && rscore) ? rscore[i] : 0.0f;

@@ -134,3 +134,28 @@ def test_invoke_leaf_search_per_split_results(gpu_ctx, synth):
     for im, r in zip(synth, results):
         want = proto.dec_leaf_search_response(cpu_split_response(im, leaf_pb, SYNTH_MAPPING))
         assert r["response"]["num_hits"] == want["num_hits"] and r["response"]["partial_hits"] == want["partial_hits"]
+
+
+def test_concurrent_leaf_searches_match_sequential(gpu_ctx, synth):
+    """qwgpu_leaf_search is callable from several host threads at once (one stream + staging slot per
+    in-flight call); interleaved requests must return what they return alone."""
+    from concurrent.futures import ThreadPoolExecutor
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in synth]
+    dm = json.dumps(SYNTH_MAPPING)
+    reqs = []
+    for q in range(8):
+        ast = bool_(should=[term("body", f"t{(q + i) % 10}") for i in range(1 + q % 4)]) if q % 2 == 0 else bool_(must=[term("body", f"t{q % 5}")])
+        kw = dict(max_hits=50 + 10 * q, sort_fields=[("_score", DESC)] if q % 2 == 0 else [("timestamp", DESC)])
+        if q == 3:
+            kw["aggs"] = {"by_sev": {"terms": {"field": "severity_text"}}}
+        reqs.append(proto.enc_leaf_search_request(search_request(ast, **kw), offsets, dm))
+
+    def hits(resp):
+        d = proto.dec_leaf_search_response(resp)
+        return d["num_hits"], d["partial_hits"], d["intermediate_aggregation_result"]
+
+    want = [hits(gpu_ctx.leaf_search(r)) for r in reqs]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for _ in range(5):
+            got = list(ex.map(lambda r: hits(gpu_ctx.leaf_search(r)), reqs))
+            assert got == want
