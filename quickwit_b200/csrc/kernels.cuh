@@ -269,6 +269,75 @@ __device__ __forceinline__ void fold_block_dyn(uint32_t blk_off, const uint8_t* 
   else { if (cn) fold_block<false, true, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); else fold_block<false, false, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); }
 }
 
+// BM25-union pipeline, first half: decode a STAGED posting block and compute the score contribution
+// of each of the lane's 4 postings (weight * tf-factor) WITHOUT touching the accumulator, so that it
+// can run ahead of the clause order; `inmask` bit j = posting j exists and lies inside the window.
+__device__ __forceinline__ void union_decode(uint32_t blk_off, uint32_t ws, uint32_t wlen, const TermTarget& tg, uint32_t lane,
+                                             uint32_t (&rel)[4], float (&contrib)[4], uint32_t& inmask) {
+  const uint8_t* blk = qw_smem + blk_off;
+  const uint4 h = *reinterpret_cast<const uint4*>(blk);  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
+  const uint32_t last_doc = h.x, prev = h.y;
+  const uint32_t doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;
+  inmask = 0;
+  if (last_doc < ws) return;
+  if (prev != QW_NO_PREV_DOC && prev + 1 >= ws + wlen) return;
+  const uint4* dp = reinterpret_cast<const uint4*>(blk + 16);
+  uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+  if (doc_bits) {
+    uint32_t bitpos = lane * doc_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = dp[wi];
+    uint4 B = (sh + doc_bits > 32) ? dp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - doc_bits);
+    v0 = __funnelshift_r(A.x, B.x, sh) & mask;
+    v1 = __funnelshift_r(A.y, B.y, sh) & mask;
+    v2 = __funnelshift_r(A.z, B.z, sh) & mask;
+    v3 = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  uint32_t d0 = v0 + 1, d1 = d0 + v1 + 1, d2 = d1 + v2 + 1, d3 = d2 + v3 + 1;
+  uint32_t incl = d3;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if ((int)lane >= o) incl += n;
+  }
+  const uint32_t basev = prev + (incl - d3) - ws;  // mod 2^32; window-relative
+  rel[0] = basev + d0; rel[1] = basev + d1; rel[2] = basev + d2; rel[3] = basev + d3;
+  const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;
+  uint32_t tf[4] = {1, 1, 1, 1};
+  if (tg.has_tf && tf_bits) {
+    const uint4* tp = dp + doc_bits;
+    uint32_t bitpos = lane * tf_bits, wi = bitpos >> 5, sh = bitpos & 31;
+    uint4 A = tp[wi];
+    uint4 B = (sh + tf_bits > 32) ? tp[wi + 1] : make_uint4(0, 0, 0, 0);
+    uint32_t mask = 0xFFFFFFFFu >> (32 - tf_bits);
+    tf[0] = __funnelshift_r(A.x, B.x, sh) & mask;
+    tf[1] = __funnelshift_r(A.y, B.y, sh) & mask;
+    tf[2] = __funnelshift_r(A.z, B.z, sh) & mask;
+    tf[3] = __funnelshift_r(A.w, B.w, sh) & mask;
+  }
+  const float* tab = tg.gtab;
+  const uint8_t* fn = qw_smem + tg.fn;
+  const bool has_fn = tg.fn != 0xFFFFFFFFu;
+  uint32_t f[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const bool in = (uint32_t)j < nvalid && rel[j] < wlen;  // rel = doc - ws (unsigned wrap before the window)
+    inmask |= (in ? 1u : 0u) << j;
+    f[j] = (has_fn && in) ? fn[rel[j]] : 1u;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    // Bm25Weight::score: weight * (tf / (tf + cache[fieldnorm_id])), f32 round-to-nearest
+    const uint32_t t = tf[j];
+    float tfn = 0.0f;
+    if ((inmask >> j) & 1) {
+      if (t < QW_TFF_ROWS) tfn = __ldg(tab + 256 + t * 256 + f[j]);
+      else { float tff = (float)t; tfn = __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + f[j]))); }
+    }
+    contrib[j] = __fmul_rn(tg.weight, tfn);
+  }
+}
+
 // Composite key + eligibility of one matched doc (sort-value extraction:
 // SortingFieldExtractorComponent, quickwit-search/src/collector.rs:139-205)
 struct DocKey {
@@ -789,7 +858,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
     // ---- phase 2: stage offsets + global block numbering (one thread), then, in ONE round of loads,
     // cp.async the packed posting bytes and read the skip entries that describe each staged block ------
     if (tid == 0) {
-      uint32_t off = 0, g = 0;
+      uint32_t off = 0, g = 0, n_direct = 0;
       for (uint32_t t = 0; t < n_terms; t++) {
         const uint32_t len = s_rng[4 * t + 1], nb = s_tblk[2 * t + 1];
         if (len && off + len <= p.stage_bytes && nb <= QW_BLK_TAB && g + nb <= QW_MAX_WBLK) {
@@ -800,9 +869,11 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         } else {
           s_rng[4 * t + 2] = 0xFFFFFFFFu;  // direct mode (or nothing to do)
           s_misc[8 + t] = g;
+          if (len) n_direct++;
         }
       }
       s_misc[0] = g;
+      s_misc[6] = n_direct;  // terms of this window that are decoded from global memory
     }
     __syncthreads();
     for (uint32_t t = warp; t < n_terms; t += QW_WARPS) {
@@ -851,8 +922,55 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         const bool scored = (in.flags & IF_SCORED) != 0;
         if (UNION && op == OP_BOOL_BEGIN) {
           if (!ssum_clean) zero_f4(sm.f32(LV.ssum), W, tid);
+          if (tid == 0) s_misc[5] = 0;  // ticket: posting blocks applied so far
           __syncthreads();
           ip++;
+          if (s_misc[6] == 0) {
+            // Every term of the window is staged: run the whole union as ONE pipelined pass over the
+            // flat block table (blocks are numbered in clause order). A warp decodes its next block
+            // right away and only the read-modify-write of the accumulator waits until every block of
+            // the EARLIER clauses has been applied (ticket counter) — the f32 sums keep the reference's
+            // clause order, but there is no block-wide barrier per clause and no warp idles while a
+            // short clause finishes. Blocks of one clause touch distinct docs, so they commute.
+            const uint32_t G = s_misc[0];
+            volatile uint32_t* ticket = (volatile uint32_t*)&s_misc[5];
+            float* score = sm.f32(LV.ssum);
+            for (uint32_t g = warp; g < G; g += QW_WARPS) {
+              const BlkRec r = s_blk[g];
+              const DInstr& ti = s_instr[s_tinstr[r.slot]];
+              TermTarget tg;
+              tg.bits = 0xFFFFFFFFu;
+              tg.cnt = 0xFFFFFFFFu;
+              tg.score = LV.ssum;
+              tg.weight = ti.f;
+              tg.has_tf = (ti.flags & IF_HAS_TF) != 0;
+              tg.fn = (ti.flags & IF_HAS_FN) ? p.sm.fn[ti.r] : 0xFFFFFFFFu;
+              tg.gtab = (const float*)P.bm25_tab[ti.r];
+              uint32_t rel[4], inmask;
+              float contrib[4];
+              union_decode(p.sm.stage + r.soff, ws, wlen, tg, lane, rel, contrib, inmask);
+              const uint32_t need = s_tblk[2 * r.slot];  // first block of this clause = blocks of earlier clauses
+              if (need) {
+                if (lane == 0) {
+                  while (*ticket < need) __nanosleep(20);
+                  __threadfence_block();
+                }
+                __syncwarp();
+              }
+              float old[4];
+#pragma unroll
+              for (int j = 0; j < 4; j++) old[j] = ((inmask >> j) & 1) ? score[rel[j]] : 0.0f;
+#pragma unroll
+              for (int j = 0; j < 4; j++) if ((inmask >> j) & 1) score[rel[j]] = __fadd_rn(old[j], contrib[j]);
+              __syncwarp();
+              if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&s_misc[5], 1u);
+              }
+            }
+            __syncthreads();
+            ip = n_instr;  // the TERM / BOOL_END instructions are done
+          }
         } else if (UNION && op == OP_BOOL_END) {
           ip++;
         } else if (UNION) {  // OP_TERM, should + scored, bitmap implied by the score
