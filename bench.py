@@ -45,9 +45,9 @@ FRACS = [0.20, 0.10, 0.05, 0.05, 0.02, 0.02, 0.01, 0.01, 0.005, 0.001]
 Q_SETS = 4
 K = 1000
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_window<COLLECT> launch on this workload, from
-# the `ncu --set full` capture summarised in profiles/r1_summary.md (170.8 MB + 4.2 MB). A constant of
+# the `ncu --set full` capture summarised in profiles/r1_summary.md (171.0 MB + 4.4 MB). A constant of
 # the workload + build, not measured live (ncu cannot run inside the timed bench).
-NCU_TRAFFIC_BYTES = 175.0e6
+NCU_TRAFFIC_BYTES = 175.4e6
 
 
 def parse_args():
@@ -248,6 +248,11 @@ def main():
                           "e2e": {"value": value, "unit": "postings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner
+    # goes to stdout) is sent to stderr, and the result is written to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -275,10 +280,12 @@ def main():
     t_build = time.perf_counter() - t_build
     part_bytes = service.partial_size(sreqs[0]) if world > 1 else 0
     if world > 1:
-        part_host = torch.zeros(part_bytes, dtype=torch.uint8).pin_memory()
-        part_dev = torch.zeros(part_bytes, dtype=torch.uint8, device="cuda")
-        gath_dev = torch.zeros(world * part_bytes, dtype=torch.uint8, device="cuda")
-        gath_host = torch.zeros(world * part_bytes, dtype=torch.uint8).pin_memory()
+        # one fixed-size partial per query of the step; the step's partials travel in ONE all-gather
+        part_host = torch.zeros(Q_SETS * part_bytes, dtype=torch.uint8).pin_memory()
+        part_dev = torch.zeros(Q_SETS * part_bytes, dtype=torch.uint8, device="cuda")
+        gath_dev = torch.zeros(world * Q_SETS * part_bytes, dtype=torch.uint8, device="cuda")
+        gath_host = torch.zeros(world * Q_SETS * part_bytes, dtype=torch.uint8).pin_memory()
+        by_query = torch.zeros(Q_SETS * world * part_bytes, dtype=torch.uint8)  # [query][rank][partial]
 
     def step():
         acc = dict(gpu_us=0.0, main_us=0.0, launches=0, postings=0, alg_bytes=0, d2h=0, h2d=0, fallbacks=0)
@@ -305,19 +312,32 @@ def main():
         t = time.perf_counter()
         r = ctx.leaf_search(lreqs[q])
         lat.append(time.perf_counter() - t)
+        if world > 1:  # this rank's merged leaf response -> fixed-size partial (typed sort values, split id, doc id)
+            service.response_to_partial(sreqs[q], r, part_host.data_ptr() + q * part_bytes, part_bytes)
         return r
 
+    def merge_query(q):
+        return service.merge_partials(sreqs[q], world, by_query.data_ptr() + q * world * part_bytes, part_bytes)
+
+    phase = [0.0, 0.0, 0.0]  # leaf searches, all-gather round trip, root merges (rank-local wall time)
+
     def step_e2e():
+        t0 = time.perf_counter()
         resps = list(pool.map(one_query, range(Q_SETS)))
+        phase[0] += time.perf_counter() - t0
+        if world > 1:
+            t0 = time.perf_counter()
+            part_dev.copy_(part_host, non_blocking=True)
+            dist.all_gather_into_tensor(gath_dev, part_dev)   # the single collective of the data path
+            gath_host.copy_(gath_dev)
+            # [rank][query][partial] -> [query][rank][partial], then every rank runs the root merge
+            by_query.view(Q_SETS, world, part_bytes).copy_(gath_host.view(world, Q_SETS, part_bytes).transpose(0, 1))
+            phase[1] += time.perf_counter() - t0
+            t0 = time.perf_counter()
+            resps = list(pool.map(merge_query, range(Q_SETS)))
+            phase[2] += time.perf_counter() - t0
         for q in range(Q_SETS):
-            resp = resps[q]
-            if world > 1:
-                service.response_to_partial(sreqs[q], resp, part_host.data_ptr(), part_bytes)
-                part_dev.copy_(part_host, non_blocking=True)
-                dist.all_gather_into_tensor(gath_dev, part_dev)   # the single collective of the data path
-                gath_host.copy_(gath_dev)
-                resp = service.merge_partials(sreqs[q], world, gath_host.data_ptr(), part_bytes)
-            last[q] = resp
+            last[q] = resps[q]
 
     def sync():
         torch.cuda.synchronize()
@@ -339,6 +359,7 @@ def main():
         step_e2e()
     sync()
     lat.clear()
+    phase[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_e2e()
@@ -380,7 +401,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
         "config": dict(workload, parallelism=f"splits_x{world}", resident_bytes_per_gpu=resident, build_seconds=round(t_build, 1)),
         "e2e": {"value": postings / wall, "unit": "postings/s", "api": "qwgpu_leaf_search (LeafSearchRequest -> LeafSearchResponse bytes)",
-                "ms_per_step": 1e3 * wall / a.steps, "concurrent_queries": Q_SETS, "mean_query_latency_ms": 1e3 * sum(lat) / max(len(lat), 1),
+                "ms_per_step": 1e3 * wall / a.steps, "concurrent_queries": Q_SETS, "phase_ms_per_step": {"leaf_search": 1e3 * phase[0] / a.steps, "all_gather": 1e3 * phase[1] / a.steps, "root_merge": 1e3 * phase[2] / a.steps}, "mean_query_latency_ms": 1e3 * sum(lat) / max(len(lat), 1),
                 "h2d_bytes_per_step": accs[0]["h2d"] + sum(len(x) for x in lreqs),
                 "d2h_bytes_per_step": Q_SETS * a.splits * (32 + 32 * K),
                 "seam_c_wall_value": postings / wall_c},
@@ -398,7 +419,8 @@ def main():
         rate, dt, rounds = cpu_oracle_rate(imgs[:n_s], plans[0][:n_s], threads)
         out["cpu_baseline"] = {"value": rate, "unit": "postings/s", "cores": threads, "kind": "port",
                                "sample": f"query set 0 over {n_s} splits x {rounds} rounds ({dt:.1f} s), one split per thread"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -139,15 +139,36 @@ pb::LeafSearchResponse merge_responses(const pb::SearchRequest& req, std::vector
       m.num_successful_splits += p.num_successful_splits;
       m.num_hits += p.num_hits;
       for (auto& f : p.failed_splits) m.failed_splits.push_back(f);
-      for (auto& h : p.partial_hits) m.partial_hits.push_back(std::move(h));
     }
     if (req.aggregation_request && !req.aggregation_request->empty()) {
       std::vector<AggReq> reqs = parse_agg_request(*req.aggregation_request);
       m.intermediate_aggregation_result = merge_intermediate_aggs(reqs, agg_parts);
     }
-    // top_k_partial_hits (collector.rs:980-992): TopK heap + sorted finalize == sort best-first, keep k
-    std::stable_sort(m.partial_hits.begin(), m.partial_hits.end(), [&](const pb::PartialHit& a, const pb::PartialHit& b) { return hit_cmp(o1, o2, a, b) > 0; });
-    if (m.partial_hits.size() > k) m.partial_hits.resize(k);
+    // top_k_partial_hits (collector.rs:980-992): TopK heap + sorted finalize == sort best-first, keep k.
+    // Leaf responses arrive sorted best-first, so this is normally an n-way merge that stops after k
+    // hits (ties go to the earlier part, like a stable sort of the concatenation); unsorted input falls
+    // back to the sort.
+    bool sorted = true;
+    for (auto& p : parts)
+      for (size_t i = 1; i < p.partial_hits.size() && sorted; i++)
+        if (hit_cmp(o1, o2, p.partial_hits[i - 1], p.partial_hits[i]) < 0) sorted = false;
+    if (sorted) {
+      std::vector<size_t> pos(parts.size(), 0);
+      while (m.partial_hits.size() < k) {
+        int best = -1;
+        for (size_t i = 0; i < parts.size(); i++) {
+          if (pos[i] >= parts[i].partial_hits.size()) continue;
+          if (best < 0 || hit_cmp(o1, o2, parts[i].partial_hits[pos[i]], parts[best].partial_hits[pos[best]]) > 0) best = (int)i;
+        }
+        if (best < 0) break;
+        m.partial_hits.push_back(std::move(parts[best].partial_hits[pos[best]++]));
+      }
+    } else {
+      for (auto& p : parts)
+        for (auto& h : p.partial_hits) m.partial_hits.push_back(std::move(h));
+      std::stable_sort(m.partial_hits.begin(), m.partial_hits.end(), [&](const pb::PartialHit& a, const pb::PartialHit& b) { return hit_cmp(o1, o2, a, b) > 0; });
+      if (m.partial_hits.size() > k) m.partial_hits.resize(k);
+    }
   }
   // merge_fruits: drop [..start_offset), truncate to max_hits (collector.rs:851-858)
   size_t drop = std::min<size_t>((size_t)req.start_offset, m.partial_hits.size());
