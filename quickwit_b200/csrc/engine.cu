@@ -189,6 +189,7 @@ struct Lowered {
   std::vector<DCol> cols;
   std::vector<uint64_t> bounds;  // raw-space histogram boundary tables of the fast aggregation path
   uint32_t bounds_base = 0;      // position of `bounds` in the batch's table region
+  std::vector<uint64_t> col_max_raw;  // parallel to cols: largest bit-packed raw value present in the column
   std::vector<DAgg> aggs;
   std::vector<int> col_map;  // image column -> DCol index
   uint32_t need_cnt = 0, need_ssum = 0, need_msum = 0, levels = 0;  // bit per level
@@ -209,6 +210,7 @@ static uint32_t use_col(Lowered& L, const SplitDev& sp, uint32_t c) {
   d.bits = ic.bits; d.card = ic.cardinality; d.type = ic.type; d.nwords64 = (sp.view.hdr->num_docs + 63) / 64;
   L.col_map[c] = (int)L.cols.size();
   L.cols.push_back(d);
+  L.col_max_raw.push_back(ic.gcd ? (ic.max_value - ic.min_value) / ic.gcd : 0);
   return (uint32_t)L.col_map[c];
 }
 
@@ -480,7 +482,10 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
     for (DAgg& d : L.aggs) {
       if (d.kind != QW_AGG_HISTOGRAM) continue;
       const DCol& c = L.cols[d.col];
-      const uint64_t raw_end = c.bits >= 64 ? ~0ull : (1ull << c.bits);  // raws are < raw_end (bits == 64: <= ~0)
+      // raws present in the column are <= max_raw; searching beyond would leave the value domain
+      // (f64 columns: bit patterns past the maximum are NaNs and break monotonicity)
+      const uint64_t max_raw = L.col_max_raw[d.col];
+      const uint64_t raw_end = max_raw == ~0ull ? max_raw : max_raw + 1;
       const uint32_t nb = d.num_buckets;
       // g(raw): bucket index clamped to [-1, nb]; monotone non-decreasing in raw
       auto g = [&](uint64_t raw) -> int64_t {
@@ -501,7 +506,7 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
       for (uint32_t k = 0; k <= nb; k++) {
         // smallest raw in [lo, raw_end] with g(raw) >= k (raw_end when there is none)
         uint64_t a = lo, b = raw_end;
-        if (c.bits >= 64 && g(~0ull) < (int64_t)k) a = b = ~0ull;  // (2^64 is not representable: saturate)
+        if (max_raw == ~0ull && g(~0ull) < (int64_t)k) a = b = ~0ull;  // (2^64 is not representable: saturate)
         while (a < b) {
           const uint64_t mid = a + (b - a) / 2;
           if (g(mid) >= (int64_t)k) b = mid; else a = mid + 1;
