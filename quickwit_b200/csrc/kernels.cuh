@@ -935,6 +935,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
             const uint32_t G = s_misc[0];
             volatile uint32_t* ticket = (volatile uint32_t*)&s_misc[5];
             float* score = sm.f32(LV.ssum);
+            // (static round-robin assignment; handing blocks out from a shared counter measured slower)
             for (uint32_t g = warp; g < G; g += QW_WARPS) {
               const BlkRec r = s_blk[g];
               const DInstr& ti = s_instr[s_tinstr[r.slot]];

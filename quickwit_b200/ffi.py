@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqwgpu.so")
+LIB_PATH = os.environ.get("QWGPU_LIB") or os.path.join(_HERE, "libqwgpu.so")  # QWGPU_LIB: development builds
 
 OK = 0
 EINTERNAL, EINVALID_QUERY, EINVALID_AGG, EINVALID_ARG, ENODEVICE, ENOTFOUND, EUNSUPPORTED = (
