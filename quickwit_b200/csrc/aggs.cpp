@@ -268,6 +268,11 @@ struct IAgg {
   // metric
   uint64_t m_count = 0;
   double m_sum = 0, m_min = INFINITY, m_max = -INFINITY;
+  // key -> position in `buckets`, built on the first merge into this node and kept up to date, so that
+  // folding n responses costs O(total buckets · log) instead of re-indexing the accumulator n times
+  bool indexed = false;
+  std::map<IKey, size_t> tindex;
+  std::map<double, size_t> hindex;
 };
 
 struct BW {
@@ -511,16 +516,16 @@ static void merge_into(const AggReq& req, IAgg& acc, IAgg&& other) {
   acc.sum_other += other.sum_other;
   acc.error_bound += other.error_bound;
   if (acc.kind == AggReq::Terms) {
-    std::map<IKey, size_t> index;
-    for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].key] = i;
+    auto& index = acc.tindex;
+    if (!acc.indexed) { for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].key] = i; acc.indexed = true; }
     for (auto& b : other.buckets) {
       auto it = index.find(b.key);
       if (it == index.end()) { index[b.key] = acc.buckets.size(); acc.buckets.push_back(std::move(b)); }
       else { IBucket& t = acc.buckets[it->second]; t.count += b.count; merge_lists(req.children, t.subs, std::move(b.subs)); }
     }
   } else {
-    std::map<double, size_t> index;
-    for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].hkey] = i;
+    auto& index = acc.hindex;
+    if (!acc.indexed) { for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].hkey] = i; acc.indexed = true; }
     for (auto& b : other.buckets) {
       auto it = index.find(b.hkey);
       if (it == index.end()) { index[b.hkey] = acc.buckets.size(); acc.buckets.push_back(std::move(b)); }
