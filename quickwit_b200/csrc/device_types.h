@@ -60,7 +60,8 @@ struct DAgg {
   // device needs no f64 arithmetic and stays bit-exact
   uint64_t bounds;       // device address of uint64[num_buckets + 1] (HISTOGRAM only)
   float inv_step;        // ~ num_buckets / (bounds[nb] - bounds[0]): first guess of the bucket
-  uint32_t pad3[3];      // keeps sizeof(DAgg) a multiple of 16 (copied to shared memory as uint4)
+  uint32_t stat_base;    // STATS on the fast path: first of this node's {sum, ~min, max} triples in shared memory
+  uint32_t pad3[2];      // keeps sizeof(DAgg) a multiple of 16 (copied to shared memory as uint4)
   uint64_t range_from[QW_MAX_AGG_RANGES], range_to[QW_MAX_AGG_RANGES];
 };
 static_assert(sizeof(DInstr) % 16 == 0 && sizeof(DCol) % 16 == 0 && sizeof(DAgg) % 16 == 0, "uint4-copied structs");
@@ -107,7 +108,9 @@ struct DSplitPlan {
   uint32_t max_hits, scoring;
   uint32_t n_fn_slots, n_cells;
   uint32_t fused_score_root;  // root bool is a pure OR of positive-weight scored terms
-  uint32_t fast_aggs;         // every aggregation is a flat bucket aggregation over a single-valued column
+  uint32_t fast_aggs;         // every aggregation is a bucket aggregation (optionally with stats children)
+                              // or a stats node over always-present single-valued columns
+  uint32_t n_stat_cells, pad1;  // fast path: number of privatised stats cells
   uint64_t fn_off[2];      // data-relative fieldnorm arrays staged per window
   uint64_t bm25_tab[2];    // device addresses of float[256] BM25 norm tables, followed by the
                            // float[QW_TFF_ROWS][256] tf-factor table of the same field

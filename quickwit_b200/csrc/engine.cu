@@ -484,10 +484,21 @@ static void lower_plan(Lowered& L, const SplitDev& sp, const uint8_t* plan, size
   // reference formula (agg_bucket in kernels.cuh == tantivy's ((val - offset) / interval).floor()),
   // which is monotone in the raw value.
   bool fast = ph->num_aggs > 0;
-  for (const DAgg& d : L.aggs)
-    if (d.parent != 0xFFFFFFFFu || d.num_children || (d.kind != QW_AGG_TERMS && d.kind != QW_AGG_HISTOGRAM) || d.col == 0xFFFFFFFFu ||
-        L.cols[d.col].card != QW_CARD_FULL || d.num_buckets > QW_SMEM_AGG_CELLS || d.num_buckets == 0)
-      fast = false;
+  P.n_stat_cells = 0;
+  for (DAgg& d : L.aggs) {
+    const bool full_col = d.col != 0xFFFFFFFFu && L.cols[d.col].card == QW_CARD_FULL;
+    if (d.kind == QW_AGG_STATS) {
+      // stats: top-level, or directly under a top-level bucket node; one {sum, min, max} triple per cell
+      if (!full_col || d.num_children || (d.parent != 0xFFFFFFFFu && L.aggs[d.parent].parent != 0xFFFFFFFFu)) fast = false;
+      d.stat_base = P.n_stat_cells;
+      P.n_stat_cells += d.parent == 0xFFFFFFFFu ? 1u : L.aggs[d.parent].num_buckets;
+    } else {
+      if (d.parent != 0xFFFFFFFFu || (d.kind != QW_AGG_TERMS && d.kind != QW_AGG_HISTOGRAM) || !full_col ||
+          d.num_buckets > QW_SMEM_AGG_CELLS || d.num_buckets == 0)
+        fast = false;
+    }
+  }
+  if (!fast) P.n_stat_cells = 0;
   if (fast) {
     for (DAgg& d : L.aggs) {
       if (d.kind != QW_AGG_HISTOGRAM) continue;
@@ -695,6 +706,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
 
   for (uint32_t i = 0; i < n; i++) {
     DSplitPlan& P = low[i].P;
+    // privatised counters + stats triples must fit the (dead at collect time) staging area
+    if (P.fast_aggs && (((size_t)P.n_cells * 4 + 7) & ~(size_t)7) + (size_t)P.n_stat_cells * 24 > stage_bytes_for(W)) P.fast_aggs = 0;
     uint8_t* ob = slot->d_out + out_off[i];
     P.out_num_hits = (uint64_t)ob;            // [0] hits, [1] eligible
     P.out_nhits = (uint64_t)(ob + 16);

@@ -1,20 +1,27 @@
 // kernels.cuh — sm_100a kernels of the per-split leaf search hot path.
 //
-// Execution model ("window engine"): a thread block owns one doc-id WINDOW (W <= 4096 docs) of one
-// split and evaluates the whole boolean query over it in shared memory:
-//   1. one dependent load per query term fetches the window-index entry (QwWinIdx) = the exact
-//      byte range of posting blocks overlapping the window; fieldnorm bytes of the window are
-//      staged with 16-byte coalesced loads at the same time;
-//   2. the packed posting bytes of ALL terms are staged with cp.async (16-byte, coalesced);
-//   3. terms are decoded block-per-warp (4-lane-interleaved bit-unpack -> warp-shuffle prefix
-//      scan -> doc ids), BM25 is applied in f32 and accumulated into per-window score arrays in
-//      FIXED clause order (bit-reproducible sums), match sets are shared-memory bitmaps combined
-//      with AND / OR / AND-NOT exactly like tantivy's BooleanWeight;
+// Execution model ("window engine"): a 512-thread block owns one doc-id WINDOW (16384 docs when shared
+// memory allows; 32768 for unscored plans) of one split and evaluates the whole boolean query over it
+// in shared memory; the grid is persistent (2 blocks per SM) and walks a static partition of the flat
+// (split, window) list of the request, so one launch covers every split:
+//   1. one load per query term fetches the window-index entry (QwWinIdx) = the exact byte range and
+//      block ordinals of the posting blocks overlapping the window; fieldnorm bytes of the window are
+//      staged with 16-byte cp.async copies at the same time;
+//   2. the packed posting bytes of ALL terms are staged with cp.async (16-byte, coalesced) while the
+//      same load round turns the terms' skip-list entries into the window's block table;
+//   3. terms are decoded block-per-warp (4-lane-interleaved bit-unpack -> warp-shuffle prefix scan ->
+//      doc ids), BM25 is applied in f32 and accumulated into per-window score arrays in the
+//      reference's clause order (bit-reproducible sums) — with a barrier per clause in the generic
+//      program, with a ticket counter and no barrier in the BM25-union instantiation (UNION) — and
+//      match sets are shared-memory bitmaps combined with AND / OR / AND-NOT exactly like tantivy's
+//      BooleanWeight;
 //   4. the matched docs of the window are counted, aggregated (bucket counts privatised in shared
-//      memory) and filtered against a per-split top-K threshold; survivors go to a candidate list
-//      that k_select sorts with the reference's total order.
+//      memory) and filtered against a per-split top-K threshold over compacted hits (full warps);
+//      survivors go to a candidate list that k_select reduces with the reference's total order.
 // This replaces tantivy's doc-at-a-time Scorer/Collector loop (SURVEY.md §3.3 step 10c, §8a rows
-// a3-a12). No tensor cores: the work is integer decode/compare, bound by HBM bandwidth.
+// a3-a12). No tensor cores: the work is integer decode / compare plus one f32 multiply-add per
+// posting; the binding resource measured on B200 is instruction issue, well before HBM bandwidth
+// (profiles/r1_summary.md).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -464,11 +471,48 @@ __device__ __forceinline__ void warp_count_few(uint32_t* ctr, uint32_t idx, bool
 // Fast aggregation path (DSplitPlan::fast_aggs): flat TERMS / HISTOGRAM nodes over single-valued
 // columns, counts privatised in shared memory. A histogram bucket is found in raw space through the
 // host-built boundary table (DAgg::bounds) — no f64 arithmetic, bit-exact by construction.
+// Privatised stats cell of the fast path: {sum (u64 wrapping, or f64 bits), max(~mapped) = min, max(mapped)}.
+// When the whole warp feeds one cell the three values are butterfly-reduced first.
+__device__ __forceinline__ void stat_update(unsigned long long* st, const DCol& c, const uint8_t* base, uint32_t cell, uint32_t doc, bool ok, uint32_t lane) {
+  const uint32_t okmask = __ballot_sync(QW_FULL, ok);
+  if (okmask == 0) return;
+  const uint64_t m = ok ? c.min_value + c.gcd * col_raw(base, c, doc) : 0ull;
+  const bool is_f64 = c.type == QW_COL_F64;
+  const bool plain = c.type == QW_COL_U64 || c.type == QW_COL_BOOL;
+  unsigned long long isum = ok ? (plain ? m : (m ^ (1ull << 63))) : 0ull;
+  double dsum = (ok && is_f64) ? mapped_to_f64(c.type, m) : 0.0;
+  unsigned long long nmin = ok ? ~m : 0ull, vmax = ok ? m : 0ull;
+  const uint32_t lead = __ffs(okmask) - 1;
+  const uint32_t lead_cell = __shfl_sync(QW_FULL, cell, lead);
+  const bool one = __ballot_sync(QW_FULL, ok && cell != lead_cell) == 0;
+  if (one) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      isum += __shfl_xor_sync(QW_FULL, isum, o);
+      if (is_f64) dsum += __shfl_xor_sync(QW_FULL, dsum, o);
+      const unsigned long long x = __shfl_xor_sync(QW_FULL, nmin, o), y = __shfl_xor_sync(QW_FULL, vmax, o);
+      nmin = x > nmin ? x : nmin;
+      vmax = y > vmax ? y : vmax;
+    }
+  }
+  if (one ? lane == lead : ok) {
+    unsigned long long* t = st + 3ull * cell;
+    if (is_f64) atomicAdd((double*)t, dsum); else atomicAdd(t, isum);
+    atomicMax(t + 1, nmin);
+    atomicMax(t + 2, vmax);
+  }
+}
 __device__ __forceinline__ void agg_collect_fast(const Sm& sm, const DSplitPlan& P, const DAgg* aggs, const DCol* cols,
                                                  const uint8_t* base, uint32_t doc, bool on, uint32_t lane) {
   uint32_t* ctr = sm.u32(sm.L->hist);
+  unsigned long long* st = (unsigned long long*)(sm.u8(sm.L->hist) + ((P.n_cells * 4u + 7u) & ~7u));
   for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
     const DAgg& g = aggs[gi];
+    if (g.parent != 0xFFFFFFFFu) continue;  // children are visited under their parent
+    if (g.kind == QW_AGG_STATS) {
+      stat_update(st, cols[g.col], base, g.stat_base, doc, on, lane);
+      continue;
+    }
     const uint64_t raw = on ? col_raw(base, cols[g.col], doc) : 0ull;
     bool ok = on;
     uint32_t bk = (uint32_t)raw;
@@ -486,6 +530,10 @@ __device__ __forceinline__ void agg_collect_fast(const Sm& sm, const DSplitPlan&
       }
     }
     warp_count_few(ctr, g.cell_base + bk, ok, lane);
+    for (uint32_t ci = 0; ci < g.num_children; ci++) {
+      const DAgg& ch = aggs[g.first_child + ci];  // STATS over an always-present column
+      stat_update(st, cols[ch.col], base, ch.stat_base + bk, doc, ok, lane);
+    }
   }
 }
 __device__ __forceinline__ void agg_count(const KParams& p, const Sm& sm, QwAggCell* cells, uint32_t cell, bool on, uint32_t lane) {
@@ -1209,6 +1257,10 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       // the histogram / privatised aggregation counters alias the (now dead) staging area
       for (uint32_t i = tid; i < (MODE == MODE_HIST ? (uint32_t)QW_HIST_BINS : P.n_cells); i += QW_THREADS) s_hist[i] = 0;
       if (rec) for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) s_l0[i] = 0;
+      if (fast_aggs && n_aggs && P.n_stat_cells) {
+        unsigned long long* st = (unsigned long long*)(sm.u8(p.sm.hist) + ((P.n_cells * 4u + 7u) & ~7u));
+        for (uint32_t i = tid; i < 3 * P.n_stat_cells; i += QW_THREADS) st[i] = 0ull;
+      }
       if (tid == 0) s_misc[4] = 0;
       __syncthreads();
     }
@@ -1325,6 +1377,30 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
         const uint32_t elig = sa_present ? s_misc[3] : (max_hits ? hits : 0);
         if (elig) atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)elig);
         if (rec) p.wmax[work] = (uint16_t)s_misc[4];
+      }
+      if (fast_aggs && n_aggs && P.n_stat_cells) {
+        // privatised stats: one set of global atomics per touched cell and window; the cell's value
+        // count is its bucket's doc count (the column is single-valued and always present)
+        const unsigned long long* st = (const unsigned long long*)(sm.u8(p.sm.hist) + ((P.n_cells * 4u + 7u) & ~7u));
+        for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
+          const DAgg& g = s_aggs[gi];
+          if (g.kind != QW_AGG_STATS) continue;
+          const bool top = g.parent == 0xFFFFFFFFu;
+          const uint32_t nc = top ? 1u : s_aggs[g.parent].num_buckets;
+          const bool is_f64 = s_cols[g.col].type == QW_COL_F64;
+          for (uint32_t c = tid; c < nc; c += QW_THREADS) {
+            const uint32_t cnt = top ? s_misc[2] : s_hist[s_aggs[g.parent].cell_base + c];
+            if (!cnt) continue;
+            const unsigned long long* t = st + 3ull * (g.stat_base + c);
+            QwAggCell* out = &cells[g.cell_base + c];
+            atomicAdd((unsigned long long*)&out->count, (unsigned long long)cnt);
+            if (is_f64) atomicAdd((double*)&out->sum_bits, __longlong_as_double((long long)t[0]));
+            else atomicAdd((unsigned long long*)&out->sum_bits, t[0]);
+            atomicMax((unsigned long long*)&out->min_mapped, t[1]);
+            atomicMax((unsigned long long*)&out->max_mapped, t[2]);
+          }
+        }
+        __syncthreads();  // the bucket counts read above are cleared below
       }
       if (p.smem_aggs && n_aggs) {
         for (uint32_t i = tid; i < P.n_cells; i += QW_THREADS) {

@@ -91,6 +91,11 @@ def test_generic_aggregations_optional_and_multivalued(gpu_ctx, splits):
         {"opt": {"histogram": {"field": "c", "interval": 250000.0}, "aggs": {"m": {"stats": {"field": "full_i"}}}}},
         {"r": {"range": {"field": "full_i", "ranges": [{"to": -100}, {"from": -100, "to": 100}, {"from": 100}]}, "aggs": {"tt": {"terms": {"field": "tags"}}}}},
         {"st": {"stats": {"field": "a"}}, "mx": {"max": {"field": "full_f"}}},
+        # privatised stats cells of the fast path (always-present single-valued columns)
+        {"by_t": {"terms": {"field": "t"}, "aggs": {"s": {"stats": {"field": "full_i"}}, "f": {"avg": {"field": "full_f"}}}}},
+        {"h": {"histogram": {"field": "full_i", "interval": 500}, "aggs": {"f": {"stats": {"field": "full_f"}}}}, "all": {"stats": {"field": "full_i"}},
+         "tt": {"terms": {"field": "t"}}},
+        {"mn": {"min": {"field": "full_f"}}, "sm": {"sum": {"field": "full_i"}}},
     ]
     for aggs in cases:
         ast = bool_(must=[term("body", "x")], must_not=[term("body", "y")])
@@ -101,13 +106,13 @@ def test_generic_aggregations_optional_and_multivalued(gpu_ctx, splits):
 
 
 def _assert_aggs_close(a, b):
-    """Equal up to f64 summation order (sum / avg of f64 values are accumulated in a different order
-    on the device; counts, keys, min and max are exact)."""
+    """Equal up to f64 summation order (sum / avg — `value` for the single-metric forms — of f64 columns
+    are accumulated in a different order on the device; counts, keys, min and max are exact)."""
     if isinstance(a, dict):
         assert isinstance(b, dict) and a.keys() == b.keys()
         for k in a:
-            if k in ("sum", "avg") and isinstance(a[k], float) and isinstance(b[k], float):
-                assert a[k] == pytest.approx(b[k], rel=1e-9, abs=1e-9)
+            if k in ("sum", "avg", "value") and isinstance(a[k], float) and isinstance(b[k], float):
+                assert a[k] == pytest.approx(b[k], rel=1e-11, abs=1e-9)
             else:
                 _assert_aggs_close(a[k], b[k])
     elif isinstance(a, list):
