@@ -981,6 +981,8 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
             // clause order, but there is no block-wide barrier per clause and no warp idles while a
             // short clause finishes. Blocks of one clause touch distinct docs, so they commute.
             const uint32_t G = s_misc[0];
+            // (measured and rejected: a spare warp prefetching the next window's bytes into L2 made the
+            // kernel 4-5 % slower — the staging phases are not DRAM-latency bound enough to pay for it)
             volatile uint32_t* ticket = (volatile uint32_t*)&s_misc[5];
             float* score = sm.f32(LV.ssum);
             // (static round-robin assignment; handing blocks out from a shared counter measured slower)
