@@ -63,6 +63,13 @@ def test_massive_ties_descend_radix_levels(gpu_ctx, splits):
             kw = dict(max_hits=k, sort_fields=sort)
             got, _ = gpu_root_search(gpu_ctx, splits, MATCH_ALL, MAPPING, **kw)
             same(got, cpu_root_search(splits, MATCH_ALL, MAPPING, **kw))
+    # BM25 with only two distinct scores over 50 000 matches (two doc lengths): the union kernels take the
+    # exact path through the score bits down to the doc-id bits
+    for sort in ([("_score", DESC)], [("_score", ASC)], [("_score", DESC), ("t", ASC)]):
+        for k in (10, 1000):
+            kw = dict(max_hits=k, sort_fields=sort)
+            got, _ = gpu_root_search(gpu_ctx, splits, term("body", "x"), MAPPING, **kw)
+            same(got, cpu_root_search(splits, term("body", "x"), MAPPING, **kw))
     page1, _ = gpu_root_search(gpu_ctx, splits, MATCH_ALL, MAPPING, max_hits=50, sort_fields=[("t", ASC)])
     kw = dict(max_hits=50, sort_fields=[("t", ASC)], search_after=page1["partial_hits"][-1])
     got, _ = gpu_root_search(gpu_ctx, splits, MATCH_ALL, MAPPING, **kw)
