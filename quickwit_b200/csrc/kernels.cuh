@@ -471,12 +471,25 @@ __device__ __forceinline__ void warp_count_few(uint32_t* ctr, uint32_t idx, bool
 // Fast aggregation path (DSplitPlan::fast_aggs): flat TERMS / HISTOGRAM nodes over single-valued
 // columns, counts privatised in shared memory. A histogram bucket is found in raw space through the
 // host-built boundary table (DAgg::bounds) — no f64 arithmetic, bit-exact by construction.
+// Bit-unpack for the fast aggregation path: single-valued column, index = doc. Columns whose packed
+// array is addressable with 32-bit bit positions and whose width is <= 32 use two 32-bit loads and
+// a funnel shift (the array is padded with 16 zero bytes, so the second word always exists).
+__device__ __forceinline__ uint64_t col_raw_doc(const uint8_t* base, const DCol& c, uint32_t doc, uint32_t num_docs) {
+  if (c.bits <= 32 && (uint64_t)num_docs * c.bits < (1ull << 32)) {
+    if (c.bits == 0) return 0;
+    const uint32_t* w = (const uint32_t*)(base + c.values_off);
+    const uint32_t bitpos = doc * c.bits, wi = bitpos >> 5, sh = bitpos & 31;
+    const uint32_t v = __funnelshift_r(__ldg(w + wi), __ldg(w + wi + 1), sh);
+    return c.bits == 32 ? v : (v & ((1u << c.bits) - 1));
+  }
+  return col_raw(base, c, doc);
+}
 // Privatised stats cell of the fast path: {sum (u64 wrapping, or f64 bits), max(~mapped) = min, max(mapped)}.
 // When the whole warp feeds one cell the three values are butterfly-reduced first.
-__device__ __forceinline__ void stat_update(unsigned long long* st, const DCol& c, const uint8_t* base, uint32_t cell, uint32_t doc, bool ok, uint32_t lane) {
+__device__ __forceinline__ void stat_update(unsigned long long* st, const DCol& c, const uint8_t* base, uint32_t cell, uint32_t doc, uint32_t num_docs, bool ok, uint32_t lane) {
   const uint32_t okmask = __ballot_sync(QW_FULL, ok);
   if (okmask == 0) return;
-  const uint64_t m = ok ? c.min_value + c.gcd * col_raw(base, c, doc) : 0ull;
+  const uint64_t m = ok ? c.min_value + c.gcd * col_raw_doc(base, c, doc, num_docs) : 0ull;
   const bool is_f64 = c.type == QW_COL_F64;
   const bool plain = c.type == QW_COL_U64 || c.type == QW_COL_BOOL;
   unsigned long long isum = ok ? (plain ? m : (m ^ (1ull << 63))) : 0ull;
@@ -510,10 +523,10 @@ __device__ __forceinline__ void agg_collect_fast(const Sm& sm, const DSplitPlan&
     const DAgg& g = aggs[gi];
     if (g.parent != 0xFFFFFFFFu) continue;  // children are visited under their parent
     if (g.kind == QW_AGG_STATS) {
-      stat_update(st, cols[g.col], base, g.stat_base, doc, on, lane);
+      stat_update(st, cols[g.col], base, g.stat_base, doc, P.num_docs, on, lane);
       continue;
     }
-    const uint64_t raw = on ? col_raw(base, cols[g.col], doc) : 0ull;
+    const uint64_t raw = on ? col_raw_doc(base, cols[g.col], doc, P.num_docs) : 0ull;
     bool ok = on;
     uint32_t bk = (uint32_t)raw;
     if (g.kind == QW_AGG_HISTOGRAM) {
@@ -529,10 +542,13 @@ __device__ __forceinline__ void agg_collect_fast(const Sm& sm, const DSplitPlan&
         while (raw >= __ldg(B + bk + 1)) bk++;
       }
     }
-    warp_count_few(ctr, g.cell_base + bk, ok, lane);
+    // histogram buckets of (time-)ordered data are usually warp-uniform; terms buckets of a
+    // low-cardinality column take a few leader rounds
+    if (g.kind == QW_AGG_HISTOGRAM) warp_count_uniform(ctr, g.cell_base + bk, ok, lane);
+    else warp_count_few(ctr, g.cell_base + bk, ok, lane);
     for (uint32_t ci = 0; ci < g.num_children; ci++) {
       const DAgg& ch = aggs[g.first_child + ci];  // STATS over an always-present column
-      stat_update(st, cols[ch.col], base, ch.stat_base + bk, doc, ok, lane);
+      stat_update(st, cols[ch.col], base, ch.stat_base + bk, doc, P.num_docs, ok, lane);
     }
   }
 }
