@@ -11,6 +11,7 @@
 //   * partial exchange for the multi-GPU root merge stand-in
 #include <algorithm>
 #include <chrono>
+#include <tuple>
 
 #include "compile.h"
 #include "engine.h"
@@ -302,18 +303,29 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
       const CompiledPlan& pp = run.jobs[run.which[s2]].plan;
       if (pp.header.sort[i].kind == QW_SORT_COLUMN && pp.header.sort[i].column != 0xFFFFFFFFu) { sft[i] = pp.sort_field_type[i]; break; }
     }
-  auto better = [&](size_t sa, const QwHit& a, size_t sb, const QwHit& b) {  // a strictly better than b
-    auto cmp_opt = [](int order, bool ha, uint64_t x, bool hb, uint64_t y) {
-      if (ha && hb) { int c = x < y ? -1 : (x > y ? 1 : 0); return order == QW_ORDER_DESC ? c : -c; }
-      return ha ? 1 : (hb ? -1 : 0);
-    };
-    int c = cmp_opt(o1, a.flags & 1, a.v1, b.flags & 1, b.v1);
-    if (!c) c = cmp_opt(o2, (a.flags >> 1) & 1, a.v2, (b.flags >> 1) & 1, b.v2);
-    if (!c) { int d = rank[sa] < rank[sb] ? -1 : (rank[sa] > rank[sb] ? 1 : (a.doc_id < b.doc_id ? -1 : (a.doc_id > b.doc_id ? 1 : 0))); c = o1 == QW_ORDER_DESC ? d : -d; }
-    return c > 0;
+  // Heads of the per-split lists as plain integer tuples, greater = better: (has1, v1', has2, v2', tie')
+  // with v' = v for a descending key and ~v for an ascending one (None — has = 0 — is last in both
+  // directions, compare_opt in quickwit-proto/src/lib.rs:122-140), tie' = (split rank, doc id) in the
+  // direction of the first key (collector.rs:1120-1153). Built only for the current head of each list.
+  struct Head {
+    uint64_t v1, v2, tie;
+    uint32_t s;
+    uint8_t has1, has2;
+    bool operator<(const Head& o) const { return std::tie(has1, v1, has2, v2, tie) < std::tie(o.has1, o.v1, o.has2, o.v2, o.tie); }
   };
-  std::vector<size_t> pos(n, 0), heap;
-  auto heap_less = [&](size_t x, size_t y) { return better(y, run.outs[y].hits[pos[y]], x, run.outs[x].hits[pos[x]]); };  // max-heap on "better"
+  auto head_of = [&](size_t sidx, const QwHit& h) {
+    Head k;
+    k.s = (uint32_t)sidx;
+    k.has1 = h.flags & 1;
+    k.has2 = (h.flags >> 1) & 1;
+    k.v1 = k.has1 ? (o1 == QW_ORDER_DESC ? h.v1 : ~h.v1) : 0;
+    k.v2 = k.has2 ? (o2 == QW_ORDER_DESC ? h.v2 : ~h.v2) : 0;
+    const uint64_t t = ((uint64_t)rank[sidx] << 32) | h.doc_id;
+    k.tie = o1 == QW_ORDER_DESC ? t : ~t;
+    return k;
+  };
+  std::vector<size_t> pos(n, 0);
+  std::vector<Head> heap;
   std::vector<std::string> agg_parts;
   pb::LeafResourceStats stats_acc;
   bool any_stats = false;
@@ -322,25 +334,27 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
     m.num_hits += o.num_hits;
     m.num_attempted_splits += 1;
     m.num_successful_splits += 1;
-    if (!o.hits.empty()) heap.push_back(s);
+    if (!o.hits.empty()) heap.push_back(head_of(s, o.hits[0]));
     const SplitJob& j = run.jobs[run.which[s]];
     if (j.plan.header.num_aggs) agg_parts.push_back(build_intermediate_aggs(j.plan, j.dev->view, o.cells.data(), o.cells.size()));
     add_leaf_stats(stats_acc, split_stats(run, s));
     any_stats = true;
   }
-  std::make_heap(heap.begin(), heap.end(), heap_less);
-  while (!heap.empty() && m.partial_hits.size() < k) {
-    std::pop_heap(heap.begin(), heap.end(), heap_less);
-    size_t s = heap.back();
+  std::make_heap(heap.begin(), heap.end());
+  // the merged hits go straight to wire form (no PartialHit temporaries: a split id is a 26-char ULID)
+  size_t taken = 0;
+  m.encoded_partial_hits.reserve(std::min<size_t>(k, 4096) * 72);
+  while (!heap.empty() && taken < k) {
+    std::pop_heap(heap.begin(), heap.end());
+    size_t s = heap.back().s;
     const SplitJob& j = run.jobs[run.which[s]];
     const QwHit& h = run.outs[s].hits[pos[s]];
-    pb::PartialHit ph;
-    ph.split_id = j.meta.split_id;
-    ph.doc_id = h.doc_id;
-    if (h.flags & 1) { ph.has_sv1 = true; ph.sv1 = typed_sort_value(p0.header.sort[0].kind, sft[0], h.v1); }
-    if (h.flags & 2) { ph.has_sv2 = true; ph.sv2 = typed_sort_value(p0.header.sort[1].kind, sft[1], h.v2); }
-    m.partial_hits.push_back(std::move(ph));
-    if (++pos[s] < run.outs[s].hits.size()) std::push_heap(heap.begin(), heap.end(), heap_less);
+    pb::SortValue sv1, sv2;
+    if (h.flags & 1) sv1 = typed_sort_value(p0.header.sort[0].kind, sft[0], h.v1);
+    if (h.flags & 2) sv2 = typed_sort_value(p0.header.sort[1].kind, sft[1], h.v2);
+    pb::append_partial_hit(m.encoded_partial_hits, 2, j.meta.split_id, 0, h.doc_id, (h.flags & 1) != 0, sv1, (h.flags & 2) != 0, sv2);
+    taken++;
+    if (++pos[s] < run.outs[s].hits.size()) { heap.back() = head_of(s, run.outs[s].hits[pos[s]]); std::push_heap(heap.begin(), heap.end()); }
     else heap.pop_back();
   }
   if (sreq.aggregation_request && !sreq.aggregation_request->empty())

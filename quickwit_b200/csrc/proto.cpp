@@ -53,6 +53,46 @@ std::string encode_partial_hit(const PartialHit& h) {
   return w.out;
 }
 
+// Same bytes as `Writer::bytes(field, encode_partial_hit(..))`, written straight into `out` through a
+// per-thread scratch buffer: a leaf response carries up to thousands of hits and the temporaries of
+// the generic path dominated its encoding time.
+void append_partial_hit(std::string& out, uint32_t field, const std::string& split_id, uint32_t segment_ord, uint32_t doc_id,
+                        bool has_sv1, const SortValue& sv1, bool has_sv2, const SortValue& sv2) {
+  // body: split_id (2) | segment_ord (3) | doc_id (4) | sort_value (10) | sort_value2 (11); a body is at
+  // most 2 + len + 6 + 6 + 2 * 13 bytes, assembled in a stack buffer and appended once
+  char stack[192];
+  std::string big;
+  char* buf = stack;
+  if (split_id.size() > sizeof(stack) - 48) { big.resize(split_id.size() + 48); buf = &big[0]; }
+  char* p = buf;
+  auto varint = [&](uint64_t v) { while (v >= 0x80) { *p++ = (char)(v | 0x80); v >>= 7; } *p++ = (char)v; };
+  auto tag = [&](uint32_t f, uint32_t wt) { varint(((uint64_t)f << 3) | wt); };
+  if (!split_id.empty()) { tag(2, 2); varint(split_id.size()); memcpy(p, split_id.data(), split_id.size()); p += split_id.size(); }
+  if (segment_ord) { tag(3, 0); varint(segment_ord); }
+  if (doc_id) { tag(4, 0); varint(doc_id); }
+  auto sort_value = [&](uint32_t f, const SortValue& v) {
+    tag(f, 2);
+    char* len = p++;  // the nested SortByValue is at most 11 bytes: one length byte
+    switch (v.kind) {
+      case SortValue::U64: tag(1, 0); varint(v.u); break;
+      case SortValue::I64: tag(2, 0); varint((uint64_t)v.i); break;
+      case SortValue::F64: { tag(3, 1); uint64_t b; memcpy(&b, &v.f, 8); memcpy(p, &b, 8); p += 8; break; }
+      case SortValue::Bool: tag(4, 0); varint(v.b ? 1 : 0); break;
+      default: break;
+    }
+    *len = (char)(p - len - 1);
+  };
+  if (has_sv1) sort_value(10, sv1);
+  if (has_sv2) sort_value(11, sv2);
+  const size_t n = (size_t)(p - buf);
+  char head[16];
+  char* q = head;
+  { uint64_t v = ((uint64_t)field << 3) | 2; while (v >= 0x80) { *q++ = (char)(v | 0x80); v >>= 7; } *q++ = (char)v; }
+  { uint64_t v = n; while (v >= 0x80) { *q++ = (char)(v | 0x80); v >>= 7; } *q++ = (char)v; }
+  out.append(head, (size_t)(q - head));
+  out.append(buf, n);
+}
+
 static SortField decode_sort_field(Reader r) {
   SortField s;
   while (!r.done()) {
@@ -235,8 +275,10 @@ LeafSearchResponse decode_leaf_search_response(const uint8_t* p, size_t n) {
 
 std::string encode_leaf_search_response(const LeafSearchResponse& q) {
   Writer w;
+  w.out.reserve(64 + q.encoded_partial_hits.size() + 72 * q.partial_hits.size());
   w.u64(1, q.num_hits);
-  for (auto& h : q.partial_hits) w.bytes(2, encode_partial_hit(h));
+  for (auto& h : q.partial_hits) append_partial_hit(w.out, 2, h.split_id, h.segment_ord, h.doc_id, h.has_sv1, h.sv1, h.has_sv2, h.sv2);
+  w.out += q.encoded_partial_hits;  // hits a merge wrote in wire form already (same field, same order)
   for (auto& e : q.failed_splits) {
     Writer s;
     s.str(1, e.error);

@@ -149,6 +149,7 @@ struct LeafResourceStats {
 struct LeafSearchResponse {
   uint64_t num_hits = 0;                          // 1
   std::vector<PartialHit> partial_hits;           // 2
+  std::string encoded_partial_hits;               // 2, already in wire form (follows partial_hits; encode-only)
   std::vector<SplitSearchError> failed_splits;    // 3
   uint64_t num_attempted_splits = 0;              // 4
   std::optional<std::string> intermediate_aggregation_result;  // 6
@@ -168,6 +169,8 @@ LeafSearchRequest decode_leaf_search_request(const uint8_t* p, size_t n);
 LeafSearchResponse decode_leaf_search_response(const uint8_t* p, size_t n);
 PartialHit decode_partial_hit(Reader r);
 std::string encode_partial_hit(const PartialHit& h);
+void append_partial_hit(std::string& out, uint32_t field, const std::string& split_id, uint32_t segment_ord, uint32_t doc_id,
+                        bool has_sv1, const SortValue& sv1, bool has_sv2, const SortValue& sv2);
 std::string encode_leaf_search_response(const LeafSearchResponse& r);
 std::string encode_search_request(const SearchRequest& r);
 // LambdaSearchResponses (search.proto:628-632): repeated LambdaSingleSplitResult split_results = 2
