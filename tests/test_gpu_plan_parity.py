@@ -167,3 +167,14 @@ def test_degenerate_ties_force_exact_radix_select(gpu_ctx):
     gpu_ctx.register_split(img)
     for order in (ffi.ORDER_ASC, ffi.ORDER_DESC):
         run_both(gpu_ctx, img, P.make_plan(P.match_all(), 100, [col_sort(img, "v", order)]), ctx=f"ties {order}")
+
+
+def test_synthetic_corpus_fixture_on_gpu(gpu_ctx):
+    """tests/golden/bm25_synth_expected.json through the CUDA path (bit-exact f32 scores)."""
+    import numpy as np
+    from test_oracle_goldens import _synth_golden
+    want, img, pl = _synth_golden()
+    gpu_ctx.register_split(img)
+    r = gpu_ctx.split_search([img.split_id], [pl])[0]
+    assert r.num_hits == want["num_hits"]
+    assert [[int(h[0]), float(np.float32(h[4]))] for h in r.hits] == want["hits"]

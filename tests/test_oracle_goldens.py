@@ -316,3 +316,24 @@ def test_fieldnorm_table_matches_lucene_smallfloat():
     for n in (0, 1, 40, 41, 57, 1000, 2**31):
         i = L.qwgpu_fieldnorm_to_id(n)
         assert table[i] <= n and (i == 255 or table[i + 1] > n)
+
+
+# ---- committed fixture: synthetic-corpus BM25 top-20 (tests/golden/bm25_synth_expected.json) -----------------
+def _synth_golden():
+    import json as _json
+    import os as _os
+    with open(_os.path.join(_os.path.dirname(__file__), "golden", "bm25_synth_expected.json")) as f:
+        want = _json.load(f)
+    from quickwit_b200 import ffi as _ffi, plan as _P
+    img = S.synth_split(20000, 3, [0.2, 0.1, 0.05, 0.01], split_id="golden-3")
+    root = _P.bool_([_P.term(img, "body", f"t{i}", occur=_ffi.OCCUR_SHOULD) for i in range(4)])
+    return want, img, _P.make_plan(root, 20, [(_ffi.SORT_SCORE, _ffi.ORDER_DESC, _ffi.ABSENT)])
+
+
+def test_synthetic_corpus_fixture():
+    """The seeded corpus generator + BM25 arithmetic reproduce the committed scores bit for bit."""
+    from oracle import oracle as _O
+    want, img, pl = _synth_golden()
+    r = _O.split_search(img, pl)
+    assert r.num_hits == want["num_hits"]
+    assert [[int(h[0]), float(np.float32(h[4]))] for h in r.hits] == want["hits"]
