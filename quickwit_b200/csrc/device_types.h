@@ -18,9 +18,7 @@
 #define QW_MAX_LEVELS QW_MAX_PLAN_DEPTH
 #define QW_MAX_TERMS 64      /* TERM instructions per plan */
 #define QW_BLK_TAB 160       /* staged blocks per (term, window) before falling back to direct mode */
-#define QW_STAGE_BYTES 16384 /* packed posting bytes staged per window */
 #define QW_MAX_WBLK 512      /* staged blocks per window over all terms */
-#define QW_ENT_BLOCKS 32     /* decoded blocks held at once (one "round"): 32 x 128 entries x 8 B */
 #define QW_HIST_BINS 2048    /* 11-bit radix digits */
 #define QW_DIGIT_BITS 11
 #define QW_KEY_BITS 192
@@ -135,8 +133,8 @@ struct SmemLayout {
   uint32_t instr, cols, aggs, key, hitq;  // hitq: per-warp compacted hit queues of the generic collect
   uint32_t rangeq;  // per-warp queues of required RANGE / EXISTS clauses (0xFFFFFFFF: probe per bitmap word)
   SmemLevel lvl[QW_MAX_LEVELS];
-  uint32_t tmp, fn[2], tab[2];  // tab[s]: float[256] norms + float[16][256] tf factors (17 KB)
-  uint32_t rng, blkrec, termblk, stage, ent, hist, misc;  // hist aliases ent (dead by collect time)
+  uint32_t tmp, fn[2];          // scratch bitmap; staged fieldnorm bytes per scored field
+  uint32_t rng, blkrec, termblk, stage, hist, misc;  // hist aliases stage (dead by collect time)
   uint32_t l0hist;  // COLLECT pass: exact level-0 digit histogram of the window's matches (0xFFFFFFFF: not recorded)
   uint32_t total;
 };

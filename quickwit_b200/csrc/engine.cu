@@ -576,7 +576,6 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   L.blkrec = take(QW_MAX_WBLK * 8);
   L.termblk = take(QW_MAX_TERMS * 8);
   L.stage = take(stage_bytes_for(W));
-  L.ent = L.stage;
   L.hist = L.stage;  // histogram / privatised aggregation counters reuse the staging area at collect time
   if (rec_l0) L.l0hist = take(QW_HIST_BINS * 4);
   if (rangeq) L.rangeq = take(QW_WARPS * (32 + 32 * 4) * 2);  // QW_WARPS x QW_HITQ_CAP uint16 (kernels.cuh)

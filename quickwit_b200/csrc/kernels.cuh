@@ -436,15 +436,11 @@ __device__ __forceinline__ uint32_t key_top11(const DSplitPlan& P, const DKeySpe
 
 // ---- aggregation collection (dense cells; mirrors oracle agg_collect) -------------------------------
 // All 32 lanes of a warp call these together (`on` = this lane holds a matched doc): lanes that hit
-// the same cell are combined with match_any before touching the counter, because time-ordered log
-// data sends whole warps to the same histogram / terms bucket and same-address atomics serialise.
+// the same cell are combined before touching the counter, because time-ordered log data sends whole
+// warps to the same histogram / terms bucket and same-address atomics serialise.
 #define QW_FULL 0xFFFFFFFFu
-__device__ __forceinline__ void warp_count(uint32_t* ctr, uint32_t idx, bool on, uint32_t lane) {
-  const uint32_t peers = __match_any_sync(QW_FULL, on ? idx : 0xFFFFFFFFu);
-  if (on && (uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(&ctr[idx], (uint32_t)__popc(peers));
-}
-// Same contract, cheaper when the counted lanes usually agree (histogram digits of time-ordered keys):
-// one broadcast + ballot decides between a single aggregated atomic and plain per-lane atomics.
+// Counters whose lanes usually agree (histogram digits / buckets of time-ordered keys): one broadcast
+// + ballot decides between a single aggregated atomic and plain per-lane atomics.
 __device__ __forceinline__ void warp_count_uniform(uint32_t* ctr, uint32_t idx, bool on, uint32_t lane) {
   const uint32_t m = __ballot_sync(QW_FULL, on);
   if (m == 0) return;
@@ -842,7 +838,6 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
   uint32_t* s_tblk = sm.u32(p.sm.termblk);  // per term slot: first global block, block count
   uint32_t* s_hist = sm.u32(p.sm.hist);
   uint8_t* s_stage = sm.u8(p.sm.stage);
-  uint2* s_ent = (uint2*)sm.u8(p.sm.ent);
   uint32_t loaded_split = 0xFFFFFFFFu;
   bool ssum_clean = false;  // level-0 should-score array is all zero (left so by a fused collect)
 
