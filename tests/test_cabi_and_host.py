@@ -146,3 +146,22 @@ def test_posting_and_column_format_roundtrip():
     assert img.columns()[img.column_ord("wide")].bits == 64
     v, p = O.column_first(img, img.column_ord("wide"))
     assert np.array_equal(v, wide)
+
+
+def test_partial_hit_wire_form_every_value_kind_and_long_split_ids():
+    """The C encoder of LeafSearchResponse.partial_hits against the pure-Python codec: every SortByValue
+    kind incl. 10-byte varints, absent sort values, and split ids longer than the encoder's stack buffer."""
+    from quickwit_b200 import proto, service
+    hits = []
+    for i, sid in enumerate(["s", "01HZXJ5QK8W9D3M7P2R4T6V8YB", "x" * 150, "y" * 400]):
+        hits += [
+            {"split_id": sid, "segment_ord": 0, "doc_id": i, "sort_value": ("u64", 2**64 - 1 - i), "sort_value2": ("i64", -(2**63) + i)},
+            {"split_id": sid, "segment_ord": 0, "doc_id": 100 + i, "sort_value": ("f64", -1.5e300 * (i + 1)), "sort_value2": ("bool", True)},
+            {"split_id": sid, "segment_ord": 0, "doc_id": 0},
+        ]
+    req = proto.enc_search_request('{"type": "match_all"}', max_hits=100)
+    resp = proto.enc_leaf_search_response(num_hits=len(hits), partial_hits=hits, num_attempted_splits=1, num_successful_splits=1)
+    out = proto.dec_leaf_search_response(service.merge_leaf_responses(req, [resp]))   # single-response shortcut: order kept
+    got = [{k: v for k, v in h.items() if v is not None} for h in out["partial_hits"]]
+    want = [{k: v for k, v in h.items()} for h in hits]
+    assert got == want
