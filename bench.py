@@ -143,7 +143,32 @@ class ClockSampler:
         self.rows = []
         self.proc = None
 
+    def _nvml_loop(self):
+        import pynvml as N
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM)
+                mask = int(get_reasons(self.handle))
+                self.nvml_rows.append((float(sm), [k for k, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def start(self):
+        # NVML polled every 2 ms (the timed regions last tens of milliseconds); nvidia-smi is the fallback
+        self.nvml_rows, self.stop_flag, self.handle = [], threading.Event(), None
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.handle = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml_max = float(N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.handle = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -161,6 +186,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if getattr(self, "handle", None) is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted({x for r in self.nvml_rows for x in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.nvml_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
