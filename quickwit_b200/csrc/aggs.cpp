@@ -10,8 +10,10 @@
 //   * final: into_final_result (quickwit-search/src/root.rs:1105-1135): buckets cut to `size`,
 //     histogram gaps filled when min_doc_count == 0, extended_bounds, key_as_string.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <map>
+#include <memory>
 
 #include "compile.h"
 
@@ -270,9 +272,11 @@ struct IAgg {
   double m_sum = 0, m_min = INFINITY, m_max = -INFINITY;
   // key -> position in `buckets`, built on the first merge into this node and kept up to date, so that
   // folding n responses costs O(total buckets · log) instead of re-indexing the accumulator n times
-  bool indexed = false;
-  std::map<IKey, size_t> tindex;
-  std::map<double, size_t> hindex;
+  struct Index {
+    std::map<IKey, size_t> terms;
+    std::map<double, size_t> hist;
+  };
+  std::shared_ptr<Index> index;  // allocated on the first merge into this node (accumulators only)
 };
 
 struct BW {
@@ -477,7 +481,11 @@ static IAgg build_node(const BuildCtx& c, uint32_t ni, uint64_t parent_cell) {
   return a;
 }
 
+static std::vector<IAgg> build_top(const CompiledPlan& cp, const ImageView& img, const QwAggCell* cells, size_t ncells);
 std::string build_intermediate_aggs(const CompiledPlan& cp, const ImageView& img, const QwAggCell* cells, size_t ncells) {
+  return ser_top(build_top(cp, img, cells, ncells));
+}
+static std::vector<IAgg> build_top(const CompiledPlan& cp, const ImageView& img, const QwAggCell* cells, size_t ncells) {
   const QwPlanHeader& h = cp.header;
   const QwAggNode* nodes = (const QwAggNode*)(cp.bytes.data() + sizeof(QwPlanHeader) + (size_t)h.num_nodes * sizeof(QwPlanNode));
   BuildCtx c{cp, img, nodes, cells, {}};
@@ -493,7 +501,7 @@ std::string build_intermediate_aggs(const CompiledPlan& cp, const ImageView& img
   if (total != ncells) fail(QWGPU_EINTERNAL, "aggregation cell count mismatch (%llu vs %zu)", (unsigned long long)total, ncells);
   std::vector<IAgg> top;
   for (uint32_t i = 0; i < h.num_aggs; i++) if (nodes[i].parent == 0xFFFFFFFFu) top.push_back(build_node(c, i, 0));
-  return ser_top(top);
+  return top;
 }
 
 // ---- merge ------------------------------------------------------------------------------------------------
@@ -516,16 +524,16 @@ static void merge_into(const AggReq& req, IAgg& acc, IAgg&& other) {
   acc.sum_other += other.sum_other;
   acc.error_bound += other.error_bound;
   if (acc.kind == AggReq::Terms) {
-    auto& index = acc.tindex;
-    if (!acc.indexed) { for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].key] = i; acc.indexed = true; }
+    if (!acc.index) { acc.index = std::make_shared<IAgg::Index>(); for (size_t i = 0; i < acc.buckets.size(); i++) acc.index->terms[acc.buckets[i].key] = i; }
+    auto& index = acc.index->terms;
     for (auto& b : other.buckets) {
       auto it = index.find(b.key);
       if (it == index.end()) { index[b.key] = acc.buckets.size(); acc.buckets.push_back(std::move(b)); }
       else { IBucket& t = acc.buckets[it->second]; t.count += b.count; merge_lists(req.children, t.subs, std::move(b.subs)); }
     }
   } else {
-    auto& index = acc.hindex;
-    if (!acc.indexed) { for (size_t i = 0; i < acc.buckets.size(); i++) index[acc.buckets[i].hkey] = i; acc.indexed = true; }
+    if (!acc.index) { acc.index = std::make_shared<IAgg::Index>(); for (size_t i = 0; i < acc.buckets.size(); i++) acc.index->hist[acc.buckets[i].hkey] = i; }
+    auto& index = acc.index->hist;
     for (auto& b : other.buckets) {
       auto it = index.find(b.hkey);
       if (it == index.end()) { index[b.hkey] = acc.buckets.size(); acc.buckets.push_back(std::move(b)); }
@@ -534,10 +542,47 @@ static void merge_into(const AggReq& req, IAgg& acc, IAgg&& other) {
   }
 }
 
+// Leaf-level merge of the splits of one request straight from their dense cells: what
+// merge_intermediate_aggs(build_intermediate_aggs(split) ...) yields, without serialising every split's
+// result only to parse it again.
+std::string build_and_merge_intermediate_aggs(const std::vector<AggReq>& reqs, const std::vector<SplitAggCells>& splits) {
+  std::vector<IAgg> acc;
+  for (const SplitAggCells& sp : splits) {
+    std::vector<IAgg> top = build_top(*sp.plan, *sp.img, sp.cells, sp.ncells);
+    if (acc.empty() && !top.empty()) {
+      // same normalisation as a serialise / parse round trip would apply: none needed — the first
+      // split's tree becomes the accumulator
+      acc = std::move(top);
+      continue;
+    }
+    merge_lists(reqs, acc, std::move(top));
+  }
+  return ser_top(acc);
+}
+
 std::string merge_intermediate_aggs(const std::vector<AggReq>& reqs, const std::vector<std::string>& parts) {
   std::vector<IAgg> acc;
-  for (auto& p : parts) merge_lists(reqs, acc, de_top(p));
-  return ser_top(acc);
+  static const bool trace = getenv("QWGPU_TRACE_AGG") != nullptr;
+  if (!trace) {
+    for (auto& p : parts) merge_lists(reqs, acc, de_top(p));
+    return ser_top(acc);
+  }
+  using clk = std::chrono::steady_clock;
+  long de = 0, mg = 0;
+  for (auto& p : parts) {
+    auto t0 = clk::now();
+    std::vector<IAgg> d = de_top(p);
+    auto t1 = clk::now();
+    merge_lists(reqs, acc, std::move(d));
+    auto t2 = clk::now();
+    de += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    mg += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
+  }
+  auto t0 = clk::now();
+  std::string out = ser_top(acc);
+  long se = std::chrono::duration_cast<std::chrono::nanoseconds>(clk::now() - t0).count();
+  fprintf(stderr, "[qwgpu] merge_intermediate_aggs: %zu parts, decode %ld us, merge %ld us, encode %ld us\n", parts.size(), de / 1000, mg / 1000, se / 1000);
+  return out;
 }
 
 // ---- finalize -----------------------------------------------------------------------------------------------

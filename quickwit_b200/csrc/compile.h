@@ -73,6 +73,13 @@ CompiledPlan compile_plan(const ImageView& img, const std::string& split_id, con
 // part iv) -----------------------------------------------------------------------------------------------
 std::string build_intermediate_aggs(const CompiledPlan& cp, const ImageView& img, const QwAggCell* cells, size_t ncells);
 std::string merge_intermediate_aggs(const std::vector<AggReq>& reqs, const std::vector<std::string>& parts);
+struct SplitAggCells {
+  const CompiledPlan* plan;
+  const ImageView* img;
+  const QwAggCell* cells;
+  size_t ncells;
+};
+std::string build_and_merge_intermediate_aggs(const std::vector<AggReq>& reqs, const std::vector<SplitAggCells>& splits);
 std::string finalize_aggs_json(const std::vector<AggReq>& reqs, const std::string& intermediate);
 
 // ---- per-split response + merging ---------------------------------------------------------------------

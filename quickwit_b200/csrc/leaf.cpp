@@ -326,7 +326,7 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
   };
   std::vector<size_t> pos(n, 0);
   std::vector<Head> heap;
-  std::vector<std::string> agg_parts;
+  std::vector<SplitAggCells> agg_parts;
   pb::LeafResourceStats stats_acc;
   bool any_stats = false;
   for (size_t s = 0; s < n; s++) {
@@ -336,7 +336,7 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
     m.num_successful_splits += 1;
     if (!o.hits.empty()) heap.push_back(head_of(s, o.hits[0]));
     const SplitJob& j = run.jobs[run.which[s]];
-    if (j.plan.header.num_aggs) agg_parts.push_back(build_intermediate_aggs(j.plan, j.dev->view, o.cells.data(), o.cells.size()));
+    if (j.plan.header.num_aggs) agg_parts.push_back({&j.plan, &j.dev->view, o.cells.data(), o.cells.size()});
     add_leaf_stats(stats_acc, split_stats(run, s));
     any_stats = true;
   }
@@ -358,7 +358,7 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
     else heap.pop_back();
   }
   if (sreq.aggregation_request && !sreq.aggregation_request->empty())
-    m.intermediate_aggregation_result = merge_intermediate_aggs(p0.agg_request, agg_parts);
+    m.intermediate_aggregation_result = build_and_merge_intermediate_aggs(p0.agg_request, agg_parts);
   if (any_stats) m.resource_stats = stats_acc;
   return m;
 }
