@@ -24,6 +24,7 @@ extern "C" {
 #endif
 
 #define QW_IMG_MAGIC 0x31474D4947575151ull /* "QQWGIMG1" */
+#define QW_IMG_VERSION 2u
 #define QW_BLOCK_LEN 128u                  /* tantivy COMPRESSION_BLOCK_SIZE */
 #define QW_TERMINATED 0x7FFFFFFFu          /* tantivy TERMINATED sentinel (i32::MAX as u32) */
 #define QW_NO_PREV_DOC 0xFFFFFFFFu
@@ -72,11 +73,13 @@ typedef struct QwImgTerm {
   uint32_t num_blocks; /* ceil(doc_freq / 128) */
   uint32_t win_shift;  /* window index granularity: one entry per 2^win_shift docs (>= 12) */
   uint64_t skip_off; /* data-relative: QwSkip[num_blocks] (CPU-style seek structure) */
-  uint64_t data_off; /* data-relative: blocks, each [QwSkip header][packed docs][packed tfs] */
+  uint64_t data_off; /* data-relative: blocks, each [QwSkip header][packed docs][packed tfs][fieldnorm ids] */
   uint64_t data_len;
   uint64_t widx_off; /* data-relative: QwWinIdx[ceil(num_docs / 2^win_shift)] */
   uint64_t tf_len;   /* bytes of data_len that are packed term frequencies (roofline accounting) */
-} QwImgTerm; /* 64 bytes */
+  uint64_t fn_len;   /* bytes of data_len that are per-posting fieldnorm ids (128 per block, see QwSkip) */
+  uint64_t reserved;
+} QwImgTerm; /* 80 bytes */
 
 /* Window index: for index-window j (docs [j<<win_shift, (j+1)<<win_shift)) the byte range
  * [start, end) of QwImgTerm data holding every block that overlaps it (start == end if none).
@@ -94,6 +97,11 @@ typedef struct QwWinIdx {
  *   (value i lives in lane i%4 at position i/4; 128-bit word w holds 32-bit word w of the four
  *   lanes) => 16*doc_bits bytes. Term frequencies follow, raw, at `tf_bits` bits => 16*tf_bits
  *   bytes (tf_bits == 0 when the field is indexed `record: basic`; tf := 1).
+ * When the field has fieldnorms, 128 bytes follow: the fieldnorm id of each posting's document
+ * (byte i = fieldnorm id of doc[i], zero padded). tantivy keeps fieldnorms per document only; the
+ * image ALSO keeps that array (QwImgField.fieldnorm_off) but denormalises the id next to every
+ * posting so that BM25 scoring reads one contiguous byte stream per block instead of a random
+ * 1-byte gather per posting (the bytes read equal SURVEY.md 8d's "1 B per scored posting").
  * The trailing partial block uses the same layout, zero padded (tantivy VInt-encodes it; a
  * real-split ingester transcodes). */
 typedef struct QwSkip {

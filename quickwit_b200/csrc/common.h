@@ -68,6 +68,7 @@ struct ImageView {
     if (n < sizeof(QwImgHeader)) fail(QWGPU_EINVALID_ARG, "split image too small");
     const QwImgHeader* h = (const QwImgHeader*)p;
     if (h->magic != QW_IMG_MAGIC) fail(QWGPU_EINVALID_ARG, "bad split image magic");
+    if (h->version != QW_IMG_VERSION) fail(QWGPU_EINVALID_ARG, "split image version %u (this library reads version %u)", h->version, QW_IMG_VERSION);
     if (h->total_len > n) fail(QWGPU_EINVALID_ARG, "split image truncated");
     base = p;
     len = n;

@@ -10,6 +10,7 @@
 
 #include "engine.h"
 #include "kernels.cuh"
+#include "union_kernel.cuh"
 
 namespace qw {
 
@@ -90,6 +91,8 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * QW_CAND_CAP));
 }
 
@@ -239,7 +242,7 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
         if (f.flags & QW_FIELD_HAS_FREQS) in.flags |= IF_HAS_TF;
         if (f.flags & QW_FIELD_HAS_FIELDNORMS) in.flags |= IF_HAS_FN;
         L.postings += t.doc_freq;
-        L.alg_bytes += t.data_len - (scored ? 0 : t.tf_len);
+        L.alg_bytes += t.data_len - t.fn_len - (scored ? 0 : t.tf_len);  // fieldnorm bytes are counted once per plan below
         if (occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER) L.min_required_df = std::min<uint64_t>(L.min_required_df, t.doc_freq);
         if (scored) {
           int slot = -1;
@@ -583,6 +586,30 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   return L;
 }
 
+// shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, QU_SLOTS staging slots
+// (block payload + records + per-term table + header), mbarriers, MODE_HIST histogram
+static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
+  qwk::USmem L;
+  memset(&L, 0, sizeof L);
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
+  L.score = take(W * 4);
+  L.bars = take(8 * (2 * QU_SLOTS + QU_CHAIN));
+  if (hist) L.hist = take(QW_HIST_BINS * 4);
+  const uint32_t fixed = QU_MAXBLK * 16 + QU_MAX_TERMS * 16 + 32 + QU_PAD;
+  uint32_t cap = budget > off + QU_SLOTS * (fixed + 2048) ? ((budget - off) / QU_SLOTS - fixed) & ~15u : 2048;
+  if (const char* e = getenv("QWGPU_UCAP")) cap = (uint32_t)atoi(e) & ~15u;
+  L.cap = cap;
+  L.payload = 0;
+  L.recs = cap + QU_PAD;
+  L.ttab = L.recs + QU_MAXBLK * 16;
+  L.hdr = L.ttab + QU_MAX_TERMS * 16;
+  L.slot_stride = L.hdr + 32;
+  L.slot0 = take(QU_SLOTS * L.slot_stride);
+  L.total = off;
+  return L;
+}
+
 void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
                     const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats) {
   const uint32_t n_in = (uint32_t)sp.size();
@@ -626,6 +653,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     if (!(L.P.fused_score_root && L.P.max_hits && !L.P.sa.present && !L.P.n_aggs && L.P.key.kind[0] == QW_SORT_SCORE &&
           L.P.key.order[0] == QW_ORDER_DESC))
       all_union = false;
+    if (L.P.n_terms > QU_MAX_TERMS || L.P.n_instr != L.P.n_terms + 2) all_union = false;  // [BOOL_BEGIN, TERM x n, BOOL_END]
     if (L.P.max_hits && L.P.key.kind[0] == QW_SORT_SCORE) rec_l0 = false;
     max_key_bits = std::max(max_key_bits, L.P.key.total_bits);
     for (const DInstr& in : L.instrs)
@@ -645,6 +673,13 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // costs — staging, program interpretation, barriers — amortise over more postings)
   uint32_t W = 32768;
   if (const char* e = getenv("QWGPU_W")) W = (uint32_t)atoi(e);
+  // BM25-union batches run the TMA + mbarrier pipeline (union_kernel.cuh): fixed 16384-doc windows,
+  // two blocks per SM; QWGPU_OLD_UNION=1 keeps the round-1 window kernel for A/B runs
+  static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
+  const bool use_union = all_union && !old_union;
+  const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / 2 - 1024 - 64;
+  qwk::USmem ulay_c, ulay_h;
+  if (use_union && !getenv("QWGPU_W")) W = 16384;
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);
@@ -652,6 +687,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     W >>= 1;
   }
   (void)scoring;
+  if (use_union) {
+    // (the generic layout above stays valid for the same W: exact radix passes below level 0 use k_window)
+    ulay_c = make_union_layout(W, false, u_budget);
+    ulay_h = make_union_layout(W, true, u_budget);
+  }
   if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
 
   // ---- device blob: plans, programs, work maps ----------------------------------------------------------
@@ -677,7 +717,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), blob_bytes = al(o_bounds + (size_t)tot_bounds * 8);
   // scratch: thresholds, histograms, candidates
   size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
-         s_wmax = al(s_state + (size_t)n * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
+         s_ctr = al(s_state + (size_t)n * 4), s_wmax = al(s_ctr + 64 * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
          scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
@@ -749,6 +789,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT, false>, QW_THREADS, lay.total));
   occ = std::max(occ, 1);
   enum { F_REC = 1, F_REFINE = 2, F_CANDS_ONLY = 4 };
+  uint32_t n_ctr = 0;  // work counters handed to k_union launches (zeroed with the scratch region)
   auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix, uint32_t flags) {
     KParams q = kp;
     q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
@@ -760,10 +801,24 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     q.refine = (flags & F_REFINE) ? 1 : 0;
     q.cands_only = (flags & F_CANDS_ONLY) ? 1 : 0;
     if (q.total_work == 0) return;
+    if (use_union && flags == 0 && (mode == qwk::MODE_COLLECT || (level == 0 && !use_prefix))) {
+      qwk::UParams u;
+      memset(&u, 0, sizeof u);
+      u.plans = kp.plans; u.instrs = kp.instrs; u.cols = kp.cols; u.thresh = kp.thresh;
+      u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride; u.W = W;
+      if (n_ctr >= 64) fail(QWGPU_EINTERNAL, "out of work counters");
+      u.work_counter = (uint32_t*)(slot->d_scratch + s_ctr) + n_ctr++;
+      u.sm = mode == qwk::MODE_HIST ? ulay_h : ulay_c;
+      const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * 2));
+      if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
+      else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
+      stats.launches++;
+      return;
+    }
     uint32_t grid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * occ));
-    if (mode == qwk::MODE_HIST && all_union && level == 0 && !use_prefix) qwk::k_window<qwk::MODE_HIST, true><<<grid, QW_THREADS, lay.total, st>>>(q);
+    if (mode == qwk::MODE_HIST && all_union && old_union && level == 0 && !use_prefix) qwk::k_window<qwk::MODE_HIST, true><<<grid, QW_THREADS, lay.total, st>>>(q);
     else if (mode == qwk::MODE_HIST) qwk::k_window<qwk::MODE_HIST, false><<<grid, QW_THREADS, lay.total, st>>>(q);
-    else if (all_union) qwk::k_window<qwk::MODE_COLLECT, true><<<grid, QW_THREADS, lay.total, st>>>(q);
+    else if (all_union && old_union) qwk::k_window<qwk::MODE_COLLECT, true><<<grid, QW_THREADS, lay.total, st>>>(q);
     else qwk::k_window<qwk::MODE_COLLECT, false><<<grid, QW_THREADS, lay.total, st>>>(q);
     stats.launches++;
   };

@@ -62,7 +62,7 @@ struct BTerm {
   std::string bytes;
   uint32_t doc_freq;
   uint32_t win_shift;
-  uint64_t tf_len = 0;
+  uint64_t tf_len = 0, fn_len = 0;
   std::vector<QwSkip> skips;
   std::vector<uint32_t> first_docs;  // first doc of each block
   std::vector<uint8_t> data;
@@ -94,6 +94,8 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
   if (field_id >= b->fields.size()) fail(QWGPU_EINVALID_ARG, "add_term: bad field id");
   if (n == 0) return;
   bool has_freqs = (b->fields[field_id].flags & QW_FIELD_HAS_FREQS) != 0;
+  bool has_fn = (b->fields[field_id].flags & QW_FIELD_HAS_FIELDNORMS) != 0;
+  const std::vector<uint8_t>& fnorms = b->fields[field_id].fieldnorms;
   BTerm t;
   t.field = field_id;
   t.bytes.assign((const char*)term, term_len);
@@ -128,10 +130,16 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
     s.tf_bits = has_freqs ? (uint8_t)bits_needed(maxtf) : 0;
     s.count = (uint16_t)cnt;
     size_t off = t.data.size();
-    t.data.resize(off + 16u + 16u * (s.doc_bits + s.tf_bits));
+    t.data.resize(off + 16u + 16u * (s.doc_bits + s.tf_bits) + (has_fn ? QW_BLOCK_LEN : 0u));
     memcpy(t.data.data() + off, &s, 16);  // inline header
     pack_block_4x(deltas, s.doc_bits, t.data.data() + off + 16u);
     pack_block_4x(tfv, s.tf_bits, t.data.data() + off + 16u + 16u * s.doc_bits);
+    if (has_fn) {
+      // per-posting fieldnorm ids (zero padded): one contiguous byte stream per block for BM25
+      uint8_t* fb = t.data.data() + off + 16u + 16u * (s.doc_bits + s.tf_bits);
+      for (uint32_t i = 0; i < cnt; i++) fb[i] = fnorms[docs[start + i]];
+      t.fn_len += QW_BLOCK_LEN;
+    }
     t.first_docs.push_back(docs[start]);
     t.tf_len += 16u * s.tf_bits;
     prev = s.last_doc;
@@ -286,6 +294,7 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     o.data_off = doff; o.data_len = t.data.size(); doff = align16(doff + t.data.size() + 16);
     o.win_shift = t.win_shift;
     o.tf_len = t.tf_len;
+    o.fn_len = t.fn_len;
     o.widx_off = doff; doff = align16(doff + t.widx.size() * sizeof(QwWinIdx));
   }
   for (uint32_t f = 0; f < nf; f++) { F[f].first_term = 0; F[f].num_terms = 0; }
@@ -308,7 +317,7 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
   uint64_t off = sizeof(QwImgHeader);
   QwImgHeader H;
   memset(&H, 0, sizeof H);
-  H.magic = QW_IMG_MAGIC; H.version = 1; H.num_docs = b->num_docs;
+  H.magic = QW_IMG_MAGIC; H.version = QW_IMG_VERSION; H.num_docs = b->num_docs;
   H.num_fields = nf; H.num_terms = nt; H.num_columns = nc;
   H.fields_off = off; off = align16(off + nf * sizeof(QwImgField));
   H.terms_off = off; off = align16(off + nt * sizeof(QwImgTerm));

@@ -1,0 +1,509 @@
+// union_kernel.cuh — the BM25 top-K shape (pure OR of positive-weight scored terms ranked by _score)
+// as a warp-specialised TMA + mbarrier pipeline for sm_100a.
+//
+// Replaces tantivy's BufferedUnionScorer + Bm25Weight + TopDocs loop behind `searcher.search`
+// (quickwit-search/src/leaf.rs:637) for the headline query shape.
+//
+// One 512-thread block = 15 consumer warps + 1 producer warp, two blocks per SM. The block owns one
+// 16384-doc window of one split at a time (f32 score accumulator of the window in shared memory);
+// windows are handed out dynamically from a global counter.
+//
+//   producer warp   per window: (1) lane = term: one load of the term's window-index entry (QwWinIdx)
+//                   gives the ordinals of the posting blocks overlapping the window; (2) lane = block:
+//                   a coalesced 16-byte load of the block's skip entry (QwSkip) tells its widths and
+//                   doc range; blocks that miss the window are dropped; the survivors are packed into
+//                   the current pipeline slot — one `cp.async.bulk` (1-D TMA) per block straight from
+//                   HBM to shared memory, completion counted on the slot's `full` mbarrier — and
+//                   described by a 16-byte record (shared address, widths, clause, interior flag).
+//                   A slot that fills up is closed and the window continues in the next slot, so any
+//                   density / term count works. No consumer ever executes a staging instruction.
+//   consumer warps  wait on `full`, take blocks round-robin, decode one block per warp (4-lane-
+//                   interleaved bit-unpack -> warp-shuffle prefix scan -> doc ids; tf unpack; the
+//                   per-posting fieldnorm id comes with the block, so BM25 = weight * tff[tf][fn] is
+//                   one PRMT + one table load per posting) and add the four contributions per lane
+//                   into the score array.
+//   clause order    f32 sums must follow the reference's clause order. Every clause of a window is a
+//                   STAGE of a per-block ring of mbarriers ("chain", one arrival per consumer warp
+//                   per stage): a warp arrives at a stage when it has no more blocks in it and waits
+//                   for stage s-1 before it touches the accumulator for stage s. Decode never waits,
+//                   only the read-modify-write does; there is no __syncthreads, no spin on shared
+//                   memory and no fence in the loop. The sweep of a finished window (count matches,
+//                   threshold test, clear) is one more stage of the same chain, so the next window's
+//                   decode overlaps the sweep of this one.
+#pragma once
+#include "kernels.cuh"
+
+namespace qwk {
+
+#define QU_NCW (QW_WARPS - 1)   /* consumer warps; warp QU_NCW is the producer */
+#define QU_NCT (QU_NCW * 32)
+#define QU_SLOTS 2
+#define QU_MAXBLK 256           /* block records per slot */
+#define QU_CHAIN 128            /* mbarriers in the stage ring (a warp is never > 70 stages ahead) */
+#define QU_MAX_TERMS 32
+#define QU_PAD 32               /* decode may read one 16-byte word past a block */
+
+enum { QU_F_FIRST = 1u, QU_F_LAST = 2u, QU_F_END = 4u };
+
+struct USmem {
+  uint32_t score;                       // float[W]
+  uint32_t slot0, slot_stride;          // QU_SLOTS slots
+  uint32_t payload, recs, ttab, hdr;    // offsets inside a slot
+  uint32_t bars;                        // full[QU_SLOTS], empty[QU_SLOTS], chain[QU_CHAIN]
+  uint32_t hist;                        // MODE_HIST: uint32[QW_HIST_BINS]
+  uint32_t cap;                         // payload bytes per slot
+  uint32_t total;
+};
+
+struct UParams {
+  const DSplitPlan* plans;
+  const DInstr* instrs;
+  const DCol* cols;
+  const DThresh* thresh;
+  const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
+  uint32_t* work_counter;      // zeroed before the launch
+  uint32_t n_splits, total_work, stride, W;
+  USmem sm;
+};
+
+struct UHdr {  // 32 bytes, written by the producer when it closes a slot
+  uint32_t ws, wlen, split, flags;
+  uint32_t n_blocks, n_terms, t_last;  // t_last: clause of the slot's last block (stages below it are final)
+  float s_lo;                          // COLLECT: f32 lower bound of the threshold bucket; HIST: score_scale
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D TMA: global -> shared, completion (bytes) on an mbarrier of this block
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// inclusive warp scan step with the shuffle's own predicate (SHFL.UP + predicated IADD)
+__device__ __forceinline__ uint32_t scan_step(uint32_t x, uint32_t o) {
+  asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0x0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(x) : "r"(o));
+  return x;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x) {
+  x = scan_step(x, 1); x = scan_step(x, 2); x = scan_step(x, 4); x = scan_step(x, 8); x = scan_step(x, 16);
+  return x;
+}
+
+// Rare path of the sweep: a doc that reaches the float lower bound builds its composite key and, if
+// it reaches the threshold key, joins the split's candidate list (k_select sorts it out).
+__device__ __noinline__ void union_emit(const DSplitPlan* plans, const DThresh* thresh, const DCol* cols, uint32_t split, uint32_t doc, float sc) {
+  const DSplitPlan& P = plans[split];
+  const DThresh& T = thresh[split];
+  const Key thr{T.key[0], T.key[1], T.key[2]};
+  const DocKey dk = doc_key(P, P.key, cols + P.col_base, (const uint8_t*)P.data_base, doc, sc);
+  if (key_ge(dk.key, thr)) {
+    const uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
+    if (pos < QW_CAND_CAP) {
+      uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
+      c[0] = dk.key.w0; c[1] = dk.key.w1; c[2] = dk.key.w2;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t W = p.W;
+  const uint32_t sbase = smem_u32(qw_smem);
+  const uint32_t bars = sbase + p.sm.bars;
+  auto bar_full = [&](uint32_t s) { return bars + 8u * s; };
+  auto bar_empty = [&](uint32_t s) { return bars + 8u * (QU_SLOTS + s); };
+  auto bar_chain = [&](uint32_t st) { return bars + 8u * (2 * QU_SLOTS + (st & (QU_CHAIN - 1))); };
+  auto chain_parity = [&](uint32_t st) { return (st / QU_CHAIN) & 1u; };
+  if (tid == 0) {
+    for (uint32_t s = 0; s < QU_SLOTS; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), QU_NCW); }
+    for (uint32_t s = 0; s < QU_CHAIN; s++) mbar_init(bar_chain(s), QU_NCW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == QU_NCW) {
+    // ================================ producer ======================================================
+    uint32_t seq = 0;            // slots closed so far
+    uint32_t cur_split = 0xFFFFFFFFu;
+    // lane = term slot of the current split's plan
+    uint64_t t_data = 0, t_widx = 0, t_skip = 0, t_tab = 0;
+    uint32_t t_nblk = 0, t_shift = 0, t_fl = 0;
+    float t_w = 0.f;
+    const uint8_t* base = nullptr;
+    uint32_t n_terms = 0, num_docs = 0;
+    float hdr_f = -1.0f;
+    auto fetch = [&]() -> uint32_t {
+      uint32_t w = 0;
+      if (lane == 0) w = atomicAdd(p.work_counter, 1u);
+      return __shfl_sync(QW_FULL, w, 0);
+    };
+    // slot state (warp-uniform)
+    bool open = false;
+    uint32_t slot = 0, off = 0, cnt = 0, last_t = 0;
+    bool first_of_window = true;
+    uint32_t ws = 0, wlen = 0;
+    auto slot_base = [&](uint32_t s) { return p.sm.slot0 + s * p.sm.slot_stride; };
+    auto open_slot = [&]() {
+      slot = seq % QU_SLOTS;
+      mbar_wait(bar_empty(slot), ((seq / QU_SLOTS) & 1u) ^ 1u);
+      open = true; off = 0; cnt = 0;
+      if (lane < n_terms) {
+        uint4 tt;
+        tt.x = __float_as_uint(t_w); tt.y = t_fl; tt.z = (uint32_t)t_tab; tt.w = (uint32_t)(t_tab >> 32);
+        *(uint4*)(qw_smem + slot_base(slot) + p.sm.ttab + 16u * lane) = tt;
+      }
+    };
+    auto close_slot = [&](uint32_t flags) {
+      if (lane == 0) {
+        UHdr h;
+        h.ws = ws; h.wlen = wlen; h.split = cur_split; h.flags = flags | (first_of_window ? QU_F_FIRST : 0u);
+        h.n_blocks = cnt; h.n_terms = n_terms; h.t_last = last_t; h.s_lo = hdr_f;
+        uint4* d = (uint4*)(qw_smem + slot_base(slot) + p.sm.hdr);
+        d[0] = make_uint4(h.ws, h.wlen, h.split, h.flags);
+        d[1] = make_uint4(h.n_blocks, h.n_terms, h.t_last, __float_as_uint(h.s_lo));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full(slot));
+      seq++;
+      open = false;
+      first_of_window = false;
+    };
+
+    uint32_t work = fetch();
+    while (work < p.total_work) {
+      // (split, window) of this work item
+      uint32_t a = 0, b = p.n_splits;
+      while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (__ldg(p.first_work + mid) <= work) a = mid; else b = mid;
+      }
+      const uint32_t split = a;
+      const uint32_t window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
+      work = fetch();  // next item: the atomic's latency hides behind this window's loads
+      if (split != cur_split) {
+        cur_split = split;
+        const DSplitPlan& P = p.plans[split];
+        base = (const uint8_t*)P.data_base;
+        n_terms = P.n_terms;
+        num_docs = P.num_docs;
+        t_nblk = 0;
+        if (lane < n_terms) {
+          const DInstr& in = p.instrs[P.instr_base + 1 + lane];  // [BOOL_BEGIN, TERM x n, BOOL_END]
+          t_data = in.a; t_widx = in.b; t_skip = in.c; t_nblk = in.n; t_shift = in.m;
+          t_fl = in.flags; t_w = in.f;
+          t_tab = P.bm25_tab[in.r];
+        }
+        if (MODE == MODE_COLLECT) {
+          // float lower bound of the threshold bucket (conservative: one part in 2^20)
+          const uint32_t thr_top = (uint32_t)(p.thresh[split].key[0] >> 53);
+          hdr_f = -1.0f;
+          if (thr_top >= 1024u) hdr_f = __fmul_rn(__fdiv_rn((float)(thr_top & 1023u), P.key.score_scale), 0.999999f);
+        } else hdr_f = P.key.score_scale;
+      }
+      ws = window * W;
+      const uint32_t we = min(ws + W, num_docs);
+      wlen = we - ws;
+      first_of_window = true;
+      // ---- lane = term: blocks of the term that overlap the window ----------------------------------
+      uint32_t fb = 0, nb = 0;
+      if (lane < n_terms && t_nblk) {
+        const uint4* wi = (const uint4*)(base + t_widx);
+        const uint32_t e0 = ws >> t_shift, e1 = (we - 1) >> t_shift;
+        const uint4 ea = __ldg(wi + e0);
+        const uint4 eb = e1 != e0 ? __ldg(wi + e1) : ea;
+        fb = ea.z;
+        nb = (eb.y > ea.x && eb.w > ea.z) ? eb.w - ea.z : 0;
+      }
+      const uint32_t incl_nb = warp_incl_scan(nb);
+      const uint32_t gbase = incl_nb - nb;
+      const uint32_t G = __shfl_sync(QW_FULL, incl_nb, 31);
+      // ---- lane = block: skip entry -> record + bulk copy -------------------------------------------
+      for (uint32_t q0 = 0; q0 < G; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        // clause of flat block q: the last term slot whose first block is <= q
+        uint32_t t = 0;
+#pragma unroll
+        for (uint32_t step = 16; step; step >>= 1) {
+          const uint32_t cand = t + step;
+          const uint32_t gb = __shfl_sync(QW_FULL, gbase, cand & 31);
+          if (cand < 32 && gb <= q) t = cand;
+        }
+        const uint32_t k = q - __shfl_sync(QW_FULL, gbase, t);
+        const uint32_t fbt = __shfl_sync(QW_FULL, fb, t);
+        const uint64_t skp = __shfl_sync(QW_FULL, t_skip, t);
+        const uint64_t dat = __shfl_sync(QW_FULL, t_data, t);
+        const uint32_t tfl = __shfl_sync(QW_FULL, t_fl, t);
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (q < G) r = __ldg((const uint4*)(base + skp) + fbt + k);  // last_doc, prev_last_doc, byte_off, widths/count
+        const uint32_t doc_bits = r.w & 0xFF, tf_bits = (r.w >> 8) & 0xFF, count = r.w >> 16;
+        const uint32_t first_lb = r.y + 1;  // lower bound of the first doc (0 when prev == 0xFFFFFFFF)
+        const bool overlaps = q < G && r.x >= ws && first_lb < we;
+        const uint32_t size = overlaps ? 16u * (doc_bits + tf_bits) + ((tfl & IF_HAS_FN) ? QW_BLOCK_LEN : 0u) : 0u;
+        const bool interior = first_lb >= ws && r.x < we && count == QW_BLOCK_LEN;
+        const uint8_t* src = base + dat + r.z + 16;
+        uint32_t pending = __ballot_sync(QW_FULL, overlaps);
+        while (pending) {
+          if (!open) open_slot();
+          const bool mine = (pending >> lane) & 1u;
+          const uint32_t sz = mine ? size : 0u;
+          const uint32_t incl = warp_incl_scan(sz);
+          const uint32_t pos = __popc(pending & ((1u << lane) - 1u));
+          const bool fits = mine && off + incl <= p.sm.cap && cnt + pos < QU_MAXBLK;
+          const uint32_t fitmask = __ballot_sync(QW_FULL, fits);  // a prefix of `pending`
+          if (fitmask) {
+            const uint32_t lastfit = 31u - __clz(fitmask);
+            const uint32_t bytes = __shfl_sync(QW_FULL, incl, lastfit);
+            if (lane == 0 && bytes) mbar_expect_tx(bar_full(slot), bytes);
+            __syncwarp();
+            if (fits) {
+              const uint32_t dst = sbase + slot_base(slot) + p.sm.payload + off + incl - sz;
+              *(uint4*)(qw_smem + slot_base(slot) + p.sm.recs + 16u * (cnt + pos)) = make_uint4(r.y, dst, r.w, t | (interior ? 256u : 0u));
+              if (sz) bulk_g2s(dst, src, sz, bar_full(slot));
+            }
+            off += bytes;
+            cnt += __popc(fitmask);
+            last_t = __shfl_sync(QW_FULL, t, lastfit);
+            pending &= ~fitmask;
+          }
+          if (pending) close_slot(0);  // slot full: the window continues in the next slot
+        }
+      }
+      if (open) close_slot(QU_F_LAST);
+      else if (!first_of_window) {
+        // the window's last slot was closed exactly at a round boundary without LAST: post an empty one
+        open_slot();
+        close_slot(QU_F_LAST);
+      }
+    }
+    // terminal slot
+    open_slot();
+    cnt = 0;
+    close_slot(QU_F_END);
+  } else {
+    // ================================ consumers =====================================================
+    float* score = (float*)(qw_smem + p.sm.score);
+    uint32_t* hist = (uint32_t*)(qw_smem + p.sm.hist);
+    {
+      float4* q = reinterpret_cast<float4*>(score);
+      for (uint32_t i = tid; i < (W >> 2); i += QU_NCT) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == MODE_HIST) for (uint32_t i = tid; i < QW_HIST_BINS; i += QU_NCT) hist[i] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_chain(0));
+    uint32_t my_stage = 1;   // stages this warp has arrived at: [0, my_stage)
+    uint32_t waited = 0;     // stages known complete: [0, waited)
+    uint32_t wbase = 1;      // stage of clause 0 of the current window
+    uint32_t next_base = 1;
+    uint32_t cur_split = 0xFFFFFFFFu;
+    uint32_t my_hits = 0;
+    auto pass_to = [&](uint32_t st) {  // arrive at every stage below st
+      if (my_stage < st) {
+        __syncwarp();
+        if (lane == 0) for (uint32_t s = my_stage; s < st; s++) mbar_arrive(bar_chain(s));
+        my_stage = st;
+      }
+    };
+    auto wait_below = [&](uint32_t st) {  // all stages below st complete
+      if (waited < st) {
+        mbar_wait(bar_chain(st - 1), chain_parity(st - 1));
+        waited = st;
+      }
+    };
+    auto flush_hits = [&]() {
+      if (MODE != MODE_COLLECT || cur_split == 0xFFFFFFFFu) return;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_down_sync(QW_FULL, my_hits, o);
+      if (lane == 0 && my_hits) {
+        const DSplitPlan& P = p.plans[cur_split];
+        atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)my_hits);
+        atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)my_hits);  // no search_after: every hit is eligible
+      }
+      my_hits = 0;
+    };
+
+    for (uint32_t seq = 0;; seq++) {
+      const uint32_t slot = seq % QU_SLOTS;
+      mbar_wait(bar_full(slot), (seq / QU_SLOTS) & 1u);
+      const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
+      const uint4 h0 = *(const uint4*)(qw_smem + sl + p.sm.hdr);
+      const uint4 h1 = *(const uint4*)(qw_smem + sl + p.sm.hdr + 16);
+      const uint32_t ws = h0.x, wlen = h0.y, split = h0.z, flags = h0.w;
+      const uint32_t G = h1.x, n_terms = h1.y, t_last = h1.z;
+      const float hdr_f = __uint_as_float(h1.w);
+      if (flags & QU_F_END) break;
+      if (flags & QU_F_FIRST) wbase = next_base;
+      if (split != cur_split) { flush_hits(); cur_split = split; }
+      const uint32_t recs = sl + p.sm.recs, ttab = sl + p.sm.ttab;
+
+      for (uint32_t g = warp; g < G; g += QU_NCW) {
+        const uint4 rec = *(const uint4*)(qw_smem + recs + 16u * g);  // prev_last_doc, shared address, widths/count, clause | interior
+        const uint32_t t = rec.w & 0xFFu;
+        const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
+        const float weight = __uint_as_float(tt.x);
+        const uint32_t tfl = tt.y;
+        const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
+        const uint32_t blk = rec.y - sbase;  // offset inside qw_smem
+        const uint32_t doc_bits = rec.z & 0xFFu, tf_bits = (rec.z >> 8) & 0xFFu;
+        // ---- doc ids: 4 values per lane from the 4-lane-interleaved words, then a warp scan ----------
+        uint32_t d0, d1, d2, d3;
+        {
+          const uint32_t bp = lane * doc_bits, sh = bp & 31u;
+          const uint8_t* a = qw_smem + blk + ((bp >> 5) << 4);
+          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, doc_bits);
+          // strictly-sorted deltas: doc[i] = doc[i-1] + v[i] + 1
+          d0 = (__funnelshift_r(A.x, B.x, sh) & mask) + 1u;
+          d1 = d0 + (__funnelshift_r(A.y, B.y, sh) & mask) + 1u;
+          d2 = d1 + (__funnelshift_r(A.z, B.z, sh) & mask) + 1u;
+          d3 = d2 + (__funnelshift_r(A.w, B.w, sh) & mask) + 1u;
+        }
+        const uint32_t incl = warp_incl_scan(d3);
+        const uint32_t basev = rec.x + (incl - d3) - ws;  // mod 2^32; window-relative
+        const uint32_t r0 = basev + d0, r1 = basev + d1, r2 = basev + d2, r3 = basev + d3;
+        // ---- term frequencies -----------------------------------------------------------------------
+        uint32_t f0 = 1, f1 = 1, f2 = 1, f3 = 1;
+        if (tf_bits) {
+          const uint32_t bp = lane * tf_bits, sh = bp & 31u;
+          const uint8_t* a = qw_smem + blk + 16u * doc_bits + ((bp >> 5) << 4);
+          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, tf_bits);
+          f0 = __funnelshift_r(A.x, B.x, sh) & mask;
+          f1 = __funnelshift_r(A.y, B.y, sh) & mask;
+          f2 = __funnelshift_r(A.z, B.z, sh) & mask;
+          f3 = __funnelshift_r(A.w, B.w, sh) & mask;
+        }
+        // ---- BM25: weight * (tf / (tf + norm[fieldnorm id])) from the tf-factor table ----------------
+        uint32_t fnw = 0x01010101u;  // no fieldnorms: constant fieldnorm id 1
+        if (tfl & IF_HAS_FN) fnw = *(const uint32_t*)(qw_smem + blk + 16u * (doc_bits + tf_bits) + 4u * lane);
+        float c0, c1, c2, c3;
+        if (tf_bits <= 4) {
+          // tf < 16: index = tf * 256 + fieldnorm id, one byte-permute per posting
+          c0 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f0, fnw, 0x2104)));
+          c1 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f1, fnw, 0x2105)));
+          c2 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f2, fnw, 0x2106)));
+          c3 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f3, fnw, 0x2107)));
+        } else {
+          auto tfn = [&](uint32_t tf, uint32_t fn) -> float {
+            if (tf < QW_TFF_ROWS) return __ldg(tab + 256 + tf * 256 + fn);
+            const float tff = (float)tf;
+            return __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + fn)));
+          };
+          c0 = __fmul_rn(weight, tfn(f0, fnw & 0xFFu));
+          c1 = __fmul_rn(weight, tfn(f1, (fnw >> 8) & 0xFFu));
+          c2 = __fmul_rn(weight, tfn(f2, (fnw >> 16) & 0xFFu));
+          c3 = __fmul_rn(weight, tfn(f3, fnw >> 24));
+        }
+        // ---- ordered accumulate: everything of the earlier clauses must be in -------------------------
+        const uint32_t st = wbase + t;
+        pass_to(st);
+        wait_below(st);
+        if (rec.w & 256u) {
+          // interior block: all 128 postings exist and lie inside the window
+          const float o0 = score[r0], o1 = score[r1], o2 = score[r2], o3 = score[r3];
+          score[r0] = __fadd_rn(o0, c0);
+          score[r1] = __fadd_rn(o1, c1);
+          score[r2] = __fadd_rn(o2, c2);
+          score[r3] = __fadd_rn(o3, c3);
+        } else {
+          const uint32_t count = rec.z >> 16;
+          const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;  // postings of this lane that exist
+          const bool in0 = nvalid > 0 && r0 < wlen, in1 = nvalid > 1 && r1 < wlen;  // r = doc - ws (unsigned wrap before the window)
+          const bool in2 = nvalid > 2 && r2 < wlen, in3 = nvalid > 3 && r3 < wlen;
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+          if (in0) o0 = score[r0];
+          if (in1) o1 = score[r1];
+          if (in2) o2 = score[r2];
+          if (in3) o3 = score[r3];
+          if (in0) score[r0] = __fadd_rn(o0, c0);
+          if (in1) score[r1] = __fadd_rn(o1, c1);
+          if (in2) score[r2] = __fadd_rn(o2, c2);
+          if (in3) score[r3] = __fadd_rn(o3, c3);
+        }
+      }
+      // this warp is done reading the slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty(slot));
+      if (!(flags & QU_F_LAST)) {
+        pass_to(wbase + t_last);  // the slot's last clause may continue in the next slot
+        continue;
+      }
+      const uint32_t end_stage = wbase + n_terms;
+      pass_to(end_stage);
+      wait_below(end_stage);  // every contribution of the window is in
+      // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
+      float4* sc4 = reinterpret_cast<float4*>(score);
+      if (MODE == MODE_COLLECT) {
+        const float s_lo = hdr_f;
+        for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
+          const float4 v = sc4[q];
+          sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          my_hits += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
+          if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= s_lo) {
+            if (v.x > 0.0f && v.x >= s_lo) union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + 0, v.x);
+            if (v.y > 0.0f && v.y >= s_lo) union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + 1, v.y);
+            if (v.z > 0.0f && v.z >= s_lo) union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + 2, v.z);
+            if (v.w > 0.0f && v.w >= s_lo) union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + 3, v.w);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage));
+        my_stage = end_stage + 1;
+        next_base = end_stage + 1;
+      } else {
+        // level-0 digit histogram of the sampled windows: digit = [1 | lin:10] (score_lin)
+        const float scale = hdr_f;
+        auto lin = [&](float s) -> uint32_t {
+          const float x = __fmul_rn(s, scale);
+          const uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
+          return 1024u | l;
+        };
+        for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
+          const float4 v = sc4[q];
+          sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (v.x > 0.0f) atomicAdd(&hist[lin(v.x)], 1u);
+          if (v.y > 0.0f) atomicAdd(&hist[lin(v.y)], 1u);
+          if (v.z > 0.0f) atomicAdd(&hist[lin(v.z)], 1u);
+          if (v.w > 0.0f) atomicAdd(&hist[lin(v.w)], 1u);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage));
+        my_stage = end_stage + 1;
+        wait_below(end_stage + 1);  // every warp has swept: the window's histogram is complete
+        uint32_t* gh = (uint32_t*)p.plans[split].out_hist;
+        for (uint32_t i = tid; i < QW_HIST_BINS; i += QU_NCT) {
+          const uint32_t v = hist[i];
+          if (v) { atomicAdd(&gh[i], v); hist[i] = 0; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage + 1));
+        my_stage = end_stage + 2;
+        next_base = end_stage + 2;
+      }
+    }
+    flush_hits();
+  }
+}
+
+}  // namespace qwk
