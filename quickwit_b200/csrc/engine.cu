@@ -809,9 +809,24 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       if (n_ctr >= 64) fail(QWGPU_EINTERNAL, "out of work counters");
       u.work_counter = (uint32_t*)(slot->d_scratch + s_ctr) + n_ctr++;
       u.sm = mode == qwk::MODE_HIST ? ulay_h : ulay_c;
+#ifdef QU_PROFILE
+      static unsigned long long* d_prof = nullptr;
+      if (!d_prof) CUDA_CHECK(cudaMalloc(&d_prof, 16 * 8));
+      if (mode == qwk::MODE_COLLECT) { CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 16 * 8, st)); u.prof = d_prof; }
+#endif
       const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * 2));
       if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
       else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
+#ifdef QU_PROFILE
+      if (u.prof && getenv("QWGPU_UPROF")) {
+        unsigned long long h[16];
+        CUDA_CHECK(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const double np = (double)ugrid, nc = (double)h[15];
+        fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, chain-wait %.0f (end-of-window %.0f), sweep %.0f, block-loop %.0f, blocks %.1f\n",
+                h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[11] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
+      }
+#endif
       stats.launches++;
       return;
     }

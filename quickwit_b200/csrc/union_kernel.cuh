@@ -63,8 +63,16 @@ struct UParams {
   const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
   uint32_t* work_counter;      // zeroed before the launch
   uint32_t n_splits, total_work, stride, W;
+  unsigned long long* prof;    // QU_PROFILE builds: cycle counters (see k_union)
   USmem sm;
 };
+#ifdef QU_PROFILE
+#define QU_T(x) const long long x = clock64()
+#define QU_ACC(acc, t0) acc += clock64() - (t0)
+#else
+#define QU_T(x)
+#define QU_ACC(acc, t0)
+#endif
 
 struct UHdr {  // 32 bytes, written by the producer when it closes a slot
   uint32_t ws, wlen, split, flags;
@@ -147,6 +155,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     // ================================ producer ======================================================
     uint32_t seq = 0;            // slots closed so far
     uint32_t cur_split = 0xFFFFFFFFu;
+#ifdef QU_PROFILE
+    long long pt_empty = 0, pt_a = 0, pt_b = 0, pt_win = 0;
+    const long long pt_start = clock64();
+#endif
     // lane = term slot of the current split's plan
     uint64_t t_data = 0, t_widx = 0, t_skip = 0, t_tab = 0;
     uint32_t t_nblk = 0, t_shift = 0, t_fl = 0;
@@ -167,7 +179,9 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     auto slot_base = [&](uint32_t s) { return p.sm.slot0 + s * p.sm.slot_stride; };
     auto open_slot = [&]() {
       slot = seq % QU_SLOTS;
+      QU_T(pt_e0);
       mbar_wait(bar_empty(slot), ((seq / QU_SLOTS) & 1u) ^ 1u);
+      QU_ACC(pt_empty, pt_e0);
       open = true; off = 0; cnt = 0;
       if (lane < n_terms) {
         uint4 tt;
@@ -193,6 +207,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
 
     uint32_t work = fetch();
     while (work < p.total_work) {
+      QU_T(pt_w0);
       // (split, window) of this work item
       uint32_t a = 0, b = p.n_splits;
       while (b - a > 1) {
@@ -237,6 +252,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
         nb = (eb.y > ea.x && eb.w > ea.z) ? eb.w - ea.z : 0;
       }
       const uint32_t incl_nb = warp_incl_scan(nb);
+      QU_ACC(pt_a, pt_w0);
       const uint32_t gbase = incl_nb - nb;
       const uint32_t G = __shfl_sync(QW_FULL, incl_nb, 31);
       // ---- lane = block: skip entry -> record + bulk copy -------------------------------------------
@@ -290,6 +306,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
           if (pending) close_slot(0);  // slot full: the window continues in the next slot
         }
       }
+#ifdef QU_PROFILE
+      pt_win++;
+      QU_ACC(pt_b, pt_w0);
+#endif
       if (open) close_slot(QU_F_LAST);
       else if (!first_of_window) {
         // the window's last slot was closed exactly at a round boundary without LAST: post an empty one
@@ -301,6 +321,16 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     open_slot();
     cnt = 0;
     close_slot(QU_F_END);
+#ifdef QU_PROFILE
+    if (lane == 0 && p.prof) {
+      atomicAdd(p.prof + 0, (unsigned long long)(clock64() - pt_start));
+      atomicAdd(p.prof + 1, (unsigned long long)pt_empty);
+      atomicAdd(p.prof + 2, (unsigned long long)pt_a);
+      atomicAdd(p.prof + 3, (unsigned long long)pt_b);
+      atomicAdd(p.prof + 4, (unsigned long long)pt_win);
+      atomicAdd(p.prof + 5, (unsigned long long)seq);
+    }
+#endif
   } else {
     // ================================ consumers =====================================================
     float* score = (float*)(qw_smem + p.sm.score);
@@ -318,6 +348,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     uint32_t next_base = 1;
     uint32_t cur_split = 0xFFFFFFFFu;
     uint32_t my_hits = 0;
+#ifdef QU_PROFILE
+    long long ct_full = 0, ct_chain = 0, ct_sweep = 0, ct_blocks = 0, ct_endwait = 0, ct_nblk = 0;
+    const long long ct_start = clock64();
+#endif
     auto pass_to = [&](uint32_t st) {  // arrive at every stage below st
       if (my_stage < st) {
         __syncwarp();
@@ -327,7 +361,9 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     };
     auto wait_below = [&](uint32_t st) {  // all stages below st complete
       if (waited < st) {
+        QU_T(t0);
         mbar_wait(bar_chain(st - 1), chain_parity(st - 1));
+        QU_ACC(ct_chain, t0);
         waited = st;
       }
     };
@@ -345,7 +381,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
 
     for (uint32_t seq = 0;; seq++) {
       const uint32_t slot = seq % QU_SLOTS;
+      QU_T(tf0);
       mbar_wait(bar_full(slot), (seq / QU_SLOTS) & 1u);
+      QU_ACC(ct_full, tf0);
+      QU_T(tb0);
       const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
       const uint4 h0 = *(const uint4*)(qw_smem + sl + p.sm.hdr);
       const uint4 h1 = *(const uint4*)(qw_smem + sl + p.sm.hdr + 16);
@@ -442,6 +481,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
           if (in3) score[r3] = __fadd_rn(o3, c3);
         }
       }
+#ifdef QU_PROFILE
+      ct_blocks += clock64() - tb0;
+      ct_nblk += (G > warp) ? (G - warp + QU_NCW - 1) / QU_NCW : 0;
+#endif
       // this warp is done reading the slot
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(slot));
@@ -451,7 +494,10 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
       }
       const uint32_t end_stage = wbase + n_terms;
       pass_to(end_stage);
+      QU_T(te0);
       wait_below(end_stage);  // every contribution of the window is in
+      QU_ACC(ct_endwait, te0);
+      QU_T(ts0);
       // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
       float4* sc4 = reinterpret_cast<float4*>(score);
       if (MODE == MODE_COLLECT) {
@@ -471,6 +517,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
         if (lane == 0) mbar_arrive(bar_chain(end_stage));
         my_stage = end_stage + 1;
         next_base = end_stage + 1;
+        QU_ACC(ct_sweep, ts0);
       } else {
         // level-0 digit histogram of the sampled windows: digit = [1 | lin:10] (score_lin)
         const float scale = hdr_f;
@@ -503,6 +550,18 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
       }
     }
     flush_hits();
+#ifdef QU_PROFILE
+    if (lane == 0 && p.prof) {
+      atomicAdd(p.prof + 8, (unsigned long long)(clock64() - ct_start));
+      atomicAdd(p.prof + 9, (unsigned long long)ct_full);
+      atomicAdd(p.prof + 10, (unsigned long long)ct_chain);   // includes the end-of-window wait
+      atomicAdd(p.prof + 11, (unsigned long long)ct_endwait);
+      atomicAdd(p.prof + 12, (unsigned long long)ct_sweep);
+      atomicAdd(p.prof + 13, (unsigned long long)ct_blocks);  // block loop incl. chain waits inside it
+      atomicAdd(p.prof + 14, (unsigned long long)ct_nblk);
+      atomicAdd(p.prof + 15, 1ull);
+    }
+#endif
   }
 }
 
