@@ -78,7 +78,7 @@ typedef struct QwImgTerm {
   uint64_t widx_off; /* data-relative: QwWinIdx[ceil(num_docs / 2^win_shift)] */
   uint64_t tf_len;   /* bytes of data_len that are packed term frequencies (roofline accounting) */
   uint64_t fn_len;   /* bytes of data_len that are per-posting fieldnorm ids (128 per block, see QwSkip) */
-  uint64_t reserved;
+  uint64_t sub_off;  /* data-relative: QwSubIdx[num_blocks] (doc-id checkpoints inside each block) */
 } QwImgTerm; /* 80 bytes */
 
 /* Window index: for index-window j (docs [j<<win_shift, (j+1)<<win_shift)) the byte range
@@ -112,6 +112,17 @@ typedef struct QwSkip {
   uint8_t tf_bits;
   uint16_t count;
 } QwSkip;
+
+/* Checkpoints inside a posting block: the doc id reached after 32, 64 and 96 postings, relative to
+ * prev_last_doc (mod 2^32), and the block's whole span. A reader that only needs the postings of a
+ * doc-id sub-range can start decoding at any 32-posting boundary (sub-block s starts from
+ * prev_last_doc + ck[s-1]) instead of prefix-summing the block from its beginning — the GPU union
+ * kernel gives every warp its own doc-id range of a window and decodes only the sub-blocks that
+ * overlap it. Sub-blocks past `count` are empty and repeat `span`. */
+typedef struct QwSubIdx {
+  uint32_t ck[3]; /* doc[32k - 1] - prev_last_doc for k = 1..3 (span when 32k > count) */
+  uint32_t span;  /* last_doc - prev_last_doc */
+} QwSubIdx;
 
 enum {
   QW_COL_U64 = 0,

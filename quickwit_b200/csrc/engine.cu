@@ -239,6 +239,7 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
         const QwImgField& f = sp.view.fields[t.field_id];
         in.a = t.data_off; in.b = t.widx_off; in.c = t.skip_off;
         in.n = t.num_blocks; in.m = t.win_shift; in.f = n.bm25_weight;
+        in.pad = (uint32_t)((t.sub_off - t.skip_off) >> 4);  // QwSubIdx[] relative to QwSkip[], in 16-byte units
         if (f.flags & QW_FIELD_HAS_FREQS) in.flags |= IF_HAS_TF;
         if (f.flags & QW_FIELD_HAS_FIELDNORMS) in.flags |= IF_HAS_FN;
         L.postings += t.doc_freq;
@@ -586,23 +587,25 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   return L;
 }
 
-// shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, QU_SLOTS staging slots
-// (block payload + records + per-term table + header), mbarriers, MODE_HIST histogram
-static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
+// shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, per-warp sub-block
+// lists and candidate buffers, mbarriers, QU_SLOTS staging slots (block payload + records + per-term
+// table + header)
+static qwk::USmem make_union_layout(uint32_t budget) {
   qwk::USmem L;
   memset(&L, 0, sizeof L);
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
-  L.score = take(W * 4);
-  L.bars = take(8 * (2 * QU_SLOTS + QU_CHAIN));
-  if (hist) L.hist = take(QW_HIST_BINS * 4);
-  const uint32_t fixed = QU_MAXBLK * 16 + QU_MAX_TERMS * 16 + 32 + QU_PAD;
+  L.score = take(QU_W * 4);
+  L.bars = take(8 * 2 * QU_SLOTS);
+  L.items = take(QU_NCW * QU_ITEMS * 2);
+  L.cands = take(QU_NCW * QU_CANDS * 8 + QU_NCW * 4);
+  const uint32_t fixed = QU_MAXBLK * 32 + QU_MAX_TERMS * 16 + 32 + QU_PAD;
   uint32_t cap = budget > off + QU_SLOTS * (fixed + 2048) ? ((budget - off) / QU_SLOTS - fixed) & ~15u : 2048;
   if (const char* e = getenv("QWGPU_UCAP")) cap = (uint32_t)atoi(e) & ~15u;
   L.cap = cap;
   L.payload = 0;
   L.recs = cap + QU_PAD;
-  L.ttab = L.recs + QU_MAXBLK * 16;
+  L.ttab = L.recs + QU_MAXBLK * 32;
   L.hdr = L.ttab + QU_MAX_TERMS * 16;
   L.slot_stride = L.hdr + 32;
   L.slot0 = take(QU_SLOTS * L.slot_stride);
@@ -678,8 +681,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
   const bool use_union = all_union && !old_union;
   const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / 2 - 1024 - 64;
-  qwk::USmem ulay_c, ulay_h;
-  if (use_union && !getenv("QWGPU_W")) W = 16384;
+  qwk::USmem ulay;
+  memset(&ulay, 0, sizeof ulay);
+  if (use_union) W = QU_W;  // 15 consumer warps x 1024 docs
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);
@@ -689,8 +693,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   (void)scoring;
   if (use_union) {
     // (the generic layout above stays valid for the same W: exact radix passes below level 0 use k_window)
-    ulay_c = make_union_layout(W, false, u_budget);
-    ulay_h = make_union_layout(W, true, u_budget);
+    if (W != QU_W) fail(QWGPU_EUNSUPPORTED, "query needs more shared memory than the union pipeline's window allows");
+    ulay = make_union_layout(u_budget);
   }
   if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
 
@@ -717,7 +721,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), blob_bytes = al(o_bounds + (size_t)tot_bounds * 8);
   // scratch: thresholds, histograms, candidates
   size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
-         s_ctr = al(s_state + (size_t)n * 4), s_wmax = al(s_ctr + 64 * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
+         s_wmax = al(s_state + (size_t)n * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
          scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
@@ -789,7 +793,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT, false>, QW_THREADS, lay.total));
   occ = std::max(occ, 1);
   enum { F_REC = 1, F_REFINE = 2, F_CANDS_ONLY = 4 };
-  uint32_t n_ctr = 0;  // work counters handed to k_union launches (zeroed with the scratch region)
   auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix, uint32_t flags) {
     KParams q = kp;
     q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
@@ -805,10 +808,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       qwk::UParams u;
       memset(&u, 0, sizeof u);
       u.plans = kp.plans; u.instrs = kp.instrs; u.cols = kp.cols; u.thresh = kp.thresh;
-      u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride; u.W = W;
-      if (n_ctr >= 64) fail(QWGPU_EINTERNAL, "out of work counters");
-      u.work_counter = (uint32_t*)(slot->d_scratch + s_ctr) + n_ctr++;
-      u.sm = mode == qwk::MODE_HIST ? ulay_h : ulay_c;
+      u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride;
+      u.sm = ulay;
 #ifdef QU_PROFILE
       static unsigned long long* d_prof = nullptr;
       if (!d_prof) CUDA_CHECK(cudaMalloc(&d_prof, 16 * 8));
@@ -823,8 +824,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
         CUDA_CHECK(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         const double np = (double)ugrid, nc = (double)h[15];
-        fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, chain-wait %.0f (end-of-window %.0f), sweep %.0f, block-loop %.0f, blocks %.1f\n",
-                h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[11] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
+        fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, record scan %.0f, sweep %.0f, slot loop (scan + decode) %.0f, decode steps %.1f\n",
+                h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
       }
 #endif
       stats.launches++;

@@ -64,6 +64,7 @@ struct BTerm {
   uint32_t win_shift;
   uint64_t tf_len = 0, fn_len = 0;
   std::vector<QwSkip> skips;
+  std::vector<QwSubIdx> subs;
   std::vector<uint32_t> first_docs;  // first doc of each block
   std::vector<uint8_t> data;
   std::vector<QwWinIdx> widx;
@@ -139,6 +140,12 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
       uint8_t* fb = t.data.data() + off + 16u + 16u * (s.doc_bits + s.tf_bits);
       for (uint32_t i = 0; i < cnt; i++) fb[i] = fnorms[docs[start + i]];
       t.fn_len += QW_BLOCK_LEN;
+    }
+    {
+      QwSubIdx si;
+      for (uint32_t k = 1; k <= 3; k++) si.ck[k - 1] = docs[start + std::min(32u * k, cnt) - 1] - prev;  // mod 2^32
+      si.span = s.last_doc - prev;
+      t.subs.push_back(si);
     }
     t.first_docs.push_back(docs[start]);
     t.tf_len += 16u * s.tf_bits;
@@ -296,6 +303,7 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     o.tf_len = t.tf_len;
     o.fn_len = t.fn_len;
     o.widx_off = doff; doff = align16(doff + t.widx.size() * sizeof(QwWinIdx));
+    o.sub_off = doff; doff = align16(doff + t.subs.size() * sizeof(QwSubIdx));
   }
   for (uint32_t f = 0; f < nf; f++) { F[f].first_term = 0; F[f].num_terms = 0; }
   for (uint32_t i = 0; i < nt; i++) {
@@ -343,6 +351,7 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     memcpy(data + T[i].skip_off, t.skips.data(), t.skips.size() * sizeof(QwSkip));
     if (!t.data.empty()) memcpy(data + T[i].data_off, t.data.data(), t.data.size());
     if (!t.widx.empty()) memcpy(data + T[i].widx_off, t.widx.data(), t.widx.size() * sizeof(QwWinIdx));
+    if (!t.subs.empty()) memcpy(data + T[i].sub_off, t.subs.data(), t.subs.size() * sizeof(QwSubIdx));
   }
   for (uint32_t c = 0; c < nc; c++) {
     const BColumn& bc = b->columns[c];

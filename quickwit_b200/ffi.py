@@ -52,7 +52,7 @@ class QwImgTerm(C.Structure):
                 ("doc_freq", C.c_uint32), ("num_blocks", C.c_uint32), ("win_shift", C.c_uint32),
                 ("skip_off", C.c_uint64), ("data_off", C.c_uint64), ("data_len", C.c_uint64),
                 ("widx_off", C.c_uint64), ("tf_len", C.c_uint64), ("fn_len", C.c_uint64),
-                ("reserved", C.c_uint64)]
+                ("sub_off", C.c_uint64)]
 
 
 class QwImgColumn(C.Structure):
