@@ -587,25 +587,24 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
   return L;
 }
 
-// shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, per-warp sub-block
-// lists and candidate buffers, mbarriers, QU_SLOTS staging slots (block payload + records + per-term
-// table + header)
-static qwk::USmem make_union_layout(uint32_t budget) {
+// shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, QU_SLOTS staging slots
+// (block payload + records + per-term table + header), mbarriers, MODE_HIST histogram
+static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
   qwk::USmem L;
   memset(&L, 0, sizeof L);
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
-  L.score = take(QU_W * 4);
-  L.bars = take(8 * 2 * QU_SLOTS);
-  L.items = take(QU_NCW * QU_ITEMS * 2);
+  L.score = take(W * 4);
+  L.bars = take(8 * (2 * QU_SLOTS + QU_CHAIN));
+  if (hist) L.hist = take(QW_HIST_BINS * 4);
   L.cands = take(QU_NCW * QU_CANDS * 8 + QU_NCW * 4);
-  const uint32_t fixed = QU_MAXBLK * 32 + QU_MAX_TERMS * 16 + 32 + QU_PAD;
+  const uint32_t fixed = QU_MAXBLK * 16 + QU_MAX_TERMS * 16 + 32 + QU_PAD;
   uint32_t cap = budget > off + QU_SLOTS * (fixed + 2048) ? ((budget - off) / QU_SLOTS - fixed) & ~15u : 2048;
   if (const char* e = getenv("QWGPU_UCAP")) cap = (uint32_t)atoi(e) & ~15u;
   L.cap = cap;
   L.payload = 0;
   L.recs = cap + QU_PAD;
-  L.ttab = L.recs + QU_MAXBLK * 32;
+  L.ttab = L.recs + QU_MAXBLK * 16;
   L.hdr = L.ttab + QU_MAX_TERMS * 16;
   L.slot_stride = L.hdr + 32;
   L.slot0 = take(QU_SLOTS * L.slot_stride);
@@ -680,21 +679,20 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // two blocks per SM; QWGPU_OLD_UNION=1 keeps the round-1 window kernel for A/B runs
   static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
   const bool use_union = all_union && !old_union;
-  const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / 2 - 1024 - 64;
-  qwk::USmem ulay;
-  memset(&ulay, 0, sizeof ulay);
-  if (use_union) W = QU_W;  // 15 consumer warps x 1024 docs
+  const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / QU_MINB - 1024 - 64;
+  qwk::USmem ulay_c, ulay_h;
+  if (use_union && !getenv("QWGPU_W")) W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : 16384u * 2 / QU_MINB;
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);
-    if ((int)lay.total + 1024 <= max_smem_optin / QW_MIN_BLOCKS_PER_SM || W == 1024) break;
+    if ((int)lay.total + 1024 <= max_smem_optin / (use_union ? 1 : QW_MIN_BLOCKS_PER_SM) || W == 1024) break;  // (union batches: k_window is only the rare exact-radix fallback)
     W >>= 1;
   }
   (void)scoring;
   if (use_union) {
     // (the generic layout above stays valid for the same W: exact radix passes below level 0 use k_window)
-    if (W != QU_W) fail(QWGPU_EUNSUPPORTED, "query needs more shared memory than the union pipeline's window allows");
-    ulay = make_union_layout(u_budget);
+    ulay_c = make_union_layout(W, false, u_budget);
+    ulay_h = make_union_layout(W, true, u_budget);
   }
   if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
 
@@ -721,7 +719,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), blob_bytes = al(o_bounds + (size_t)tot_bounds * 8);
   // scratch: thresholds, histograms, candidates
   size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
-         s_wmax = al(s_state + (size_t)n * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
+         s_ctr = al(s_state + (size_t)n * 4), s_wmax = al(s_ctr + 64 * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
          scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
@@ -793,6 +791,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, qwk::k_window<qwk::MODE_COLLECT, false>, QW_THREADS, lay.total));
   occ = std::max(occ, 1);
   enum { F_REC = 1, F_REFINE = 2, F_CANDS_ONLY = 4 };
+  uint32_t n_ctr = 0;  // work counters handed to k_union launches (zeroed with the scratch region)
   auto launch_window = [&](int mode, bool sampled, uint32_t level, uint32_t use_prefix, uint32_t flags) {
     KParams q = kp;
     q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
@@ -808,24 +807,24 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       qwk::UParams u;
       memset(&u, 0, sizeof u);
       u.plans = kp.plans; u.instrs = kp.instrs; u.cols = kp.cols; u.thresh = kp.thresh;
-      u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride;
-      u.sm = ulay;
+      u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride; u.W = W;
+      u.sm = mode == qwk::MODE_HIST ? ulay_h : ulay_c;
 #ifdef QU_PROFILE
       static unsigned long long* d_prof = nullptr;
       if (!d_prof) CUDA_CHECK(cudaMalloc(&d_prof, 16 * 8));
       if (mode == qwk::MODE_COLLECT) { CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 16 * 8, st)); u.prof = d_prof; }
 #endif
-      const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * 2));
-      if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
-      else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QW_THREADS, u.sm.total, st>>>(u);
+      const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * QU_MINB));
+      if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
+      else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
 #ifdef QU_PROFILE
       if (u.prof && getenv("QWGPU_UPROF")) {
         unsigned long long h[16];
         CUDA_CHECK(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         const double np = (double)ugrid, nc = (double)h[15];
-        fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, record scan %.0f, sweep %.0f, slot loop (scan + decode) %.0f, decode steps %.1f\n",
-                h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
+        fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, chain-wait %.0f (end-of-window %.0f), sweep %.0f, block-loop %.0f, blocks %.1f\n",
+                h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[11] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
       }
 #endif
       stats.launches++;

@@ -5,58 +5,59 @@
 // (quickwit-search/src/leaf.rs:637) for the headline query shape.
 //
 // One 512-thread block = 15 consumer warps + 1 producer warp, two blocks per SM. The block owns one
-// 15360-doc window of one split at a time and walks a contiguous chunk of the request's flat
-// (split, window) list. The window's f32 score accumulator lives in shared memory and is PARTITIONED
-// BY DOC RANGE: consumer warp w owns docs [1024 w, 1024 (w + 1)) of the window and is the only one
-// that ever touches them.
+// 16384-doc window of one split at a time (f32 score accumulator of the window in shared memory);
+// windows are handed out dynamically from a global counter.
 //
 //   producer warp   per window: (1) lane = term: one load of the term's window-index entry (QwWinIdx)
-//                   gives the ordinals of the posting blocks overlapping the window (issued one window
-//                   ahead); (2) lane = block: coalesced 16-byte loads of the block's skip entry
-//                   (QwSkip) and checkpoint entry (QwSubIdx), one round ahead; blocks that miss the
-//                   window are dropped, the rest is packed into the current pipeline slot — one
-//                   `cp.async.bulk` (1-D TMA) per run of consecutive blocks of a term, straight from HBM
-//                   to shared memory, completion counted on the slot's `full` mbarrier — and described
-//                   by a 32-byte record (shared address, widths, clause, checkpoints). A slot that
-//                   fills up is closed and the window continues in the next slot, so any density /
-//                   term count works. No consumer ever executes a staging instruction.
-//   consumer warps  wait on `full`, scan the slot's block records for the 32-posting SUB-BLOCKS that
-//                   overlap their own doc range (checkpoints make every 32-posting boundary a decode
-//                   entry point) and decode four sub-blocks per step, 8 lanes x 4 postings each
-//                   (4-lane-interleaved bit-unpack -> 8-lane shuffle scan -> doc ids; tf unpack; the
-//                   per-posting fieldnorm id comes with the block, so BM25 = weight * tff[tf][fn] is one
-//                   PRMT + one table load per posting), then add the contributions of the postings
-//                   inside their range into their part of the accumulator.
-//   clause order    f32 sums must follow the reference's clause order. Records are in clause order, a
-//                   warp walks them in order and nobody else writes its docs, so the order holds by
-//                   construction: there is no inter-warp dependency at all — no ticket, no barrier per
-//                   clause, no __syncthreads; a warp sweeps its own range (count matches, threshold
-//                   test, clear) as soon as it has folded the window's last record and moves on to the
-//                   next window while its neighbours are still busy. The only block-wide events are
-//                   the slots' `full` / `empty` mbarriers.
+//                   gives the ordinals of the posting blocks overlapping the window; (2) lane = block:
+//                   a coalesced 16-byte load of the block's skip entry (QwSkip) tells its widths and
+//                   doc range; blocks that miss the window are dropped; the survivors are packed into
+//                   the current pipeline slot — one `cp.async.bulk` (1-D TMA) per block straight from
+//                   HBM to shared memory, completion counted on the slot's `full` mbarrier — and
+//                   described by a 16-byte record (shared address, widths, clause, interior flag).
+//                   A slot that fills up is closed and the window continues in the next slot, so any
+//                   density / term count works. No consumer ever executes a staging instruction.
+//   consumer warps  wait on `full`, take blocks round-robin, decode one block per warp (4-lane-
+//                   interleaved bit-unpack -> warp-shuffle prefix scan -> doc ids; tf unpack; the
+//                   per-posting fieldnorm id comes with the block, so BM25 = weight * tff[tf][fn] is
+//                   one PRMT + one table load per posting) and add the four contributions per lane
+//                   into the score array.
+//   clause order    f32 sums must follow the reference's clause order. Every clause of a window is a
+//                   STAGE of a per-block ring of mbarriers ("chain", one arrival per consumer warp
+//                   per stage): a warp arrives at a stage when it has no more blocks in it and waits
+//                   for stage s-1 before it touches the accumulator for stage s. Decode never waits,
+//                   only the read-modify-write does; there is no __syncthreads, no spin on shared
+//                   memory and no fence in the loop. The sweep of a finished window (count matches,
+//                   threshold test, clear) is one more stage of the same chain, so the next window's
+//                   decode overlaps the sweep of this one.
 #pragma once
 #include "kernels.cuh"
 
 namespace qwk {
 
-#define QU_NCW (QW_WARPS - 1)   /* consumer warps; warp QU_NCW is the producer */
-#define QU_RANGE 1024u          /* docs per consumer warp */
-#define QU_W (QU_NCW * QU_RANGE) /* docs per window */
+#ifndef QU_THREADS
+#define QU_THREADS 512
+#endif
+#define QU_NCW (QU_THREADS / 32 - 1)   /* consumer warps; warp QU_NCW is the producer */
+#define QU_NCT (QU_NCW * 32)
 #define QU_SLOTS 2
-#define QU_MAXBLK 128           /* block records per slot */
+#define QU_MAXBLK 256           /* block records per slot */
+#define QU_CHAIN 128            /* mbarriers in the stage ring (a warp is never > 70 stages ahead) */
 #define QU_MAX_TERMS 32
 #define QU_PAD 32               /* decode may read one 16-byte word past a block */
-#define QU_ITEMS 136            /* per-warp sub-block list: 32 records x 4 sub-blocks + carry-over */
 #define QU_CANDS 32             /* per-warp buffer of docs that reached the score lower bound */
+#ifndef QU_MINB
+#define QU_MINB 2               /* blocks per SM */
+#endif
 
 enum { QU_F_FIRST = 1u, QU_F_LAST = 2u, QU_F_END = 4u };
 
 struct USmem {
-  uint32_t score;                       // float[QU_W]
+  uint32_t score;                       // float[W]
   uint32_t slot0, slot_stride;          // QU_SLOTS slots
   uint32_t payload, recs, ttab, hdr;    // offsets inside a slot
-  uint32_t bars;                        // full[QU_SLOTS], empty[QU_SLOTS]
-  uint32_t items;                       // uint16[QU_NCW][QU_ITEMS]
+  uint32_t bars;                        // full[QU_SLOTS], empty[QU_SLOTS], chain[QU_CHAIN]
+  uint32_t hist;                        // MODE_HIST: uint32[QW_HIST_BINS]
   uint32_t cands;                       // uint2[QU_NCW][QU_CANDS], then uint32 count[QU_NCW]
   uint32_t cap;                         // payload bytes per slot
   uint32_t total;
@@ -68,7 +69,7 @@ struct UParams {
   const DCol* cols;
   const DThresh* thresh;
   const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
-  uint32_t n_splits, total_work, stride, pad0;
+  uint32_t n_splits, total_work, stride, W;
   unsigned long long* prof;    // QU_PROFILE builds: cycle counters (see k_union)
   USmem sm;
 };
@@ -79,6 +80,12 @@ struct UParams {
 #define QU_T(x)
 #define QU_ACC(acc, t0)
 #endif
+
+struct UHdr {  // 32 bytes, written by the producer when it closes a slot
+  uint32_t ws, wlen, split, flags;
+  uint32_t n_blocks, n_terms, t_last;  // t_last: clause of the slot's last block (stages below it are final)
+  float s_lo;                          // COLLECT: f32 lower bound of the threshold bucket; HIST: score_scale
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -107,40 +114,50 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
-// inclusive scan step over segments of `1 << LOGW` lanes, with the shuffle's own predicate
-// (SHFL.UP + predicated IADD)
-template <int LOGW>
+// inclusive warp scan step with the shuffle's own predicate (SHFL.UP + predicated IADD)
 __device__ __forceinline__ uint32_t scan_step(uint32_t x, uint32_t o) {
-  constexpr uint32_t c = (32u - (1u << LOGW)) << 8;
-  asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(x) : "r"(o), "n"(c));
+  asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0x0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(x) : "r"(o));
   return x;
 }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x) {
-  x = scan_step<5>(x, 1); x = scan_step<5>(x, 2); x = scan_step<5>(x, 4); x = scan_step<5>(x, 8); x = scan_step<5>(x, 16);
-  return x;
-}
-__device__ __forceinline__ uint32_t seg8_incl_scan(uint32_t x) {
-  x = scan_step<3>(x, 1); x = scan_step<3>(x, 2); x = scan_step<3>(x, 4);
+  x = scan_step(x, 1); x = scan_step(x, 2); x = scan_step(x, 4); x = scan_step(x, 8); x = scan_step(x, 16);
   return x;
 }
 
-// Block record written by the producer (32 bytes):
-//   w0 prev_last_doc   w1 shared address of the payload   w2 doc_bits | tf_bits << 8 | count << 16 | clause << 24
-//   w3 0 (checkpoint 0)   w4..w6 checkpoints 1..3   w7 span        (sub-block s: docs (prev + w[3+s], prev + w[4+s]])
+// Rare path of the sweep: a doc that reaches the float lower bound builds its composite key and, if
+// it reaches the threshold key, joins the split's candidate list (k_select sorts it out).
+__device__ __noinline__ void union_emit(const DSplitPlan* plans, const DThresh* thresh, const DCol* cols, uint32_t split, uint32_t doc, float sc) {
+  const DSplitPlan& P = plans[split];
+  const DThresh& T = thresh[split];
+  const Key thr{T.key[0], T.key[1], T.key[2]};
+  const DocKey dk = doc_key(P, P.key, cols + P.col_base, (const uint8_t*)P.data_base, doc, sc);
+  if (key_ge(dk.key, thr)) {
+    const uint32_t pos = atomicAdd((uint32_t*)P.out_cand_count, 1u);
+    if (pos < QW_CAND_CAP) {
+      uint64_t* c = (uint64_t*)P.out_cands + 3ull * pos;
+      c[0] = dk.key.w0; c[1] = dk.key.w1; c[2] = dk.key.w2;
+    }
+  }
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
+__global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t W = p.W;
   const uint32_t sbase = smem_u32(qw_smem);
   const uint32_t bars = sbase + p.sm.bars;
   auto bar_full = [&](uint32_t s) { return bars + 8u * s; };
   auto bar_empty = [&](uint32_t s) { return bars + 8u * (QU_SLOTS + s); };
+  auto bar_chain = [&](uint32_t st) { return bars + 8u * (2 * QU_SLOTS + (st & (QU_CHAIN - 1))); };
+  auto chain_parity = [&](uint32_t st) { return (st / QU_CHAIN) & 1u; };
   if (tid == 0) {
     for (uint32_t s = 0; s < QU_SLOTS; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), QU_NCW); }
+    for (uint32_t s = 0; s < QU_CHAIN; s++) mbar_init(bar_chain(s), QU_NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+
   // this block's chunk of the flat (split, window) list
   const uint32_t w_begin = (uint32_t)(((uint64_t)p.total_work * blockIdx.x) / gridDim.x);
   const uint32_t w_end = (uint32_t)(((uint64_t)p.total_work * (blockIdx.x + 1)) / gridDim.x);
@@ -162,7 +179,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     float hdr_f = -1.0f;
     // slot state (warp-uniform)
     bool open = false;
-    uint32_t slot = 0, off = 0, cnt = 0;
+    uint32_t slot = 0, off = 0, cnt = 0, last_t = 0, last_t_l = 0;
     bool first_of_window = true;
     uint32_t ws = 0, wlen = 0;
     auto slot_base = [&](uint32_t s) { return p.sm.slot0 + s * p.sm.slot_stride; };
@@ -182,7 +199,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
       if (lane == 0) {
         uint4* d = (uint4*)(qw_smem + slot_base(slot) + p.sm.hdr);
         d[0] = make_uint4(ws, wlen, cur_split, flags | (first_of_window ? QU_F_FIRST : 0u));
-        d[1] = make_uint4(cnt, n_terms, 0u, __float_as_uint(hdr_f));
+        d[1] = make_uint4(cnt, n_terms, last_t, __float_as_uint(hdr_f));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full(slot));
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     uint4 wa = make_uint4(0, 0, 0, 0), wb = wa;  // this lane's window-index entries (first / last index window)
     auto load_widx = [&](uint32_t window) {
       wa = wb = make_uint4(0, 0, 0, 0);
-      const uint32_t s = window * QU_W, e = min(s + QU_W, num_docs);
+      const uint32_t s = window * W, e = min(s + W, num_docs);
       if (lane < n_terms && t_nblk) {
         const uint4* wi = (const uint4*)(base + t_widx);
         const uint32_t e0 = s >> t_shift, e1 = (e - 1) >> t_shift;
@@ -239,8 +256,8 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
     for (uint32_t work = w_begin; work < w_end; work++) {
       QU_T(pt_w0);
       const uint32_t window = window_of(work, split);
-      ws = window * QU_W;
-      const uint32_t we = min(ws + QU_W, num_docs);
+      ws = window * W;
+      const uint32_t we = min(ws + W, num_docs);
       wlen = we - ws;
       first_of_window = true;
       // ---- lane = term: blocks of the term that overlap the window (entries loaded one window ago) --
@@ -267,11 +284,8 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
         dat_out = __shfl_sync(QW_FULL, t_data, t);
         tfl_out = __shfl_sync(QW_FULL, t_fl, t);
         r_out = c_out = make_uint4(0, 0, 0, 0);
-        if (q < G) {
-          const uint4* sk = (const uint4*)(base + skp) + fbt + k;
-          r_out = __ldg(sk);                  // last_doc, prev_last_doc, byte_off, widths/count
-          c_out = __ldg(sk + (size_t)sub16);  // checkpoints 1..3, span
-        }
+        if (q < G) r_out = __ldg((const uint4*)(base + skp) + fbt + k);  // last_doc, prev_last_doc, byte_off, widths/count
+        (void)sub16;
         t_out = t;
       };
       uint32_t t = 0, tfl = 0;
@@ -320,13 +334,14 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
             const uint32_t run_end = __shfl_sync(QW_FULL, incl, last & 31u);
             const uint32_t dst = sbase + slot_base(slot) + p.sm.payload + off + incl - sz;
             if (fits) {
-              uint4* rec = (uint4*)(qw_smem + slot_base(slot) + p.sm.recs + 32u * (cnt + pos));
-              rec[0] = make_uint4(r.y, dst + 16u, (r.w & 0x00FFFFFFu) | (t << 24), 0u);
-              rec[1] = ck;
+              const bool interior = first_lb >= ws && r.x < we && (r.w >> 16) == QW_BLOCK_LEN;
+              *(uint4*)(qw_smem + slot_base(slot) + p.sm.recs + 16u * (cnt + pos)) = make_uint4(r.y, dst + 16u, r.w, t | (interior ? 256u : 0u));
+              last_t_l = t;
             }
             if (head) bulk_g2s(dst, src, run_end - (incl - sz), bar_full(slot));
             off += bytes;
             cnt += __popc(fitmask);
+            last_t = __shfl_sync(QW_FULL, last_t_l, lastfit);
             pending &= ~fitmask;
           }
           if (pending) close_slot(0);  // slot full: the window continues in the next slot
@@ -360,21 +375,43 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
 #endif
   } else {
     // ================================ consumers =====================================================
-    float* score = (float*)(qw_smem + p.sm.score) + warp * QU_RANGE;   // this warp's docs of the window
-    uint16_t* items = (uint16_t*)(qw_smem + p.sm.items) + warp * QU_ITEMS;
-    uint2* cands = (uint2*)(qw_smem + p.sm.cands) + warp * QU_CANDS;
-    uint32_t* ncand = (uint32_t*)(qw_smem + p.sm.cands + QU_NCW * QU_CANDS * 8) + warp;
-    for (uint32_t i = lane; i < QU_RANGE / 4; i += 32) reinterpret_cast<float4*>(score)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) *ncand = 0;
+    float* score = (float*)(qw_smem + p.sm.score);
+    uint32_t* hist = (uint32_t*)(qw_smem + p.sm.hist);
+    {
+      float4* q = reinterpret_cast<float4*>(score);
+      for (uint32_t i = tid; i < (W >> 2); i += QU_NCT) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE == MODE_HIST) for (uint32_t i = tid; i < QW_HIST_BINS; i += QU_NCT) hist[i] = 0;
+    }
     __syncwarp();
-    const uint32_t lo = warp * QU_RANGE;  // window-relative first doc of this warp
-    const uint32_t l8 = lane & 7u, grp = lane >> 3;
+    if (lane == 0) mbar_arrive(bar_chain(0));
+    uint32_t my_stage = 1;   // stages this warp has arrived at: [0, my_stage)
+    uint32_t waited = 0;     // stages known complete: [0, waited)
+    uint32_t wbase = 1;      // stage of clause 0 of the current window
+    uint32_t next_base = 1;
     uint32_t cur_split = 0xFFFFFFFFu;
     uint32_t my_hits = 0;
+    uint2* cands = (uint2*)(qw_smem + p.sm.cands) + warp * QU_CANDS;
+    uint32_t* ncand = (uint32_t*)(qw_smem + p.sm.cands + QU_NCW * QU_CANDS * 8) + warp;
+    if (lane == 0) *ncand = 0;
 #ifdef QU_PROFILE
-    long long ct_full = 0, ct_sweep = 0, ct_blocks = 0, ct_list = 0, ct_nblk = 0;
+    long long ct_full = 0, ct_chain = 0, ct_sweep = 0, ct_blocks = 0, ct_endwait = 0, ct_nblk = 0;
     const long long ct_start = clock64();
 #endif
+    auto pass_to = [&](uint32_t st) {  // arrive at every stage below st
+      if (my_stage < st) {
+        __syncwarp();
+        if (lane == 0) for (uint32_t s = my_stage; s < st; s++) mbar_arrive(bar_chain(s));
+        my_stage = st;
+      }
+    };
+    auto wait_below = [&](uint32_t st) {  // all stages below st complete
+      if (waited < st) {
+        QU_T(t0);
+        mbar_wait(bar_chain(st - 1), chain_parity(st - 1));
+        QU_ACC(ct_chain, t0);
+        waited = st;
+      }
+    };
     // candidates -> composite key -> the split's candidate list (k_select sorts it out); lane-parallel
     auto flush_cands = [&]() {
       __syncwarp();
@@ -406,17 +443,15 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
       if (lane == 0) *ncand = 0;
       __syncwarp();
     };
-    auto flush_split = [&]() {
-      if (cur_split == 0xFFFFFFFFu) return;
-      if (MODE == MODE_COLLECT) {
-        flush_cands();
+    auto flush_hits = [&]() {
+      if (MODE != MODE_COLLECT || cur_split == 0xFFFFFFFFu) return;
+      flush_cands();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_down_sync(QW_FULL, my_hits, o);
-        if (lane == 0 && my_hits) {
-          const DSplitPlan& P = p.plans[cur_split];
-          atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)my_hits);
-          atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)my_hits);  // no search_after: every hit is eligible
-        }
+      for (int o = 16; o > 0; o >>= 1) my_hits += __shfl_down_sync(QW_FULL, my_hits, o);
+      if (lane == 0 && my_hits) {
+        const DSplitPlan& P = p.plans[cur_split];
+        atomicAdd((unsigned long long*)P.out_num_hits, (unsigned long long)my_hits);
+        atomicAdd((unsigned long long*)P.out_num_hits + 1, (unsigned long long)my_hits);  // no search_after: every hit is eligible
       }
       my_hits = 0;
     };
@@ -426,178 +461,125 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
       QU_T(tf0);
       mbar_wait(bar_full(slot), (seq / QU_SLOTS) & 1u);
       QU_ACC(ct_full, tf0);
+      QU_T(tb0);
       const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
       const uint4 h0 = *(const uint4*)(qw_smem + sl + p.sm.hdr);
       const uint4 h1 = *(const uint4*)(qw_smem + sl + p.sm.hdr + 16);
       const uint32_t ws = h0.x, wlen = h0.y, split = h0.z, flags = h0.w;
-      const uint32_t G = h1.x;
+      const uint32_t G = h1.x, n_terms = h1.y, t_last = h1.z;
       const float hdr_f = __uint_as_float(h1.w);
       if (flags & QU_F_END) break;
-      if (split != cur_split) { flush_split(); cur_split = split; }
+      if (flags & QU_F_FIRST) wbase = next_base;
+      if (split != cur_split) { flush_hits(); cur_split = split; }
       const uint32_t recs = sl + p.sm.recs, ttab = sl + p.sm.ttab;
-      const uint32_t rlo = ws + lo;                                      // absolute first doc of this warp's range
-      const uint32_t rlen = wlen > lo ? min(wlen - lo, QU_RANGE) : 0u;  // docs of the range that exist
-      QU_T(tb0);
-      uint32_t n_items = 0;  // sub-blocks waiting in `items` (warp-uniform)
-      for (uint32_t g0 = 0; rlen; g0 += 32) {
-        // ---- the sub-blocks of the next 32 records that overlap this warp's docs ----------------------
+
+      for (uint32_t g = warp; g < G; g += QU_NCW) {
+        const uint4 rec = *(const uint4*)(qw_smem + recs + 16u * g);  // prev_last_doc, shared address, widths/count, clause | interior
+        const uint32_t t = rec.w & 0xFFu;
+        const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
+        const float weight = __uint_as_float(tt.x);
+        const uint32_t tfl = tt.y;
+        const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
+        const uint32_t blk = rec.y - sbase;  // offset inside qw_smem
+        const uint32_t doc_bits = rec.z & 0xFFu, tf_bits = (rec.z >> 8) & 0xFFu;
+        // ---- doc ids: 4 values per lane from the 4-lane-interleaved words, then a warp scan ----------
+        uint32_t d0, d1, d2, d3;
         {
-          QU_T(tl0);
-          const uint32_t g = g0 + lane;
-          uint32_t mask = 0;
-          if (g < G) {
-            const uint4 ra = *(const uint4*)(qw_smem + recs + 32u * g);
-            const uint4 rb = *(const uint4*)(qw_smem + recs + 32u * g + 16);
-            const uint32_t count = (ra.z >> 16) & 0xFFu;
-            // sub-block s holds docs [prev + ck[s] + 1, prev + ck[s + 1]] (mod 2^32), ck = {0, rb.x, rb.y, rb.z, rb.w};
-            // relative to the range and signed (docs < 2^31): overlap <=> first < rlen and last >= 0
-            const int32_t pr = (int32_t)(ra.x - rlo);
-            const int32_t k1 = pr + (int32_t)rb.x, k2 = pr + (int32_t)rb.y, k3 = pr + (int32_t)rb.z, k4 = pr + (int32_t)rb.w;
-            const int32_t rl = (int32_t)rlen;
-            mask = ((pr + 1 < rl && k1 >= 0) ? 1u : 0u) | ((k1 + 1 < rl && k2 >= 0 && count > 32u) ? 2u : 0u) |
-                   ((k2 + 1 < rl && k3 >= 0 && count > 64u) ? 4u : 0u) | ((k3 + 1 < rl && k4 >= 0 && count > 96u) ? 8u : 0u);
-          }
-          const uint32_t c = __popc(mask);
-          const uint32_t incl = warp_incl_scan(c);
-          uint32_t o = n_items + incl - c;
-          for (uint32_t m = mask; m; m &= m - 1) items[o++] = (uint16_t)(g | ((__ffs(m) - 1) << 8));
-          n_items += __shfl_sync(QW_FULL, incl, 31);
-          __syncwarp();
-          QU_ACC(ct_list, tl0);
+          const uint32_t bp = lane * doc_bits, sh = bp & 31u;
+          const uint8_t* a = qw_smem + blk + ((bp >> 5) << 4);
+          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, doc_bits);
+          // strictly-sorted deltas: doc[i] = doc[i-1] + v[i] + 1
+          d0 = (__funnelshift_r(A.x, B.x, sh) & mask) + 1u;
+          d1 = d0 + (__funnelshift_r(A.y, B.y, sh) & mask) + 1u;
+          d2 = d1 + (__funnelshift_r(A.z, B.z, sh) & mask) + 1u;
+          d3 = d2 + (__funnelshift_r(A.w, B.w, sh) & mask) + 1u;
         }
-        // ---- decode four sub-blocks per step (8 lanes x 4 postings each); a tail of < 4 waits for more --
-        const bool last_round = g0 + 32 >= G;
-        uint32_t done = 0;
-        while (done + 4 <= n_items || (last_round && done < n_items)) {
-          const uint32_t ii = done + grp;
-          const bool on = ii < n_items;
-          const uint32_t it = on ? items[ii] : items[done];
-          done += 4;
-#ifdef QU_PROFILE
-          ct_nblk++;
-#endif
-          const uint32_t g = it & 0xFFu, s = it >> 8;
-          const uint32_t rw = recs + 32u * g;
-          const uint4 ra = *(const uint4*)(qw_smem + rw);              // prev_last_doc, shared address, widths/count/clause, 0
-          const uint32_t cks = *(const uint32_t*)(qw_smem + rw + 12u + 4u * s);  // checkpoint s
-          const uint32_t t = ra.z >> 24;
-          const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
-          const float weight = __uint_as_float(tt.x);
-          const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
-          const uint32_t blk = ra.y - sbase;  // offset of the payload inside qw_smem
-          const uint32_t doc_bits = ra.z & 0xFFu, tf_bits = (ra.z >> 8) & 0xFFu, count = (ra.z >> 16) & 0xFFu;
-          const uint32_t pp = 8u * s + l8;  // this lane's position in the block (4 postings per position)
-          // ---- doc ids: 4 values per lane from the 4-lane-interleaved words, then an 8-lane scan --------
-          uint32_t d0, d1, d2, d3;
-          {
-            const uint32_t bp = pp * doc_bits, sh = bp & 31u;
-            const uint8_t* a = qw_smem + blk + ((bp >> 5) << 4);
-            const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
-            const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, doc_bits);
-            // strictly-sorted deltas: doc[i] = doc[i-1] + v[i] + 1
-            d0 = (__funnelshift_r(A.x, B.x, sh) & mask) + 1u;
-            d1 = d0 + (__funnelshift_r(A.y, B.y, sh) & mask) + 1u;
-            d2 = d1 + (__funnelshift_r(A.z, B.z, sh) & mask) + 1u;
-            d3 = d2 + (__funnelshift_r(A.w, B.w, sh) & mask) + 1u;
-          }
-          const uint32_t incl = seg8_incl_scan(d3);
-          const uint32_t basev = ra.x + cks + (incl - d3) - rlo;  // mod 2^32; relative to this warp's first doc
-          const uint32_t r0 = basev + d0, r1 = basev + d1, r2 = basev + d2, r3 = basev + d3;
-          // ---- term frequencies -----------------------------------------------------------------------
-          uint32_t f0 = 1, f1 = 1, f2 = 1, f3 = 1;
-          if (tf_bits) {
-            const uint32_t bp = pp * tf_bits, sh = bp & 31u;
-            const uint8_t* a = qw_smem + blk + 16u * doc_bits + ((bp >> 5) << 4);
-            const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
-            const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, tf_bits);
-            f0 = __funnelshift_r(A.x, B.x, sh) & mask;
-            f1 = __funnelshift_r(A.y, B.y, sh) & mask;
-            f2 = __funnelshift_r(A.z, B.z, sh) & mask;
-            f3 = __funnelshift_r(A.w, B.w, sh) & mask;
-          }
-          // ---- BM25: weight * (tf / (tf + norm[fieldnorm id])) from the tf-factor table ----------------
-          uint32_t fnw = 0x01010101u;  // no fieldnorms: constant fieldnorm id 1
-          if (tt.y & IF_HAS_FN) fnw = *(const uint32_t*)(qw_smem + blk + 16u * (doc_bits + tf_bits) + 4u * pp);
-          float c0, c1, c2, c3;
-          if (tf_bits <= 4) {
-            // tf < 16: index = tf * 256 + fieldnorm id, one byte-permute per posting
-            c0 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f0, fnw, 0x2104)));
-            c1 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f1, fnw, 0x2105)));
-            c2 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f2, fnw, 0x2106)));
-            c3 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f3, fnw, 0x2107)));
-          } else {
-            auto tfn = [&](uint32_t tf, uint32_t fn) -> float {
-              if (tf < QW_TFF_ROWS) return __ldg(tab + 256 + tf * 256 + fn);
-              const float tff = (float)tf;
-              return __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + fn)));
-            };
-            c0 = __fmul_rn(weight, tfn(f0, fnw & 0xFFu));
-            c1 = __fmul_rn(weight, tfn(f1, (fnw >> 8) & 0xFFu));
-            c2 = __fmul_rn(weight, tfn(f2, (fnw >> 16) & 0xFFu));
-            c3 = __fmul_rn(weight, tfn(f3, fnw >> 24));
-          }
-          // ---- accumulate the postings that exist and fall into this warp's docs ------------------------
-          const uint32_t nvalid = !on ? 0u : (count > pp * 4u ? count - pp * 4u : 0u);
-          const bool in0 = nvalid > 0 && r0 < rlen, in1 = nvalid > 1 && r1 < rlen;  // r = doc - first doc of the range (unsigned wrap below it)
-          const bool in2 = nvalid > 2 && r2 < rlen, in3 = nvalid > 3 && r3 < rlen;
-          // the sub-blocks of a step are in clause order; two of them can hold the same doc only if their
-          // clauses differ, so the groups accumulate one after the other unless all share a clause
-          const uint32_t t_first = __shfl_sync(QW_FULL, t, 0);
-          const uint32_t t_max = __reduce_max_sync(QW_FULL, on ? t : 0u);
-          if (t_first == t_max) {
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-            if (in0) o0 = score[r0];
-            if (in1) o1 = score[r1];
-            if (in2) o2 = score[r2];
-            if (in3) o3 = score[r3];
-            if (in0) score[r0] = __fadd_rn(o0, c0);
-            if (in1) score[r1] = __fadd_rn(o1, c1);
-            if (in2) score[r2] = __fadd_rn(o2, c2);
-            if (in3) score[r3] = __fadd_rn(o3, c3);
-          } else {
-#pragma unroll 1
-            for (uint32_t qg = 0; qg < 4; qg++) {
-              if (grp == qg) {
-                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-                if (in0) o0 = score[r0];
-                if (in1) o1 = score[r1];
-                if (in2) o2 = score[r2];
-                if (in3) o3 = score[r3];
-                if (in0) score[r0] = __fadd_rn(o0, c0);
-                if (in1) score[r1] = __fadd_rn(o1, c1);
-                if (in2) score[r2] = __fadd_rn(o2, c2);
-                if (in3) score[r3] = __fadd_rn(o3, c3);
-              }
-              __syncwarp();
-            }
-          }
-          __syncwarp();  // the next step may touch the same docs from other lanes
+        const uint32_t incl = warp_incl_scan(d3);
+        const uint32_t basev = rec.x + (incl - d3) - ws;  // mod 2^32; window-relative
+        const uint32_t r0 = basev + d0, r1 = basev + d1, r2 = basev + d2, r3 = basev + d3;
+        // ---- term frequencies -----------------------------------------------------------------------
+        uint32_t f0 = 1, f1 = 1, f2 = 1, f3 = 1;
+        if (tf_bits) {
+          const uint32_t bp = lane * tf_bits, sh = bp & 31u;
+          const uint8_t* a = qw_smem + blk + 16u * doc_bits + ((bp >> 5) << 4);
+          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, tf_bits);
+          f0 = __funnelshift_r(A.x, B.x, sh) & mask;
+          f1 = __funnelshift_r(A.y, B.y, sh) & mask;
+          f2 = __funnelshift_r(A.z, B.z, sh) & mask;
+          f3 = __funnelshift_r(A.w, B.w, sh) & mask;
         }
-        // move the (< 4) sub-blocks that wait for the next records to the front of the list
-        if (done < n_items) {
-          const uint32_t rem = n_items - done;
-          const uint16_t v = lane < rem ? items[done + lane] : (uint16_t)0;
-          __syncwarp();
-          if (lane < rem) items[lane] = v;
-          n_items = rem;
-        } else n_items = 0;
-        __syncwarp();
-        if (last_round) break;
+        // ---- BM25: weight * (tf / (tf + norm[fieldnorm id])) from the tf-factor table ----------------
+        uint32_t fnw = 0x01010101u;  // no fieldnorms: constant fieldnorm id 1
+        if (tfl & IF_HAS_FN) fnw = *(const uint32_t*)(qw_smem + blk + 16u * (doc_bits + tf_bits) + 4u * lane);
+        float c0, c1, c2, c3;
+        if (tf_bits <= 4) {
+          // tf < 16: index = tf * 256 + fieldnorm id, one byte-permute per posting
+          c0 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f0, fnw, 0x2104)));
+          c1 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f1, fnw, 0x2105)));
+          c2 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f2, fnw, 0x2106)));
+          c3 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f3, fnw, 0x2107)));
+        } else {
+          auto tfn = [&](uint32_t tf, uint32_t fn) -> float {
+            if (tf < QW_TFF_ROWS) return __ldg(tab + 256 + tf * 256 + fn);
+            const float tff = (float)tf;
+            return __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + fn)));
+          };
+          c0 = __fmul_rn(weight, tfn(f0, fnw & 0xFFu));
+          c1 = __fmul_rn(weight, tfn(f1, (fnw >> 8) & 0xFFu));
+          c2 = __fmul_rn(weight, tfn(f2, (fnw >> 16) & 0xFFu));
+          c3 = __fmul_rn(weight, tfn(f3, fnw >> 24));
+        }
+        // ---- ordered accumulate: everything of the earlier clauses must be in -------------------------
+        const uint32_t st = wbase + t;
+        pass_to(st);
+        wait_below(st);
+        if (rec.w & 256u) {
+          // interior block: all 128 postings exist and lie inside the window
+          const float o0 = score[r0], o1 = score[r1], o2 = score[r2], o3 = score[r3];
+          score[r0] = __fadd_rn(o0, c0);
+          score[r1] = __fadd_rn(o1, c1);
+          score[r2] = __fadd_rn(o2, c2);
+          score[r3] = __fadd_rn(o3, c3);
+        } else {
+          const uint32_t count = rec.z >> 16;
+          const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;  // postings of this lane that exist
+          const bool in0 = nvalid > 0 && r0 < wlen, in1 = nvalid > 1 && r1 < wlen;  // r = doc - ws (unsigned wrap before the window)
+          const bool in2 = nvalid > 2 && r2 < wlen, in3 = nvalid > 3 && r3 < wlen;
+          float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+          if (in0) o0 = score[r0];
+          if (in1) o1 = score[r1];
+          if (in2) o2 = score[r2];
+          if (in3) o3 = score[r3];
+          if (in0) score[r0] = __fadd_rn(o0, c0);
+          if (in1) score[r1] = __fadd_rn(o1, c1);
+          if (in2) score[r2] = __fadd_rn(o2, c2);
+          if (in3) score[r3] = __fadd_rn(o3, c3);
+        }
       }
 #ifdef QU_PROFILE
       ct_blocks += clock64() - tb0;
+      ct_nblk += (G > warp) ? (G - warp + QU_NCW - 1) / QU_NCW : 0;
 #endif
       // this warp is done reading the slot
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(slot));
-      if (!(flags & QU_F_LAST)) continue;
-      // ---- sweep this warp's docs: count matches (score > 0), test against the threshold, clear ------
+      if (!(flags & QU_F_LAST)) {
+        pass_to(wbase + t_last);  // the slot's last clause may continue in the next slot
+        continue;
+      }
+      const uint32_t end_stage = wbase + n_terms;
+      pass_to(end_stage);
+      QU_T(te0);
+      wait_below(end_stage);  // every contribution of the window is in
+      QU_ACC(ct_endwait, te0);
       QU_T(ts0);
+      // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
       float4* sc4 = reinterpret_cast<float4*>(score);
       if (MODE == MODE_COLLECT) {
         const float s_lo = hdr_f;
-#pragma unroll 2
-        for (uint32_t q = lane; q < QU_RANGE / 4; q += 32) {
+        for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
           const float4 v = sc4[q];
           sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           my_hits += (v.x > 0.0f) + (v.y > 0.0f) + (v.z > 0.0f) + (v.w > 0.0f);
@@ -607,56 +589,58 @@ __global__ void __launch_bounds__(QW_THREADS, 2) k_union(const UParams p) {
             for (int j = 0; j < 4; j++) {
               if (vv[j] > 0.0f && vv[j] >= s_lo) {
                 const uint32_t pos = atomicAdd(ncand, 1u);
-                if (pos < QU_CANDS) cands[pos] = make_uint2(rlo + 4 * q + j, __float_as_uint(vv[j]));
-                else {
-                  // buffer full (no threshold yet / a burst of high scores): take the slow road now
-                  const DSplitPlan& P = p.plans[cur_split];
-                  const DThresh& T = p.thresh[cur_split];
-                  const Key thr{T.key[0], T.key[1], T.key[2]};
-                  const DocKey dk = doc_key(P, P.key, p.cols + P.col_base, (const uint8_t*)P.data_base, rlo + 4 * q + j, vv[j]);
-                  if (key_ge(dk.key, thr)) {
-                    const uint32_t gp = atomicAdd((uint32_t*)P.out_cand_count, 1u);
-                    if (gp < QW_CAND_CAP) {
-                      uint64_t* c = (uint64_t*)P.out_cands + 3ull * gp;
-                      c[0] = dk.key.w0; c[1] = dk.key.w1; c[2] = dk.key.w2;
-                    }
-                  }
-                }
+                if (pos < QU_CANDS) cands[pos] = make_uint2(ws + 4 * q + j, __float_as_uint(vv[j]));
+                else union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + j, vv[j]);  // buffer full: slow road now
               }
             }
           }
         }
         __syncwarp();
-        if (*ncand >= QU_CANDS / 2) flush_cands();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage));
+        my_stage = end_stage + 1;
+        next_base = end_stage + 1;
+        if (*ncand >= QU_CANDS / 2) flush_cands();  // (after the arrival: nobody waits for the global atomics)
+        QU_ACC(ct_sweep, ts0);
       } else {
         // level-0 digit histogram of the sampled windows: digit = [1 | lin:10] (score_lin)
         const float scale = hdr_f;
-        uint32_t* gh = (uint32_t*)p.plans[split].out_hist;
-        auto lin = [&](float sc) -> uint32_t {
-          const float x = __fmul_rn(sc, scale);
+        auto lin = [&](float s) -> uint32_t {
+          const float x = __fmul_rn(s, scale);
           const uint32_t l = x >= 1023.0f ? 1023u : (x > 0.0f ? (uint32_t)x : 0u);
           return 1024u | l;
         };
-        for (uint32_t q = lane; q < QU_RANGE / 4; q += 32) {
+        for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
           const float4 v = sc4[q];
           sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (v.x > 0.0f) atomicAdd(&gh[lin(v.x)], 1u);
-          if (v.y > 0.0f) atomicAdd(&gh[lin(v.y)], 1u);
-          if (v.z > 0.0f) atomicAdd(&gh[lin(v.z)], 1u);
-          if (v.w > 0.0f) atomicAdd(&gh[lin(v.w)], 1u);
+          if (v.x > 0.0f) atomicAdd(&hist[lin(v.x)], 1u);
+          if (v.y > 0.0f) atomicAdd(&hist[lin(v.y)], 1u);
+          if (v.z > 0.0f) atomicAdd(&hist[lin(v.z)], 1u);
+          if (v.w > 0.0f) atomicAdd(&hist[lin(v.w)], 1u);
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage));
+        my_stage = end_stage + 1;
+        wait_below(end_stage + 1);  // every warp has swept: the window's histogram is complete
+        uint32_t* gh = (uint32_t*)p.plans[split].out_hist;
+        for (uint32_t i = tid; i < QW_HIST_BINS; i += QU_NCT) {
+          const uint32_t v = hist[i];
+          if (v) { atomicAdd(&gh[i], v); hist[i] = 0; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_chain(end_stage + 1));
+        my_stage = end_stage + 2;
+        next_base = end_stage + 2;
       }
-      QU_ACC(ct_sweep, ts0);
     }
-    flush_split();
+    flush_hits();
 #ifdef QU_PROFILE
     if (lane == 0 && p.prof) {
       atomicAdd(p.prof + 8, (unsigned long long)(clock64() - ct_start));
       atomicAdd(p.prof + 9, (unsigned long long)ct_full);
-      atomicAdd(p.prof + 10, (unsigned long long)ct_list);
+      atomicAdd(p.prof + 10, (unsigned long long)ct_chain);   // includes the end-of-window wait
+      atomicAdd(p.prof + 11, (unsigned long long)ct_endwait);
       atomicAdd(p.prof + 12, (unsigned long long)ct_sweep);
-      atomicAdd(p.prof + 13, (unsigned long long)ct_blocks);  // record scan + decode steps
+      atomicAdd(p.prof + 13, (unsigned long long)ct_blocks);  // block loop incl. chain waits inside it
       atomicAdd(p.prof + 14, (unsigned long long)ct_nblk);
       atomicAdd(p.prof + 15, 1ull);
     }
