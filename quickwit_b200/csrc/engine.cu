@@ -606,7 +606,7 @@ static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
   L.recs = cap + QU_PAD;
   L.ttab = L.recs + QU_MAXBLK * 16;
   L.hdr = L.ttab + QU_MAX_TERMS * 16;
-  L.slot_stride = L.hdr + 32;
+  L.slot_stride = L.hdr + 48;  // header (32 B) + block hand-out counter
   L.slot0 = take(QU_SLOTS * L.slot_stride);
   L.total = off;
   return L;
@@ -681,7 +681,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   const bool use_union = all_union && !old_union;
   const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / QU_MINB - 1024 - 64;
   qwk::USmem ulay_c, ulay_h;
-  if (use_union && !getenv("QWGPU_W")) W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : 16384u * 2 / QU_MINB;
+  if (use_union && !getenv("QWGPU_W")) W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : 15360u * 2 / QU_MINB;
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);

@@ -41,11 +41,11 @@ namespace qwk {
 #define QU_NCW (QU_THREADS / 32 - 1)   /* consumer warps; warp QU_NCW is the producer */
 #define QU_NCT (QU_NCW * 32)
 #define QU_SLOTS 2
-#define QU_MAXBLK 256           /* block records per slot */
+#define QU_MAXBLK 128           /* block records per slot */
 #define QU_CHAIN 128            /* mbarriers in the stage ring (a warp is never > 70 stages ahead) */
 #define QU_MAX_TERMS 32
 #define QU_PAD 32               /* decode may read one 16-byte word past a block */
-#define QU_CANDS 32             /* per-warp buffer of docs that reached the score lower bound */
+#define QU_CANDS 16             /* per-warp buffer of docs that reached the score lower bound */
 #ifndef QU_MINB
 #define QU_MINB 2               /* blocks per SM */
 #endif
@@ -114,13 +114,20 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
-// inclusive warp scan step with the shuffle's own predicate (SHFL.UP + predicated IADD)
+// inclusive scan step over segments of `1 << LOGW` lanes, with the shuffle's own predicate
+// (SHFL.UP + predicated IADD)
+template <int LOGW>
 __device__ __forceinline__ uint32_t scan_step(uint32_t x, uint32_t o) {
-  asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0x0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(x) : "r"(o));
+  constexpr uint32_t c = (32u - (1u << LOGW)) << 8;
+  asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(x) : "r"(o), "n"(c));
+  return x;
+}
+__device__ __forceinline__ uint32_t seg16_incl_scan(uint32_t x) {
+  x = scan_step<4>(x, 1); x = scan_step<4>(x, 2); x = scan_step<4>(x, 4); x = scan_step<4>(x, 8);
   return x;
 }
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x) {
-  x = scan_step(x, 1); x = scan_step(x, 2); x = scan_step(x, 4); x = scan_step(x, 8); x = scan_step(x, 16);
+  x = scan_step<5>(x, 1); x = scan_step<5>(x, 2); x = scan_step<5>(x, 4); x = scan_step<5>(x, 8); x = scan_step<5>(x, 16);
   return x;
 }
 
@@ -189,6 +196,7 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       mbar_wait(bar_empty(slot), ((seq / QU_SLOTS) & 1u) ^ 1u);
       QU_ACC(pt_empty, pt_e0);
       open = true; off = 0; cnt = 0;
+      if (lane == 0) *(uint32_t*)(qw_smem + slot_base(slot) + p.sm.hdr + 32) = 0;  // next block to hand out
       if (lane < n_terms) {
         uint4 tt;
         tt.x = __float_as_uint(t_w); tt.y = t_fl; tt.z = (uint32_t)t_tab; tt.w = (uint32_t)(t_tab >> 32);
@@ -473,94 +481,133 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       if (split != cur_split) { flush_hits(); cur_split = split; }
       const uint32_t recs = sl + p.sm.recs, ttab = sl + p.sm.ttab;
 
-      for (uint32_t g = warp; g < G; g += QU_NCW) {
-        const uint4 rec = *(const uint4*)(qw_smem + recs + 16u * g);  // prev_last_doc, shared address, widths/count, clause | interior
+      // Two blocks per warp step: half-warp `half` decodes block g0 + half, 16 lanes x 8 postings each (two
+      // positions of the 4-lane-interleaved words per lane) — fewer warp instructions per block than a
+      // 32 x 4 split, a 4-step scan, and eight independent postings per lane for the scheduler to overlap.
+      const uint32_t half = lane >> 4, hl = lane & 15u;
+      for (uint32_t g0 = 2u * warp; g0 < G; g0 += 2u * QU_NCW) {
+#ifdef QU_PROFILE
+        ct_nblk += (g0 + 1 < G) ? 2 : 1;
+#endif
+        const bool on = g0 + half < G;
+        const uint4 rec = *(const uint4*)(qw_smem + recs + 16u * (on ? g0 + half : g0));  // prev_last_doc, shared address, widths/count, clause | interior
         const uint32_t t = rec.w & 0xFFu;
         const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
         const float weight = __uint_as_float(tt.x);
-        const uint32_t tfl = tt.y;
         const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
         const uint32_t blk = rec.y - sbase;  // offset inside qw_smem
         const uint32_t doc_bits = rec.z & 0xFFu, tf_bits = (rec.z >> 8) & 0xFFu;
-        // ---- doc ids: 4 values per lane from the 4-lane-interleaved words, then a warp scan ----------
-        uint32_t d0, d1, d2, d3;
+        // ---- doc ids: two positions x 4 values per lane, in-lane prefix, then a 16-lane scan -------------
+        uint32_t d[8];
         {
-          const uint32_t bp = lane * doc_bits, sh = bp & 31u;
-          const uint8_t* a = qw_smem + blk + ((bp >> 5) << 4);
-          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t bp0 = 2u * hl * doc_bits, bp1 = bp0 + doc_bits;
+          const uint8_t* a0 = qw_smem + blk + ((bp0 >> 5) << 4);
+          const uint8_t* a1 = qw_smem + blk + ((bp1 >> 5) << 4);
+          const uint4 A0 = *(const uint4*)a0, B0 = *(const uint4*)(a0 + 16);
+          const uint4 A1 = *(const uint4*)a1, B1 = *(const uint4*)(a1 + 16);
+          const uint32_t sh0 = bp0 & 31u, sh1 = bp1 & 31u;
           const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, doc_bits);
           // strictly-sorted deltas: doc[i] = doc[i-1] + v[i] + 1
-          d0 = (__funnelshift_r(A.x, B.x, sh) & mask) + 1u;
-          d1 = d0 + (__funnelshift_r(A.y, B.y, sh) & mask) + 1u;
-          d2 = d1 + (__funnelshift_r(A.z, B.z, sh) & mask) + 1u;
-          d3 = d2 + (__funnelshift_r(A.w, B.w, sh) & mask) + 1u;
+          d[0] = (__funnelshift_r(A0.x, B0.x, sh0) & mask) + 1u;
+          d[1] = d[0] + (__funnelshift_r(A0.y, B0.y, sh0) & mask) + 1u;
+          d[2] = d[1] + (__funnelshift_r(A0.z, B0.z, sh0) & mask) + 1u;
+          d[3] = d[2] + (__funnelshift_r(A0.w, B0.w, sh0) & mask) + 1u;
+          d[4] = d[3] + (__funnelshift_r(A1.x, B1.x, sh1) & mask) + 1u;
+          d[5] = d[4] + (__funnelshift_r(A1.y, B1.y, sh1) & mask) + 1u;
+          d[6] = d[5] + (__funnelshift_r(A1.z, B1.z, sh1) & mask) + 1u;
+          d[7] = d[6] + (__funnelshift_r(A1.w, B1.w, sh1) & mask) + 1u;
         }
-        const uint32_t incl = warp_incl_scan(d3);
-        const uint32_t basev = rec.x + (incl - d3) - ws;  // mod 2^32; window-relative
-        const uint32_t r0 = basev + d0, r1 = basev + d1, r2 = basev + d2, r3 = basev + d3;
+        const uint32_t incl = seg16_incl_scan(d[7]);
+        const uint32_t basev = rec.x + (incl - d[7]) - ws;  // mod 2^32; window-relative
+        uint32_t r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = basev + d[j];
         // ---- term frequencies -----------------------------------------------------------------------
-        uint32_t f0 = 1, f1 = 1, f2 = 1, f3 = 1;
+        uint32_t f[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = 1;
         if (tf_bits) {
-          const uint32_t bp = lane * tf_bits, sh = bp & 31u;
-          const uint8_t* a = qw_smem + blk + 16u * doc_bits + ((bp >> 5) << 4);
-          const uint4 A = *(const uint4*)a, B = *(const uint4*)(a + 16);
+          const uint32_t bp0 = 2u * hl * tf_bits, bp1 = bp0 + tf_bits;
+          const uint8_t* a0 = qw_smem + blk + 16u * doc_bits + ((bp0 >> 5) << 4);
+          const uint8_t* a1 = qw_smem + blk + 16u * doc_bits + ((bp1 >> 5) << 4);
+          const uint4 A0 = *(const uint4*)a0, B0 = *(const uint4*)(a0 + 16);
+          const uint4 A1 = *(const uint4*)a1, B1 = *(const uint4*)(a1 + 16);
+          const uint32_t sh0 = bp0 & 31u, sh1 = bp1 & 31u;
           const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, tf_bits);
-          f0 = __funnelshift_r(A.x, B.x, sh) & mask;
-          f1 = __funnelshift_r(A.y, B.y, sh) & mask;
-          f2 = __funnelshift_r(A.z, B.z, sh) & mask;
-          f3 = __funnelshift_r(A.w, B.w, sh) & mask;
+          f[0] = __funnelshift_r(A0.x, B0.x, sh0) & mask;
+          f[1] = __funnelshift_r(A0.y, B0.y, sh0) & mask;
+          f[2] = __funnelshift_r(A0.z, B0.z, sh0) & mask;
+          f[3] = __funnelshift_r(A0.w, B0.w, sh0) & mask;
+          f[4] = __funnelshift_r(A1.x, B1.x, sh1) & mask;
+          f[5] = __funnelshift_r(A1.y, B1.y, sh1) & mask;
+          f[6] = __funnelshift_r(A1.z, B1.z, sh1) & mask;
+          f[7] = __funnelshift_r(A1.w, B1.w, sh1) & mask;
         }
         // ---- BM25: weight * (tf / (tf + norm[fieldnorm id])) from the tf-factor table ----------------
-        uint32_t fnw = 0x01010101u;  // no fieldnorms: constant fieldnorm id 1
-        if (tfl & IF_HAS_FN) fnw = *(const uint32_t*)(qw_smem + blk + 16u * (doc_bits + tf_bits) + 4u * lane);
-        float c0, c1, c2, c3;
-        if (tf_bits <= 4) {
+        uint2 fnw = make_uint2(0x01010101u, 0x01010101u);  // no fieldnorms: constant fieldnorm id 1
+        if (tt.y & IF_HAS_FN) fnw = *(const uint2*)(qw_smem + blk + 16u * (doc_bits + tf_bits) + 8u * hl);
+        float c[8];
+        if (__all_sync(QW_FULL, tf_bits <= 4)) {
           // tf < 16: index = tf * 256 + fieldnorm id, one byte-permute per posting
-          c0 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f0, fnw, 0x2104)));
-          c1 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f1, fnw, 0x2105)));
-          c2 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f2, fnw, 0x2106)));
-          c3 = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f3, fnw, 0x2107)));
+          c[0] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[0], fnw.x, 0x2104)));
+          c[1] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[1], fnw.x, 0x2105)));
+          c[2] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[2], fnw.x, 0x2106)));
+          c[3] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[3], fnw.x, 0x2107)));
+          c[4] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[4], fnw.y, 0x2104)));
+          c[5] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[5], fnw.y, 0x2105)));
+          c[6] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[6], fnw.y, 0x2106)));
+          c[7] = __fmul_rn(weight, __ldg(tab + 256 + __byte_perm(f[7], fnw.y, 0x2107)));
         } else {
-          auto tfn = [&](uint32_t tf, uint32_t fn) -> float {
-            if (tf < QW_TFF_ROWS) return __ldg(tab + 256 + tf * 256 + fn);
-            const float tff = (float)tf;
-            return __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + fn)));
-          };
-          c0 = __fmul_rn(weight, tfn(f0, fnw & 0xFFu));
-          c1 = __fmul_rn(weight, tfn(f1, (fnw >> 8) & 0xFFu));
-          c2 = __fmul_rn(weight, tfn(f2, (fnw >> 16) & 0xFFu));
-          c3 = __fmul_rn(weight, tfn(f3, fnw >> 24));
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t fn = ((j < 4 ? fnw.x : fnw.y) >> (8 * (j & 3))) & 0xFFu;
+            float tfn;
+            if (f[j] < QW_TFF_ROWS) tfn = __ldg(tab + 256 + f[j] * 256 + fn);
+            else { const float tff = (float)f[j]; tfn = __fdiv_rn(tff, __fadd_rn(tff, __ldg(tab + fn))); }
+            c[j] = __fmul_rn(weight, tfn);
+          }
         }
         // ---- ordered accumulate: everything of the earlier clauses must be in -------------------------
         const uint32_t st = wbase + t;
-        pass_to(st);
-        wait_below(st);
-        if (rec.w & 256u) {
-          // interior block: all 128 postings exist and lie inside the window
-          const float o0 = score[r0], o1 = score[r1], o2 = score[r2], o3 = score[r3];
-          score[r0] = __fadd_rn(o0, c0);
-          score[r1] = __fadd_rn(o1, c1);
-          score[r2] = __fadd_rn(o2, c2);
-          score[r3] = __fadd_rn(o3, c3);
-        } else {
-          const uint32_t count = rec.z >> 16;
-          const uint32_t nvalid = count > lane * 4 ? count - lane * 4 : 0;  // postings of this lane that exist
-          const bool in0 = nvalid > 0 && r0 < wlen, in1 = nvalid > 1 && r1 < wlen;  // r = doc - ws (unsigned wrap before the window)
-          const bool in2 = nvalid > 2 && r2 < wlen, in3 = nvalid > 3 && r3 < wlen;
-          float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-          if (in0) o0 = score[r0];
-          if (in1) o1 = score[r1];
-          if (in2) o2 = score[r2];
-          if (in3) o3 = score[r3];
-          if (in0) score[r0] = __fadd_rn(o0, c0);
-          if (in1) score[r1] = __fadd_rn(o1, c1);
-          if (in2) score[r2] = __fadd_rn(o2, c2);
-          if (in3) score[r3] = __fadd_rn(o3, c3);
+        const uint32_t st_lo = __shfl_sync(QW_FULL, st, 0);
+        const uint32_t st_hi = __shfl_sync(QW_FULL, on ? st : 0u, 16);  // (0: the upper half has no block)
+        const uint32_t count = rec.z >> 16;
+        const uint32_t nvalid = !on ? 0u : (count > hl * 8u ? count - hl * 8u : 0u);  // postings of this lane that exist
+        const bool all_interior = __all_sync(QW_FULL, on && (rec.w & 256u));
+        auto apply = [&]() {
+          if (all_interior) {
+            // both blocks: all 128 postings exist and lie inside the window
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = score[r[j]];
+#pragma unroll
+            for (int j = 0; j < 8; j++) score[r[j]] = __fadd_rn(o[j], c[j]);
+          } else {
+            float o[8];
+            bool in[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              in[j] = (uint32_t)j < nvalid && r[j] < wlen;  // r = doc - ws (unsigned wrap before the window)
+              o[j] = 0.f;
+              if (in[j]) o[j] = score[r[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) if (in[j]) score[r[j]] = __fadd_rn(o[j], c[j]);
+          }
+        };
+        pass_to(st_lo);
+        wait_below(st_lo);
+        if (st_hi == st_lo || st_hi == 0u) apply();  // (lanes of an absent upper block have nvalid == 0)
+        else {
+          // the two blocks belong to different clauses: lower clause first
+          if (half == 0) apply();
+          pass_to(st_hi);  // (syncs the warp first: the lower block's stores are done)
+          wait_below(st_hi);
+          if (half == 1) apply();
         }
       }
 #ifdef QU_PROFILE
       ct_blocks += clock64() - tb0;
-      ct_nblk += (G > warp) ? (G - warp + QU_NCW - 1) / QU_NCW : 0;
 #endif
       // this warp is done reading the slot
       __syncwarp();
@@ -579,6 +626,7 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       float4* sc4 = reinterpret_cast<float4*>(score);
       if (MODE == MODE_COLLECT) {
         const float s_lo = hdr_f;
+#pragma unroll 4
         for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
           const float4 v = sc4[q];
           sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
