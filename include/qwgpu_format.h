@@ -274,10 +274,14 @@ typedef struct QwHit {
 /* Dense aggregation result. Every QwAggNode owns `cells(node)` = Π num_buckets over its ancestor
  * chain (itself included; metric nodes count 1) cells, laid out row-major (outermost ancestor
  * slowest). Bucket nodes use only `count` (doc_count). Metric nodes (QW_AGG_STATS) use all four:
- * `sum_bits` is a wrapping two's-complement integer sum for integer-typed columns (u64, i64,
- * datetime, bool) or the bit pattern of an f64 sum for f64 columns; min/max are in the column's
- * mapped-u64 space (initialised to UINT64_MAX / 0). The host converts to f64 when it builds the
- * intermediate aggregation result. */
+ * `sum_bits`: for integer-typed columns (u64, i64, datetime, bool) whose bit-packed raw width is at
+ * most QW_SUM_EXACT_BITS, the exact integer sum of the RAW offsets (value = min_value + gcd * raw in
+ * the mapped space) — the host rebuilds count * min + gcd * sum in 128-bit arithmetic, so e.g. an avg
+ * over nanosecond timestamps cannot overflow; for f64 columns and wider raws, the bit pattern of an
+ * f64 sum of the typed values (what tantivy accumulates). min/max are in the column's mapped-u64 space
+ * (initialised to UINT64_MAX / 0). The host converts to f64 when it builds the intermediate
+ * aggregation result. */
+#define QW_SUM_EXACT_BITS 40u /* 2^40 * 2^24 docs per split: the raw sum cannot wrap */
 typedef struct QwAggCell {
   uint64_t count;
   uint64_t sum_bits;

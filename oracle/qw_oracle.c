@@ -465,11 +465,13 @@ static void agg_collect(Aggs* A, uint32_t ni, uint32_t doc, uint64_t parent_cell
     for (uint64_t i = a; i < b; i++) {
       uint64_t m = o_col_mapped(A->im, col, i);
       c->count++;
-      if (col->type == QW_COL_F64) {
+      if (col->type == QW_COL_F64 || col->bits > QW_SUM_EXACT_BITS) {
+        /* tantivy: sum += value as f64, in doc order */
         double s; memcpy(&s, &c->sum_bits, 8); s += o_mapped_to_f64(col->type, m); memcpy(&c->sum_bits, &s, 8);
       } else {
-        /* integer-typed columns: exact wrapping integer sum of the typed value */
-        c->sum_bits += (col->type == QW_COL_U64 || col->type == QW_COL_BOOL) ? m : (m ^ (1ull << 63));
+        /* integer-typed columns: exact integer sum of the raw offsets (QwAggCell contract: the host
+         * rebuilds count * min + gcd * sum in 128 bits; no overflow for nanosecond timestamps) */
+        c->sum_bits += o_col_raw(A->im, col, i);
       }
       if (m < c->min_mapped) c->min_mapped = m;
       if (m > c->max_mapped) c->max_mapped = m;

@@ -446,9 +446,15 @@ static IAgg build_node(const BuildCtx& c, uint32_t ni, uint64_t parent_cell) {
     a.m_count = cell.count;
     if (cell.count && b.column >= 0) {
       uint32_t t = b.col_type;
-      if (t == QW_COL_F64) memcpy(&a.m_sum, &cell.sum_bits, 8);
-      else if (t == QW_COL_U64 || t == QW_COL_BOOL) a.m_sum = (double)cell.sum_bits;
-      else a.m_sum = (double)(int64_t)cell.sum_bits;
+      const QwImgColumn& col = c.img.columns[b.column];
+      if (t == QW_COL_F64 || col.bits > QW_SUM_EXACT_BITS) memcpy(&a.m_sum, &cell.sum_bits, 8);
+      else {
+        // exact: sum of the typed values = count * min + gcd * (sum of raw offsets); the mapped u64 of an
+        // i64 / datetime is value + 2^63
+        __int128 sum = (__int128)(unsigned __int128)col.min_value * (__int128)cell.count + (__int128)((unsigned __int128)col.gcd * cell.sum_bits);
+        if (!(t == QW_COL_U64 || t == QW_COL_BOOL)) sum -= ((__int128)1 << 63) * (__int128)cell.count;
+        a.m_sum = (double)sum;
+      }
       a.m_min = mapped_to_f64(t, cell.min_mapped);
       a.m_max = mapped_to_f64(t, cell.max_mapped);
     }

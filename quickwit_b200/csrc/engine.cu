@@ -11,6 +11,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "union_kernel.cuh"
+#include "agg_kernel.cuh"
 
 namespace qw {
 
@@ -93,6 +94,7 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_aggscan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * QW_CAND_CAP));
 }
 
@@ -680,6 +682,38 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
   const bool use_union = all_union && !old_union;
   const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / QU_MINB - 1024 - 64;
+  // match_all + flat terms / histogram aggregations, no hits: the streaming column kernel (agg_kernel.cuh)
+  static const bool old_aggs = getenv("QWGPU_OLD_AGGS") != nullptr;
+  bool use_aggscan = !old_aggs;
+  qwk::ASmem alay;
+  memset(&alay, 0, sizeof alay);
+  {
+    uint32_t maxbits[QW_MAX_DAGGS] = {0};
+    for (auto& L : low) {
+      if (!(L.P.n_instr == 3 && L.instrs[1].op == OP_ALL && L.P.max_hits == 0 && L.P.n_aggs > 0 && L.P.n_cells <= QA_MAX_CELLS)) { use_aggscan = false; break; }
+      for (uint32_t gi = 0; gi < L.P.n_aggs; gi++) {
+        const DAgg& d = L.aggs[gi];
+        const bool flat = d.parent == 0xFFFFFFFFu && d.num_children == 0 && (d.kind == QW_AGG_TERMS || d.kind == QW_AGG_HISTOGRAM) && !d.has_missing;
+        if (!flat || !L.P.fast_aggs || d.col == 0xFFFFFFFFu || L.cols[d.col].card != QW_CARD_FULL || L.cols[d.col].bits > 32) { use_aggscan = false; break; }
+        maxbits[gi] = std::max(maxbits[gi], L.cols[d.col].bits);
+      }
+      if (!use_aggscan) break;
+    }
+    if (use_aggscan) {
+      uint32_t off = 0;
+      auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
+      for (uint32_t gi = 0; gi < QW_MAX_DAGGS; gi++) alay.col_off[gi] = take(maxbits[gi] ? QA_CHUNK / 8 * maxbits[gi] + 16 : 0);
+      alay.hdr = take(16);
+      alay.slot_stride = off;
+      off = 0;
+      alay.bars = take(8 * 2 * QA_SLOTS);
+      alay.cells = take(QA_MAX_CELLS * 4);
+      alay.slot0 = take(QA_SLOTS * alay.slot_stride);
+      alay.total = off;
+      if ((int)alay.total + 1024 > max_smem_optin / 2) use_aggscan = false;
+    }
+  }
+  if (use_aggscan) W = QA_CHUNK;  // the flat work list is the list of 8192-doc chunks
   qwk::USmem ulay_c, ulay_h;
   if (use_union && !getenv("QWGPU_W")) W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : 15360u * 2 / QU_MINB;
   SmemLayout lay;
@@ -689,6 +723,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     W >>= 1;
   }
   (void)scoring;
+  if (use_aggscan && W != QA_CHUNK) use_aggscan = false;
   if (use_union) {
     // (the generic layout above stays valid for the same W: exact radix passes below level 0 use k_window)
     ulay_c = make_union_layout(W, false, u_budget);
@@ -803,6 +838,17 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     q.refine = (flags & F_REFINE) ? 1 : 0;
     q.cands_only = (flags & F_CANDS_ONLY) ? 1 : 0;
     if (q.total_work == 0) return;
+    if (use_aggscan && mode == qwk::MODE_COLLECT && flags == 0) {
+      qwk::AParams a;
+      memset(&a, 0, sizeof a);
+      a.plans = kp.plans; a.cols = kp.cols; a.aggs = kp.aggs;
+      a.first_work = q.first_work; a.n_splits = n; a.total_work = q.total_work;
+      a.sm = alay;
+      const uint32_t agrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * 2));
+      qwk::k_aggscan<<<agrid, QA_THREADS, alay.total, st>>>(a);
+      stats.launches++;
+      return;
+    }
     if (use_union && flags == 0 && (mode == qwk::MODE_COLLECT || (level == 0 && !use_prefix))) {
       qwk::UParams u;
       memset(&u, 0, sizeof u);

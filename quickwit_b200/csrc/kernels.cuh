@@ -480,15 +480,19 @@ __device__ __forceinline__ uint64_t col_raw_doc(const uint8_t* base, const DCol&
   }
   return col_raw(base, c, doc);
 }
+// how a stats cell sums a column (also aggs.cpp build_node and the oracle)
+__device__ __forceinline__ bool stat_sum_f64(const DCol& c) { return c.type == QW_COL_F64 || c.bits > QW_SUM_EXACT_BITS; }
 // Privatised stats cell of the fast path: {sum (u64 wrapping, or f64 bits), max(~mapped) = min, max(mapped)}.
 // When the whole warp feeds one cell the three values are butterfly-reduced first.
 __device__ __forceinline__ void stat_update(unsigned long long* st, const DCol& c, const uint8_t* base, uint32_t cell, uint32_t doc, uint32_t num_docs, bool ok, uint32_t lane) {
   const uint32_t okmask = __ballot_sync(QW_FULL, ok);
   if (okmask == 0) return;
-  const uint64_t m = ok ? c.min_value + c.gcd * col_raw_doc(base, c, doc, num_docs) : 0ull;
-  const bool is_f64 = c.type == QW_COL_F64;
-  const bool plain = c.type == QW_COL_U64 || c.type == QW_COL_BOOL;
-  unsigned long long isum = ok ? (plain ? m : (m ^ (1ull << 63))) : 0ull;
+  const uint64_t raw = ok ? col_raw_doc(base, c, doc, num_docs) : 0ull;
+  const uint64_t m = ok ? c.min_value + c.gcd * raw : 0ull;
+  // sums: exact integer sum of the RAW offsets (the host rebuilds count * min + gcd * sum in 128 bits, so
+  // nanosecond timestamps cannot overflow); f64 columns and raws wider than QW_SUM_EXACT_BITS add doubles
+  const bool is_f64 = stat_sum_f64(c);
+  unsigned long long isum = ok ? raw : 0ull;
   double dsum = (ok && is_f64) ? mapped_to_f64(c.type, m) : 0.0;
   unsigned long long nmin = ok ? ~m : 0ull, vmax = ok ? m : 0ull;
   const uint32_t lead = __ffs(okmask) - 1;
@@ -560,18 +564,17 @@ __device__ __forceinline__ void agg_stats(const DAgg& g, const DCol& c, const ui
   if (on) col_range(base, c, doc, a, b);
   const uint32_t nv = (uint32_t)(b - a);
   const uint32_t maxv = __reduce_max_sync(QW_FULL, nv);
-  const bool is_f64 = c.type == QW_COL_F64;
-  const bool plain = c.type == QW_COL_U64 || c.type == QW_COL_BOOL;
+  const bool is_f64 = stat_sum_f64(c);
   for (uint32_t k = 0; k < maxv; k++) {
     const bool ok = k < nv;
     const uint32_t okmask = __ballot_sync(QW_FULL, ok);
-    uint64_t m = 0;
-    if (ok) m = c.min_value + c.gcd * col_raw(base, c, a + k);
+    uint64_t m = 0, raw = 0;
+    if (ok) { raw = col_raw(base, c, a + k); m = c.min_value + c.gcd * raw; }
     const uint32_t peers = __match_any_sync(QW_FULL, ok ? cell : 0xFFFFFFFFu);
     QwAggCell* out = &cells[g.cell_base + cell];
     if (__all_sync(QW_FULL, !ok || peers == okmask)) {
       // the whole warp feeds one cell: butterfly-reduce, one lane issues the four atomics
-      unsigned long long isum = ok ? (plain ? m : (m ^ (1ull << 63))) : 0ull;
+      unsigned long long isum = ok ? raw : 0ull;
       double dsum = (ok && is_f64) ? mapped_to_f64(c.type, m) : 0.0;
       unsigned long long nmin = ok ? ~m : 0ull, vmax = ok ? m : 0ull;
 #pragma unroll
@@ -592,7 +595,7 @@ __device__ __forceinline__ void agg_stats(const DAgg& g, const DCol& c, const ui
     } else if (ok) {
       atomicAdd((unsigned long long*)&out->count, 1ull);
       if (is_f64) atomicAdd((double*)&out->sum_bits, mapped_to_f64(c.type, m));
-      else atomicAdd((unsigned long long*)&out->sum_bits, (unsigned long long)(plain ? m : (m ^ (1ull << 63))));
+      else atomicAdd((unsigned long long*)&out->sum_bits, (unsigned long long)raw);
       atomicMax((unsigned long long*)&out->min_mapped, (unsigned long long)~m);
       atomicMax((unsigned long long*)&out->max_mapped, (unsigned long long)m);
     }
@@ -1400,7 +1403,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           if (g.kind != QW_AGG_STATS) continue;
           const bool top = g.parent == 0xFFFFFFFFu;
           const uint32_t nc = top ? 1u : s_aggs[g.parent].num_buckets;
-          const bool is_f64 = s_cols[g.col].type == QW_COL_F64;
+          const bool is_f64 = stat_sum_f64(s_cols[g.col]);
           for (uint32_t c = tid; c < nc; c += QW_THREADS) {
             const uint32_t cnt = top ? s_misc[2] : s_hist[s_aggs[g.parent].cell_base + c];
             if (!cnt) continue;

@@ -44,6 +44,9 @@ namespace qwk {
 #define QU_MAXBLK 128           /* block records per slot */
 #define QU_CHAIN 128            /* mbarriers in the stage ring (a warp is never > 70 stages ahead) */
 #define QU_MAX_TERMS 32
+#ifndef QU_SUSPEND_NS
+#define QU_SUSPEND_NS 100000u   /* try_wait suspend-time hint: a waiting warp sleeps in hardware instead of polling */
+#endif
 #define QU_PAD 32               /* decode may read one 16-byte word past a block */
 #define QU_CANDS 16             /* per-warp buffer of docs that reached the score lower bound */
 #ifndef QU_MINB
@@ -102,11 +105,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
+      "}" ::"r"(bar), "r"(parity), "r"(QU_SUSPEND_NS) : "memory");
 }
 // 1-D TMA: global -> shared, completion (bytes) on an mbarrier of this block
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

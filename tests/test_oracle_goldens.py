@@ -3,6 +3,8 @@ golden vector the reference's own tests hold for this path. CPU
 import json
 
 import numpy as np
+import time
+
 import pytest
 
 from quickwit_b200 import ffi, proto, service, splitgen as S
@@ -241,6 +243,27 @@ def test_agg_date_histogram(agg_splits):
     exists = bool_(must=[{"type": "field_presence", "field": "response"}])
     got = _aggs(agg_splits, nested, query=exists)["date_histo"]["buckets"]
     assert (got[0]["doc_count"], got[1]["doc_count"]) == (4, 2) and got[0]["response"]["sum"] == 340.0
+
+
+def test_stats_over_a_datetime_column_does_not_overflow():
+    """avg / sum / stats over a nanosecond timestamp column: the typed values are ~1.4e18 each, so a
+    wrapping 64-bit sum of them overflows after half a dozen docs; the cells carry the sum of the raw
+    offsets instead and the host rebuilds the exact sum in 128 bits (QwAggCell, qwgpu_format.h).
+    Reference semantics: docs/reference/aggregation.md "stats" (f64 sum / count / min / max / avg)."""
+    n = 40
+    secs = [1_420_070_400 + 86_400 * i + 7 * (i % 5) for i in range(n)]
+    docs = [{"id": i, "date": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(t))} for i, t in enumerate(secs)]
+    img = S.build_split(docs, AGG_MAPPING, "dates")
+    got = _aggs([img], {"d": {"stats": {"field": "date"}}, "a": {"avg": {"field": "date"}}})
+    ns = [t * 1_000_000_000 for t in secs]
+    # tantivy reports datetime metrics in the column's f64 space (nanoseconds)
+    assert got["d"]["count"] == n and got["d"]["min"] == float(min(ns)) and got["d"]["max"] == float(max(ns))
+    assert got["d"]["sum"] == float(sum(ns))          # exactly rounded, not a wrapped i64
+    assert got["d"]["avg"] == float(sum(ns)) / n and got["a"]["value"] == got["d"]["avg"]
+    # two splits: the merged sum is the sum of the per-split f64 sums
+    a, b = S.build_split(docs[:17], AGG_MAPPING, "dates-a"), S.build_split(docs[17:], AGG_MAPPING, "dates-b")
+    two = _aggs([a, b], {"d": {"stats": {"field": "date"}}})
+    assert two["d"]["count"] == n and two["d"]["sum"] == float(sum(ns[:17])) + float(sum(ns[17:]))
 
 
 def test_agg_range_and_histogram(agg_splits):
