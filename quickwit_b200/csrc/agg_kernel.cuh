@@ -34,7 +34,8 @@ namespace qwk {
 #define QA_THREADS ((QA_CW + 1) * 32)
 #define QA_GROUPS (QA_CW * 32)   /* 32-doc groups per chunk: one per consumer thread */
 #define QA_CHUNK (QA_GROUPS * 32)
-#define QA_SLOTS 4
+#define QA_SLOTS 2               /* per block; four blocks per SM keep eight chunks in flight */
+#define QA_MINB 4
 #define QA_MAX_CELLS 4096
 
 struct ASmem {
@@ -42,7 +43,9 @@ struct ASmem {
   uint32_t col_off[QW_MAX_DAGGS];  // bytes of aggregation i's column inside a slot
   uint32_t hdr;                    // uint4 {split, first doc, docs, flags} inside a slot
   uint32_t bars;                   // full[QA_SLOTS], empty[QA_SLOTS]
-  uint32_t cells;                  // uint32[QA_MAX_CELLS]
+  uint32_t atab;                   // AggRow[QW_MAX_DAGGS]: the current split's aggregations
+  uint32_t bcache;                 // uint4[QA_CW][QW_MAX_DAGGS]: per warp, the histogram bucket it is in
+  uint32_t cells;                  // uint32[n_cells]
   uint32_t total;
 };
 
@@ -53,6 +56,14 @@ struct AParams {
   const uint32_t* first_work;  // prefix over splits of chunk counts; [n_splits + 1]
   uint32_t n_splits, total_work;
   ASmem sm;
+};
+
+struct AggRow {  // 48 bytes
+  uint32_t kind, bits, cell_base, nb;
+  float inv_step;
+  uint32_t pad;
+  uint64_t bounds;  // device address of uint64[nb + 1]
+  uint64_t b0, bn;  // bounds[0], bounds[nb]
 };
 
 // 32 values of a group, bit-packed little-endian at B bits (tantivy-bitpacker layout), words in registers
@@ -95,19 +106,19 @@ __device__ __forceinline__ bool hist_bucket(const uint64_t* B, uint32_t nb, floa
   return true;
 }
 
-__global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
+__global__ void __launch_bounds__(QA_THREADS, QA_MINB) k_aggscan(const AParams p) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t sbase = smem_u32(qw_smem);
   const uint32_t bars = sbase + p.sm.bars;
   auto bar_full = [&](uint32_t s) { return bars + 8u * s; };
   auto bar_empty = [&](uint32_t s) { return bars + 8u * (QA_SLOTS + s); };
   uint32_t* cells = (uint32_t*)(qw_smem + p.sm.cells);
+  AggRow* atab = (AggRow*)(qw_smem + p.sm.atab);
   if (tid == 0) {
     for (uint32_t s = 0; s < QA_SLOTS; s++) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), QA_CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (uint32_t i = tid; i < QA_MAX_CELLS; i += QA_THREADS) cells[i] = 0;
   __syncthreads();
   const uint32_t w_begin = (uint32_t)(((uint64_t)p.total_work * blockIdx.x) / gridDim.x);
   const uint32_t w_end = (uint32_t)(((uint64_t)p.total_work * (blockIdx.x + 1)) / gridDim.x);
@@ -122,35 +133,43 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
   }
 
   if (warp == QA_CW) {
-    // ================================ producer ======================================================
-    if (lane == 0) {
-      for (uint32_t work = w_begin, seq = 0; work < w_end; work++, seq++) {
-        while (__ldg(p.first_work + split + 1) <= work) split++;
+    // ================================ producer: lane = aggregation ====================================
+    uint32_t cur = 0xFFFFFFFFu, n_aggs = 0, num_docs = 0, bits = 0;
+    const uint8_t* src0 = nullptr;
+    for (uint32_t work = w_begin, seq = 0; work < w_end; work++, seq++) {
+      while (__ldg(p.first_work + split + 1) <= work) split++;
+      if (split != cur) {
+        cur = split;
         const DSplitPlan& P = p.plans[split];
-        const uint32_t d0 = (work - __ldg(p.first_work + split)) * QA_CHUNK;
-        const uint32_t nd = min((uint32_t)QA_CHUNK, P.num_docs - d0);
-        const uint32_t slot = seq % QA_SLOTS;
-        mbar_wait(bar_empty(slot), ((seq / QA_SLOTS) & 1u) ^ 1u);
-        const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
-        *(uint4*)(qw_smem + sl + p.sm.hdr) = make_uint4(split, d0, nd, 0u);
-        uint32_t total = 0;
-        for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
-          const DCol& c = p.cols[P.col_base + p.aggs[P.agg_base + gi].col];
-          total += (uint32_t)(((uint64_t)nd * c.bits + 127) >> 7) << 4;
-        }
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full(slot)), "r"(total) : "memory");
-        for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
-          const DCol& c = p.cols[P.col_base + p.aggs[P.agg_base + gi].col];
-          const uint32_t bytes = (uint32_t)(((uint64_t)nd * c.bits + 127) >> 7) << 4;  // whole 16-byte words (the array is padded)
-          if (bytes) bulk_g2s(sbase + sl + p.sm.col_off[gi], (const uint8_t*)P.data_base + c.values_off + ((uint64_t)d0 * c.bits >> 3), bytes, bar_full(slot));
+        n_aggs = P.n_aggs; num_docs = P.num_docs; bits = 0;
+        if (lane < n_aggs) {
+          const DCol& c = p.cols[P.col_base + p.aggs[P.agg_base + lane].col];
+          bits = c.bits;
+          src0 = (const uint8_t*)P.data_base + c.values_off;
         }
       }
+      const uint32_t d0 = (work - __ldg(p.first_work + split)) * QA_CHUNK;
+      const uint32_t nd = min((uint32_t)QA_CHUNK, num_docs - d0);
+      const uint32_t slot = seq % QA_SLOTS;
+      mbar_wait(bar_empty(slot), ((seq / QA_SLOTS) & 1u) ^ 1u);
+      const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
+      const uint32_t bytes = (uint32_t)(((uint64_t)nd * bits + 127) >> 7) << 4;  // whole 16-byte words (the array is padded)
+      uint32_t total = bytes;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(QW_FULL, total, o);
+      if (lane == 0) {
+        *(uint4*)(qw_smem + sl + p.sm.hdr) = make_uint4(split, d0, nd, 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full(slot)), "r"(total) : "memory");
+      }
+      __syncwarp();
+      if (bytes) bulk_g2s(sbase + sl + p.sm.col_off[lane & (QW_MAX_DAGGS - 1)], src0 + ((uint64_t)d0 * bits >> 3), bytes, bar_full(slot));
     }
   } else {
     // ================================ consumers =====================================================
-    uint32_t cur_split = 0xFFFFFFFFu;
-    unsigned long long my_docs = 0;  // warp 0 lane 0 counts the docs of the current split
-    auto flush = [&]() {
+    uint32_t cur_split = 0xFFFFFFFFu, n_aggs = 0;
+    unsigned long long my_docs = 0;  // thread 0 counts the docs of the current split
+    uint4* bcache = (uint4*)(qw_smem + p.sm.bcache) + warp * QW_MAX_DAGGS;  // {lo, hi, bucket, valid} per aggregation
+    auto enter_split = [&](uint32_t next) {
       // all consumer warps have added their counts of the old split: named barrier over the consumers
       asm volatile("bar.sync 1, %0;" ::"n"(QA_CW * 32) : "memory");
       if (cur_split != 0xFFFFFFFFu) {
@@ -158,11 +177,26 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
         QwAggCell* out = (QwAggCell*)P.out_cells;
         for (uint32_t i = tid; i < P.n_cells; i += QA_CW * 32) {
           const uint32_t v = cells[i];
-          if (v) { atomicAdd((unsigned long long*)&out[i].count, (unsigned long long)v); cells[i] = 0; }
+          if (v) atomicAdd((unsigned long long*)&out[i].count, (unsigned long long)v);
         }
         if (tid == 0 && my_docs) atomicAdd((unsigned long long*)P.out_num_hits, my_docs);
       }
       my_docs = 0;
+      cur_split = next;
+      if (next != 0xFFFFFFFFu) {
+        const DSplitPlan& P = p.plans[next];
+        n_aggs = P.n_aggs;
+        for (uint32_t i = tid; i < P.n_cells; i += QA_CW * 32) cells[i] = 0;
+        if (tid < n_aggs) {
+          const DAgg& a = p.aggs[P.agg_base + tid];
+          AggRow r;
+          r.kind = a.kind; r.bits = p.cols[P.col_base + a.col].bits; r.cell_base = a.cell_base; r.nb = a.num_buckets;
+          r.inv_step = a.inv_step; r.pad = 0; r.bounds = a.bounds; r.b0 = 0; r.bn = 0;
+          if (a.kind == QW_AGG_HISTOGRAM) { r.b0 = __ldg((const uint64_t*)a.bounds); r.bn = __ldg((const uint64_t*)a.bounds + a.num_buckets); }
+          atab[tid] = r;
+        }
+        if (lane < QW_MAX_DAGGS) bcache[lane] = make_uint4(1u, 0u, 0u, 0u);  // empty interval: lo > hi
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(QA_CW * 32) : "memory");
     };
     for (uint32_t work = w_begin, seq = 0; work < w_end; work++, seq++) {
@@ -170,35 +204,40 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
       mbar_wait(bar_full(slot), (seq / QA_SLOTS) & 1u);
       const uint32_t sl = p.sm.slot0 + slot * p.sm.slot_stride;
       const uint4 h = *(const uint4*)(qw_smem + sl + p.sm.hdr);
-      if (h.x != cur_split) { flush(); cur_split = h.x; }
-      const DSplitPlan& P = p.plans[cur_split];
+      if (h.x != cur_split) enter_split(h.x);
       const uint32_t nd = h.z;
       if (tid == 0) my_docs += nd;
       const uint32_t g = tid;                                     // this thread's group of the chunk
       const uint32_t gv = nd > 32u * g ? min(32u, nd - 32u * g) : 0u;  // docs of the group that exist
-      for (uint32_t gi = 0; gi < P.n_aggs; gi++) {
-        const DAgg& a = p.aggs[P.agg_base + gi];
-        const uint32_t bits = p.cols[P.col_base + a.col].bits;
+      const bool warp_full = nd >= 32u * (tid | 31u) + 32u;            // all 32 groups of this warp are whole
+      for (uint32_t gi = 0; gi < n_aggs; gi++) {
+        const uint4 r0 = *(const uint4*)&atab[gi];  // kind, bits, cell_base, nb
+        const uint32_t bits = r0.y;
         const uint32_t* w = (const uint32_t*)(qw_smem + sl + p.sm.col_off[gi]) + g * bits;
-        uint32_t* ctr = cells + a.cell_base;
-        if (a.kind == QW_AGG_HISTOGRAM) {
-          const uint64_t* B = (const uint64_t*)a.bounds;
-          const uint32_t nb = a.num_buckets;
-          const uint64_t b0 = __ldg(B), bn = __ldg(B + nb);
-          const float inv_step = a.inv_step;
+        uint32_t* ctr = cells + r0.z;
+        if (r0.x == QW_AGG_HISTOGRAM) {
           uint32_t mn = 0xFFFFFFFFu, mx = 0;
           if (bits == 0) mn = 0;
-          else if (gv == 32u) unpack32_dyn(bits, w, [&](int, uint32_t x) { mn = min(mn, x); mx = max(mx, x); });
+          else if (gv == 32u) {
+            uint32_t px = 0;
+            unpack32_dyn(bits, w, [&](int v, uint32_t x) {
+              if (v & 1) { mn = __vimin3_u32(mn, px, x); mx = __vimax3_u32(mx, px, x); } else px = x;
+            });
+          }
+          // the warp's 1024 docs against the bucket the warp was in last time (time-ordered logs stay in
+          // a bucket for many chunks): two warp reductions and two compares instead of two table searches
+          const uint4 bc = bcache[gi];
+          if (warp_full && __reduce_min_sync(QW_FULL, mn) >= bc.x && __reduce_max_sync(QW_FULL, mx) <= bc.y) {
+            if (lane == 0) atomicAdd(&ctr[bc.z], 1024u);
+            continue;
+          }
+          const AggRow& row = atab[gi];
+          const uint64_t* B = (const uint64_t*)row.bounds;
           uint32_t bk_lo = 0, bk_hi = 1;
-          const bool whole = gv == 32u && hist_bucket(B, nb, inv_step, b0, bn, mn, bk_lo) &&
-                             hist_bucket(B, nb, inv_step, b0, bn, mx, bk_hi) && bk_lo == bk_hi;
-          // a warp whose 32 groups fall into one bucket (time-ordered logs) adds 1024 at once
-          const uint32_t lead = __shfl_sync(QW_FULL, bk_lo, 0);
-          if (__all_sync(QW_FULL, whole && bk_lo == lead)) {
-            if (lane == 0) atomicAdd(&ctr[lead], 1024u);
-          } else if (whole) {
-            atomicAdd(&ctr[bk_lo], 32u);
-          } else if (gv) {
+          const bool whole = gv == 32u && hist_bucket(B, r0.w, row.inv_step, row.b0, row.bn, mn, bk_lo) &&
+                             hist_bucket(B, r0.w, row.inv_step, row.b0, row.bn, mx, bk_hi) && bk_lo == bk_hi;
+          if (whole) atomicAdd(&ctr[bk_lo], 32u);
+          else if (gv) {
             // the group straddles a bucket boundary / the hard bounds, or is the split's last: per doc
             for (uint32_t v = 0; v < gv; v++) {
               uint32_t x = 0;
@@ -207,9 +246,20 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
                 x = __funnelshift_r(w[bp >> 5], w[(bp >> 5) + 1], sh) & __funnelshift_lc(0xFFFFFFFFu, 0u, bits);
               }
               uint32_t bk;
-              if (hist_bucket(B, nb, inv_step, b0, bn, x, bk)) atomicAdd(&ctr[bk], 1u);
+              if (hist_bucket(B, r0.w, row.inv_step, row.b0, row.bn, x, bk)) atomicAdd(&ctr[bk], 1u);
             }
           }
+          // remember the bucket of the warp's last whole group: raws in [B[bk], B[bk + 1]) (32-bit raws)
+          const uint32_t wm = __ballot_sync(QW_FULL, whole);
+          if (wm) {
+            const uint32_t src = 31u - __clz(wm);
+            const uint32_t bk = __shfl_sync(QW_FULL, bk_lo, src);
+            if (lane == 0) {
+              const uint64_t lo = __ldg(B + bk), hi = __ldg(B + bk + 1) - 1;
+              bcache[gi] = make_uint4((uint32_t)lo, hi > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)hi, bk, 1u);
+            }
+          }
+          __syncwarp();
         } else {
           // TERMS: dense index = raw value (ordinal of a string column)
           if (bits == 0) {
@@ -231,20 +281,15 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
               vm = m0 | (m1 << 1);
             }
             lo &= vm; hi &= vm;
-            uint32_t t3 = __popc(lo & hi), t1 = __popc(lo) - t3, t2 = __popc(hi) - t3, t0 = __popc(vm) - t1 - t2 - t3;
-            // warp totals (all 32 lanes are here: the branch is uniform), one atomic per ordinal and warp
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              t0 += __shfl_xor_sync(QW_FULL, t0, o);
-              t1 += __shfl_xor_sync(QW_FULL, t1, o);
-              t2 += __shfl_xor_sync(QW_FULL, t2, o);
-              t3 += __shfl_xor_sync(QW_FULL, t3, o);
-            }
+            const uint32_t t3 = __popc(lo & hi), t1 = __popc(lo) - t3, t2 = __popc(hi) - t3, t0 = __popc(vm) - t1 - t2 - t3;
+            // warp totals (all 32 lanes are here: the branch is uniform): each count is <= 32, so the four
+            // fit one 32-bit word as 8-bit fields x 32 lanes = 10-bit sums -> two packed reductions
+            const uint32_t s01 = __reduce_add_sync(QW_FULL, t0 | (t1 << 16)), s23 = __reduce_add_sync(QW_FULL, t2 | (t3 << 16));
             if (lane == 0) {
-              if (t0) atomicAdd(&ctr[0], t0);
-              if (t1) atomicAdd(&ctr[1], t1);
-              if (t2) atomicAdd(&ctr[2], t2);
-              if (t3) atomicAdd(&ctr[3], t3);
+              if (s01 & 0xFFFFu) atomicAdd(&ctr[0], s01 & 0xFFFFu);
+              if (s01 >> 16) atomicAdd(&ctr[1], s01 >> 16);
+              if (s23 & 0xFFFFu) atomicAdd(&ctr[2], s23 & 0xFFFFu);
+              if (s23 >> 16) atomicAdd(&ctr[3], s23 >> 16);
             }
           } else {
             for (uint32_t v = 0; v < gv; v++) {
@@ -258,7 +303,7 @@ __global__ void __launch_bounds__(QA_THREADS, 2) k_aggscan(const AParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(slot));
     }
-    flush();
+    enter_split(0xFFFFFFFFu);
   }
 }
 

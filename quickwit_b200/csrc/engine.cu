@@ -706,11 +706,15 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       alay.hdr = take(16);
       alay.slot_stride = off;
       off = 0;
+      uint32_t a_cells = 1;
+      for (auto& L : low) a_cells = std::max(a_cells, L.P.n_cells);
       alay.bars = take(8 * 2 * QA_SLOTS);
-      alay.cells = take(QA_MAX_CELLS * 4);
+      alay.atab = take(QW_MAX_DAGGS * sizeof(qwk::AggRow));
+      alay.bcache = take(QA_CW * QW_MAX_DAGGS * 16);
+      alay.cells = take(a_cells * 4);
       alay.slot0 = take(QA_SLOTS * alay.slot_stride);
       alay.total = off;
-      if ((int)alay.total + 1024 > max_smem_optin / 2) use_aggscan = false;
+      if ((int)alay.total + 1024 > max_smem_optin) use_aggscan = false;
     }
   }
   if (use_aggscan) W = QA_CHUNK;  // the flat work list is the list of 8192-doc chunks
@@ -844,7 +848,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       a.plans = kp.plans; a.cols = kp.cols; a.aggs = kp.aggs;
       a.first_work = q.first_work; a.n_splits = n; a.total_work = q.total_work;
       a.sm = alay;
-      const uint32_t agrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * 2));
+      int aocc = 1;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&aocc, qwk::k_aggscan, QA_THREADS, alay.total));
+      const uint32_t agrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * std::max(aocc, 1)));
       qwk::k_aggscan<<<agrid, QA_THREADS, alay.total, st>>>(a);
       stats.launches++;
       return;
