@@ -44,10 +44,16 @@ sys.path.insert(0, ROOT)
 FRACS = [0.20, 0.10, 0.05, 0.05, 0.02, 0.02, 0.01, 0.01, 0.005, 0.001]
 Q_SETS = 4
 K = 1000
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_window<COLLECT> launch on this workload, from
-# the `ncu --set full` capture summarised in profiles/r1_summary.md (171.0 MB + 4.4 MB). A constant of
-# the workload + build, not measured live (ncu cannot run inside the timed bench).
-NCU_TRAFFIC_BYTES = 175.4e6
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) cannot be measured inside the
+# timed bench; it is read from profiles/r2_traffic.json, which tools/ncu_traffic.py writes from an
+# `ncu --set full` capture of this same command (the capture file is named there).
+def ncu_traffic(kernel: str):
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        e = t["kernels"][kernel]
+        return float(e["dram_bytes_per_launch"]), f"{t['capture']} ({e['launches']} launches, workload {e['workload']})"
+    except Exception:
+        return None, None
 
 
 def parse_args():
@@ -60,6 +66,7 @@ def parse_args():
     ap.add_argument("--docs-per-split", type=int, default=3_125_000)
     ap.add_argument("--cpu-sample-splits", type=int, default=0, help="splits in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config block (C1 / C3 / C4)")
     return ap.parse_args()
 
 
@@ -209,26 +216,83 @@ class ClockSampler:
 
 
 def cpu_oracle_rate(imgs, plans_q0, threads: int, min_seconds: float = 10.0):
-    """Times the CPU oracle (one split per thread) on a bounded sample; returns postings/s."""
+    """Times the CPU baseline — oracle/qw_oracle.c's windowed-union / SIMD-unpack organisation of the reference
+    algorithm, one (split, query) at a time per C thread (qwo_search_many) — on a bounded sample; postings/s."""
     from oracle import oracle as O
-    O.lib()
-    n = len(imgs)
-
-    def one(i):
-        r = O.split_search(imgs[i], plans_q0[i])
-        return sum(imgs[i].doc_freq(imgs[i].term_ord("body", f"t{j}")) for j in range(10)), r.num_hits
+    many = O.ManySearch(imgs, plans_q0)
+    many.run(threads)  # warm-up (page in the images)
     t0 = time.perf_counter()
-    postings = 0
-    rounds = 0
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        while True:
-            for p, _ in ex.map(one, range(n)):
-                postings += p
-            rounds += 1
-            if time.perf_counter() - t0 >= min_seconds or rounds >= 50:
-                break
+    postings = rounds = 0
+    while True:
+        postings += many.run(threads)[1]
+        rounds += 1
+        if time.perf_counter() - t0 >= min_seconds or rounds >= 200:
+            break
     dt = time.perf_counter() - t0
     return postings / dt, dt, rounds
+
+
+T0_SECS = 1_700_000_000
+SYNTH_MAPPING = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
+                                    {"name": "severity_text", "type": "text", "tokenizer": "raw", "fast": True},
+                                    {"name": "timestamp", "type": "datetime", "fast": True, "fast_precision": "seconds"},
+                                    {"name": "tenant_id", "type": "u64", "fast": True}], "timestamp_field": "timestamp"}
+
+
+def other_configs(ctx, imgs, peak, reps: int = 20, lat_runs: int = 60):
+    """The other single-GPU BASELINE configs on the same resident index (rank 0, N = 1): device time and
+    main-kernel time through seam C (CUDA events inside the library), p50 through qwgpu_leaf_search, and
+    the main kernel's roofline fraction from the algorithmic bytes the library accounts per split.
+    C1: single term, top-10. C3: term AND timestamp range, top-1000 by timestamp. C4: match_all with
+    terms(severity_text) + date_histogram(1h). Units: postings visited (C3: + one column probe each);
+    C4: (doc, aggregation) column reads."""
+    from quickwit_b200 import proto, service
+    n = len(imgs)
+    span = 86_400 * n
+    term = lambda f, v: {"type": "term", "field": f, "value": v}
+    cfgs = {
+        "c1_term_top10": (term("severity_text", "ERROR"), dict(max_hits=10), None),
+        "c3_term_and_ts_range_top1000_by_ts": ({"type": "bool", "must": [term("body", "t2")]},
+                                               dict(max_hits=1000, sort_fields=[("timestamp", 1)], start_timestamp=T0_SECS + span // 4,
+                                                    end_timestamp=T0_SECS + 3 * span // 4), None),
+        "c4_terms_date_histogram": ({"type": "match_all"}, dict(max_hits=0),
+                                    {"by_sev": {"terms": {"field": "severity_text"}},
+                                     "over_time": {"date_histogram": {"field": "timestamp", "fixed_interval": "1h"}}}),
+    }
+    dm = json.dumps(SYNTH_MAPPING)
+    ids = [im.split_id for im in imgs]
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
+    out = {}
+    for name, (ast, kw, aggs) in cfgs.items():
+        sreq = proto.enc_search_request(json.dumps(ast), aggregation_request=json.dumps(aggs) if aggs else None, **kw)
+        lreq = proto.enc_leaf_search_request(sreq, offsets, dm)
+        plans = [service.compile_plan(im, sreq, dm) for im in imgs]
+        rs = RawSearch(ctx, ids, plans)
+        for _ in range(3):
+            rs.run(); rs.free()
+        gpu_us = main_us = 0.0
+        for _ in range(reps):
+            r = rs.run(); rs.free()
+            gpu_us += r["gpu_us"]; main_us += r["main_us"]
+        gpu_us /= reps; main_us /= reps
+        lat = []
+        for i in range(lat_runs + 5):
+            t = time.perf_counter()
+            resp = ctx.leaf_search(lreq)
+            if i >= 5:
+                lat.append(time.perf_counter() - t)
+        lat.sort()
+        dec = proto.dec_leaf_search_response(resp)
+        docs = sum(im.num_docs for im in imgs)
+        units = r["postings"] if r["postings"] else docs * len(aggs or {})
+        achieved = r["alg_bytes"] / main_us / 1e3 if main_us else 0.0
+        traffic, tsrc = ncu_traffic(name)
+        out[name] = {"value": units / (gpu_us * 1e-6), "unit": "postings/s" if r["postings"] else "column values/s",
+                     "num_hits": dec["num_hits"], "device_us": gpu_us, "main_kernel_us": main_us, "launches": r["launches"],
+                     "exact_fallbacks": r["fallbacks"], "leaf_search_p50_ms": 1e3 * lat[len(lat) // 2],
+                     "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                  "algorithmic_bytes_per_launch": r["alg_bytes"], "traffic": traffic, "traffic_source": tsrc}}
+    return out
 
 
 def main():
@@ -254,24 +318,17 @@ def main():
         imgs = build_splits(0, n_s, a.docs_per_split, threads=min(cores, 32))
         plans = make_plans(imgs)
         from oracle import oracle as O
-        O.lib()
-
-        def one(args):
-            q, i = args
-            O.split_search(imgs[i], plans[q][i])
-            return sum(imgs[i].doc_freq(imgs[i].term_ord("body", f"t{q * 10 + j}")) for j in range(10))
-        work = [(q, i) for q in range(Q_SETS) for i in range(n_s)]
+        many = O.ManySearch([imgs[i] for q in range(Q_SETS) for i in range(n_s)], [plans[q][i] for q in range(Q_SETS) for i in range(n_s)])
         times, postings_step = [], 0
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            for s in range(a.warmup + a.steps):
-                t0 = time.perf_counter()
-                postings_step = sum(ex.map(one, work))
-                dt = time.perf_counter() - t0
-                if s >= a.warmup:
-                    times.append(dt)
+        for s in range(a.warmup + a.steps):
+            t0 = time.perf_counter()
+            postings_step = many.run(threads)[1]
+            dt = time.perf_counter() - t0
+            if s >= a.warmup:
+                times.append(dt)
         total = sum(times)
         value = postings_step * len(times) / total
-        sample = f"{Q_SETS} queries x {n_s} of {a.splits} splits ({n_s * a.docs_per_split} docs) per step, {threads} threads"
+        sample = f"{Q_SETS} queries x {n_s} of {a.splits} splits ({n_s * a.docs_per_split} docs) per step, {threads} C threads, windowed union + SIMD unpack"
         print(json.dumps({"impl": "reference", "metric": "docs_scored_per_sec", "value": value, "unit": "postings/s",
                           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32",
@@ -445,7 +502,8 @@ def main():
         "metric": "docs_scored_per_sec", "value": postings / gpu_s, "unit": "postings/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": 1e3 * gpu_s / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
-        "config": dict(workload, parallelism=f"splits_x{world}", resident_bytes_per_gpu=resident, build_seconds=round(t_build, 1)),
+        "config": workload,
+        "setup": {"parallelism": f"splits_x{world}", "resident_bytes_per_gpu": resident, "build_seconds": round(t_build, 1)},
         "e2e": {"value": postings / wall, "unit": "postings/s", "api": "qwgpu_leaf_search (LeafSearchRequest -> LeafSearchResponse bytes)",
                 "ms_per_step": 1e3 * wall / a.steps, "concurrent_queries": Q_SETS,
                 "single_query_latency_ms": {"p50": 1e3 * single[len(single) // 2], "p90": 1e3 * single[int(len(single) * 0.9)],
@@ -456,18 +514,22 @@ def main():
                 "seam_c_wall_value": postings / wall_c},
         "gpu_launches": launches,
         "exact_fallbacks": sum(x["fallbacks"] for x in accs),
-        "roofline": {"bound": "hbm", "kernel": "k_window<COLLECT>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "k_union<COLLECT>", "achieved": achieved, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if (a.splits, a.docs_per_split) == (32, 3_125_000) else None,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("k_union<COLLECT>")[0] if (a.splits, a.docs_per_split) == (32, 3_125_000) else None,
+                     "traffic_source": ncu_traffic("k_union<COLLECT>")[1],
                      "algorithmic_bytes_per_launch": alg_bytes / n_main, "avg_launch_us": 1e6 * main_s / n_main},
         "clocks": clocks,
     }
+    if world == 1 and not a.no_configs:
+        out["configs"] = other_configs(ctx, imgs, peak)
     if not a.no_cpu_baseline and world == 1:
         n_s = a.cpu_sample_splits or min(a.splits, max(4, min(cores, 32)))
         threads = min(cores, n_s)
         rate, dt, rounds = cpu_oracle_rate(imgs[:n_s], plans[0][:n_s], threads)
         out["cpu_baseline"] = {"value": rate, "unit": "postings/s", "cores": threads, "kind": "port",
-                               "sample": f"query set 0 over {n_s} splits x {rounds} rounds ({dt:.1f} s), one split per thread"}
+                               "sample": f"query set 0 over {n_s} splits x {rounds} rounds ({dt:.1f} s), {threads} C threads, windowed union + SIMD unpack"}
     sys.stdout.flush()
     os.write(result_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

@@ -44,6 +44,9 @@ def lib() -> C.CDLL:
         L.qwo_split_search.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(OHit),
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(OCell),
                                        C.c_uint64, C.POINTER(C.c_uint64)]
+        L.qwo_split_search_fast.argtypes = L.qwo_split_search.argtypes
+        L.qwo_search_many.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                      C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
         L.qwo_decode_postings.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.qwo_column_first.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = L
@@ -58,8 +61,31 @@ class OracleResult:
         self.postings_visited = visited
 
 
-def split_search(img, plan: bytes, max_cells: int = 1 << 22) -> OracleResult:
-    """img: quickwit_b200.splitgen.SplitImage (only .ptr/.nbytes are used)."""
+class ManySearch:
+    """Pre-marshalled (split, plan) pairs for qwo_search_many: the CPU reference arm of bench.py runs the
+    searches from a pool of C threads (no Python in the timed region)."""
+
+    def __init__(self, imgs, plans):
+        n = len(imgs)
+        self.n = n
+        self.bufs = [C.create_string_buffer(p, len(p)) for p in plans]
+        self.imgs = (C.c_void_p * n)(*[im.ptr for im in imgs])
+        self.img_lens = (C.c_uint64 * n)(*[im.nbytes for im in imgs])
+        self.plans = (C.c_void_p * n)(*[C.addressof(b) for b in self.bufs])
+        self.plan_lens = (C.c_uint64 * n)(*[len(p) for p in plans])
+        self._keep = list(imgs)
+
+    def run(self, threads: int, fast: bool = True):
+        tot = (C.c_uint64 * 2)()
+        rc = lib().qwo_search_many(self.imgs, self.img_lens, self.plans, self.plan_lens, self.n, threads, int(fast), tot)
+        if rc != 0:
+            raise RuntimeError(f"oracle failed: {rc}")
+        return int(tot[0]), int(tot[1])  # hits, postings visited
+
+
+def split_search(img, plan: bytes, max_cells: int = 1 << 22, fast: bool = False) -> OracleResult:
+    """img: quickwit_b200.splitgen.SplitImage (only .ptr/.nbytes are used). fast=True: the windowed-union /
+    SIMD-unpack organisation of the same arithmetic (the CPU baseline bench.py times)."""
     L = lib()
     k = int.from_bytes(plan[16:20], "little")
     num_aggs = int.from_bytes(plan[12:16], "little")
@@ -68,8 +94,8 @@ def split_search(img, plan: bytes, max_cells: int = 1 << 22) -> OracleResult:
     cells = (OCell * ncap)()
     n, nh, vis = C.c_uint32(), C.c_uint64(), C.c_uint64()
     pbuf = C.create_string_buffer(plan, len(plan))
-    rc = L.qwo_split_search(img.ptr, img.nbytes, C.addressof(pbuf), len(plan), hits, C.byref(n), C.byref(nh),
-                            cells, ncap, C.byref(vis))
+    fn = L.qwo_split_search_fast if fast else L.qwo_split_search
+    rc = fn(img.ptr, img.nbytes, C.addressof(pbuf), len(plan), hits, C.byref(n), C.byref(nh), cells, ncap, C.byref(vis))
     if rc != 0:
         raise RuntimeError(f"oracle failed: {rc}")
     out_hits = [(h.doc_id, h.flags, h.v1, h.v2, h.score) for h in hits[: n.value]]

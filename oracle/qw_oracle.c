@@ -330,7 +330,15 @@ static DocSet* build(Arena* a, const OImg* im, const QwPlanNode* nodes, uint32_t
       s->tdata = im->data + t->data_off;
       s->nblocks = t->num_blocks;
       s->has_tf = (f->flags & QW_FIELD_HAS_FREQS) != 0;
-      s->weight = n->bm25_weight;
+      /* Bm25Weight::for_one_term + boost_by (tantivy), computed HERE from the
+       * split's own statistics, not read from the plan: idf = ln(1 + (N - n + 0.5) / (n + 0.5)), weight =
+       * idf * (1 + K1) * boost, all f32. (The plan's bm25_weight field is the product's; a mismatch shows
+       * up as a score difference in every parity test.) */
+      {
+        float nn = (float)t->doc_freq, N = (float)im->hdr->num_docs;
+        float idf = logf(1.0f + ((N - nn) + 0.5f) / (nn + 0.5f));
+        s->weight = idf * (1.0f + 1.2f) * n->boost;
+      }
       s->fieldnorms = (f->flags & QW_FIELD_HAS_FIELDNORMS) ? im->data + f->fieldnorm_off : NULL;
       s->cache = bm25_cache(a, im, f);
       if (!s->fieldnorms) {
@@ -444,7 +452,7 @@ static void topkc_push(TopKC* t, const OHit* x) {
 /* Dense-cell restatement of tantivy's segment aggregation collectors for the shapes the plan
  * supports (terms / histogram / date_histogram / range buckets, stats-family metrics; semantics
  * per docs/reference/aggregation.md:140-560 and SURVEY.md Appendix A.6). */
-typedef struct { const QwAggNode* nodes; uint32_t n; uint64_t* cell_off; QwAggCell* cells; const OImg* im; } Aggs;
+typedef struct { const QwAggNode* nodes; uint32_t n; uint64_t* cell_off; QwAggCell* cells; const OImg* im; uint64_t geometry_errors; } Aggs;
 
 static void agg_collect(Aggs* A, uint32_t ni, uint32_t doc, uint64_t parent_cell) {
   const QwAggNode* g = &A->nodes[ni];
@@ -488,6 +496,7 @@ static void agg_collect(Aggs* A, uint32_t ni, uint32_t doc, uint64_t parent_cell
     uint64_t raw = o_col_raw(A->im, col, i);
     uint64_t m = col->min_value + col->gcd * raw;
     if (g->kind == QW_AGG_TERMS) {
+      if (raw >= g->num_buckets - (g->has_missing ? 1u : 0u)) { A->geometry_errors++; continue; }
       uint64_t cell = parent_cell * g->num_buckets + raw;
       base[cell].count++;
       for (uint32_t c = 0; c < g->num_children; c++) agg_collect(A, g->first_child + c, doc, cell);
@@ -496,7 +505,9 @@ static void agg_collect(Aggs* A, uint32_t ni, uint32_t doc, uint64_t parent_cell
       if (g->has_bounds && !(val >= g->bound_min && val <= g->bound_max)) continue;
       double pos = floor((val - g->offset) / g->interval);
       int64_t idx = (int64_t)pos - g->base_pos;
-      if (idx < 0 || idx >= (int64_t)g->num_buckets) continue;
+      /* the dense bucket range [base_pos, base_pos + num_buckets) is the product's cell LAYOUT; a value
+       * inside the hard bounds that falls outside it means the layout is wrong: reported as an error */
+      if (idx < 0 || idx >= (int64_t)g->num_buckets) { A->geometry_errors++; continue; }
       uint64_t cell = parent_cell * g->num_buckets + (uint64_t)idx;
       base[cell].count++;
       for (uint32_t c = 0; c < g->num_children; c++) agg_collect(A, g->first_child + c, doc, cell);
@@ -614,7 +625,189 @@ int qwo_split_search(const uint8_t* img, uint64_t img_len, const uint8_t* plan, 
   if (postings_visited) *postings_visited = visited;
   free(heap.h); free(tk.buf); free(A.cell_off);
   arena_free(&arena);
+  return A.geometry_errors ? -4 : 0;  /* -4: a value fell outside the plan's dense bucket layout */
+}
+
+/* ------------------------------------------------------------------ CPU baseline fast path ---- */
+/* What bench.py times as the reference's CPU algorithm for the BM25-union shape: the same arithmetic
+ * as qwo_split_search, organised the way tantivy runs it — BitPacker4x blocks unpacked four lanes at a
+ * time (SSE2 through GCC vector types) and a BufferedUnionScorer-style 4096-doc horizon (bitset + f32
+ * accumulator, scorers folded in clause order, matches swept in doc order) feeding the binary-heap TopK —
+ * instead of the doc-at-a-time min-scan above. tests/test_oracle_goldens.py checks that both paths
+ * return identical hits, scores and counts. Plans that are not a pure OR of scored terms ranked by
+ * _score (no search_after, no aggregations) fall back to qwo_split_search. */
+typedef uint32_t v4u __attribute__((vector_size(16)));
+static void o_unpack_4x_simd(const uint8_t* p, uint32_t bits, uint32_t* out) {
+  if (bits == 0) { memset(out, 0, 4 * QW_BLOCK_LEN); return; }
+  const uint32_t m = bits == 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+  const v4u mask = {m, m, m, m};
+  for (uint32_t k = 0; k < 32; k++) {
+    const uint32_t bitpos = k * bits, wi = bitpos >> 5, sh = bitpos & 31;
+    v4u lo, hi;
+    memcpy(&lo, p + 16u * wi, 16);
+    v4u v = lo >> sh;
+    if (sh + bits > 32) { memcpy(&hi, p + 16u * (wi + 1), 16); v |= hi << (32 - sh); }
+    v &= mask;
+    memcpy(out + 4 * k, &v, 16);
+  }
+}
+typedef struct {
+  const QwSkip* skips; const uint8_t* tdata; const uint8_t* fieldnorms;
+  uint32_t nblocks, blk, pos, cnt, has_tf, doc;
+  float weight, cache[256];
+  uint32_t docs[QW_BLOCK_LEN], tfs[QW_BLOCK_LEN];
+} FTerm;
+static void fterm_load(FTerm* t, uint64_t* visited) {
+  const QwSkip* sk = &t->skips[t->blk];
+  uint32_t deltas[QW_BLOCK_LEN];
+  o_unpack_4x_simd(t->tdata + sk->byte_off + 16u, sk->doc_bits, deltas);
+  uint32_t prev = sk->prev_last_doc;
+  for (uint32_t i = 0; i < sk->count; i++) { prev = prev + deltas[i] + 1; t->docs[i] = prev; }
+  if (t->has_tf) o_unpack_4x_simd(t->tdata + sk->byte_off + 16u + 16u * sk->doc_bits, sk->tf_bits, t->tfs);
+  t->cnt = sk->count; t->pos = 0; t->doc = t->docs[0];
+  *visited += sk->count;
+}
+#define QWO_HORIZON 4096u /* tantivy BufferedUnionScorer: 64 words of 64 docs */
+static int fast_union_eligible(const QwPlanHeader* ph, const QwPlanNode* nodes) {
+  if (!ph->scoring || ph->max_hits == 0 || ph->num_aggs || ph->search_after.present) return 0;
+  if (ph->sort[0].kind != QW_SORT_SCORE || ph->sort[0].order != QW_ORDER_DESC || ph->sort[1].kind != QW_SORT_NONE) return 0;
+  if (nodes[0].kind != QW_NODE_BOOL || nodes[0].num_children == 0 || nodes[0].num_children > 64) return 0;
+  if (nodes[0].min_should_match != 0xFFFFFFFFu && nodes[0].min_should_match > 1) return 0;
+  for (uint32_t c = 0; c < nodes[0].num_children; c++) {
+    const QwPlanNode* n = &nodes[nodes[0].first_child + c];
+    if (n->kind != QW_NODE_TERM || n->occur != QW_OCCUR_SHOULD) return 0;
+  }
+  return 1;
+}
+int qwo_split_search_fast(const uint8_t* img, uint64_t img_len, const uint8_t* plan, uint64_t plan_len,
+                          QwHit* hits_out, uint32_t* n_hits_out, uint64_t* num_hits_out,
+                          QwAggCell* cells_out, uint64_t cells_cap, uint64_t* postings_visited) {
+  OImg im;
+  if (oimg_open(&im, img, img_len)) return -1;
+  if (plan_len < sizeof(QwPlanHeader)) return -2;
+  const QwPlanHeader* ph = (const QwPlanHeader*)plan;
+  if (ph->magic != QW_PLAN_MAGIC) return -2;
+  const QwPlanNode* nodes = (const QwPlanNode*)(plan + sizeof(QwPlanHeader));
+  if (!fast_union_eligible(ph, nodes))
+    return qwo_split_search(img, img_len, plan, plan_len, hits_out, n_hits_out, num_hits_out, cells_out, cells_cap, postings_visited);
+  const uint32_t nt = nodes[0].num_children, N = im.hdr->num_docs, K = ph->max_hits;
+  FTerm* T = (FTerm*)calloc(nt, sizeof(FTerm));
+  uint64_t visited = 0;
+  uint32_t live = 0;
+  for (uint32_t c = 0; c < nt; c++) {
+    const QwPlanNode* n = &nodes[nodes[0].first_child + c];
+    FTerm* t = &T[c];
+    t->doc = QW_TERMINATED;
+    if (n->term_ord == 0xFFFFFFFFu) continue;
+    const QwImgTerm* it = &im.terms[n->term_ord];
+    const QwImgField* f = &im.fields[it->field_id];
+    t->skips = (const QwSkip*)(im.data + it->skip_off);
+    t->tdata = im.data + it->data_off;
+    t->nblocks = it->num_blocks;
+    t->has_tf = (f->flags & QW_FIELD_HAS_FREQS) != 0;
+    t->fieldnorms = (f->flags & QW_FIELD_HAS_FIELDNORMS) ? im.data + f->fieldnorm_off : NULL;
+    float nn = (float)it->doc_freq, Nf = (float)N;
+    t->weight = logf(1.0f + ((Nf - nn) + 0.5f) / (nn + 0.5f)) * (1.0f + 1.2f) * n->boost;
+    float avg = (float)f->total_num_tokens / (float)N;
+    for (uint32_t id = 0; id < 256; id++) t->cache[id] = 1.2f * (1.0f - 0.75f + 0.75f * (float)o_id_to_fieldnorm(id) / avg);
+    if (!t->fieldnorms) t->cache[0] = 1.2f * (1.0f - 0.75f + 0.75f * 1.0f / avg);
+    if (t->nblocks) { fterm_load(t, &visited); live++; }
+  }
+  Heap heap; memset(&heap, 0, sizeof heap);
+  heap.h = (OHit*)malloc((size_t)K * sizeof(OHit)); heap.k = K;
+  Orders ord = { QW_ORDER_DESC, QW_ORDER_DESC };
+  heap.o = ord;
+  float* acc = (float*)calloc(QWO_HORIZON, sizeof(float));
+  uint64_t bits[QWO_HORIZON / 64];
+  uint64_t num_hits = 0;
+  while (live) {
+    uint32_t base = QW_TERMINATED;
+    for (uint32_t c = 0; c < nt; c++) if (T[c].doc < base) base = T[c].doc;
+    if (base == QW_TERMINATED) break;
+    memset(bits, 0, sizeof bits);
+    const uint32_t end = base + QWO_HORIZON;  /* (docs < 2^31: no wrap) */
+    for (uint32_t c = 0; c < nt; c++) {  /* clause order = the order of the f32 sums */
+      FTerm* t = &T[c];
+      while (t->doc < end) {
+        const uint32_t i = t->doc - base;
+        const float tf = t->has_tf ? (float)t->tfs[t->pos] : 1.0f;
+        const float norm = t->cache[t->fieldnorms ? t->fieldnorms[t->doc] : 0];
+        acc[i] += t->weight * (tf / (tf + norm));
+        bits[i >> 6] |= 1ull << (i & 63);
+        if (++t->pos >= t->cnt) {
+          if (++t->blk >= t->nblocks) { t->doc = QW_TERMINATED; live--; break; }
+          fterm_load(t, &visited);
+        } else t->doc = t->docs[t->pos];
+      }
+    }
+    for (uint32_t w = 0; w < QWO_HORIZON / 64; w++) {
+      uint64_t m = bits[w];
+      while (m) {
+        const uint32_t i = 64 * w + (uint32_t)__builtin_ctzll(m);
+        m &= m - 1;
+        OHit h; memset(&h, 0, sizeof h);
+        h.doc = base + i; h.score = acc[i]; h.v1 = o_f64_to_u64((double)h.score); h.flags = 1;
+        acc[i] = 0.0f;
+        num_hits++;
+        heap_add(&heap, &h);
+      }
+    }
+  }
+  t_orders = &ord;
+  qsort(heap.h, heap.n, sizeof(OHit), qsort_desc);
+  for (uint32_t i = 0; i < heap.n; i++) {
+    hits_out[i].v1 = heap.h[i].v1; hits_out[i].v2 = 0; hits_out[i].doc_id = heap.h[i].doc;
+    hits_out[i].flags = heap.h[i].flags; hits_out[i].score = heap.h[i].score; hits_out[i].reserved = 0;
+  }
+  *n_hits_out = heap.n;
+  *num_hits_out = num_hits;
+  if (postings_visited) *postings_visited = visited;
+  free(heap.h); free(acc); free(T);
   return 0;
+}
+
+/* The same search over many (split, plan) pairs from a pool of C threads (one pair at a time per thread):
+ * the CPU reference arm of bench.py. Returns 0, or the first error; sums in totals[0..1] = hits, postings. */
+#include <pthread.h>
+typedef struct {
+  const uint8_t* const* imgs; const uint64_t* img_lens; const uint8_t* const* plans; const uint64_t* plan_lens;
+  uint32_t n, next, fast; int err; uint64_t hits, postings; pthread_mutex_t mu;
+} ManyCtx;
+static void* many_worker(void* arg) {
+  ManyCtx* c = (ManyCtx*)arg;
+  QwHit* hits = NULL; uint32_t cap = 0;
+  for (;;) {
+    pthread_mutex_lock(&c->mu);
+    uint32_t i = c->next < c->n ? c->next++ : 0xFFFFFFFFu;
+    pthread_mutex_unlock(&c->mu);
+    if (i == 0xFFFFFFFFu) break;
+    const QwPlanHeader* ph = (const QwPlanHeader*)c->plans[i];
+    uint32_t k = ph->max_hits ? ph->max_hits : 1;
+    if (k > cap) { free(hits); hits = (QwHit*)malloc((size_t)k * sizeof(QwHit)); cap = k; }
+    uint32_t nh = 0; uint64_t total = 0, vis = 0;
+    QwAggCell dummy;
+    int rc = (c->fast ? qwo_split_search_fast : qwo_split_search)(c->imgs[i], c->img_lens[i], c->plans[i], c->plan_lens[i], hits, &nh, &total, &dummy, 0, &vis);
+    pthread_mutex_lock(&c->mu);
+    if (rc && !c->err) c->err = rc;
+    c->hits += total; c->postings += vis;
+    pthread_mutex_unlock(&c->mu);
+  }
+  free(hits);
+  return NULL;
+}
+int qwo_search_many(const uint8_t* const* imgs, const uint64_t* img_lens, const uint8_t* const* plans, const uint64_t* plan_lens,
+                    uint32_t n, uint32_t threads, uint32_t fast, uint64_t* totals) {
+  ManyCtx c; memset(&c, 0, sizeof c);
+  c.imgs = imgs; c.img_lens = img_lens; c.plans = plans; c.plan_lens = plan_lens; c.n = n; c.fast = fast;
+  pthread_mutex_init(&c.mu, NULL);
+  if (threads == 0) threads = 1;
+  if (threads > 256) threads = 256;
+  pthread_t th[256];
+  for (uint32_t t = 0; t < threads; t++) pthread_create(&th[t], NULL, many_worker, &c);
+  for (uint32_t t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  pthread_mutex_destroy(&c.mu);
+  if (totals) { totals[0] = c.hits; totals[1] = c.postings; }
+  return c.err;
 }
 
 /* Posting-list decode only (for format round-trip tests): writes up to cap (doc, tf) pairs. */

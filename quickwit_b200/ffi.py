@@ -199,6 +199,38 @@ def lib() -> C.CDLL:
     return L
 
 
+_img_lib = None
+
+
+def img_lib():
+    """libqwimg.so: the host-only split-image writer (same qwgpu_imgb_* / qwgpu_synth_split entry points as
+    libqwgpu.so, built from the same sources, no CUDA). Corpus generation never maps the GPU library."""
+    global _img_lib
+    if _img_lib is None:
+        L = C.CDLL(os.environ.get("QWIMG_LIB") or os.path.join(_HERE, "libqwimg.so"))
+        vp, cp, u32, u64 = C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint64
+        for name, argtypes, restype in [
+                ("qwgpu_last_error", [], cp), ("qwgpu_buf_free", [vp], None),
+                ("qwgpu_imgb_new", [u32], vp), ("qwgpu_imgb_free", [vp], None),
+                ("qwgpu_imgb_add_field", [vp, cp, u32, u32, vp, u64], C.c_int),
+                ("qwgpu_imgb_add_term", [vp, u32, vp, u32, vp, vp, u32], C.c_int),
+                ("qwgpu_imgb_add_column", [vp, cp, u32, u32, vp, u64, vp, vp, vp, u32], C.c_int),
+                ("qwgpu_imgb_finish", [vp, C.POINTER(vp), C.POINTER(u64)], C.c_int),
+                ("qwgpu_synth_split", [C.POINTER(SynthSpec), C.POINTER(vp), C.POINTER(u64)], C.c_int),
+                ("qwgpu_bm25_weight", [u64, u64, C.c_float], C.c_float),
+                ("qwgpu_fieldnorm_to_id", [u32], C.c_uint8), ("qwgpu_id_to_fieldnorm", [C.c_uint8], u32)]:
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = argtypes, restype
+        _img_lib = L
+    return _img_lib
+
+
+def img_check(rc: int) -> int:
+    if rc < 0:
+        raise QwGpuError(rc, img_lib().qwgpu_last_error().decode("utf-8", "replace"))
+    return rc
+
+
 def check(rc: int) -> int:
     if rc < 0:
         raise QwGpuError(rc, lib().qwgpu_last_error().decode("utf-8", "replace"))

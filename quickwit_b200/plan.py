@@ -19,7 +19,7 @@ from .splitgen import SplitImage
 def bm25_weight(doc_freq: int, num_docs: int, boost: float = 1.0) -> float:
     """tantivy Bm25Weight: idf * (1 + K1) * boost in f32 — computed by the
     C++ host (`qwgpu_bm25_weight`) so hand-built plans carry the exact weights compiled plans do."""
-    return float(ffi.lib().qwgpu_bm25_weight(doc_freq, num_docs, boost))
+    return float(ffi.img_lib().qwgpu_bm25_weight(doc_freq, num_docs, boost))
 
 
 class Node:

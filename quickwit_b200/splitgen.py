@@ -178,13 +178,13 @@ def tokenize(text: str, tokenizer: str) -> List[str]:
 
 class _Builder:
     def __init__(self, num_docs: int):
-        self.L = ffi.lib()
+        self.L = ffi.img_lib()
         self.b = self.L.qwgpu_imgb_new(num_docs)
         self.num_docs = num_docs
 
     def add_field(self, name, flags, tok, fieldnorm_ids: Optional[np.ndarray], total_tokens: int) -> int:
         p = fieldnorm_ids.ctypes.data if fieldnorm_ids is not None else None
-        return ffi.check(self.L.qwgpu_imgb_add_field(self.b, name.encode(), flags, tok, p, total_tokens))
+        return ffi.img_check(self.L.qwgpu_imgb_add_field(self.b, name.encode(), flags, tok, p, total_tokens))
 
     def add_term(self, field_id: int, term: bytes, docs: np.ndarray, tfs: Optional[np.ndarray]):
         docs = np.ascontiguousarray(docs, dtype=np.uint32)
@@ -193,7 +193,7 @@ class _Builder:
             tfs = np.ascontiguousarray(tfs, dtype=np.uint32)
             tfp = tfs.ctypes.data
         buf = C.create_string_buffer(term, len(term))
-        ffi.check(self.L.qwgpu_imgb_add_term(self.b, field_id, C.addressof(buf), len(term),
+        ffi.img_check(self.L.qwgpu_imgb_add_term(self.b, field_id, C.addressof(buf), len(term),
                                              docs.ctypes.data, tfp, len(docs)))
 
     def add_column(self, name: str, ctype: int, card: int, values: np.ndarray,
@@ -213,13 +213,13 @@ class _Builder:
             dbuf = C.create_string_buffer(blob, max(len(blob), 1))
             dbytes, doffs = C.addressof(dbuf), offs.ctypes.data
             self._keep = (dbuf, offs)
-        ffi.check(self.L.qwgpu_imgb_add_column(self.b, name.encode(), ctype, card, values.ctypes.data,
+        ffi.img_check(self.L.qwgpu_imgb_add_column(self.b, name.encode(), ctype, card, values.ctypes.data,
                                                len(values), ip, dbytes, doffs, dn))
 
     def finish(self, split_id: str) -> SplitImage:
         out, n = C.c_void_p(), C.c_uint64()
         try:
-            ffi.check(self.L.qwgpu_imgb_finish(self.b, C.byref(out), C.byref(n)))
+            ffi.img_check(self.L.qwgpu_imgb_finish(self.b, C.byref(out), C.byref(n)))
         finally:
             self.L.qwgpu_imgb_free(self.b)
             self.b = None
@@ -320,7 +320,7 @@ def build_split(docs: Sequence[Dict[str, Any]], doc_mapping: Dict[str, Any], spl
                         for t in toks:
                             postings.setdefault(t.encode(), {}).setdefault(d, 0)
                             postings[t.encode()][d] += 1
-                L = ffi.lib()
+                L = ffi.img_lib()
                 fn = np.array([L.qwgpu_fieldnorm_to_id(int(x)) for x in lengths], dtype=np.uint8) if fieldnorms else None
                 fid = b.add_field(name, flags, ffi.TOK_RAW if tokenizer == "raw" else ffi.TOK_DEFAULT, fn, int(lengths.sum()))
                 for term in sorted(postings):
@@ -345,12 +345,12 @@ def synth_split(num_docs: int, split_ord: int, term_fracs: Iterable[float], seed
                 ts_start_secs: int = 1_700_000_000, ts_span_secs: int = 86_400, num_tenants: int = 100,
                 split_id: Optional[str] = None) -> SplitImage:
     """Synthetic hdfs-logs-shaped split; generation is done by the C++ writer."""
-    L = ffi.lib()
+    L = ffi.img_lib()
     fr = np.ascontiguousarray(list(term_fracs), dtype=np.float64)
     spec = ffi.SynthSpec(num_docs, split_ord, seed, len(fr), fr.ctypes.data_as(C.POINTER(C.c_double)),
                          ts_start_secs, ts_span_secs, num_tenants)
     out, n = C.c_void_p(), C.c_uint64()
-    ffi.check(L.qwgpu_synth_split(C.byref(spec), C.byref(out), C.byref(n)))
+    ffi.img_check(L.qwgpu_synth_split(C.byref(spec), C.byref(out), C.byref(n)))
     arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
     L.qwgpu_buf_free(out)
     return SplitImage(arr, split_id or f"split-{split_ord:04d}")

@@ -360,3 +360,26 @@ def test_synthetic_corpus_fixture():
     r = _O.split_search(img, pl)
     assert r.num_hits == want["num_hits"]
     assert [[int(h[0]), float(np.float32(h[4]))] for h in r.hits] == want["hits"]
+
+
+def test_cpu_baseline_fast_path_equals_the_oracle():
+    """The windowed-union / SIMD-unpack organisation that bench.py times as the CPU baseline returns exactly
+    what the doc-at-a-time oracle returns (doc ids, f32 score bits, hit counts, postings visited), also from
+    the C thread pool."""
+    from quickwit_b200 import plan as P
+    img = S.synth_split(60_000, 3, [0.2, 0.1, 0.05, 0.02, 0.01, 0.004, 0.0008], split_id="fast-0")
+    plans = []
+    for terms, k in [(range(7), 100), ([0], 10), ([6, 5, 4], 1000), ([1, 3, 5], 37)]:
+        root = P.bool_([P.term(img, "body", f"t{i}", occur=ffi.OCCUR_SHOULD) for i in terms] + [P.term(img, "body", "absent", occur=ffi.OCCUR_SHOULD)])
+        plans.append(P.make_plan(root, k, [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)]))
+    for pl in plans:
+        a, b = O.split_search(img, pl), O.split_search(img, pl, fast=True)
+        assert (a.num_hits, a.postings_visited) == (b.num_hits, b.postings_visited)
+        assert [(h[0], h[1], h[2]) for h in a.hits] == [(h[0], h[1], h[2]) for h in b.hits]
+        assert np.array_equal(np.array([h[4] for h in a.hits], np.float32).view(np.uint32), np.array([h[4] for h in b.hits], np.float32).view(np.uint32))
+    many = O.ManySearch([img] * len(plans), plans)
+    want = (sum(O.split_search(img, pl).num_hits for pl in plans), sum(O.split_search(img, pl).postings_visited for pl in plans))
+    assert many.run(threads=3, fast=True) == want and many.run(threads=2, fast=False) == want
+    # a shape the fast path does not cover falls back to the oracle proper
+    pl = P.make_plan(P.bool_([P.term(img, "body", "t0"), P.term(img, "body", "t1")]), 10, [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)])
+    assert O.split_search(img, pl, fast=True).hits == O.split_search(img, pl).hits
