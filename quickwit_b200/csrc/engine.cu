@@ -615,7 +615,8 @@ static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
 }
 
 void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
-                    const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats) {
+                    const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats,
+                    const MergeSpec* merge, std::vector<MergedHit>* merged) {
   const uint32_t n_in = (uint32_t)sp.size();
   outs.assign(n_in, SplitOutput());
   static const bool trace = getenv("QWGPU_TRACE") != nullptr;  // host phase timings on stderr
@@ -755,17 +756,25 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
-         o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), blob_bytes = al(o_bounds + (size_t)tot_bounds * 8);
+         o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), o_rank = al(o_bounds + (size_t)tot_bounds * 8),
+         blob_bytes = al(o_rank + (size_t)n * 4);
+  // device-side cross-split merge: the per-split hit lists stay in scratch, only the merged top-K comes back
+  const bool do_merge = merge && merged && merge->k > 0 && any_topk && merge->rank.size() == n_in;
+  uint32_t kmax = 1;
+  for (auto& L : low) kmax = std::max(kmax, L.P.max_hits);
   // scratch: thresholds, histograms, candidates
   size_t s_thr = 0, s_hist = al(s_thr + n * sizeof(DThresh)), s_state = al(s_hist + (size_t)n * QW_HIST_BINS * 4),
          s_ctr = al(s_state + (size_t)n * 4), s_wmax = al(s_ctr + 64 * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
-         scratch_bytes = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0));
+         s_hits = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0)),
+         s_cut = al(s_hits + (do_merge ? (size_t)n * kmax * sizeof(QwHit) : 0)),
+         scratch_bytes = al(s_cut + (size_t)n * 4);
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
   out_off[0] = 0;
   for (uint32_t i = 0; i < n; i++)
-    out_off[i + 1] = al(out_off[i] + 32 + (size_t)low[i].P.max_hits * sizeof(QwHit) + (size_t)low[i].P.n_cells * sizeof(QwAggCell));
-  size_t out_bytes = out_off[n];
+    out_off[i + 1] = al(out_off[i] + 32 + (do_merge ? 0 : (size_t)low[i].P.max_hits * sizeof(QwHit)) + (size_t)low[i].P.n_cells * sizeof(QwAggCell));
+  const size_t o_merged = out_off[n];  // [u32 count, pad][DMergedHit x k]
+  size_t out_bytes = do_merge ? al(o_merged + 16 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : out_off[n];
 
   CallSlot* slot = nullptr;
   {
@@ -792,8 +801,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     P.out_num_hits = (uint64_t)ob;            // [0] hits, [1] eligible
     P.out_nhits = (uint64_t)(ob + 16);
     P.out_cand_count = (uint64_t)(ob + 20);
-    P.out_hits = (uint64_t)(ob + 32);
-    P.out_cells = (uint64_t)(ob + 32 + (size_t)P.max_hits * sizeof(QwHit));
+    P.out_hits = do_merge ? (uint64_t)(slot->d_scratch + s_hits + (size_t)i * kmax * sizeof(QwHit)) : (uint64_t)(ob + 32);
+    P.out_cells = (uint64_t)(ob + 32 + (do_merge ? 0 : (size_t)P.max_hits * sizeof(QwHit)));
     P.out_hist = (uint64_t)(slot->d_scratch + s_hist + (size_t)i * QW_HIST_BINS * 4);
     P.out_cands = (uint64_t)(slot->d_scratch + s_cand + (size_t)i * QW_CAND_CAP * 24);
     memcpy(slot->h_blob + o_plans + i * sizeof(DSplitPlan), &P, sizeof P);
@@ -805,6 +814,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     if (P.n_aggs) memcpy(slot->h_blob + o_aggs + P.agg_base * sizeof(DAgg), low[i].aggs.data(), P.n_aggs * sizeof(DAgg));
     if (!low[i].bounds.empty()) memcpy(slot->h_blob + o_bounds + (size_t)low[i].bounds_base * 8, low[i].bounds.data(), low[i].bounds.size() * 8);
   }
+  if (do_merge) for (uint32_t i = 0; i < n; i++) ((uint32_t*)(slot->h_blob + o_rank))[i] = merge->rank[idx[i]];
   memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
@@ -896,6 +906,14 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     launch_window(qwk::MODE_COLLECT, false, 0, 0, flags);
     CUDA_CHECK(cudaEventRecord(slot->ev3, st));
     if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans, kp.cols); stats.launches++; }
+    if (do_merge) {
+      uint32_t* d_cut = (uint32_t*)(slot->d_scratch + s_cut);
+      qwk::k_merge_prep<<<1, 1024, 0, st>>>(kp.plans, (const uint32_t*)(slot->d_blob + o_rank), n, merge->k, merge->order1, merge->order2, d_cut);
+      const uint64_t threads = (uint64_t)n * kmax * 32;  // one warp per hit (warps of pruned hits leave at once)
+      qwk::k_merge<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(kp.plans, (const uint32_t*)(slot->d_blob + o_rank), d_cut, n, kmax, merge->k, merge->order1, merge->order2,
+                                                          (qwk::DMergedHit*)(slot->d_out + o_merged + 16), (uint32_t*)(slot->d_out + o_merged));
+      stats.launches += 2;
+    }
     CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     stats.d2h_bytes += out_bytes;
   };
@@ -999,9 +1017,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     const uint8_t* ob = slot->h_out + out_off[i];
     o.num_hits = ((const uint64_t*)ob)[0];
     uint32_t nh = *(const uint32_t*)(ob + 16);
-    o.hits.assign((const QwHit*)(ob + 32), (const QwHit*)(ob + 32) + nh);
-    if (P.key.kind[0] == QW_SORT_DOCID) for (auto& h : o.hits) { h.flags &= ~1u; h.v1 = 0; }
-    const QwAggCell* c = (const QwAggCell*)(ob + 32 + (size_t)P.max_hits * sizeof(QwHit));
+    if (!do_merge) {
+      o.hits.assign((const QwHit*)(ob + 32), (const QwHit*)(ob + 32) + nh);
+      if (P.key.kind[0] == QW_SORT_DOCID) for (auto& h : o.hits) { h.flags &= ~1u; h.v1 = 0; }
+    }
+    const QwAggCell* c = (const QwAggCell*)(ob + 32 + (do_merge ? 0 : (size_t)P.max_hits * sizeof(QwHit)));
     o.cells.assign(c, c + P.n_cells);
     for (auto& cell : o.cells) cell.min_mapped = ~cell.min_mapped;  // device keeps max(~m); see agg_stats
     o.postings_scored = low[i].postings;
@@ -1021,6 +1041,18 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     const QwAggNode* an = (const QwAggNode*)(plans[idx[i]] + sizeof(QwPlanHeader) + (size_t)ph->num_nodes * sizeof(QwPlanNode));
     for (uint32_t a = 0; a < ph->num_aggs; a++) if (an[a].column != 0xFFFFFFFFu) bytes += col_bytes(an[a].column, o.num_hits);
     o.algorithmic_bytes = bytes;
+  }
+  if (do_merge) {
+    const uint32_t nm = *(const uint32_t*)(slot->h_out + o_merged);
+    const qwk::DMergedHit* mh = (const qwk::DMergedHit*)(slot->h_out + o_merged + 16);
+    merged->resize(nm);
+    for (uint32_t j = 0; j < nm; j++) {
+      MergedHit& m = (*merged)[j];
+      m.hit = mh[j].hit;
+      m.split = idx[mh[j].split];
+      m.pad = 0;
+      if (low[mh[j].split].P.key.kind[0] == QW_SORT_DOCID) { m.hit.flags &= ~1u; m.hit.v1 = 0; }
+    }
   }
   if (trace) {
     auto us = [](tclock::time_point a, tclock::time_point b) { return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count(); };

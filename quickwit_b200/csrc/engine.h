@@ -31,6 +31,19 @@ struct SplitOutput {
   uint64_t postings_scored = 0;
   uint64_t algorithmic_bytes = 0;
 };
+// Cross-split merge on the device (leaf-level merge of collector.rs:1195-1313 for seam A): when given, the
+// per-split top-K lists never leave the GPU; the batch returns its best `k` hits in the leaf's total order
+// (sort values in the request's directions, then split id, then doc id in the direction of the first key).
+struct MergeSpec {
+  uint32_t k = 0;
+  uint32_t order1 = QW_ORDER_DESC, order2 = QW_ORDER_DESC;
+  std::vector<uint32_t> rank;  // per input split: rank of its split id among the batch's split ids
+};
+struct MergedHit {
+  QwHit hit;
+  uint32_t split;  // index into the caller's split array
+  uint32_t pad;
+};
 struct BatchStats {
   float gpu_time_us = 0;
   float main_kernel_us = 0;
@@ -55,7 +68,8 @@ struct Engine {
   std::shared_ptr<SplitDev> find(const std::string& id);
   // Runs plan[i] on splits[i]; fills outs[i] (status per split). Throws only on whole-call errors.
   void search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
-              const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats);
+              const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats,
+              const MergeSpec* merge = nullptr, std::vector<MergedHit>* merged = nullptr);
 };
 
 // plan validation helper shared with the compiler: total agg cells + per-node bases

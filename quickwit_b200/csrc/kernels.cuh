@@ -1700,4 +1700,122 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const 
   if (tid == 0) *(uint32_t*)P.out_nhits = out_n;
 }
 
+
+// Leaf-level merge on the device (IncrementalCollector / top_k_partial_hits, quickwit-search/src/
+// collector.rs:1195-1313, 980-992): the per-split lists written by k_select are sorted best-first; a hit's
+// position in the merged order is the number of hits of ALL lists that beat it — its own index plus one
+// binary search per other list — so every hit finds its slot independently and the best K land in
+// out[0..K) already sorted. Order = PartialHitSortingKey: (sort value 1, sort value 2) in the request's
+// directions with None last, then (split id rank, doc id) in the direction of the first key
+// (collector.rs:1120-1153); keys are unique, so the ranks are a permutation.
+struct MKey {
+  uint64_t v1, v2, tie;
+  uint32_t has;  // has1 << 1 | has2 (None is last in both directions)
+};
+__device__ __forceinline__ MKey merge_key(const QwHit& h, uint32_t rank, uint32_t o1, uint32_t o2) {
+  MKey k;
+  const uint32_t has1 = h.flags & 1u, has2 = (h.flags >> 1) & 1u;
+  k.has = has1 << 1 | has2;
+  k.v1 = has1 ? (o1 == QW_ORDER_DESC ? h.v1 : ~h.v1) : 0ull;
+  k.v2 = has2 ? (o2 == QW_ORDER_DESC ? h.v2 : ~h.v2) : 0ull;
+  const uint64_t t = ((uint64_t)rank << 32) | h.doc_id;
+  k.tie = o1 == QW_ORDER_DESC ? t : ~t;
+  return k;
+}
+__device__ __forceinline__ bool mkey_gt(const MKey& a, const MKey& b) {  // a beats b
+  const uint32_t a1 = a.has >> 1, b1 = b.has >> 1;
+  if (a1 != b1) return a1 > b1;
+  if (a.v1 != b.v1) return a.v1 > b.v1;
+  const uint32_t a2 = a.has & 1u, b2 = b.has & 1u;
+  if (a2 != b2) return a2 > b2;
+  if (a.v2 != b.v2) return a.v2 > b.v2;
+  return a.tie > b.tie;
+}
+struct DMergedHit {
+  QwHit hit;
+  uint32_t split, pad;
+};
+// Pruning before the merge: with m = ceil(K / #lists), every list holds min(m, len) hits that are at least as
+// good as its own m-th hit, so if those add up to K the K-th best hit overall is at least as good as the WORST of
+// the lists' m-th hits (tau) and only hits >= tau can reach the merged top-K. cut[s] = number of such hits in
+// list s (all of the list when the short lists leave fewer than K guaranteed hits). One block, warp = list.
+__global__ void __launch_bounds__(1024) k_merge_prep(const DSplitPlan* plans, const uint32_t* rank, uint32_t n_splits, uint32_t K,
+                                                      uint32_t o1, uint32_t o2, uint32_t* cut) {
+  __shared__ MKey s_key[64];
+  __shared__ uint32_t s_have[64];
+  __shared__ MKey s_tau;
+  __shared__ uint32_t s_prune;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t nonempty = 0;
+  for (uint32_t s = 0; s < n_splits; s++) nonempty += *(const uint32_t*)plans[s].out_nhits ? 1u : 0u;
+  const uint32_t m = nonempty ? (K + nonempty - 1) / nonempty : 0;
+  if (n_splits > 64) {  // more lists than the shared tables hold: no pruning
+    for (uint32_t s = threadIdx.x; s < n_splits; s += blockDim.x) cut[s] = min(*(const uint32_t*)plans[s].out_nhits, K);
+    return;
+  }
+  for (uint32_t s = warp; s < n_splits; s += nw) {
+    if (lane == 0) {
+      const uint32_t nh = min(*(const uint32_t*)plans[s].out_nhits, K), ms = min(m, nh);
+      s_have[s] = ms;
+      if (ms) s_key[s] = merge_key(((const QwHit*)plans[s].out_hits)[ms - 1], __ldg(rank + s), o1, o2);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t have = 0, first = 1;
+    MKey tau;
+    tau.v1 = tau.v2 = tau.tie = 0; tau.has = 0;
+    for (uint32_t s = 0; s < n_splits; s++) {
+      have += s_have[s];
+      if (s_have[s] && (first || mkey_gt(tau, s_key[s]))) { tau = s_key[s]; first = 0; }
+    }
+    s_tau = tau;
+    s_prune = have >= K ? 1u : 0u;
+  }
+  __syncthreads();
+  const MKey tau = s_tau;
+  for (uint32_t s = warp; s < n_splits; s += nw) {
+    if (lane != 0) continue;
+    const uint32_t nh = min(*(const uint32_t*)plans[s].out_nhits, K);
+    uint32_t lo = 0, hi = nh;  // first index whose hit is worse than tau
+    if (s_prune) {
+      const QwHit* L = (const QwHit*)plans[s].out_hits;
+      const uint32_t rk = __ldg(rank + s);
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (mkey_gt(tau, merge_key(L[mid], rk, o1, o2))) hi = mid; else lo = mid + 1;
+      }
+    } else lo = nh;
+    cut[s] = lo;
+  }
+}
+__global__ void __launch_bounds__(256) k_merge(const DSplitPlan* plans, const uint32_t* rank, const uint32_t* cut, uint32_t n_splits, uint32_t kmax,
+                                               uint32_t K, uint32_t o1, uint32_t o2, DMergedHit* out, uint32_t* out_n) {
+  // one warp per surviving hit; lane = one of the other lists (the binary searches of a hit run side by side)
+  const uint32_t lane = threadIdx.x & 31, e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (e == 0 && lane == 0) {
+    uint64_t total = 0;
+    for (uint32_t s = 0; s < n_splits; s++) total += *(const uint32_t*)plans[s].out_nhits;
+    *out_n = (uint32_t)(total < K ? total : K);
+  }
+  const uint32_t s = e / kmax, i = e % kmax;
+  if (s >= n_splits || i >= __ldg(cut + s)) return;
+  const QwHit mine = ((const QwHit*)plans[s].out_hits)[i];
+  const MKey key = merge_key(mine, __ldg(rank + s), o1, o2);
+  uint32_t r = 0;
+  for (uint32_t s2 = lane; s2 < n_splits; s2 += 32) {
+    if (s2 == s) continue;
+    const QwHit* L = (const QwHit*)plans[s2].out_hits;
+    const uint32_t rk = __ldg(rank + s2);
+    uint32_t lo = 0, hi = __ldg(cut + s2);  // first index whose hit does not beat `key` (hits past the cut never do)
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (mkey_gt(merge_key(L[mid], rk, o1, o2), key)) lo = mid + 1; else hi = mid;
+    }
+    r += lo;
+  }
+  r = __reduce_add_sync(0xFFFFFFFFu, r) + i;
+  if (lane == 0 && r < K) { DMergedHit m; m.hit = mine; m.split = s; m.pad = 0; out[r] = m; }
+}
+
 }  // namespace qwk

@@ -193,9 +193,23 @@ struct LeafRun {
   std::vector<SplitOutput> outs;
   BatchStats st;
   uint64_t wall_us = 0;
+  bool merged_valid = false;       // the engine merged the per-split top-K lists on the device
+  std::vector<MergedHit> merged;   // best-first; .split = index into `jobs`
 };
 
-static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run) {
+static bool same_sort_types(const std::vector<SplitJob>& jobs, const std::vector<size_t>& which) {
+  for (size_t k = 1; k < which.size(); k++) {
+    const CompiledPlan &a = jobs[which[0]].plan, &b = jobs[which[k]].plan;
+    for (int i = 0; i < 2; i++)
+      if (a.header.sort[i].kind != b.header.sort[i].kind || (a.header.sort[i].kind == QW_SORT_COLUMN && a.sort_field_type[i] != b.sort_field_type[i] &&
+                                                              a.header.sort[i].column != 0xFFFFFFFFu && b.header.sort[i].column != 0xFFFFFFFFu))
+        return false;
+  }
+  return true;
+}
+static void sort_orders(const pb::SearchRequest& r, int* o1, int* o2);
+
+static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run, bool want_merged = false) {
   using clock = std::chrono::steady_clock;
   const pb::SearchRequest& sreq = lr.search_request;
   const auto t_compile = clock::now();
@@ -232,7 +246,25 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
   auto t0 = clock::now();
   if (getenv("QWGPU_TRACE"))
     fprintf(stderr, "[qwgpu] compile: %ld us for %zu splits\n", (long)std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_compile).count(), run.jobs.size());
-  if (!devs.empty()) eng.search(devs, plans, lens, run.outs, run.st);
+  static const bool host_merge = getenv("QWGPU_HOST_MERGE") != nullptr;
+  MergeSpec ms;
+  if (want_merged && !host_merge && devs.size() > 1 && sreq.max_hits + sreq.start_offset > 0 && same_sort_types(run.jobs, run.which)) {
+    int o1, o2;
+    sort_orders(sreq, &o1, &o2);
+    ms.k = (uint32_t)(sreq.max_hits + sreq.start_offset);
+    ms.order1 = (uint32_t)o1; ms.order2 = (uint32_t)o2;
+    const size_t n = run.which.size();
+    std::vector<size_t> by_id(n);
+    for (size_t i = 0; i < n; i++) by_id[i] = i;
+    std::sort(by_id.begin(), by_id.end(), [&](size_t a, size_t b) { return run.jobs[run.which[a]].meta.split_id < run.jobs[run.which[b]].meta.split_id; });
+    ms.rank.resize(n);
+    for (size_t r = 0; r < n; r++) ms.rank[by_id[r]] = (uint32_t)r;
+  }
+  if (!devs.empty()) eng.search(devs, plans, lens, run.outs, run.st, ms.k ? &ms : nullptr, ms.k ? &run.merged : nullptr);
+  if (ms.k) {
+    run.merged_valid = true;
+    for (auto& m : run.merged) m.split = (uint32_t)run.which[m.split];
+  }
   run.wall_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t0).count();
 }
 
@@ -344,6 +376,19 @@ static pb::LeafSearchResponse leaf_merge_fast(const pb::SearchRequest& sreq, Lea
   // the merged hits go straight to wire form (no PartialHit temporaries: a split id is a 26-char ULID)
   size_t taken = 0;
   m.encoded_partial_hits.reserve(std::min<size_t>(k, 4096) * 72);
+  if (run.merged_valid) {
+    // the engine already merged on the device (k_merge): same total order, hits arrive best-first
+    for (const MergedHit& mh : run.merged) {
+      if (taken >= k) break;
+      const QwHit& h = mh.hit;
+      pb::SortValue sv1, sv2;
+      if (h.flags & 1) sv1 = typed_sort_value(p0.header.sort[0].kind, sft[0], h.v1);
+      if (h.flags & 2) sv2 = typed_sort_value(p0.header.sort[1].kind, sft[1], h.v2);
+      pb::append_partial_hit(m.encoded_partial_hits, 2, run.jobs[mh.split].meta.split_id, 0, h.doc_id, (h.flags & 1) != 0, sv1, (h.flags & 2) != 0, sv2);
+      taken++;
+    }
+    heap.clear();
+  }
   while (!heap.empty() && taken < k) {
     std::pop_heap(heap.begin(), heap.end());
     size_t s = heap.back().s;
@@ -416,7 +461,7 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
   qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
   auto t_dec = tclock::now();
   qw::LeafRun run;
-  qw::run_leaf_raw(eng, lr, run);
+  qw::run_leaf_raw(eng, lr, run, /*want_merged=*/true);
   auto t_run = tclock::now();
   // the leaf keeps [0, start_offset + max_hits) (root.rs:1775-1777): nothing is drained here
   qw::pb::SearchRequest mreq = lr.search_request;
@@ -435,14 +480,7 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
     run.which.swap(w2);
     run.outs.swap(o2);
   }
-  bool same_types = true;
-  for (size_t k = 1; k < run.which.size(); k++) {
-    const qw::CompiledPlan &a = run.jobs[run.which[0]].plan, &b = run.jobs[run.which[k]].plan;
-    for (int i = 0; i < 2; i++)
-      if (a.header.sort[i].kind != b.header.sort[i].kind || (a.header.sort[i].kind == QW_SORT_COLUMN && a.sort_field_type[i] != b.sort_field_type[i] &&
-                                                              a.header.sort[i].column != 0xFFFFFFFFu && b.header.sort[i].column != 0xFFFFFFFFu))
-        same_types = false;
-  }
+  const bool same_types = run.merged_valid || qw::same_sort_types(run.jobs, run.which);
   qw::pb::LeafSearchResponse merged;
   if (run.which.empty()) {
     if (mreq.aggregation_request && !mreq.aggregation_request->empty())
