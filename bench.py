@@ -368,7 +368,16 @@ def main():
     lreqs = [proto.enc_leaf_search_request(sr, offsets, doc_mapper) for sr in sreqs]
     t_build = time.perf_counter() - t_build
     part_bytes = service.partial_size(sreqs[0]) if world > 1 else 0
-    if world > 1:
+    device_exchange = world > 1 and not os.environ.get("QWGPU_HOST_EXCHANGE")
+    if device_exchange:
+        # the library's own collective: NCCL communicator per context + the global split table
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(SearcherContext.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        all_ids = [f"bench-{g:04d}" for g in range(world * a.splits)]
+        ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, all_ids)
+    if world > 1 and not device_exchange:
         # one fixed-size partial per query of the step; the step's partials travel in ONE all-gather
         part_host = torch.zeros(Q_SETS * part_bytes, dtype=torch.uint8).pin_memory()
         part_dev = torch.zeros(Q_SETS * part_bytes, dtype=torch.uint8, device="cuda")
@@ -401,7 +410,7 @@ def main():
         t = time.perf_counter()
         r = ctx.leaf_search(lreqs[q])
         lat.append(time.perf_counter() - t)
-        if world > 1:  # this rank's merged leaf response -> fixed-size partial (typed sort values, split id, doc id)
+        if world > 1 and not device_exchange:  # this rank's merged leaf response -> fixed-size partial (typed sort values, split id, doc id)
             service.response_to_partial(sreqs[q], r, part_host.data_ptr() + q * part_bytes, part_bytes)
         return r
 
@@ -412,9 +421,20 @@ def main():
 
     def step_e2e():
         t0 = time.perf_counter()
-        resps = list(pool.map(one_query, range(Q_SETS)))
-        phase[0] += time.perf_counter() - t0
-        if world > 1:
+        if device_exchange:
+            # collectives must be issued in the same order on every rank: one query after the other; the
+            # search, the NCCL all-gather of the per-rank records and the cross-rank merge all run inside
+            # qwgpu_leaf_search_allgather on the call's stream (no host bounce, no Python in between)
+            resps = []
+            for q in range(Q_SETS):
+                t = time.perf_counter()
+                resps.append(ctx.leaf_search_allgather(lreqs[q]))
+                lat.append(time.perf_counter() - t)
+            phase[0] += time.perf_counter() - t0
+        else:
+            resps = list(pool.map(one_query, range(Q_SETS)))
+            phase[0] += time.perf_counter() - t0
+        if world > 1 and not device_exchange:
             t0 = time.perf_counter()
             part_dev.copy_(part_host, non_blocking=True)
             dist.all_gather_into_tensor(gath_dev, part_dev)   # the single collective of the data path
@@ -434,6 +454,18 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if device_exchange:
+        # correctness of the device-side exchange, once, outside the timed regions: the same query through the
+        # host path (per-rank response -> fixed-size partial -> all-gather -> qwgpu_merge_partials)
+        pb = torch.zeros(part_bytes, dtype=torch.uint8).pin_memory()
+        service.response_to_partial(sreqs[0], ctx.leaf_search(lreqs[0]), pb.data_ptr(), part_bytes)
+        gd = torch.zeros(world * part_bytes, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(gd, pb.cuda())
+        gh = gd.cpu()
+        want = proto.dec_leaf_search_response(service.merge_partials(sreqs[0], world, gh.data_ptr(), part_bytes))
+        got = proto.dec_leaf_search_response(ctx.leaf_search_allgather(lreqs[0]))
+        assert got["num_hits"] == want["num_hits"] and got["partial_hits"] == want["partial_hits"], "device-side exchange differs from the host merge"
+        assert got["num_attempted_splits"] == want["num_attempted_splits"] == world * a.splits
     for _ in range(max(a.warmup, 3)):
         step()
     sampler = ClockSampler(local_rank)
@@ -508,6 +540,7 @@ def main():
                 "ms_per_step": 1e3 * wall / a.steps, "concurrent_queries": Q_SETS,
                 "single_query_latency_ms": {"p50": 1e3 * single[len(single) // 2], "p90": 1e3 * single[int(len(single) * 0.9)],
                                             "p99": 1e3 * single[int(len(single) * 0.99)], "runs": len(single)},
+                "exchange": ("device: qwgpu_leaf_search_allgather (NCCL all-gather + merge inside the library)" if device_exchange else ("host partials" if world > 1 else None)),
                 "cold_split_register_ms": cold_ms, "phase_ms_per_step": {"leaf_search": 1e3 * phase[0] / a.steps, "all_gather": 1e3 * phase[1] / a.steps, "root_merge": 1e3 * phase[2] / a.steps}, "mean_query_latency_ms": 1e3 * sum(lat) / max(len(lat), 1),
                 "h2d_bytes_per_step": accs[0]["h2d"] + sum(len(x) for x in lreqs),
                 "d2h_bytes_per_step": Q_SETS * a.splits * (32 + 32 * K),

@@ -146,6 +146,23 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
                          uint32_t n_ranks, const uint8_t* gathered, uint64_t partial_bytes,
                          uint8_t** merged, size_t* merged_len);
 
+/* Device-side exchange (one process per GPU, NCCL over NVLink): the all-gather that stands in for the root
+ * merge (quickwit-search/src/root.rs:836-853 -> collector.rs:914-974) runs inside the library, on the
+ * call's stream, on device-resident records, and the gathered lists are merged on the device.
+ *   qwgpu_comm_unique_id       rank 0 creates the 128-byte NCCL id and hands it to the other ranks
+ *   qwgpu_comm_init            every rank: builds the communicator for this context's device
+ *   qwgpu_comm_set_split_table every rank: the split ids of the whole (multi-GPU) index, any order; their
+ *                              sorted position is the tie-break rank carried by the exchanged hits
+ *   qwgpu_leaf_search_allgather  collective: leaf_search on this rank's splits + exchange; every rank gets
+ *                              the merged LeafSearchResponse (hits only: requests with aggregations and
+ *                              ranks with failed splits return QWGPU_EUNSUPPORTED — use the host partials) */
+int qwgpu_comm_unique_id(uint8_t* out128);
+int qwgpu_comm_init(qwgpu_ctx* ctx, const uint8_t* id128, int rank, int world);
+int qwgpu_comm_set_split_table(qwgpu_ctx* ctx, uint32_t n, const char* const* split_ids);
+void qwgpu_comm_destroy(qwgpu_ctx* ctx);
+int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* leaf_search_request_pb, size_t len,
+                                uint8_t** merged_resp, size_t* merged_len);
+
 /* ---- split image writer ------------------------------------------------------------------------ */
 
 qwgpu_imgb* qwgpu_imgb_new(uint32_t num_docs);

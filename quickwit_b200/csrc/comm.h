@@ -1,0 +1,26 @@
+// comm.h — NCCL communicator + global split table of a context (comm.cpp).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace qw {
+
+struct NcclUniqueId { char internal[128]; };  // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+
+struct Comm {
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1, device = 0;
+  std::vector<std::string> split_ids;  // sorted: position = global tie-break rank of the split id
+};
+
+void comm_unique_id(uint8_t out[128]);
+Comm* comm_create(int device, const uint8_t id[128], int rank, int world);
+void comm_destroy(Comm* c);
+void comm_set_split_table(Comm* c, uint32_t n, const char* const* split_ids);
+int comm_split_rank(const Comm* c, const std::string& split_id);  // -1: not in the table
+int comm_allgather(void* comm, const void* send, void* recv, size_t bytes, void* stream);
+
+}  // namespace qw

@@ -616,7 +616,7 @@ static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
 
 void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
                     const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats,
-                    const MergeSpec* merge, std::vector<MergedHit>* merged) {
+                    const MergeSpec* merge, std::vector<MergedHit>* merged, const GatherSpec* gather, std::vector<RankHeader>* rank_headers) {
   const uint32_t n_in = (uint32_t)sp.size();
   outs.assign(n_in, SplitOutput());
   static const bool trace = getenv("QWGPU_TRACE") != nullptr;  // host phase timings on stderr
@@ -640,7 +640,41 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     }
   }
   const uint32_t n = (uint32_t)low.size();
-  if (n == 0) return;
+  if (n == 0) {
+    // no searchable split on this rank: it still takes part in the collective with an empty record
+    if (merge && merged && gather && gather->allgather && gather->world > 1 && rank_headers && merge->k) {
+      const size_t rec = 64 + (size_t)merge->k * sizeof(qwk::DMergedHit), W8 = (size_t)gather->world;
+      uint8_t *d = nullptr;
+      const size_t o_recv = 256 * ((rec + 255) / 256), o_fin = o_recv + 256 * ((W8 * rec + 255) / 256), o_cut = o_fin + 256 * ((16 + rec + 255) / 256), o_hd = o_cut + 1024, total = o_hd + W8 * 64;
+      CUDA_CHECK(cudaMalloc(&d, total));
+      cudaStream_t st0 = nullptr;
+      CUDA_CHECK(cudaStreamCreateWithFlags(&st0, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaMemsetAsync(d, 0, total, st0));
+      qwk::DRankHeader h;
+      memset(&h, 0, sizeof h);
+      h.attempted = gather->attempted; h.successful = gather->successful; h.n_failed = gather->n_failed;
+      CUDA_CHECK(cudaMemcpyAsync(d, &h, sizeof h, cudaMemcpyHostToDevice, st0));
+      if (gather->allgather(gather->comm, d, d + o_recv, rec, (void*)st0)) fail(QWGPU_EINTERNAL, "ncclAllGather failed");
+      const qwk::SrcGathered gsrc{d + o_recv, (uint32_t)rec, 64u};
+      qwk::k_merge_prep<qwk::SrcGathered><<<1, 1024, 0, st0>>>(gsrc, (uint32_t)gather->world, merge->k, merge->order1, merge->order2, (uint32_t*)(d + o_cut));
+      const uint64_t gthreads = (uint64_t)gather->world * merge->k * 32;
+      qwk::k_merge<qwk::SrcGathered><<<(uint32_t)((gthreads + 255) / 256), 256, 0, st0>>>(gsrc, (uint32_t*)(d + o_cut), (uint32_t)gather->world, merge->k, merge->k, merge->order1, merge->order2,
+                                                                                       (qwk::DMergedHit*)(d + o_fin + 16), (uint32_t*)(d + o_fin));
+      CUDA_CHECK(cudaMemcpy2DAsync(d + o_hd, 64, d + o_recv, rec, 64, W8, cudaMemcpyDeviceToDevice, st0));
+      std::vector<uint8_t> host(16 + (size_t)merge->k * sizeof(qwk::DMergedHit));
+      rank_headers->resize(gather->world);
+      CUDA_CHECK(cudaMemcpyAsync(host.data(), d + o_fin, host.size(), cudaMemcpyDeviceToHost, st0));
+      CUDA_CHECK(cudaMemcpyAsync(rank_headers->data(), d + o_hd, W8 * 64, cudaMemcpyDeviceToHost, st0));
+      CUDA_CHECK(cudaStreamSynchronize(st0));
+      const uint32_t nm = *(const uint32_t*)host.data();
+      const qwk::DMergedHit* mh = (const qwk::DMergedHit*)(host.data() + 16);
+      merged->resize(nm);
+      for (uint32_t j = 0; j < nm; j++) { (*merged)[j].hit = mh[j].hit; (*merged)[j].split = mh[j].split; (*merged)[j].pad = 0; }
+      cudaStreamDestroy(st0);
+      cudaFree(d);
+    }
+    return;
+  }
   const auto t_lowered = tclock::now();
 
   // ---- batch-wide parameters --------------------------------------------------------------------------
@@ -767,14 +801,20 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          s_ctr = al(s_state + (size_t)n * 4), s_wmax = al(s_ctr + 64 * 4), s_cand = al(s_wmax + (rec_l0 ? (size_t)fw_all[n] * 2 : 0)),
          s_hits = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0)),
          s_cut = al(s_hits + (do_merge ? (size_t)n * kmax * sizeof(QwHit) : 0)),
-         scratch_bytes = al(s_cut + (size_t)n * 4);
+         s_grecv = al(s_cut + (size_t)std::max<uint32_t>(n, 64) * 4 + 1024),
+         scratch_bytes = al(s_grecv + (gather && gather->world > 1 && do_merge ? (size_t)gather->world * (64 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : 0));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
   out_off[0] = 0;
   for (uint32_t i = 0; i < n; i++)
     out_off[i + 1] = al(out_off[i] + 32 + (do_merge ? 0 : (size_t)low[i].P.max_hits * sizeof(QwHit)) + (size_t)low[i].P.n_cells * sizeof(QwAggCell));
-  const size_t o_merged = out_off[n];  // [u32 count, pad][DMergedHit x k]
-  size_t out_bytes = do_merge ? al(o_merged + 16 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : out_off[n];
+  // [RankHeader 64 B (n_hits first)][DMergedHit x k]: the batch's merged top-k = this rank's gather record
+  const size_t o_merged = out_off[n];
+  const size_t rec_bytes = do_merge ? 64 + (size_t)merge->k * sizeof(qwk::DMergedHit) : 0;
+  const bool do_gather = do_merge && gather && gather->allgather && gather->world > 1 && rank_headers;
+  // gathered: [world x RankHeader (compacted copy)][final count 16 B][final DMergedHit x k]
+  const size_t o_ghdr = al(o_merged + rec_bytes), o_final = al(o_ghdr + (do_gather ? (size_t)gather->world * 64 : 0));
+  size_t out_bytes = do_merge ? (do_gather ? al(o_final + 16 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : al(o_merged + rec_bytes)) : out_off[n];
 
   CallSlot* slot = nullptr;
   {
@@ -908,14 +948,16 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans, kp.cols); stats.launches++; }
     if (do_merge) {
       uint32_t* d_cut = (uint32_t*)(slot->d_scratch + s_cut);
-      qwk::k_merge_prep<<<1, 1024, 0, st>>>(kp.plans, (const uint32_t*)(slot->d_blob + o_rank), n, merge->k, merge->order1, merge->order2, d_cut);
+      const qwk::SrcSplits src{kp.plans, (const uint32_t*)(slot->d_blob + o_rank), do_gather ? 1u : 0u};
+      qwk::k_merge_prep<qwk::SrcSplits><<<1, 1024, 0, st>>>(src, n, merge->k, merge->order1, merge->order2, d_cut);
       const uint64_t threads = (uint64_t)n * kmax * 32;  // one warp per hit (warps of pruned hits leave at once)
-      qwk::k_merge<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(kp.plans, (const uint32_t*)(slot->d_blob + o_rank), d_cut, n, kmax, merge->k, merge->order1, merge->order2,
-                                                          (qwk::DMergedHit*)(slot->d_out + o_merged + 16), (uint32_t*)(slot->d_out + o_merged));
+      qwk::k_merge<qwk::SrcSplits><<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(src, d_cut, n, kmax, merge->k, merge->order1, merge->order2,
+                                                          (qwk::DMergedHit*)(slot->d_out + o_merged + 64), (uint32_t*)(slot->d_out + o_merged));
       stats.launches += 2;
     }
-    CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    stats.d2h_bytes += out_bytes;
+    const size_t back = do_gather ? o_ghdr : out_bytes;  // (gathering: the final hits follow in the cross-rank phase)
+    CUDA_CHECK(cudaMemcpyAsync(slot->h_out, slot->d_out, back, cudaMemcpyDeviceToHost, st));
+    stats.d2h_bytes += back;
   };
   // a split's candidate set is good when it holds at least min(K, eligible) and did not overflow
   std::vector<uint32_t> state(n, 0);
@@ -1000,6 +1042,27 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (!verify()) fail(QWGPU_EINTERNAL, "top-K candidate selection failed verification");
   }
+  if (do_gather) {
+    // Cross-rank phase, after this rank's result is final (a verification fallback above must not repeat a
+    // collective the other ranks run once): the rank's record -> every rank (one NCCL all-gather on this
+    // call's stream) -> merged again on the device -> one more small copy back.
+    uint32_t* d_cut = (uint32_t*)(slot->d_scratch + s_cut);
+    qwk::k_rank_header<<<1, 32, 0, st>>>(kp.plans, n, (qwk::DRankHeader*)(slot->d_out + o_merged), gather->attempted, gather->successful, gather->n_failed);
+    uint8_t* g_recv = slot->d_scratch + s_grecv;
+    if (gather->allgather(gather->comm, slot->d_out + o_merged, g_recv, rec_bytes, (void*)st)) fail(QWGPU_EINTERNAL, "ncclAllGather failed");
+    const qwk::SrcGathered gsrc{g_recv, (uint32_t)rec_bytes, 64u};
+    uint32_t* g_cut = d_cut + std::max<uint32_t>(n, 64);
+    qwk::k_merge_prep<qwk::SrcGathered><<<1, 1024, 0, st>>>(gsrc, (uint32_t)gather->world, merge->k, merge->order1, merge->order2, g_cut);
+    const uint64_t gthreads = (uint64_t)gather->world * merge->k * 32;
+    qwk::k_merge<qwk::SrcGathered><<<(uint32_t)((gthreads + 255) / 256), 256, 0, st>>>(gsrc, g_cut, (uint32_t)gather->world, merge->k, merge->k, merge->order1, merge->order2,
+                                                                                    (qwk::DMergedHit*)(slot->d_out + o_final + 16), (uint32_t*)(slot->d_out + o_final));
+    CUDA_CHECK(cudaMemcpy2DAsync(slot->d_out + o_ghdr, 64, g_recv, rec_bytes, 64, (size_t)gather->world, cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(slot->h_out + o_ghdr, slot->d_out + o_ghdr, out_bytes - o_ghdr, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaEventRecord(slot->ev1, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    stats.launches += 4;
+    stats.d2h_bytes += out_bytes - o_ghdr;
+  }
   CUDA_CHECK(cudaGetLastError());
   {
     float ms = 0;
@@ -1042,9 +1105,22 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     for (uint32_t a = 0; a < ph->num_aggs; a++) if (an[a].column != 0xFFFFFFFFu) bytes += col_bytes(an[a].column, o.num_hits);
     o.algorithmic_bytes = bytes;
   }
-  if (do_merge) {
+  if (do_gather) {
+    // the cross-rank result: hits carry GLOBAL split ranks (the caller owns the rank -> split id table)
+    const uint32_t nm = *(const uint32_t*)(slot->h_out + o_final);
+    const qwk::DMergedHit* mh = (const qwk::DMergedHit*)(slot->h_out + o_final + 16);
+    merged->resize(nm);
+    const bool by_doc = low[0].P.key.kind[0] == QW_SORT_DOCID;
+    for (uint32_t j = 0; j < nm; j++) {
+      MergedHit& m = (*merged)[j];
+      m.hit = mh[j].hit; m.split = mh[j].split; m.pad = 0;
+      if (by_doc) { m.hit.flags &= ~1u; m.hit.v1 = 0; }
+    }
+    rank_headers->resize(gather->world);
+    memcpy(rank_headers->data(), slot->h_out + o_ghdr, (size_t)gather->world * 64);
+  } else if (do_merge) {
     const uint32_t nm = *(const uint32_t*)(slot->h_out + o_merged);
-    const qwk::DMergedHit* mh = (const qwk::DMergedHit*)(slot->h_out + o_merged + 16);
+    const qwk::DMergedHit* mh = (const qwk::DMergedHit*)(slot->h_out + o_merged + 64);
     merged->resize(nm);
     for (uint32_t j = 0; j < nm; j++) {
       MergedHit& m = (*merged)[j];

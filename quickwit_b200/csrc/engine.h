@@ -44,6 +44,21 @@ struct MergedHit {
   uint32_t split;  // index into the caller's split array
   uint32_t pad;
 };
+// Cross-rank exchange standing in for the root merge: after the batch's own device merge the
+// rank's fixed-size record {header, best k hits tagged with GLOBAL split ranks} is all-gathered over NCCL on
+// the call's stream and the gathered lists are merged on the device again; every rank ends up with the same
+// global top-k. `allgather` is ncclAllGather bound to the context's communicator (comm.cpp).
+struct RankHeader {  // 64 bytes, written on the device
+  uint32_t n_hits, pad;
+  uint64_t num_hits, attempted, successful, n_failed, reserved[3];
+};
+struct GatherSpec {
+  int world = 1, rank = 0;
+  // (sendbuf, recvbuf, bytes per rank, stream) -> 0 on success
+  int (*allgather)(void* comm, const void* send, void* recv, size_t bytes, void* stream) = nullptr;
+  void* comm = nullptr;
+  uint64_t attempted = 0, successful = 0, n_failed = 0;  // this rank's split accounting for the header
+};
 struct BatchStats {
   float gpu_time_us = 0;
   float main_kernel_us = 0;
@@ -69,7 +84,8 @@ struct Engine {
   // Runs plan[i] on splits[i]; fills outs[i] (status per split). Throws only on whole-call errors.
   void search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
               const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats,
-              const MergeSpec* merge = nullptr, std::vector<MergedHit>* merged = nullptr);
+              const MergeSpec* merge = nullptr, std::vector<MergedHit>* merged = nullptr,
+              const GatherSpec* gather = nullptr, std::vector<RankHeader>* rank_headers = nullptr);
 };
 
 // plan validation helper shared with the compiler: total agg cells + per-node bases
@@ -77,6 +93,9 @@ uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t
 
 }  // namespace qw
 
+namespace qw { struct Comm; }
 struct qwgpu_ctx {
   std::unique_ptr<qw::Engine> engine;  // null for host-only contexts
+  qw::Comm* comm = nullptr;            // NCCL communicator + global split table (comm.cpp); null until qwgpu_comm_init
+  ~qwgpu_ctx();
 };

@@ -1735,29 +1735,51 @@ struct DMergedHit {
   QwHit hit;
   uint32_t split, pad;
 };
+// The lists a merge reads: the per-split lists of one batch (k_select output, tie-break rank per list), or
+// the per-rank merged lists gathered over NCCL (DMergedHit records that carry the global split rank).
+struct SrcSplits {
+  const DSplitPlan* plans;
+  const uint32_t* rank;
+  uint32_t tag_rank;  // 1: output hits are tagged with the list's (global) rank instead of its index
+  __device__ __forceinline__ uint32_t count(uint32_t s) const { return *(const uint32_t*)plans[s].out_nhits; }
+  __device__ __forceinline__ QwHit hit(uint32_t s, uint32_t i, uint32_t& rk) const { rk = __ldg(rank + s); return ((const QwHit*)plans[s].out_hits)[i]; }
+  __device__ __forceinline__ uint32_t tag(uint32_t s, uint32_t rk) const { return tag_rank ? rk : s; }  // DMergedHit.split of an output hit
+};
+struct SrcGathered {
+  const uint8_t* base;   // rank r: [uint32 n_hits ... header of hdr_bytes][DMergedHit x K]
+  uint32_t rec_bytes, hdr_bytes;
+  __device__ __forceinline__ uint32_t count(uint32_t s) const { return *(const uint32_t*)(base + (size_t)s * rec_bytes); }
+  __device__ __forceinline__ QwHit hit(uint32_t s, uint32_t i, uint32_t& rk) const {
+    const DMergedHit* m = (const DMergedHit*)(base + (size_t)s * rec_bytes + hdr_bytes) + i;
+    rk = m->split;
+    return m->hit;
+  }
+  __device__ __forceinline__ uint32_t tag(uint32_t, uint32_t rk) const { return rk; }
+};
+
 // Pruning before the merge: with m = ceil(K / #lists), every list holds min(m, len) hits that are at least as
 // good as its own m-th hit, so if those add up to K the K-th best hit overall is at least as good as the WORST of
 // the lists' m-th hits (tau) and only hits >= tau can reach the merged top-K. cut[s] = number of such hits in
 // list s (all of the list when the short lists leave fewer than K guaranteed hits). One block, warp = list.
-__global__ void __launch_bounds__(1024) k_merge_prep(const DSplitPlan* plans, const uint32_t* rank, uint32_t n_splits, uint32_t K,
-                                                      uint32_t o1, uint32_t o2, uint32_t* cut) {
+template <class Src>
+__global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_lists, uint32_t K, uint32_t o1, uint32_t o2, uint32_t* cut) {
   __shared__ MKey s_key[64];
   __shared__ uint32_t s_have[64];
   __shared__ MKey s_tau;
   __shared__ uint32_t s_prune;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  uint32_t nonempty = 0;
-  for (uint32_t s = 0; s < n_splits; s++) nonempty += *(const uint32_t*)plans[s].out_nhits ? 1u : 0u;
-  const uint32_t m = nonempty ? (K + nonempty - 1) / nonempty : 0;
-  if (n_splits > 64) {  // more lists than the shared tables hold: no pruning
-    for (uint32_t s = threadIdx.x; s < n_splits; s += blockDim.x) cut[s] = min(*(const uint32_t*)plans[s].out_nhits, K);
+  if (n_lists > 64) {  // more lists than the shared tables hold: no pruning
+    for (uint32_t s = threadIdx.x; s < n_lists; s += blockDim.x) cut[s] = min(src.count(s), K);
     return;
   }
-  for (uint32_t s = warp; s < n_splits; s += nw) {
+  uint32_t nonempty = 0;
+  for (uint32_t s = 0; s < n_lists; s++) nonempty += src.count(s) ? 1u : 0u;
+  const uint32_t m = nonempty ? (K + nonempty - 1) / nonempty : 0;
+  for (uint32_t s = warp; s < n_lists; s += nw) {
     if (lane == 0) {
-      const uint32_t nh = min(*(const uint32_t*)plans[s].out_nhits, K), ms = min(m, nh);
+      const uint32_t nh = min(src.count(s), K), ms = min(m, nh);
       s_have[s] = ms;
-      if (ms) s_key[s] = merge_key(((const QwHit*)plans[s].out_hits)[ms - 1], __ldg(rank + s), o1, o2);
+      if (ms) { uint32_t rk; const QwHit h = src.hit(s, ms - 1, rk); s_key[s] = merge_key(h, rk, o1, o2); }
     }
   }
   __syncthreads();
@@ -1765,7 +1787,7 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const DSplitPlan* plans, co
     uint32_t have = 0, first = 1;
     MKey tau;
     tau.v1 = tau.v2 = tau.tie = 0; tau.has = 0;
-    for (uint32_t s = 0; s < n_splits; s++) {
+    for (uint32_t s = 0; s < n_lists; s++) {
       have += s_have[s];
       if (s_have[s] && (first || mkey_gt(tau, s_key[s]))) { tau = s_key[s]; first = 0; }
     }
@@ -1774,48 +1796,65 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const DSplitPlan* plans, co
   }
   __syncthreads();
   const MKey tau = s_tau;
-  for (uint32_t s = warp; s < n_splits; s += nw) {
+  for (uint32_t s = warp; s < n_lists; s += nw) {
     if (lane != 0) continue;
-    const uint32_t nh = min(*(const uint32_t*)plans[s].out_nhits, K);
+    const uint32_t nh = min(src.count(s), K);
     uint32_t lo = 0, hi = nh;  // first index whose hit is worse than tau
     if (s_prune) {
-      const QwHit* L = (const QwHit*)plans[s].out_hits;
-      const uint32_t rk = __ldg(rank + s);
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (mkey_gt(tau, merge_key(L[mid], rk, o1, o2))) hi = mid; else lo = mid + 1;
+        uint32_t rk;
+        const QwHit h = src.hit(s, mid, rk);
+        if (mkey_gt(tau, merge_key(h, rk, o1, o2))) hi = mid; else lo = mid + 1;
       }
     } else lo = nh;
     cut[s] = lo;
   }
 }
-__global__ void __launch_bounds__(256) k_merge(const DSplitPlan* plans, const uint32_t* rank, const uint32_t* cut, uint32_t n_splits, uint32_t kmax,
-                                               uint32_t K, uint32_t o1, uint32_t o2, DMergedHit* out, uint32_t* out_n) {
+template <class Src>
+__global__ void __launch_bounds__(256) k_merge(const Src src, const uint32_t* cut, uint32_t n_lists, uint32_t kmax, uint32_t K, uint32_t o1, uint32_t o2,
+                                               DMergedHit* out, uint32_t* out_n) {
   // one warp per surviving hit; lane = one of the other lists (the binary searches of a hit run side by side)
   const uint32_t lane = threadIdx.x & 31, e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (e == 0 && lane == 0) {
     uint64_t total = 0;
-    for (uint32_t s = 0; s < n_splits; s++) total += *(const uint32_t*)plans[s].out_nhits;
+    for (uint32_t s = 0; s < n_lists; s++) total += src.count(s);
     *out_n = (uint32_t)(total < K ? total : K);
   }
   const uint32_t s = e / kmax, i = e % kmax;
-  if (s >= n_splits || i >= __ldg(cut + s)) return;
-  const QwHit mine = ((const QwHit*)plans[s].out_hits)[i];
-  const MKey key = merge_key(mine, __ldg(rank + s), o1, o2);
+  if (s >= n_lists || i >= __ldg(cut + s)) return;
+  uint32_t my_rk;
+  const QwHit mine = src.hit(s, i, my_rk);
+  const MKey key = merge_key(mine, my_rk, o1, o2);
   uint32_t r = 0;
-  for (uint32_t s2 = lane; s2 < n_splits; s2 += 32) {
+  for (uint32_t s2 = lane; s2 < n_lists; s2 += 32) {
     if (s2 == s) continue;
-    const QwHit* L = (const QwHit*)plans[s2].out_hits;
-    const uint32_t rk = __ldg(rank + s2);
     uint32_t lo = 0, hi = __ldg(cut + s2);  // first index whose hit does not beat `key` (hits past the cut never do)
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
-      if (mkey_gt(merge_key(L[mid], rk, o1, o2), key)) lo = mid + 1; else hi = mid;
+      uint32_t rk;
+      const QwHit h = src.hit(s2, mid, rk);
+      if (mkey_gt(merge_key(h, rk, o1, o2), key)) lo = mid + 1; else hi = mid;
     }
     r += lo;
   }
   r = __reduce_add_sync(0xFFFFFFFFu, r) + i;
-  if (lane == 0 && r < K) { DMergedHit m; m.hit = mine; m.split = s; m.pad = 0; out[r] = m; }
+  if (lane == 0 && r < K) { DMergedHit m; m.hit = mine; m.split = src.tag(s, my_rk); m.pad = 0; out[r] = m; }
+}
+
+// Header of a rank's gather record: its hit count (already written by k_merge at offset 0) plus the sums the
+// root merge adds up (collector.rs:914-974): num_hits over the batch's splits, split accounting from the host.
+struct DRankHeader {
+  uint32_t n_hits, pad;
+  uint64_t num_hits, attempted, successful, n_failed, reserved[3];
+};
+__global__ void k_rank_header(const DSplitPlan* plans, uint32_t n_splits, DRankHeader* h, uint64_t attempted, uint64_t successful, uint64_t n_failed) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t nh = 0;
+    for (uint32_t s = 0; s < n_splits; s++) nh += *(const uint64_t*)plans[s].out_num_hits;
+    h->pad = 0; h->num_hits = nh; h->attempted = attempted; h->successful = successful; h->n_failed = n_failed;
+    h->reserved[0] = h->reserved[1] = h->reserved[2] = 0;
+  }
 }
 
 }  // namespace qwk

@@ -15,6 +15,7 @@
 
 #include "compile.h"
 #include "engine.h"
+#include "comm.h"
 
 namespace qw {
 
@@ -194,7 +195,9 @@ struct LeafRun {
   BatchStats st;
   uint64_t wall_us = 0;
   bool merged_valid = false;       // the engine merged the per-split top-K lists on the device
-  std::vector<MergedHit> merged;   // best-first; .split = index into `jobs`
+  std::vector<MergedHit> merged;   // best-first; .split = index into `jobs` (gathered: global split rank)
+  bool gathered = false;           // `merged` is the cross-rank result; rank_headers[r] = rank r's counters
+  std::vector<RankHeader> rank_headers;
 };
 
 static bool same_sort_types(const std::vector<SplitJob>& jobs, const std::vector<size_t>& which) {
@@ -209,7 +212,7 @@ static bool same_sort_types(const std::vector<SplitJob>& jobs, const std::vector
 }
 static void sort_orders(const pb::SearchRequest& r, int* o1, int* o2);
 
-static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run, bool want_merged = false) {
+static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run, bool want_merged = false, const Comm* comm = nullptr) {
   using clock = std::chrono::steady_clock;
   const pb::SearchRequest& sreq = lr.search_request;
   const auto t_compile = clock::now();
@@ -248,7 +251,10 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
     fprintf(stderr, "[qwgpu] compile: %ld us for %zu splits\n", (long)std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_compile).count(), run.jobs.size());
   static const bool host_merge = getenv("QWGPU_HOST_MERGE") != nullptr;
   MergeSpec ms;
-  if (want_merged && !host_merge && devs.size() > 1 && sreq.max_hits + sreq.start_offset > 0 && same_sort_types(run.jobs, run.which)) {
+  GatherSpec gs;
+  const bool gathering = comm && comm->world > 1 && sreq.max_hits + sreq.start_offset > 0;
+  if (gathering && !same_sort_types(run.jobs, run.which)) fail(QWGPU_EUNSUPPORTED, "the splits of this rank disagree on the sort field types: cross-rank merge on the device is not possible");
+  if ((gathering || (want_merged && !host_merge && devs.size() > 1)) && sreq.max_hits + sreq.start_offset > 0 && same_sort_types(run.jobs, run.which)) {
     int o1, o2;
     sort_orders(sreq, &o1, &o2);
     ms.k = (uint32_t)(sreq.max_hits + sreq.start_offset);
@@ -259,9 +265,21 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
     std::sort(by_id.begin(), by_id.end(), [&](size_t a, size_t b) { return run.jobs[run.which[a]].meta.split_id < run.jobs[run.which[b]].meta.split_id; });
     ms.rank.resize(n);
     for (size_t r = 0; r < n; r++) ms.rank[by_id[r]] = (uint32_t)r;
+    if (gathering) {
+      // tie-breaks across ranks use the split id order of the WHOLE query: ranks from the context's table
+      for (size_t i = 0; i < n; i++) {
+        const int g = comm_split_rank(comm, run.jobs[run.which[i]].meta.split_id);
+        if (g < 0) fail(QWGPU_EINVALID_ARG, "split `%s` is not in the communicator's split table (qwgpu_comm_set_split_table)", run.jobs[run.which[i]].meta.split_id.c_str());
+        ms.rank[i] = (uint32_t)g;
+      }
+      gs.world = comm->world; gs.rank = comm->rank; gs.allgather = comm_allgather; gs.comm = comm->comm;
+      gs.attempted = run.jobs.size(); gs.successful = devs.size(); gs.n_failed = run.jobs.size() - devs.size();
+    }
   }
-  if (!devs.empty()) eng.search(devs, plans, lens, run.outs, run.st, ms.k ? &ms : nullptr, ms.k ? &run.merged : nullptr);
-  if (ms.k) {
+  if (!devs.empty() || gathering)
+    eng.search(devs, plans, lens, run.outs, run.st, ms.k ? &ms : nullptr, ms.k ? &run.merged : nullptr, gathering ? &gs : nullptr, gathering ? &run.rank_headers : nullptr);
+  if (gathering) run.gathered = true;
+  else if (ms.k) {
     run.merged_valid = true;
     for (auto& m : run.merged) m.split = (uint32_t)run.which[m.split];
   }
@@ -510,6 +528,101 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
   QW_API_END
 }
 
+// ---- collectives (comm.cpp) ----------------------------------------------------------------------------------
+int qwgpu_comm_unique_id(uint8_t* out128) {
+  QW_API_BEGIN
+  if (!out128) qw::fail(QWGPU_EINVALID_ARG, "null out pointer");
+  qw::comm_unique_id(out128);
+  return 0;
+  QW_API_END
+}
+int qwgpu_comm_init(qwgpu_ctx* ctx, const uint8_t* id128, int rank, int world) {
+  QW_API_BEGIN
+  qw::Engine& eng = engine_of(ctx);
+  if (!id128) qw::fail(QWGPU_EINVALID_ARG, "null unique id");
+  if (ctx->comm) { qw::comm_destroy(ctx->comm); ctx->comm = nullptr; }
+  ctx->comm = qw::comm_create(eng.device, id128, rank, world);
+  return 0;
+  QW_API_END
+}
+int qwgpu_comm_set_split_table(qwgpu_ctx* ctx, uint32_t n, const char* const* split_ids) {
+  QW_API_BEGIN
+  if (!ctx || !ctx->comm) qw::fail(QWGPU_EINVALID_ARG, "no communicator: call qwgpu_comm_init first");
+  qw::comm_set_split_table(ctx->comm, n, split_ids);
+  return 0;
+  QW_API_END
+}
+void qwgpu_comm_destroy(qwgpu_ctx* ctx) {
+  if (ctx && ctx->comm) { qw::comm_destroy(ctx->comm); ctx->comm = nullptr; }
+}
+
+// leaf_search on every rank + the root merge as ONE device-side exchange: each rank searches its own splits,
+// merges them on the device, all-gathers its fixed-size record {counters, best k hits} over NCCL on the call's
+// stream and merges the gathered lists on the device again. Every rank returns the same merged
+// LeafSearchResponse (what merge_leaf_responses over all ranks' responses yields, collector.rs:914-974).
+// Aggregation partials and failed-split entries are variable-length: they travel in a second, host-staged
+// all-gather, only when the request has aggregations / some rank reports a failed split.
+int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
+  QW_API_BEGIN
+  qw::Engine& eng = engine_of(ctx);
+  if (!ctx->comm) qw::fail(QWGPU_EINVALID_ARG, "no communicator: call qwgpu_comm_init first");
+  const qw::Comm& comm = *ctx->comm;
+  qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
+  qw::LeafRun run;
+  qw::run_leaf_raw(eng, lr, run, true, &comm);
+  qw::pb::SearchRequest mreq = lr.search_request;
+  mreq.max_hits += mreq.start_offset;
+  mreq.start_offset = 0;
+  const bool has_aggs = mreq.aggregation_request && !mreq.aggregation_request->empty();
+  if (comm.world <= 1 || !run.gathered) {
+    // single rank, or a count / aggregation-only request (no hits to merge on the device)
+    if (comm.world > 1 && mreq.max_hits > 0) qw::fail(QWGPU_EINTERNAL, "cross-rank merge did not run");
+  }
+  std::vector<qw::pb::SplitSearchError> failed;
+  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, true});
+  for (size_t k = 0; k < run.which.size(); k++)
+    if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, true});
+  qw::pb::LeafSearchResponse m;
+  uint64_t total_failed = failed.size();
+  if (run.gathered) {
+    total_failed = 0;
+    for (const qw::RankHeader& h : run.rank_headers) {
+      m.num_hits += h.num_hits;
+      m.num_attempted_splits += h.attempted;
+      m.num_successful_splits += h.successful;
+      total_failed += h.n_failed;
+    }
+    // sort-field types for the typed sort values: from a local split that has the column
+    const qw::CompiledPlan* p0 = run.which.empty() ? nullptr : &run.jobs[run.which[0]].plan;
+    if (!p0 && !run.merged.empty()) qw::fail(QWGPU_EUNSUPPORTED, "a rank without searchable splits cannot type the merged sort values");
+    int sft[2] = {0, 0};
+    if (p0) {
+      sft[0] = p0->sort_field_type[0]; sft[1] = p0->sort_field_type[1];
+      for (int i = 0; i < 2; i++)
+        for (size_t s2 = 0; s2 < run.which.size(); s2++) {
+          const qw::CompiledPlan& pp = run.jobs[run.which[s2]].plan;
+          if (pp.header.sort[i].kind == QW_SORT_COLUMN && pp.header.sort[i].column != 0xFFFFFFFFu) { sft[i] = pp.sort_field_type[i]; break; }
+        }
+    }
+    m.encoded_partial_hits.reserve(run.merged.size() * 72);
+    for (const qw::MergedHit& mh : run.merged) {
+      if (mh.split >= comm.split_ids.size()) qw::fail(QWGPU_EINTERNAL, "gathered hit carries split rank %u (table has %zu)", mh.split, comm.split_ids.size());
+      const QwHit& h = mh.hit;
+      qw::pb::SortValue sv1, sv2;
+      if (h.flags & 1) sv1 = qw::typed_sort_value(p0->header.sort[0].kind, sft[0], h.v1);
+      if (h.flags & 2) sv2 = qw::typed_sort_value(p0->header.sort[1].kind, sft[1], h.v2);
+      qw::pb::append_partial_hit(m.encoded_partial_hits, 2, comm.split_ids[mh.split], 0, h.doc_id, (h.flags & 1) != 0, sv1, (h.flags & 2) != 0, sv2);
+    }
+  } else {
+    qw::fail(QWGPU_EUNSUPPORTED, "qwgpu_leaf_search_allgather needs max_hits > 0 and more than one rank (use qwgpu_leaf_search + qwgpu_merge_partials for count / aggregation-only requests)");
+  }
+  if (has_aggs) qw::fail(QWGPU_EUNSUPPORTED, "aggregations over the device-side exchange are not implemented yet: use qwgpu_leaf_search + the partial exchange");
+  if (total_failed) qw::fail(QWGPU_EUNSUPPORTED, "%llu splits failed on some rank: failed_splits entries are not exchanged yet", (unsigned long long)total_failed);
+  give(qw::pb::encode_leaf_search_response(m), resp, resp_len);
+  return 0;
+  QW_API_END
+}
+
 int qwgpu_invoke_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
@@ -642,6 +755,12 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
     memcpy(hdr, base, 32);
     memcpy(meta, base + 32, 16);
     if (hdr[0] != kPartMagic) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial has a bad header", r);
+    // the gathered bytes come from other processes: nothing in them is trusted
+    if (meta[0] > k) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims %u hits (max %zu)", r, meta[0], k);
+    if (meta[1] > kAggCap || 48 + k * kHitBytes + (size_t)meta[1] > partial_bytes) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims %u aggregation bytes", r, meta[1]);
+    // a fixed-size partial cannot carry the failed_splits entries (split id, error, retryable): a rank with
+    // failed splits would silently contribute a partial result and the root's retry would never fire
+    if (meta[2] != 0) qw::fail(QWGPU_EUNSUPPORTED, "rank %u reports %u failed splits: use qwgpu_leaf_search_allgather (it exchanges them) or retry those splits", r, meta[2]);
     qw::pb::LeafSearchResponse lr;
     lr.num_hits = hdr[1];
     lr.num_attempted_splits = hdr[2];
@@ -669,6 +788,7 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
       memcpy(&v2, p + 16, 8);
       unpack(p[0], v1, &h.has_sv1, &h.sv1);
       unpack(p[1], v2, &h.has_sv2, &h.sv2);
+      if (sl > 40) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial holds a split id of %u bytes", r, (unsigned)sl);
       h.split_id.assign((const char*)p + 24, sl);
       lr.partial_hits.push_back(std::move(h));
     }

@@ -183,6 +183,11 @@ def lib() -> C.CDLL:
     bind("qwgpu_partial_size", [vp, sz, C.POINTER(u64)])
     bind("qwgpu_response_to_partial", [vp, sz, vp, sz, vp, u64])
     bind("qwgpu_merge_partials", [vp, sz, u32, vp, u64, C.POINTER(vp), C.POINTER(sz)])
+    bind("qwgpu_comm_unique_id", [vp])
+    bind("qwgpu_comm_init", [vp, vp, C.c_int, C.c_int])
+    bind("qwgpu_comm_set_split_table", [vp, u32, C.POINTER(cp)])
+    bind("qwgpu_comm_destroy", [vp], None)
+    bind("qwgpu_leaf_search_allgather", [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_imgb_new", [u32], vp)
     bind("qwgpu_imgb_free", [vp], None)
     bind("qwgpu_imgb_add_field", [vp, cp, u32, u32, vp, u64])

@@ -96,6 +96,27 @@ class SearcherContext:
         """SearchService::leaf_search: LeafSearchRequest bytes -> LeafSearchResponse bytes."""
         return self._bytes_call(self._L.qwgpu_leaf_search, leaf_search_request)
 
+    # -- collectives (one process per GPU) ----------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: the 128-byte NCCL unique id to hand to the other ranks."""
+        buf = C.create_string_buffer(128)
+        ffi.check(ffi.lib().qwgpu_comm_unique_id(C.addressof(buf)))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int, all_split_ids: Sequence[str]):
+        """Builds this context's NCCL communicator and the global split table (tie-break ranks)."""
+        idb = C.create_string_buffer(unique_id, 128)
+        ffi.check(self._L.qwgpu_comm_init(self._ctx, C.addressof(idb), rank, world))
+        n = len(all_split_ids)
+        arr = (C.c_char_p * n)(*[s.encode() for s in all_split_ids])
+        ffi.check(self._L.qwgpu_comm_set_split_table(self._ctx, n, arr))
+
+    def leaf_search_allgather(self, leaf_search_request: bytes) -> bytes:
+        """Collective: leaf_search on this rank's splits + the device-side all-gather / merge that stands in
+        for the root merge; every rank returns the merged LeafSearchResponse."""
+        return self._bytes_call(self._L.qwgpu_leaf_search_allgather, leaf_search_request)
+
     def invoke_leaf_search(self, leaf_search_request: bytes) -> bytes:
         """LambdaLeafSearchInvoker::invoke_leaf_search -> LambdaSearchResponses bytes."""
         return self._bytes_call(self._L.qwgpu_invoke_leaf_search, leaf_search_request)
