@@ -70,6 +70,16 @@ struct ImageView {
     if (h->magic != QW_IMG_MAGIC) fail(QWGPU_EINVALID_ARG, "bad split image magic");
     if (h->version != QW_IMG_VERSION) fail(QWGPU_EINVALID_ARG, "split image version %u (this library reads version %u)", h->version, QW_IMG_VERSION);
     if (h->total_len > n) fail(QWGPU_EINVALID_ARG, "split image truncated");
+    // every section lies inside the image; every data-relative range inside the data region (those offsets
+    // become device pointers in the kernels)
+    const uint64_t tl = h->total_len;
+    auto inside = [](uint64_t off, uint64_t count, uint64_t size, uint64_t limit) {
+      return off <= limit && count <= (limit - off) / (size ? size : 1);
+    };
+    if (!inside(h->fields_off, h->num_fields, sizeof(QwImgField), tl) || !inside(h->terms_off, h->num_terms, sizeof(QwImgTerm), tl) ||
+        !inside(h->columns_off, h->num_columns, sizeof(QwImgColumn), tl) || !inside(h->term_bytes_off, h->term_bytes_len, 1, tl) ||
+        !inside(h->strings_off, h->strings_len, 1, tl) || !inside(h->data_off, h->data_len, 1, tl) || (h->data_len & 15))
+      fail(QWGPU_EINVALID_ARG, "split image: a section lies outside the image");
     base = p;
     len = n;
     hdr = h;
@@ -79,6 +89,29 @@ struct ImageView {
     term_bytes = p + h->term_bytes_off;
     strings = p + h->strings_off;
     data = p + h->data_off;
+    const uint64_t dl = h->data_len, nd = h->num_docs;
+    for (uint32_t f = 0; f < h->num_fields; f++) {
+      const QwImgField& F = fields[f];
+      if (!inside(F.name_off, F.name_len, 1, h->strings_len) || !inside(F.first_term, F.num_terms, 1, h->num_terms) ||
+          ((F.flags & QW_FIELD_HAS_FIELDNORMS) && !inside(F.fieldnorm_off, nd, 1, dl)))
+        fail(QWGPU_EINVALID_ARG, "split image: field %u points outside the image", f);
+    }
+    for (uint32_t t = 0; t < h->num_terms; t++) {
+      const QwImgTerm& T = terms[t];
+      const uint64_t nwin = T.win_shift < 32 ? ((nd + (1ull << T.win_shift) - 1) >> T.win_shift) : 0;
+      if (!inside(T.bytes_off, T.bytes_len, 1, h->term_bytes_len) || T.field_id >= h->num_fields ||
+          T.num_blocks != (T.doc_freq + 127) / 128 || T.doc_freq > nd || !inside(T.skip_off, T.num_blocks, sizeof(QwSkip), dl) ||
+          !inside(T.data_off, T.data_len, 1, dl) || !inside(T.widx_off, nwin, sizeof(QwWinIdx), dl) ||
+          !inside(T.sub_off, T.num_blocks, sizeof(QwSubIdx), dl) || T.tf_len > T.data_len || T.fn_len > T.data_len)
+        fail(QWGPU_EINVALID_ARG, "split image: term %u points outside the image", t);
+    }
+    for (uint32_t c = 0; c < h->num_columns; c++) {
+      const QwImgColumn& C = columns[c];
+      if (!inside(C.name_off, C.name_len, 1, h->strings_len) || !inside(C.values_off, C.values_len, 1, dl) ||
+          !inside(C.index_off, C.index_len, 1, dl) || !inside(C.dict_off, C.dict_len, 1, h->strings_len) || C.bits > 64 ||
+          C.values_len < (C.num_vals * C.bits + 7) / 8)
+        fail(QWGPU_EINVALID_ARG, "split image: column %u points outside the image", c);
+    }
   }
   std::string field_name(uint32_t f) const {
     return std::string((const char*)strings + fields[f].name_off, fields[f].name_len);

@@ -162,5 +162,6 @@ struct KParams {
   uint32_t cands_only;    // COLLECT: emit candidates only
   uint16_t* wmax;         // per flat window: 1 + best level-0 digit among its matches (0: no match)
   const uint32_t* split_state;  // per split: 1 = needs refinement
+  const uint32_t* sample_win;   // sampled passes: per work item, window | edge << 31 (null: strided formula)
   SmemLayout sm;
 };

@@ -131,7 +131,8 @@ void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
   const size_t kTab = 256 + QW_TFF_ROWS * 256;
   std::vector<float> tabs((size_t)std::max(nf, 1u) * kTab);
   for (uint32_t f = 0; f < nf; f++) {
-    float avg = (float)full.fields[f].total_num_tokens / (float)full.hdr->num_docs;
+    // an empty split scores nothing; keep its tables finite
+    float avg = full.hdr->num_docs ? (float)full.fields[f].total_num_tokens / (float)full.hdr->num_docs : 1.0f;
     float* t = tabs.data() + f * kTab;
     for (uint32_t i = 0; i < 256; i++)
       t[i] = BM25_K1 * (1.0f - BM25_B + BM25_B * (float)id_to_fieldnorm((uint8_t)i) / avg);
@@ -781,17 +782,29 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // histogram pass but the looser threshold costs about as much in the collect pass)
   static const uint32_t stride_cap = getenv("QWGPU_STRIDE_CAP") ? (uint32_t)atoi(getenv("QWGPU_STRIDE_CAP")) : 16u;
   uint32_t stride = std::min(std::max(stride_cap, 1u), std::max(1u, max_windows / 8));
+  // the generic kernels sample an explicit window list: strided windows + the first and last window of each
+  // split (weight 1 in the histogram); the union pipeline keeps the plain strided sample (scores do not
+  // follow doc order)
+  const bool edge_sample = !use_union && stride > 1;
+  std::vector<uint32_t> sample_win;
   fw_all[0] = fw_smp[0] = 0;
   for (uint32_t i = 0; i < n; i++) {
     uint32_t nw = low[i].P.num_windows, phase = stride > 1 ? i % stride : 0;
     fw_all[i + 1] = fw_all[i] + nw;
-    fw_smp[i + 1] = fw_smp[i] + (nw > phase ? (nw - phase + stride - 1) / stride : 0);
+    if (edge_sample) {
+      uint32_t cnt = 0;
+      for (uint32_t w = 0; w < nw; w++) {
+        const bool edge = w == 0 || w + 1 == nw, strided = w % stride == phase;
+        if (edge || strided) { sample_win.push_back(w | (edge ? 0x80000000u : 0u)); cnt++; }
+      }
+      fw_smp[i + 1] = fw_smp[i] + cnt;
+    } else fw_smp[i + 1] = fw_smp[i] + (nw > phase ? (nw - phase + stride - 1) / stride : 0);
   }
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), o_rank = al(o_bounds + (size_t)tot_bounds * 8),
-         blob_bytes = al(o_rank + (size_t)n * 4);
+         o_smp = al(o_rank + (size_t)n * 4), blob_bytes = al(o_smp + sample_win.size() * 4);
   // device-side cross-split merge: the per-split hit lists stay in scratch, only the merged top-K comes back
   const bool do_merge = merge && merged && merge->k > 0 && any_topk && merge->rank.size() == n_in;
   uint32_t kmax = 1;
@@ -829,7 +842,16 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaEventCreate(&slot->ev2));
     CUDA_CHECK(cudaEventCreate(&slot->ev3));
   }
-  struct Release { Engine* e; CallSlot* s; ~Release() { std::lock_guard<std::mutex> g(e->mu); e->free_slots.push_back(s); } } rel{this, slot};
+  // the slot goes back to the pool only once its stream is idle: on an error path copies / kernels of this
+  // call may still be in flight, and the next call would reuse the pinned buffers under them
+  struct Release {
+    Engine* e; CallSlot* s;
+    ~Release() {
+      cudaStreamSynchronize(s->stream);
+      std::lock_guard<std::mutex> g(e->mu);
+      e->free_slots.push_back(s);
+    }
+  } rel{this, slot};
   slot->ensure(blob_bytes, scratch_bytes, out_bytes);
   cudaStream_t st = slot->stream;
 
@@ -855,6 +877,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     if (!low[i].bounds.empty()) memcpy(slot->h_blob + o_bounds + (size_t)low[i].bounds_base * 8, low[i].bounds.data(), low[i].bounds.size() * 8);
   }
   if (do_merge) for (uint32_t i = 0; i < n; i++) ((uint32_t*)(slot->h_blob + o_rank))[i] = merge->rank[idx[i]];
+  if (!sample_win.empty()) memcpy(slot->h_blob + o_smp, sample_win.data(), sample_win.size() * 4);
   memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
@@ -886,6 +909,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     q.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fws : o_fwa));
     q.total_work = sampled ? fw_smp[n] : fw_all[n];
     q.stride = sampled ? stride : 1;
+    q.sample_win = (sampled && edge_sample) ? (const uint32_t*)(slot->d_blob + o_smp) : nullptr;
     q.level = level;
     q.use_prefix = use_prefix;
     q.rec_l0 = (flags & F_REC) ? 1 : 0;
@@ -983,7 +1007,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (any_topk && stride > 1) {
     // fast path: threshold from a 1/stride sample of the windows, verified after the collect pass
     launch_window(qwk::MODE_HIST, true, 0, 0, 0);
-    qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 1, stride, nullptr);
+    qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, edge_sample ? 2 : 1, stride, nullptr);
     stats.launches++;
     if (rec_l0) CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
     run_collect(rec_l0 ? F_REC : 0);

@@ -859,7 +859,15 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
 
   for (uint32_t work = w_begin; work < w_end; work++) {
     while (__ldg(p.first_work + split + 1) <= work) split++;
-    const uint32_t window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
+    // sampled passes with an explicit window list: the strided sample plus the first and last window of every
+    // split (keys that follow doc order — doc id, timestamps of time-ordered logs — have their best K there);
+    // a strided window stands for `stride` windows in the histogram, an edge window for itself
+    uint32_t window, hist_weight = 1;
+    if (p.sample_win) {
+      const uint32_t e = __ldg(p.sample_win + work);
+      window = e & 0x7FFFFFFFu;
+      hist_weight = (e >> 31) ? 1u : p.stride;
+    } else window = (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
     if (p.refine) {
       // second-chance passes: verified splits are final, and a window whose best level-0 digit is
       // below the threshold digit cannot hold a candidate (block-uniform tests)
@@ -1468,7 +1476,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
       uint32_t* gh = (uint32_t*)P.out_hist;
       for (uint32_t i = tid; i < QW_HIST_BINS; i += QW_THREADS) {
         uint32_t v = s_hist[i];
-        if (v) { atomicAdd(&gh[i], v); s_hist[i] = 0; }
+        if (v) { atomicAdd(&gh[i], v * hist_weight); s_hist[i] = 0; }
       }
     }
   }
@@ -1504,7 +1512,10 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
   for (uint32_t t = 0; t < tid; t++) above_me += s_part[t];
   uint32_t K = P.max_hits;
   uint32_t target, base_above = 0;
-  if (sampled) {
+  if (sampled == 2) {
+    // weighted sample (counts are estimates of the true counts): twice K plus the same slack in windows
+    target = 2 * K + 24 * stride;
+  } else if (sampled) {
     // conservative sample rank: 2x the expected sample share of K plus slack
     target = (2 * K + stride - 1) / stride + 24;
   } else {

@@ -212,6 +212,11 @@ static bool same_sort_types(const std::vector<SplitJob>& jobs, const std::vector
 }
 static void sort_orders(const pb::SearchRequest& r, int* o1, int* o2);
 
+// A failed split is reported retryable (leaf.rs:1989-2004: the root retries it on another node) unless the
+// failure is a property of the request itself: a query shape or a top-K size this library does not execute
+// fails the same way on every node, and retrying would only run it twice.
+static inline bool retryable(int code) { return code != QWGPU_EUNSUPPORTED; }
+
 static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& run, bool want_merged = false, const Comm* comm = nullptr) {
   using clock = std::chrono::steady_clock;
   const pb::SearchRequest& sreq = lr.search_request;
@@ -486,13 +491,13 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
   mreq.max_hits += mreq.start_offset;
   mreq.start_offset = 0;
   std::vector<qw::pb::SplitSearchError> failed;
-  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, true});  // retryable (leaf.rs:1989-2004)
+  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, qw::retryable(j.error_code)});
   // drop splits whose search failed on the device from the merge set
   {
     std::vector<size_t> w2;
     std::vector<qw::SplitOutput> o2;
     for (size_t k = 0; k < run.which.size(); k++) {
-      if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, true});
+      if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, qw::retryable(run.outs[k].status)});
       else { w2.push_back(run.which[k]); o2.push_back(std::move(run.outs[k])); }
     }
     run.which.swap(w2);
@@ -579,9 +584,9 @@ int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* req, size_t req_l
     if (comm.world > 1 && mreq.max_hits > 0) qw::fail(QWGPU_EINTERNAL, "cross-rank merge did not run");
   }
   std::vector<qw::pb::SplitSearchError> failed;
-  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, true});
+  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, qw::retryable(j.error_code)});
   for (size_t k = 0; k < run.which.size(); k++)
-    if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, true});
+    if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, qw::retryable(run.outs[k].status)});
   qw::pb::LeafSearchResponse m;
   uint64_t total_failed = failed.size();
   if (run.gathered) {

@@ -165,3 +165,43 @@ def test_partial_hit_wire_form_every_value_kind_and_long_split_ids():
     got = [{k: v for k, v in h.items() if v is not None} for h in out["partial_hits"]]
     want = [{k: v for k, v in h.items()} for h in hits]
     assert got == want
+
+
+def test_corrupt_split_images_are_rejected():
+    """Every offset of a split image is checked before it is followed (they end up as device pointers):
+    truncated images and out-of-range sections / terms / columns fail with EINVALID_ARG."""
+    img = S.synth_split(5000, 3, [0.2, 0.1], split_id="corrupt")
+    dm = json.dumps({"field_mappings": [], "timestamp_field": "timestamp"})
+    req = search_request(term("body", "t0"), max_hits=3)
+    assert service.compile_plan(img, req, dm)
+    hdr = img.header()
+    H, T, CO = ffi.QwImgHeader, ffi.QwImgTerm, ffi.QwImgColumn
+
+    def broken(mutate):
+        raw = img.array.copy()
+        mutate(raw)
+        with pytest.raises(ffi.QwGpuError) as e:
+            service.compile_plan(S.SplitImage(raw, "corrupt"), req, dm)
+        assert e.value.code == ffi.EINVALID_ARG, e.value.msg
+
+    def put64(raw, off, v):
+        raw[off:off + 8] = np.frombuffer(np.uint64(v).tobytes(), dtype=np.uint8)
+
+    with pytest.raises(ffi.QwGpuError):
+        service.compile_plan(S.SplitImage(img.array[: img.nbytes - 64].copy(), "corrupt"), req, dm)
+    broken(lambda r: put64(r, H.terms_off.offset, hdr.total_len - 8))
+    broken(lambda r: put64(r, H.data_len.offset, hdr.data_len + 4096))
+    broken(lambda r: put64(r, H.strings_len.offset, 1 << 40))
+    broken(lambda r: put64(r, hdr.terms_off + T.data_off.offset, hdr.data_len))            # first term: blocks past the data region
+    broken(lambda r: put64(r, hdr.terms_off + T.widx_off.offset, hdr.data_len - 8))
+    broken(lambda r: put64(r, hdr.columns_off + CO.values_off.offset, hdr.data_len - 8))
+    broken(lambda r: put64(r, hdr.columns_off + CO.index_len.offset, 1 << 50))
+
+
+def test_unsupported_requests_are_not_marked_retryable():
+    """leaf.rs:1989-2004 marks failed splits retryable so that the root re-runs them on another node; a
+    request this library does not execute would fail there the same way (the C++ side reports it with
+    retryable_error = false). Checked on the source: the leaf path needs a device."""
+    src = open(os.path.join(ROOT, "quickwit_b200", "csrc", "leaf.cpp")).read()
+    assert "return code != QWGPU_EUNSUPPORTED" in src
+    assert not re.search(r"failed\.push_back\(\{[^}]*, true\}\)", src)

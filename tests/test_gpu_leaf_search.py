@@ -123,6 +123,12 @@ def test_failed_split_is_reported_not_fatal(gpu_ctx, synth):
     with pytest.raises(ffi.QwGpuError) as e:
         gpu_ctx.leaf_search(proto.enc_leaf_search_request(search_request(term("nope", "x"), max_hits=5), offsets[:1], json.dumps(SYNTH_MAPPING)))
     assert e.value.code == ffi.EINVALID_QUERY
+    # a request this library does not execute (top-K above the 4096 cap) fails the same way on every node:
+    # the split is reported failed but NOT retryable, so the root does not run it twice
+    big = proto.enc_leaf_search_request(search_request(term("body", "t0"), max_hits=5000), offsets[:1], json.dumps(SYNTH_MAPPING))
+    resp = proto.dec_leaf_search_response(gpu_ctx.leaf_search(big))
+    assert resp["num_successful_splits"] == 0 and len(resp["failed_splits"]) == 1
+    assert resp["failed_splits"][0]["retryable_error"] is False and resp["failed_splits"][0]["split_id"] == synth[0].split_id
 
 
 def test_invoke_leaf_search_per_split_results(gpu_ctx, synth):
