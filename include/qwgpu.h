@@ -121,6 +121,14 @@ int qwgpu_build_leaf_response(const uint8_t* img, uint64_t img_len, const char* 
                               uint32_t num_partial_hits, const QwAggCell* cells, uint32_t num_cells,
                               uint8_t** resp, size_t* resp_len);
 
+/* Pre-search pruning, host only: what qwgpu_leaf_search does to the request of every
+ * split before it searches — CanSplitDoBetter::{from_request, optimize_split_order, optimize}
+ * (quickwit-search/src/leaf.rs:1072-1242), disable_search_request_hits (leaf.rs:1438-1443) and
+ * is_metadata_count_request_with_ast (root.rs:665-686; leaf.rs:525-528 answers such a split from num_docs).
+ * `json_out` (qwgpu_buf_free) = [{"split_id", "max_hits", "hits_disabled", "metadata_count"}, ...] in the
+ * reference's processing order, one entry per split of the request. */
+int qwgpu_optimize_leaf_request(const uint8_t* leaf_search_request_pb, size_t req_len, uint8_t** json_out, size_t* json_len);
+
 /* ---- merge / finalize -------------------------------------------------------------------------- */
 
 /* Merges N LeafSearchResponse protobufs under `search_request_pb` (sort orders, max_hits,

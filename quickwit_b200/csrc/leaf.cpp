@@ -186,6 +186,7 @@ struct SplitJob {
   CompiledPlan plan;
   std::string error;
   int error_code = 0;
+  bool metadata_count = false;  // answered from the split's num_docs alone (no plan, no device work)
 };
 
 struct LeafRun {
@@ -212,6 +213,88 @@ static bool same_sort_types(const std::vector<SplitJob>& jobs, const std::vector
 }
 static void sort_orders(const pb::SearchRequest& r, int* o1, int* o2);
 
+// ---- pre-search pruning ---------------------------------------------------------------
+// CanSplitDoBetter::{from_request, optimize_split_order, optimize} (leaf.rs:1072-1242), is_simple_all_query
+// (leaf.rs:1047-1069), disable_search_request_hits (leaf.rs:1438-1443), is_metadata_count_request_with_ast
+// (root.rs:665-686). For a match-all request the split metadata alone says which splits can hold the top hits:
+// the others are demoted to count-only requests, and a count-only match-all request without time bounds or
+// aggregations is answered from `num_docs` without touching the split (leaf.rs:525-528).
+// The reference also tightens the filter while the splits of a request run one after another
+// (can_be_better / record_new_worst_hit, leaf.rs:1244-1285, 2012): the hits it removes are hits that cannot
+// reach the top-K, so the response is the same; here all splits of a request run in one batch and that
+// feedback has nothing to act on.
+struct SplitFilter {
+  enum Kind { Uninformative, SplitIdHigher, SplitTimestampHigher, SplitTimestampLower } kind = Uninformative;
+};
+static SplitFilter split_filter_from_request(const pb::SearchRequest& r, const std::string& timestamp_field) {
+  SplitFilter f;
+  if (r.sort_fields.empty()) f.kind = SplitFilter::SplitIdHigher;
+  else if (!timestamp_field.empty() && r.sort_fields[0].field_name == timestamp_field)
+    f.kind = r.sort_fields[0].sort_order == 0 ? SplitFilter::SplitTimestampLower : SplitFilter::SplitTimestampHigher;
+  return f;
+}
+static bool is_match_all_ast(const Json& ast) { return ast.type == Json::Obj && ast.str_or("type", "") == "match_all"; }
+static bool is_simple_all_query(const pb::SearchRequest& r, const Json& ast) {
+  if (r.aggregation_request || r.search_after || r.start_timestamp || r.end_timestamp) return false;
+  return is_match_all_ast(ast);
+}
+static bool is_metadata_count_request(const pb::SearchRequest& r, const Json& ast) {
+  return is_match_all_ast(ast) && r.max_hits == 0 && !r.start_timestamp && !r.end_timestamp && !r.aggregation_request && r.snippet_fields.empty();
+}
+static void disable_search_request_hits(pb::SearchRequest& r) {
+  r.max_hits = 0;
+  r.start_offset = 0;
+  r.sort_fields.clear();
+  r.search_after.reset();
+}
+struct SplitRequest {
+  size_t input_pos;         // position of the split in the LeafRequestRef
+  bool hits_disabled;       // demoted to a count-only request
+  bool metadata_count;      // answered from num_docs
+};
+// the splits of one LeafRequestRef in the reference's processing order, with the per-split request rewrite
+static std::vector<SplitRequest> optimize_split_requests(const pb::SearchRequest& r, const Json& ast, const std::string& timestamp_field,
+                                                         const std::vector<pb::SplitIdAndFooterOffsets>& splits) {
+  const SplitFilter f = split_filter_from_request(r, timestamp_field);
+  auto ts_start = [&](size_t i) { return splits[i].timestamp_start.value_or(0); };  // prost getters: unset = 0
+  auto ts_end = [&](size_t i) { return splits[i].timestamp_end.value_or(0); };
+  std::vector<size_t> order(splits.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  if (f.kind == SplitFilter::SplitIdHigher) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return splits[a].split_id > splits[b].split_id; });
+  else if (f.kind == SplitFilter::SplitTimestampHigher) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ts_end(a) > ts_end(b); });
+  else if (f.kind == SplitFilter::SplitTimestampLower) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ts_start(a) < ts_start(b); });
+  std::vector<SplitRequest> out;
+  for (size_t i : order) out.push_back({i, false, false});
+  if (is_simple_all_query(r, ast)) {
+    const uint64_t wanted = r.start_offset + r.max_hits;
+    // splits guaranteed to deliver enough docs: the first prefix whose doc counts reach `wanted`
+    size_t min_required = 1;
+    uint64_t partial = 0;
+    for (size_t k = 0; k < out.size(); k++) {
+      partial += splits[out[k].input_pos].num_docs;
+      if (partial < wanted) min_required++; else break;
+    }
+    if (f.kind == SplitFilter::SplitIdHigher) {
+      for (size_t k = min_required; k < out.size(); k++) out[k].hits_disabled = true;
+    } else if (f.kind == SplitFilter::SplitTimestampLower) {
+      // only splits that start after every required split has ended cannot hold an earlier doc
+      int64_t biggest_end = INT64_MIN;
+      for (size_t k = 0; k < std::min(min_required, out.size()); k++) biggest_end = std::max(biggest_end, ts_end(out[k].input_pos));
+      for (size_t k = min_required; k < out.size(); k++) if (ts_start(out[k].input_pos) > biggest_end) out[k].hits_disabled = true;
+    } else if (f.kind == SplitFilter::SplitTimestampHigher) {
+      int64_t smallest_start = INT64_MAX;
+      for (size_t k = 0; k < std::min(min_required, out.size()); k++) smallest_start = std::min(smallest_start, ts_start(out[k].input_pos));
+      for (size_t k = min_required; k < out.size(); k++) if (ts_end(out[k].input_pos) < smallest_start) out[k].hits_disabled = true;
+    }
+  }
+  for (SplitRequest& q : out) {
+    pb::SearchRequest rr = r;  // (only the fields the test reads)
+    if (q.hits_disabled) disable_search_request_hits(rr);
+    q.metadata_count = is_metadata_count_request(rr, ast);
+  }
+  return out;
+}
+
 // A failed split is reported retryable (leaf.rs:1989-2004: the root retries it on another node) unless the
 // failure is a property of the request itself: a query shape or a top-K size this library does not execute
 // fails the same way on every node, and retrying would only run it twice.
@@ -225,13 +308,34 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
   for (auto& ref : lr.leaf_requests) {
     if (ref.doc_mapper_ord >= lr.doc_mappers.size()) fail(QWGPU_EINVALID_ARG, "Internal error: doc_mapper_ord out of bounds");
     DocMapperInfo dm = parse_doc_mapper(lr.doc_mappers[ref.doc_mapper_ord]);
-    for (auto& so : ref.split_offsets) {
+    // per-split request rewrite (a16); the jobs keep the request's split order (the processing order of a
+    // batch is not observable). Across ranks every split goes to the device: the counters of the exchanged
+    // record are built there.
+    std::vector<SplitRequest> opt = optimize_split_requests(sreq, ast, dm.timestamp_field, ref.split_offsets);
+    std::vector<const SplitRequest*> by_pos(ref.split_offsets.size(), nullptr);
+    for (const SplitRequest& q : opt) by_pos[q.input_pos] = &q;
+    static const bool no_prune = getenv("QWGPU_NO_PRUNING") != nullptr;
+    pb::SearchRequest count_req;
+    bool have_count_req = false;
+    for (size_t si = 0; si < ref.split_offsets.size(); si++) {
+      const pb::SplitIdAndFooterOffsets& so = ref.split_offsets[si];
+      const SplitRequest& q = *by_pos[si];
       SplitJob j;
       j.meta = so;
+      if (q.metadata_count && !comm && !no_prune) {
+        j.metadata_count = true;
+        run.jobs.push_back(std::move(j));
+        continue;
+      }
+      const pb::SearchRequest* req = &sreq;
+      if (q.hits_disabled && !no_prune) {
+        if (!have_count_req) { count_req = sreq; disable_search_request_hits(count_req); have_count_req = true; }
+        req = &count_req;
+      }
       j.dev = eng.find(so.split_id);
       try {
         if (!j.dev) fail(QWGPU_ENOTFOUND, "split `%s` is not resident on this GPU", so.split_id.c_str());
-        j.plan = compile_plan(j.dev->view, so.split_id, sreq, dm, &so, &ast);
+        j.plan = compile_plan(j.dev->view, so.split_id, *req, dm, &so, &ast);
       } catch (const Error& e) {
         // malformed queries / aggregations fail the whole request like the reference (service.rs:182-184)
         if (e.code == QWGPU_EINVALID_QUERY || e.code == QWGPU_EINVALID_AGG || e.code == QWGPU_EINVALID_ARG) throw;
@@ -245,7 +349,7 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
   std::vector<const uint8_t*> plans;
   std::vector<size_t> lens;
   for (size_t i = 0; i < run.jobs.size(); i++)
-    if (!run.jobs[i].error_code) {
+    if (!run.jobs[i].error_code && !run.jobs[i].metadata_count) {
       devs.push_back(run.jobs[i].dev);
       plans.push_back((const uint8_t*)run.jobs[i].plan.bytes.data());
       lens.push_back(run.jobs[i].plan.bytes.size());
@@ -319,6 +423,12 @@ static std::vector<pb::LambdaSingleSplitResult> run_leaf(Engine& eng, const pb::
   for (size_t i = 0; i < run.jobs.size(); i++) {
     results[i].split_id = run.jobs[i].meta.split_id;
     if (run.jobs[i].error_code) { results[i].is_error = true; results[i].error = run.jobs[i].error; }
+    if (run.jobs[i].metadata_count) {  // get_leaf_resp_from_count (leaf.rs:474-484)
+      pb::LeafSearchResponse r;
+      r.num_hits = run.jobs[i].meta.num_docs;
+      r.num_attempted_splits = r.num_successful_splits = 1;
+      results[i].response = std::move(r);
+    }
   }
   for (size_t k = 0; k < run.which.size(); k++) {
     size_t i = run.which[k];
@@ -522,6 +632,12 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
     merged = parts.size() == 1 ? std::move(parts[0]) : qw::merge_responses(mreq, std::move(parts));
   }
   for (auto& f : failed) { merged.failed_splits.push_back(f); merged.num_attempted_splits += 1; }
+  for (auto& j : run.jobs)
+    if (j.metadata_count) {  // get_leaf_resp_from_count (leaf.rs:474-484) merged in: counters only
+      merged.num_hits += j.meta.num_docs;
+      merged.num_attempted_splits += 1;
+      merged.num_successful_splits += 1;
+    }
   auto t_merge = tclock::now();
   give(qw::pb::encode_leaf_search_response(merged), resp, resp_len);
   if (trace) {
@@ -529,6 +645,31 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
     fprintf(stderr, "[qwgpu] leaf_search: decode %ld us, compile+search %ld us (engine wall %lu us, device %.0f us, %u launches), merge %ld us, encode %ld us\n",
             us(t_start, t_dec), us(t_dec, t_run), (unsigned long)run.wall_us, run.st.gpu_time_us, run.st.launches, us(t_run, t_merge), us(t_merge, tclock::now()));
   }
+  return 0;
+  QW_API_END
+}
+
+// Host only: the per-split request rewrite of a LeafSearchRequest as JSON, in the reference's processing order:
+// [{"split_id", "max_hits", "hits_disabled", "metadata_count"} ...] per LeafRequestRef (concatenated).
+int qwgpu_optimize_leaf_request(const uint8_t* req, size_t req_len, uint8_t** out, size_t* out_len) {
+  QW_API_BEGIN
+  if (!req || !out || !out_len) qw::fail(QWGPU_EINVALID_ARG, "null argument");
+  qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
+  qw::Json ast = qw::parse_json(lr.search_request.query_ast, QWGPU_EINVALID_QUERY);
+  std::string js = "[";
+  for (auto& ref : lr.leaf_requests) {
+    if (ref.doc_mapper_ord >= lr.doc_mappers.size()) qw::fail(QWGPU_EINVALID_ARG, "Internal error: doc_mapper_ord out of bounds");
+    qw::DocMapperInfo dm = qw::parse_doc_mapper(lr.doc_mappers[ref.doc_mapper_ord]);
+    for (const qw::SplitRequest& q : qw::optimize_split_requests(lr.search_request, ast, dm.timestamp_field, ref.split_offsets)) {
+      if (js.size() > 1) js += ",";
+      std::string id;
+      for (char c : ref.split_offsets[q.input_pos].split_id) { if (c == '"' || c == '\\') id += '\\'; id += c; }
+      js += "{\"split_id\":\"" + id + "\",\"max_hits\":" + std::to_string(q.hits_disabled ? 0 : lr.search_request.max_hits) +
+            ",\"hits_disabled\":" + (q.hits_disabled ? "true" : "false") + ",\"metadata_count\":" + (q.metadata_count ? "true" : "false") + "}";
+    }
+  }
+  js += "]";
+  give(js, out, out_len);
   return 0;
   QW_API_END
 }

@@ -179,6 +179,7 @@ def lib() -> C.CDLL:
     bind("qwgpu_build_leaf_response", [vp, u64, cp, vp, sz, cp, u64, vp, u32, vp, u32, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_merge_leaf_responses", [vp, sz, u32, C.POINTER(vp), C.POINTER(sz),
                                         C.POINTER(vp), C.POINTER(sz)])
+    bind("qwgpu_optimize_leaf_request", [vp, sz, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_finalize_aggregation", [cp, vp, sz, C.POINTER(vp)])
     bind("qwgpu_partial_size", [vp, sz, C.POINTER(u64)])
     bind("qwgpu_response_to_partial", [vp, sz, vp, sz, vp, u64])

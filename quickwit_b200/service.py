@@ -132,6 +132,18 @@ def compile_plan(img: SplitImage, search_request_pb: bytes, doc_mapper_json: str
     return ffi.take_bytes(out, n.value)
 
 
+def optimize_leaf_request(leaf_search_request_pb: bytes) -> list:
+    """CanSplitDoBetter::optimize + metadata-count detection for every split of a LeafSearchRequest
+    (leaf.rs:1072-1242, root.rs:665-686): [{"split_id", "max_hits", "hits_disabled", "metadata_count"}]
+    in the reference's processing order. Host only."""
+    import json
+    L = ffi.lib()
+    buf = C.create_string_buffer(leaf_search_request_pb, len(leaf_search_request_pb))
+    out, n = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_optimize_leaf_request(C.addressof(buf), len(leaf_search_request_pb), C.byref(out), C.byref(n)))
+    return json.loads(ffi.take_bytes(out, n.value))
+
+
 def merge_leaf_responses(search_request_pb: bytes, responses: Sequence[bytes]) -> bytes:
     """merge_leaf_responses / QuickwitCollector::merge_fruits (collector.rs:832-974)."""
     L = ffi.lib()

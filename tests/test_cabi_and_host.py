@@ -205,3 +205,50 @@ def test_unsupported_requests_are_not_marked_retryable():
     src = open(os.path.join(ROOT, "quickwit_b200", "csrc", "leaf.cpp")).read()
     assert "return code != QWGPU_EUNSUPPORTED" in src
     assert not re.search(r"failed\.push_back\(\{[^}]*, true\}\)", src)
+
+
+def _optimized(ast, splits, mapping=None, **req_kw):
+    """splits: [(split_id, num_docs, ts_start, ts_end)] -> qwgpu_optimize_leaf_request rows"""
+    mapping = mapping or {"field_mappings": [{"name": "ts", "type": "datetime", "fast": True}, {"name": "body", "type": "text"},
+                                             {"name": "n", "type": "u64", "fast": True}], "timestamp_field": "ts"}
+    offsets = [proto.enc_split_offsets(sid, nd, a, b) for sid, nd, a, b in splits]
+    return service.optimize_leaf_request(proto.enc_leaf_search_request(search_request(ast, **req_kw), offsets, json.dumps(mapping)))
+
+
+def test_can_split_do_better_static_pruning():
+    """CanSplitDoBetter::optimize (leaf.rs:1141-1242) + is_metadata_count_request_with_ast (root.rs:665-686)."""
+    row = lambda r: (r["split_id"], r["hits_disabled"], r["metadata_count"])
+    # no sort: splits in descending split-id order; once the doc counts reach start_offset + max_hits the rest only count
+    got = _optimized(MATCH_ALL, [("a", 2, None, None), ("b", 5, None, None), ("c", 1, None, None), ("0", 9, None, None)], max_hits=2, start_offset=1)
+    assert [row(r) for r in got] == [("c", False, False), ("b", False, False), ("a", True, True), ("0", True, True)]
+    assert [r["max_hits"] for r in got] == [2, 2, 0, 0]
+    # the first split alone is enough
+    got = _optimized(MATCH_ALL, [("a", 2, None, None), ("b", 5, None, None)], max_hits=5)
+    assert [row(r) for r in got] == [("b", False, False), ("a", True, True)]
+    # sort by the timestamp field, descending: order by timestamp_end desc; a later split is demoted only when it
+    # ends before every required split starts (ranges may overlap)
+    splits = [("s1", 5, 0, 4), ("s2", 5, 11, 20), ("s3", 5, 5, 25), ("s4", 5, 3, 9)]
+    got = _optimized(MATCH_ALL, splits, max_hits=4, sort_fields=[("ts", DESC)])
+    assert [row(r) for r in got] == [("s3", False, False), ("s2", False, False), ("s4", False, False), ("s1", True, True)]
+    got = _optimized(MATCH_ALL, splits, max_hits=7, sort_fields=[("ts", DESC)])   # two splits required: smallest start = 5
+    assert [row(r) for r in got] == [("s3", False, False), ("s2", False, False), ("s4", False, False), ("s1", True, True)]
+    # ascending: order by timestamp_start; demoted when it starts after every required split has ended
+    got = _optimized(MATCH_ALL, splits, max_hits=4, sort_fields=[("ts", ASC)])
+    assert [row(r) for r in got] == [("s1", False, False), ("s4", False, False), ("s3", True, True), ("s2", True, True)]
+    got = _optimized(MATCH_ALL, splits, max_hits=6, sort_fields=[("ts", ASC)])    # s1 + s4 required: biggest end = 9
+    assert [row(r) for r in got] == [("s1", False, False), ("s4", False, False), ("s3", False, False), ("s2", True, True)]
+    # a sort field that is not the timestamp field says nothing: request order, nothing demoted
+    got = _optimized(MATCH_ALL, splits, max_hits=1, sort_fields=[("n", DESC)])
+    assert [row(r) for r in got] == [(s[0], False, False) for s in splits]
+    # not a match-all query / time bounds / aggregation / search_after: ordered, never demoted
+    got = _optimized(term("body", "x"), splits, max_hits=1, sort_fields=[("ts", DESC)])
+    assert [row(r) for r in got] == [("s3", False, False), ("s2", False, False), ("s4", False, False), ("s1", False, False)]
+    for kw in (dict(start_timestamp=3), dict(end_timestamp=30), dict(aggs={"c": {"terms": {"field": "n"}}}),
+               dict(search_after={"split_id": "s2", "segment_ord": 0, "doc_id": 1, "sort_value": ("i64", 5)})):
+        got = _optimized(MATCH_ALL, splits, max_hits=1, sort_fields=[("ts", DESC)], **kw)
+        assert not any(r["hits_disabled"] or r["metadata_count"] for r in got), kw
+    # count requests: match-all without bounds or aggregations is answered from num_docs
+    assert all(r["metadata_count"] for r in _optimized(MATCH_ALL, splits, max_hits=0))
+    assert not any(r["metadata_count"] for r in _optimized(MATCH_ALL, splits, max_hits=0, aggs={"c": {"terms": {"field": "n"}}}))
+    assert not any(r["metadata_count"] for r in _optimized(MATCH_ALL, splits, max_hits=0, end_timestamp=7))
+    assert not any(r["metadata_count"] for r in _optimized(term("body", "x"), splits, max_hits=0))

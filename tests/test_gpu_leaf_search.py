@@ -165,3 +165,37 @@ def test_concurrent_leaf_searches_match_sequential(gpu_ctx, synth):
         for _ in range(5):
             got = list(ex.map(lambda r: hits(gpu_ctx.leaf_search(r)), reqs))
             assert got == want
+
+
+def test_pre_search_pruning_keeps_the_response(gpu_ctx):
+    """a16: with the split metadata in the request (time ranges, doc counts) match-all top-K requests demote the
+    splits that cannot reach the top to count-only / metadata-count requests (leaf.rs:1141-1242, 525-528).
+    The merged response must not change; the device sees fewer splits."""
+    mapping = {"field_mappings": [{"name": "ts", "type": "datetime", "fast": True}, {"name": "body", "type": "text"}], "timestamp_field": "ts"}
+    t0 = 1_700_000_000
+    imgs, ranges = [], []
+    for i in range(5):
+        lo, hi = t0 + 100 * i, t0 + 100 * i + 60 + (80 if i == 2 else 0)   # split 2 overlaps split 3
+        docs = [{"ts": lo + (j * 7) % (hi - lo + 1), "body": "hello"} for j in range(40)]
+        imgs.append(S.build_split(docs, mapping, f"prune-{i}"))
+        ranges.append((min(d["ts"] for d in docs), max(d["ts"] for d in docs)))
+        gpu_ctx.register_split(imgs[-1])
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs, a, b) for im, (a, b) in zip(imgs, ranges)]
+    for kw in (dict(max_hits=5, sort_fields=[("ts", DESC)]), dict(max_hits=50, sort_fields=[("ts", ASC)]), dict(max_hits=7),
+               dict(max_hits=45, start_offset=40), dict(max_hits=0)):
+        lreq = proto.enc_leaf_search_request(search_request(MATCH_ALL, **leafify(kw)), offsets, json.dumps(mapping))
+        plan = service.optimize_leaf_request(lreq)
+        leaf = proto.dec_leaf_search_response(gpu_ctx.leaf_search(lreq))
+        got = proto.dec_leaf_search_response(service.merge_leaf_responses(search_request(MATCH_ALL, **kw), [gpu_ctx.leaf_search(lreq)]))
+        want = cpu_root_search(imgs, MATCH_ALL, mapping, **kw)   # no pruning on this side
+        assert got["num_hits"] == want["num_hits"] == 200 and got["partial_hits"] == want["partial_hits"], kw
+        assert leaf["num_attempted_splits"] == 5 and leaf["num_successful_splits"] == 5 and not leaf["failed_splits"]
+        n_meta = sum(r["metadata_count"] for r in plan)
+        assert n_meta >= 1, (kw, plan)
+        on_device = leaf["resource_stats"]["localexec_num_splits"] if leaf["resource_stats"] else 0
+        assert on_device == 5 - n_meta, (kw, plan)
+    # a non-resident split that only has to be counted is answered from its metadata
+    offs = offsets + [proto.enc_split_offsets("prune-ghost", 123, t0 - 500, t0 - 400)]
+    lreq = proto.enc_leaf_search_request(search_request(MATCH_ALL, max_hits=5, sort_fields=[("ts", DESC)]), offs, json.dumps(mapping))
+    leaf = proto.dec_leaf_search_response(gpu_ctx.leaf_search(lreq))
+    assert leaf["num_hits"] == 323 and not leaf["failed_splits"] and leaf["num_successful_splits"] == 6
