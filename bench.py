@@ -255,9 +255,7 @@ def other_configs(ctx, imgs, peak, reps: int = 20, lat_runs: int = 60):
         "c3_term_and_ts_range_top1000_by_ts": ({"type": "bool", "must": [term("body", "t2")]},
                                                dict(max_hits=1000, sort_fields=[("timestamp", 1)], start_timestamp=T0_SECS + span // 4,
                                                     end_timestamp=T0_SECS + 3 * span // 4), None),
-        "c4_terms_date_histogram": ({"type": "match_all"}, dict(max_hits=0),
-                                    {"by_sev": {"terms": {"field": "severity_text"}},
-                                     "over_time": {"date_histogram": {"field": "timestamp", "fixed_interval": "1h"}}}),
+        "c4_terms_date_histogram": ({"type": "match_all"}, dict(max_hits=0), C4_AGGS),
     }
     dm = json.dumps(SYNTH_MAPPING)
     ids = [im.split_id for im in imgs]
@@ -293,6 +291,50 @@ def other_configs(ctx, imgs, peak, reps: int = 20, lat_runs: int = 60):
                      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                   "algorithmic_bytes_per_launch": r["alg_bytes"], "traffic": traffic, "traffic_source": tsrc}}
     return out
+
+
+C4_AGGS = {"by_sev": {"terms": {"field": "severity_text"}},
+           "over_time": {"date_histogram": {"field": "timestamp", "fixed_interval": "1h"}}}
+
+
+def config4_strong(ctx, imgs, world: int, rank: int, reps: int = 10):
+    """BASELINE config 4's shape at N > 1 (strong scaling): the 32-split / 100 M-doc corpus sharded over the N
+    GPUs (32 / N splits per rank), match_all + terms(severity_text) + date_histogram(1 h), no hits. One
+    qwgpu_leaf_search_allgather per query on every rank: the per-rank aggregation partials travel in the
+    library's host-staged NCCL all-gather and are merged on every rank. Timed end to end (host bytes in / out),
+    barrier on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from quickwit_b200 import proto, service
+    per = max(1, len(imgs) // world)
+    mine = imgs[:per]
+    sreq = proto.enc_search_request(json.dumps({"type": "match_all"}), aggregation_request=json.dumps(C4_AGGS), max_hits=0)
+    lreq = proto.enc_leaf_search_request(sreq, [proto.enc_split_offsets(im.split_id, im.num_docs) for im in mine], json.dumps(SYNTH_MAPPING))
+    got = proto.dec_leaf_search_response(ctx.leaf_search_allgather(lreq))
+    # check against the host road: per-rank response -> partial -> torch all-gather -> qwgpu_merge_partials
+    nb = service.partial_size(sreq)
+    pbuf = torch.zeros(nb, dtype=torch.uint8).pin_memory()
+    service.response_to_partial(sreq, ctx.leaf_search(lreq), pbuf.data_ptr(), nb)
+    gd = torch.zeros(world * nb, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(gd, pbuf.cuda())
+    gh = gd.cpu()
+    want = proto.dec_leaf_search_response(service.merge_partials(sreq, world, gh.data_ptr(), nb))
+    assert got["num_hits"] == want["num_hits"] == world * sum(im.num_docs for im in mine)
+    assert got["intermediate_aggregation_result"] == want["intermediate_aggregation_result"], "aggregation exchange differs from the host merge"
+    for _ in range(3):
+        ctx.leaf_search_allgather(lreq)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.leaf_search_allgather(lreq)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item()) / reps
+    docs = world * sum(im.num_docs for im in mine)
+    return {"workload": "c4_terms_date_histogram, corpus sharded over the ranks (strong scaling)", "docs": docs, "splits_per_rank": per,
+            "ms_per_query": 1e3 * wall, "docs_per_s": docs / wall, "column_values_per_s": docs * len(C4_AGGS) / wall,
+            "api": "qwgpu_leaf_search_allgather (aggregation partials: host-staged NCCL all-gather inside the library)"}
 
 
 def main():
@@ -511,6 +553,12 @@ def main():
     launches = sum(x["launches"] for x in accs)
     n_main = a.steps * Q_SETS
     postings_rank0 = postings
+    c4_strong = None
+    if world > 1 and device_exchange and not a.no_configs and a.splits % world == 0:
+        try:
+            c4_strong = config4_strong(ctx, imgs, world, rank)
+        except AssertionError as e:  # (the same data on every rank: a mismatch shows on all of them)
+            c4_strong = {"error": str(e)}
     if world > 1:
         t = torch.tensor([gpu_s, wall, main_s, wall_c], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -557,6 +605,8 @@ def main():
     }
     if world == 1 and not a.no_configs:
         out["configs"] = other_configs(ctx, imgs, peak)
+    if c4_strong:
+        out["config4_strong"] = c4_strong
     if not a.no_cpu_baseline and world == 1:
         n_s = a.cpu_sample_splits or min(a.splits, max(4, min(cores, 32)))
         threads = min(cores, n_s)

@@ -142,8 +142,9 @@ int qwgpu_finalize_aggregation(const char* aggregation_request_json, const uint8
                                size_t intermediate_len, char** json_out);
 
 /* ---- multi-GPU partial exchange -------------------------------------------------
- * Fixed-size per-rank partial: what one rank contributes to the single all-gather that stands in
- * for the root merge. The caller (one process per GPU) all-gathers `partial_bytes` from every
+ * Fixed-layout per-rank partial: what one rank contributes to the single all-gather that stands in
+ * for the root merge — counters, up to max_hits + start_offset typed hits, a bounded tail holding the
+ * failed_splits entries and resource statistics, and the intermediate aggregation bytes. The caller (one process per GPU) all-gathers `partial_bytes` from every
  * rank (NCCL) and calls qwgpu_merge_partials on the gathered buffer (every rank or rank 0). */
 int qwgpu_partial_size(const uint8_t* search_request_pb, size_t search_request_len,
                        uint64_t* partial_bytes);
@@ -162,8 +163,15 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
  *   qwgpu_comm_set_split_table every rank: the split ids of the whole (multi-GPU) index, any order; their
  *                              sorted position is the tie-break rank carried by the exchanged hits
  *   qwgpu_leaf_search_allgather  collective: leaf_search on this rank's splits + exchange; every rank gets
- *                              the merged LeafSearchResponse (hits only: requests with aggregations and
- *                              ranks with failed splits return QWGPU_EUNSUPPORTED — use the host partials) */
+ *                              the merged LeafSearchResponse. Top-K requests without aggregations take the
+ *                              device road (record = counters + best k hits, one ncclAllGather on the call's
+ *                              stream, device merge). Requests with aggregations or without hits, and any
+ *                              request for which some rank reports a failed split, take the host-staged
+ *                              road: each rank's complete response as a fixed-layout partial (hits,
+ *                              aggregation bytes, failed_splits entries, resource statistics), only its used
+ *                              prefix on the wire (two ncclAllGather calls: lengths, then payload), merged
+ *                              with qwgpu_merge_partials' code on every rank. A rank whose own search fails
+ *                              still takes part and reports its splits as failed (retryable). */
 int qwgpu_comm_unique_id(uint8_t* out128);
 int qwgpu_comm_init(qwgpu_ctx* ctx, const uint8_t* id128, int rank, int world);
 int qwgpu_comm_set_split_table(qwgpu_ctx* ctx, uint32_t n, const char* const* split_ids);

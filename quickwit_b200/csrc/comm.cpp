@@ -79,8 +79,29 @@ Comm* comm_create(int device, const uint8_t id_bytes[128], int rank, int world) 
   return c.release();
 }
 
+void comm_allgather_host(Comm* c, const uint8_t* send, uint8_t* recv, size_t bytes) {
+  auto cu = [](cudaError_t e, const char* what) { if (e != cudaSuccess) fail(QWGPU_EINTERNAL, "%s: %s", what, cudaGetErrorString(e)); };
+  cu(cudaSetDevice(c->device), "cudaSetDevice");
+  if (!c->stream) { cudaStream_t s; cu(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate"); c->stream = s; }
+  const size_t need = bytes * (size_t)(c->world + 1);
+  if (need > c->stage_cap) {
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr; c->stage_cap = 0;
+    cu(cudaMalloc((void**)&c->d_stage, need), "cudaMalloc (exchange staging)");
+    c->stage_cap = need;
+  }
+  cudaStream_t st = (cudaStream_t)c->stream;
+  uint8_t *d_send = c->d_stage, *d_recv = c->d_stage + bytes;
+  cu(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, st), "H2D of the partial");
+  check_nccl(nccl().AllGather(d_send, d_recv, bytes, /*ncclChar*/ 0, c->comm, st), "ncclAllGather");
+  cu(cudaMemcpyAsync(recv, d_recv, bytes * (size_t)c->world, cudaMemcpyDeviceToHost, st), "D2H of the gathered partials");
+  cu(cudaStreamSynchronize(st), "exchange stream");
+}
+
 void comm_destroy(Comm* c) {
   if (!c) return;
+  if (c->d_stage) cudaFree(c->d_stage);
+  if (c->stream) cudaStreamDestroy((cudaStream_t)c->stream);
   if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
   delete c;
 }

@@ -572,13 +572,20 @@ namespace {
 // fixed-size per-rank partial for the single all-gather:
 //   [u64 magic][u64 num_hits][u64 attempted][u64 successful][u32 n_hits][u32 agg_len][u32 n_failed][u32 pad]
 //   n_hits x [u8 kind1, u8 kind2, u16 split_len, u32 doc_id, u64 v1, u64 v2, char split_id[40]]
-//   agg bytes (<= kAggCap)
+//   tail (kTailCap reserved): LeafSearchResponse{failed_splits, resource_stats}
+//   agg bytes (<= kAggCap) — last, so that the used part of a partial is a prefix of it (partial_used_bytes)
 const uint64_t kPartMagic = 0x5452415057515157ull;
-const size_t kHitBytes = 64, kAggCap = 1 << 20;
+const size_t kHitBytes = 64, kAggCap = 1 << 20, kTailCap = 4096;
 uint64_t partial_bytes_for(const qw::pb::SearchRequest& r) {
   size_t k = (size_t)(r.max_hits + r.start_offset);
   bool aggs = r.aggregation_request && !r.aggregation_request->empty();
-  return 48 + k * kHitBytes + (aggs ? kAggCap : 0);
+  return 48 + k * kHitBytes + (aggs ? kAggCap : 0) + kTailCap;
+}
+// bytes of a filled partial that carry information (a prefix): header, hit slots, tail, the aggregation bytes in use
+uint64_t partial_used_bytes(const qw::pb::SearchRequest& r, const uint8_t* partial) {
+  uint32_t meta[4];
+  memcpy(meta, partial + 32, 16);
+  return 48 + (size_t)(r.max_hits + r.start_offset) * kHitBytes + kTailCap + std::min<size_t>(meta[1], kAggCap);
 }
 }  // namespace
 
@@ -708,30 +715,49 @@ void qwgpu_comm_destroy(qwgpu_ctx* ctx) {
 // LeafSearchResponse (what merge_leaf_responses over all ranks' responses yields, collector.rs:914-974).
 // Aggregation partials and failed-split entries are variable-length: they travel in a second, host-staged
 // all-gather, only when the request has aggregations / some rank reports a failed split.
+// The host-staged exchange: this rank's LeafSearchResponse -> fixed-layout partial -> all ranks (only the used
+// prefix travels: one 8-byte all-gather of the lengths, one of the longest prefix) -> merge_leaf_responses over
+// the gathered partials. Carries everything a response holds (hits, aggregation bytes, failed_splits, stats).
+static void exchange_responses(qw::Comm& comm, const qw::pb::SearchRequest& mreq, const uint8_t* mreq_pb, size_t mreq_len,
+                               const uint8_t* local, size_t local_len, uint8_t** resp, size_t* resp_len) {
+  const uint64_t stride = partial_bytes_for(mreq);
+  std::vector<uint8_t> mine(stride);
+  if (int rc = qwgpu_response_to_partial(mreq_pb, mreq_len, local, local_len, mine.data(), stride)) qw::fail(rc, "%s", qwgpu_last_error());
+  uint64_t used = partial_used_bytes(mreq, mine.data());
+  std::vector<uint64_t> lens((size_t)comm.world);
+  qw::comm_allgather_host(&comm, (const uint8_t*)&used, (uint8_t*)lens.data(), 8);
+  uint64_t longest = 0;
+  for (uint64_t l : lens) longest = std::max(longest, l);
+  if (longest > stride) qw::fail(QWGPU_EINTERNAL, "a rank announced a partial of %llu bytes (layout holds %llu)", (unsigned long long)longest, (unsigned long long)stride);
+  longest = (longest + 15) & ~15ull;
+  longest = std::min<uint64_t>(longest, stride);
+  std::vector<uint8_t> packed(longest * (size_t)comm.world), gathered(stride * (size_t)comm.world);
+  qw::comm_allgather_host(&comm, mine.data(), packed.data(), longest);
+  for (int r = 0; r < comm.world; r++) memcpy(gathered.data() + (size_t)r * stride, packed.data() + (size_t)r * longest, longest);
+  if (int rc = qwgpu_merge_partials(mreq_pb, mreq_len, (uint32_t)comm.world, gathered.data(), stride, resp, resp_len)) qw::fail(rc, "%s", qwgpu_last_error());
+}
+
 int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
   if (!ctx->comm) qw::fail(QWGPU_EINVALID_ARG, "no communicator: call qwgpu_comm_init first");
-  const qw::Comm& comm = *ctx->comm;
+  qw::Comm& comm = *ctx->comm;
   qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
-  qw::LeafRun run;
-  qw::run_leaf_raw(eng, lr, run, true, &comm);
   qw::pb::SearchRequest mreq = lr.search_request;
   mreq.max_hits += mreq.start_offset;
   mreq.start_offset = 0;
   const bool has_aggs = mreq.aggregation_request && !mreq.aggregation_request->empty();
-  if (comm.world <= 1 || !run.gathered) {
-    // single rank, or a count / aggregation-only request (no hits to merge on the device)
-    if (comm.world > 1 && mreq.max_hits > 0) qw::fail(QWGPU_EINTERNAL, "cross-rank merge did not run");
-  }
-  std::vector<qw::pb::SplitSearchError> failed;
-  for (auto& j : run.jobs) if (j.error_code) failed.push_back({j.error, j.meta.split_id, qw::retryable(j.error_code)});
-  for (size_t k = 0; k < run.which.size(); k++)
-    if (run.outs[k].status) failed.push_back({run.outs[k].error, run.jobs[run.which[k]].meta.split_id, qw::retryable(run.outs[k].status)});
+  if (comm.world <= 1) return qwgpu_leaf_search(ctx, req, req_len, resp, resp_len);
+  // every rank takes the same road: the request decides (hits without aggregations -> device-side exchange),
+  // and after it the gathered counters do (a failed split anywhere -> the host-staged exchange carries the entries)
+  bool staged = has_aggs || mreq.max_hits == 0;
   qw::pb::LeafSearchResponse m;
-  uint64_t total_failed = failed.size();
-  if (run.gathered) {
-    total_failed = 0;
+  if (!staged) {
+  qw::LeafRun run;
+  qw::run_leaf_raw(eng, lr, run, true, &comm);
+  if (!run.gathered) qw::fail(QWGPU_EINTERNAL, "cross-rank merge did not run");
+  uint64_t total_failed = 0;
+  {
     for (const qw::RankHeader& h : run.rank_headers) {
       m.num_hits += h.num_hits;
       m.num_attempted_splits += h.attempted;
@@ -759,12 +785,29 @@ int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* req, size_t req_l
       if (h.flags & 2) sv2 = qw::typed_sort_value(p0->header.sort[1].kind, sft[1], h.v2);
       qw::pb::append_partial_hit(m.encoded_partial_hits, 2, comm.split_ids[mh.split], 0, h.doc_id, (h.flags & 1) != 0, sv1, (h.flags & 2) != 0, sv2);
     }
-  } else {
-    qw::fail(QWGPU_EUNSUPPORTED, "qwgpu_leaf_search_allgather needs max_hits > 0 and more than one rank (use qwgpu_leaf_search + qwgpu_merge_partials for count / aggregation-only requests)");
   }
-  if (has_aggs) qw::fail(QWGPU_EUNSUPPORTED, "aggregations over the device-side exchange are not implemented yet: use qwgpu_leaf_search + the partial exchange");
-  if (total_failed) qw::fail(QWGPU_EUNSUPPORTED, "%llu splits failed on some rank: failed_splits entries are not exchanged yet", (unsigned long long)total_failed);
-  give(qw::pb::encode_leaf_search_response(m), resp, resp_len);
+  staged = total_failed != 0;
+  }
+  if (!staged) {
+    give(qw::pb::encode_leaf_search_response(m), resp, resp_len);
+    return 0;
+  }
+  // host-staged road: this rank's complete response (a plain leaf search), exchanged and merged on every rank
+  uint8_t* local = nullptr;
+  size_t local_len = 0;
+  if (qwgpu_leaf_search(ctx, req, req_len, &local, &local_len)) {
+    // the other ranks are already waiting in the exchange: take part with a response that reports every split
+    // of this rank as failed (the root retries them) instead of leaving the collective
+    qw::pb::LeafSearchResponse err;
+    const std::string why = qwgpu_last_error();
+    for (auto& ref : lr.leaf_requests)
+      for (auto& so : ref.split_offsets) { err.failed_splits.push_back({why, so.split_id, true}); err.num_attempted_splits++; }
+    if (err.failed_splits.size() > 16) err.failed_splits.resize(16);  // (bounded tail; the counters still tell the whole story)
+    give(qw::pb::encode_leaf_search_response(err), &local, &local_len);
+  }
+  struct Free { uint8_t* p; ~Free() { free(p); } } guard{local};
+  const std::string mreq_pb = qw::pb::encode_search_request(mreq);
+  exchange_responses(comm, mreq, (const uint8_t*)mreq_pb.data(), mreq_pb.size(), local, local_len, resp, resp_len);
   return 0;
   QW_API_END
 }
@@ -880,7 +923,18 @@ int qwgpu_response_to_partial(const uint8_t* search_request_pb, size_t search_re
   if (r.intermediate_aggregation_result) {
     if (r.intermediate_aggregation_result->size() > kAggCap) qw::fail(QWGPU_EUNSUPPORTED, "intermediate aggregation result exceeds the fixed partial capacity");
     meta[1] = (uint32_t)r.intermediate_aggregation_result->size();
-    memcpy(partial + 48 + k * kHitBytes, r.intermediate_aggregation_result->data(), meta[1]);
+    memcpy(partial + 48 + k * kHitBytes + kTailCap, r.intermediate_aggregation_result->data(), meta[1]);
+  }
+  // tail: what the root needs besides hits and buckets — the failed_splits entries (its retry is keyed on them)
+  // and the resource statistics — as a LeafSearchResponse message holding only those fields
+  if (!r.failed_splits.empty() || r.resource_stats) {
+    qw::pb::LeafSearchResponse t;
+    t.failed_splits = r.failed_splits;
+    t.resource_stats = r.resource_stats;
+    const std::string tail = qw::pb::encode_leaf_search_response(t);
+    if (tail.size() > kTailCap) qw::fail(QWGPU_EUNSUPPORTED, "%zu failed splits do not fit the fixed-size partial (%zu bytes)", r.failed_splits.size(), (size_t)kTailCap);
+    meta[3] = (uint32_t)tail.size();
+    memcpy(partial + 48 + k * kHitBytes, tail.data(), tail.size());
   }
   memcpy(partial + 32, meta, 16);
   return 0;
@@ -903,10 +957,8 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
     if (hdr[0] != kPartMagic) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial has a bad header", r);
     // the gathered bytes come from other processes: nothing in them is trusted
     if (meta[0] > k) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims %u hits (max %zu)", r, meta[0], k);
-    if (meta[1] > kAggCap || 48 + k * kHitBytes + (size_t)meta[1] > partial_bytes) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims %u aggregation bytes", r, meta[1]);
-    // a fixed-size partial cannot carry the failed_splits entries (split id, error, retryable): a rank with
-    // failed splits would silently contribute a partial result and the root's retry would never fire
-    if (meta[2] != 0) qw::fail(QWGPU_EUNSUPPORTED, "rank %u reports %u failed splits: use qwgpu_leaf_search_allgather (it exchanges them) or retry those splits", r, meta[2]);
+    if (meta[1] > kAggCap || 48 + k * kHitBytes + kTailCap + (size_t)meta[1] > partial_bytes) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims %u aggregation bytes", r, meta[1]);
+    if (meta[3] > kTailCap) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial claims a tail of %u bytes", r, meta[3]);
     qw::pb::LeafSearchResponse lr;
     lr.num_hits = hdr[1];
     lr.num_attempted_splits = hdr[2];
@@ -938,7 +990,13 @@ int qwgpu_merge_partials(const uint8_t* search_request_pb, size_t search_request
       h.split_id.assign((const char*)p + 24, sl);
       lr.partial_hits.push_back(std::move(h));
     }
-    if (meta[1]) lr.intermediate_aggregation_result = std::string((const char*)base + 48 + k * kHitBytes, meta[1]);
+    if (meta[1]) lr.intermediate_aggregation_result = std::string((const char*)base + 48 + k * kHitBytes + kTailCap, meta[1]);
+    if (meta[3]) {
+      qw::pb::LeafSearchResponse t = qw::pb::decode_leaf_search_response(base + 48 + k * kHitBytes, meta[3]);
+      lr.failed_splits = std::move(t.failed_splits);
+      lr.resource_stats = t.resource_stats;
+    }
+    if (lr.failed_splits.size() != meta[2]) qw::fail(QWGPU_EINVALID_ARG, "rank %u partial reports %u failed splits but carries %zu", r, meta[2], lr.failed_splits.size());
     parts.push_back(std::move(lr));
   }
   qw::pb::LeafSearchResponse m = qw::merge_responses(req, std::move(parts));

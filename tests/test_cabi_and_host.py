@@ -252,3 +252,36 @@ def test_can_split_do_better_static_pruning():
     assert not any(r["metadata_count"] for r in _optimized(MATCH_ALL, splits, max_hits=0, aggs={"c": {"terms": {"field": "n"}}}))
     assert not any(r["metadata_count"] for r in _optimized(MATCH_ALL, splits, max_hits=0, end_timestamp=7))
     assert not any(r["metadata_count"] for r in _optimized(term("body", "x"), splits, max_hits=0))
+
+
+def test_partial_exchange_carries_failed_splits_and_rejects_corrupt_partials():
+    """The fixed-size per-rank partial: hits, aggregation bytes, failed_splits entries and resource
+    statistics survive response -> partial -> merge; sizes claimed inside a gathered partial are checked."""
+    import torch
+    hit = lambda split, doc, v: {"split_id": split, "segment_ord": 0, "doc_id": doc, "sort_value": ("i64", v)}
+    req = search_request(MATCH_ALL, max_hits=3, sort_fields=[("ts", DESC)])
+    stats = lambda cpu: proto.enc_leaf_resource_stats(cpu, cpu, 1)
+    r0 = proto.enc_leaf_search_response(10, [hit("a", 1, 50), hit("a", 2, 40)], [("boom", "x-1", True), ("nope", "x-2", False)], 4, 2, resource_stats=stats(100))
+    r1 = proto.enc_leaf_search_response(7, [hit("b", 9, 45)], [], 1, 1, resource_stats=stats(30))
+    nbytes = service.partial_size(req)
+    buf = torch.zeros(2 * nbytes, dtype=torch.uint8)
+    service.response_to_partial(req, r0, buf.data_ptr(), nbytes)
+    service.response_to_partial(req, r1, buf.data_ptr() + nbytes, nbytes)
+    out = proto.dec_leaf_search_response(service.merge_partials(req, 2, buf.data_ptr(), nbytes))
+    want = proto.dec_leaf_search_response(service.merge_leaf_responses(req, [r0, r1]))
+    assert out == want
+    assert out["failed_splits"] == [{"error": "boom", "split_id": "x-1", "retryable_error": True}, {"error": "nope", "split_id": "x-2", "retryable_error": False}]
+    assert (out["num_attempted_splits"], out["num_successful_splits"]) == (5, 3)
+    assert out["resource_stats"]["split_resources_sum"]["cpu_search_microsecs"] == 130
+    # corrupt counts inside a gathered partial: n_hits > k, aggregation length, tail length, failed-split count
+    for word, value in ((8, 4), (9, 1 << 24), (11, 1 << 20), (10, 7)):
+        bad = buf.clone()
+        bad.view(torch.int32)[word] = value
+        with pytest.raises(ffi.QwGpuError) as e:
+            service.merge_partials(req, 2, bad.data_ptr(), nbytes)
+        assert e.value.code == ffi.EINVALID_ARG, (word, e.value.msg)
+    # more failed splits than the tail holds: refused at the sender, never truncated
+    many = proto.enc_leaf_search_response(0, [], [("e" * 60, f"split-{i:04d}", True) for i in range(100)], 100, 0)
+    with pytest.raises(ffi.QwGpuError) as e:
+        service.response_to_partial(req, many, buf.data_ptr(), nbytes)
+    assert e.value.code == ffi.EUNSUPPORTED
