@@ -189,6 +189,11 @@ int qwgpu_imgb_add_field(qwgpu_imgb* b, const char* name, uint32_t flags, uint32
 /* docs strictly increasing; tfs NULL when the field has no freqs. */
 int qwgpu_imgb_add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint32_t term_len,
                         const uint32_t* docs, const uint32_t* tfs, uint32_t n);
+/* Fields with QW_FIELD_HAS_POSITIONS (`record: position`): the same plus the token positions of every posting —
+ * tfs[i] strictly increasing positions per posting, concatenated in posting order (n_positions = sum of tfs). */
+int qwgpu_imgb_add_term_positions(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint32_t term_len,
+                                  const uint32_t* docs, const uint32_t* tfs, uint32_t n,
+                                  const uint32_t* positions, uint64_t n_positions);
 /* values: mapped-u64 values. index: FULL -> NULL (num_vals == num_docs);
  * OPTIONAL -> sorted doc ids (num_vals of them); MULTI -> start offsets (num_docs + 1).
  * STR columns pass ordinals as values plus the sorted dictionary. */
@@ -214,6 +219,8 @@ int qwgpu_synth_split(const qwgpu_synth_spec* spec, uint8_t** img, uint64_t* img
 /* Bm25Weight of one term: idf(doc_freq, num_docs) * (1 + K1) * boost in f32 (what
  * qwgpu_compile_plan writes into QwPlanNode.bm25_weight); for hand-built seam-C plans. */
 float qwgpu_bm25_weight(uint64_t doc_freq, uint64_t num_docs, float boost);
+/* PhraseWeight's Bm25Weight::for_terms: (sum of the terms' idf in phrase order, f32) * (1 + K1) * boost. */
+float qwgpu_bm25_phrase_weight(const uint64_t* doc_freqs, uint32_t n, uint64_t num_docs, float boost);
 
 /* tantivy fieldnorm <-> id table (tantivy::fieldnorm::{fieldnorm_to_id,id_to_fieldnorm}). */
 uint8_t qwgpu_fieldnorm_to_id(uint32_t fieldnorm);

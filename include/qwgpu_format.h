@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define QW_IMG_MAGIC 0x31474D4947575151ull /* "QQWGIMG1" */
-#define QW_IMG_VERSION 2u
+#define QW_IMG_VERSION 3u
 #define QW_BLOCK_LEN 128u                  /* tantivy COMPRESSION_BLOCK_SIZE */
 #define QW_TERMINATED 0x7FFFFFFFu          /* tantivy TERMINATED sentinel (i32::MAX as u32) */
 #define QW_NO_PREV_DOC 0xFFFFFFFFu
@@ -79,7 +79,13 @@ typedef struct QwImgTerm {
   uint64_t tf_len;   /* bytes of data_len that are packed term frequencies (roofline accounting) */
   uint64_t fn_len;   /* bytes of data_len that are per-posting fieldnorm ids (128 per block, see QwSkip) */
   uint64_t sub_off;  /* data-relative: QwSubIdx[num_blocks] (doc-id checkpoints inside each block) */
-} QwImgTerm; /* 80 bytes */
+  /* positions (fields indexed with `record: position`, QW_FIELD_HAS_POSITIONS; both 0 otherwise): the token
+   * positions of every posting, in posting order — posting i owns tf[i] consecutive entries, ascending
+   * (tantivy's .pos stream keeps them delta-bit-packed per 128 positions; here they are plain uint32) */
+  uint64_t pos_off;  /* data-relative: uint32 positions[sum of tf] */
+  uint64_t pidx_off; /* data-relative: uint32 first_pos[num_blocks + 1] — index into positions[] of the first
+                        position of each block; [num_blocks] = sum of tf */
+} QwImgTerm; /* 96 bytes */
 
 /* Window index: for index-window j (docs [j<<win_shift, (j+1)<<win_shift)) the byte range
  * [start, end) of QwImgTerm data holding every block that overlaps it (start == end if none).
@@ -161,6 +167,7 @@ typedef struct QwImgColumn {
 
 #define QW_PLAN_MAGIC 0x4E4C5051u /* "QPLN" */
 #define QW_MAX_PLAN_DEPTH 4
+#define QW_MAX_PHRASE_TERMS 8
 
 enum {
   QW_NODE_TERM = 1,   /* tantivy TermQuery */
@@ -168,7 +175,13 @@ enum {
   QW_NODE_BOOL = 3,   /* tantivy BooleanQuery */
   QW_NODE_ALL = 4,    /* AllQuery; score 1 */
   QW_NODE_NONE = 5,   /* EmptyQuery */
-  QW_NODE_EXISTS = 6  /* ExistsQuery on a column; const score 1 */
+  QW_NODE_EXISTS = 6, /* ExistsQuery on a column; const score 1 */
+  QW_NODE_PHRASE = 7  /* tantivy PhraseQuery, slop 0: children = its TERM nodes in phrase order, all of one field
+                         with positions; child k's `lo` = position offset of the term inside the phrase. A doc
+                         matches when some base position b has term k at b + lo_k for every k; phrase_count =
+                         number of such b. Score = bm25_weight * tf-factor(phrase_count, fieldnorm) with
+                         bm25_weight = (sum of the terms' idf, duplicates included) * (1 + K1) * boost
+                         (Bm25Weight::for_terms). */
 };
 enum { QW_OCCUR_MUST = 0, QW_OCCUR_SHOULD = 1, QW_OCCUR_MUST_NOT = 2, QW_OCCUR_FILTER = 3 };
 

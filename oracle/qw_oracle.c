@@ -145,6 +145,8 @@ struct DocSet {
   /* BOOL */
   DocSet** kids; uint32_t nkids; uint32_t n_req, n_should, n_not, required_should;
   int scoring;
+  /* PHRASE (kids = its terms; a TERM kid of a phrase also carries its positions) */
+  const uint32_t* positions; const uint32_t* first_pos; uint32_t pos_offset; uint32_t phrase_count;
 };
 
 static void term_load_block(DocSet* s) {
@@ -191,6 +193,58 @@ static float term_score(DocSet* s) {
   uint32_t fid = s->fieldnorms ? s->fieldnorms[s->doc] : 0;
   float norm = s->cache[fid];
   return s->weight * (tf / (tf + norm));
+}
+
+/* PhraseScorer, slop 0 (tantivy phrase_scorer.rs; recalled): intersection of the terms'
+ * docsets, then of their position lists shifted by the terms' offsets; phrase_count = size of that intersection. */
+static void term_positions(DocSet* t, const uint32_t** p, uint32_t* n) {
+  uint32_t at = t->first_pos[t->blk];
+  for (uint32_t i = 0; i < t->pos; i++) at += t->tfs[i];
+  *p = t->positions + at;
+  *n = t->tfs[t->pos];
+}
+static uint32_t phrase_count_here(DocSet* s) {
+  uint32_t max_off = 0;
+  for (uint32_t k = 0; k < s->nkids; k++) if (s->kids[k]->pos_offset > max_off) max_off = s->kids[k]->pos_offset;
+  const uint32_t* p0; uint32_t n0;
+  term_positions(s->kids[0], &p0, &n0);
+  uint32_t count = 0;
+  for (uint32_t i = 0; i < n0; i++) {
+    const uint32_t shifted = p0[i] + (max_off - s->kids[0]->pos_offset);  /* = base + max_off */
+    int all = 1;
+    for (uint32_t k = 1; k < s->nkids && all; k++) {
+      const uint32_t* pk; uint32_t nk;
+      term_positions(s->kids[k], &pk, &nk);
+      const uint32_t add = max_off - s->kids[k]->pos_offset;
+      int found = 0;
+      for (uint32_t j = 0; j < nk; j++) if (pk[j] + add == shifted) { found = 1; break; }
+      all = found;
+    }
+    count += (uint32_t)all;
+  }
+  return count;
+}
+static uint32_t phrase_next(DocSet* s, uint32_t from) {
+  uint32_t cand = from;
+  for (;;) {
+    if (cand >= QW_TERMINATED) return s->doc = QW_TERMINATED;
+    uint32_t i = 0, agreed = 0;
+    while (agreed < s->nkids) {
+      uint32_t d = ds_seek(s->kids[i], cand);
+      if (d == QW_TERMINATED) return s->doc = QW_TERMINATED;
+      if (d > cand) { cand = d; agreed = 1; } else agreed++;
+      i = (i + 1) % s->nkids;
+    }
+    s->phrase_count = phrase_count_here(s);
+    if (s->phrase_count) return s->doc = cand;
+    cand++;
+  }
+}
+static float phrase_score(DocSet* s) {
+  if (!s->scoring) return 0.0f;
+  float tf = (float)s->phrase_count;
+  uint32_t fid = s->fieldnorms ? s->fieldnorms[s->doc] : 0;
+  return s->weight * (tf / (tf + s->cache[fid]));
 }
 
 static int range_match(DocSet* s, uint32_t d) {
@@ -271,6 +325,7 @@ static uint32_t ds_advance(DocSet* s) {
     case QW_NODE_TERM: return term_advance(s);
     case QW_NODE_NONE: return s->doc = QW_TERMINATED;
     case QW_NODE_BOOL: return s->doc == QW_TERMINATED ? s->doc : bool_next(s, s->doc + 1);
+    case QW_NODE_PHRASE: return s->doc == QW_TERMINATED ? s->doc : phrase_next(s, s->doc + 1);
     default: return s->doc == QW_TERMINATED ? s->doc : scan_from(s, s->doc + 1);
   }
 }
@@ -280,6 +335,7 @@ static uint32_t ds_seek(DocSet* s, uint32_t target) {
     case QW_NODE_TERM: return term_seek(s, target);
     case QW_NODE_NONE: return s->doc = QW_TERMINATED;
     case QW_NODE_BOOL: return bool_next(s, target);
+    case QW_NODE_PHRASE: return phrase_next(s, target);
     default: return scan_from(s, target);
   }
 }
@@ -287,6 +343,7 @@ static float ds_score(DocSet* s) {
   switch (s->kind) {
     case QW_NODE_TERM: return term_score(s);
     case QW_NODE_BOOL: return bool_score(s);
+    case QW_NODE_PHRASE: return phrase_score(s);
     case QW_NODE_NONE: return 0.0f;
     default: return s->scoring ? s->boost : 0.0f; /* ConstScorer(1.0 * boost) */
   }
@@ -372,6 +429,40 @@ static DocSet* build(Arena* a, const OImg* im, const QwPlanNode* nodes, uint32_t
       uint32_t msm = n->min_should_match == 0xFFFFFFFFu ? 0 : n->min_should_match;
       s->required_should = msm > 0 ? msm : (s->n_req == 0 ? 1 : 0);
       bool_next(s, 0);
+      break;
+    }
+    case QW_NODE_PHRASE: {
+      /* PhraseWeight: any term missing from the split -> no scorer; Bm25Weight::for_terms = summed idf */
+      int ok = n->num_children >= 2;
+      for (uint32_t c = 0; c < n->num_children && ok; c++) {
+        const QwPlanNode* cn = &nodes[n->first_child + c];
+        if (cn->kind != QW_NODE_TERM || cn->term_ord == 0xFFFFFFFFu || im->terms[cn->term_ord].pidx_off == 0) ok = 0;
+      }
+      if (!ok) { s->kind = QW_NODE_NONE; s->doc = QW_TERMINATED; break; }
+      s->nkids = n->num_children;
+      s->kids = (DocSet**)calloc(n->num_children, sizeof(DocSet*));
+      float idf_sum = 0.0f;
+      const QwImgField* f = NULL;
+      for (uint32_t c = 0; c < n->num_children; c++) {
+        const QwPlanNode* cn = &nodes[n->first_child + c];
+        const QwImgTerm* t = &im->terms[cn->term_ord];
+        DocSet* k = build(a, im, nodes, n->first_child + c, /*scoring: the tfs locate the positions*/ 1, visited);
+        k->positions = (const uint32_t*)(im->data + t->pos_off);
+        k->first_pos = (const uint32_t*)(im->data + t->pidx_off);
+        k->pos_offset = (uint32_t)cn->lo;
+        s->kids[c] = k;
+        f = &im->fields[t->field_id];
+        float nn = (float)t->doc_freq, N = (float)im->hdr->num_docs;
+        idf_sum += logf(1.0f + ((N - nn) + 0.5f) / (nn + 0.5f));
+      }
+      s->weight = idf_sum * (1.0f + 1.2f) * n->boost;
+      s->fieldnorms = (f->flags & QW_FIELD_HAS_FIELDNORMS) ? im->data + f->fieldnorm_off : NULL;
+      s->cache = bm25_cache(a, im, f);
+      if (!s->fieldnorms) {
+        float avg = (float)f->total_num_tokens / (float)im->hdr->num_docs;
+        ((float*)s->cache)[0] = 1.2f * (1.0f - 0.75f + 0.75f * 1.0f / avg);
+      }
+      phrase_next(s, 0);
       break;
     }
     default: s->kind = QW_NODE_NONE; s->doc = QW_TERMINATED;

@@ -14,4 +14,9 @@ float qwgpu_bm25_weight(uint64_t doc_freq, uint64_t num_docs, float boost) {
   float w = qw::bm25_idf(doc_freq, num_docs) * (1.0f + qw::BM25_K1);
   return w * boost;
 }
+float qwgpu_bm25_phrase_weight(const uint64_t* doc_freqs, uint32_t n, uint64_t num_docs, float boost) {
+  float idf_sum = 0.0f;  // Bm25Weight::for_terms: the terms' idfs summed in phrase order (f32)
+  for (uint32_t i = 0; i < n; i++) idf_sum += qw::bm25_idf(doc_freqs[i], num_docs);
+  return idf_sum * (1.0f + qw::BM25_K1) * boost;
+}
 }

@@ -102,7 +102,8 @@ struct ImageView {
       if (!inside(T.bytes_off, T.bytes_len, 1, h->term_bytes_len) || T.field_id >= h->num_fields ||
           T.num_blocks != (T.doc_freq + 127) / 128 || T.doc_freq > nd || !inside(T.skip_off, T.num_blocks, sizeof(QwSkip), dl) ||
           !inside(T.data_off, T.data_len, 1, dl) || !inside(T.widx_off, nwin, sizeof(QwWinIdx), dl) ||
-          !inside(T.sub_off, T.num_blocks, sizeof(QwSubIdx), dl) || T.tf_len > T.data_len || T.fn_len > T.data_len)
+          !inside(T.sub_off, T.num_blocks, sizeof(QwSubIdx), dl) || T.tf_len > T.data_len || T.fn_len > T.data_len ||
+          (T.pidx_off && (!inside(T.pidx_off, (uint64_t)T.num_blocks + 1, 4, dl) || !inside(T.pos_off, 0, 4, dl))))
         fail(QWGPU_EINVALID_ARG, "split image: term %u points outside the image", t);
     }
     for (uint32_t c = 0; c < h->num_columns; c++) {

@@ -337,6 +337,7 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
       L.instrs.push_back(en);
       break;
     }
+    case QW_NODE_PHRASE: fail(QWGPU_EUNSUPPORTED, "phrase queries are compiled but not executed on the GPU yet");
     default: fail(QWGPU_EINVALID_ARG, "unknown plan node kind %u", n.kind);
   }
 }

@@ -68,6 +68,8 @@ struct BTerm {
   std::vector<uint32_t> first_docs;  // first doc of each block
   std::vector<uint8_t> data;
   std::vector<QwWinIdx> widx;
+  std::vector<uint32_t> positions;  // fields with positions: tf[i] ascending token positions per posting
+  std::vector<uint32_t> first_pos;  // [num_blocks + 1] index into `positions`
 };
 struct BColumn {
   std::string name;
@@ -91,10 +93,22 @@ struct qwgpu_imgb {
 namespace qw {
 
 static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint32_t term_len,
-                     const uint32_t* docs, const uint32_t* tfs, uint32_t n) {
+                     const uint32_t* docs, const uint32_t* tfs, uint32_t n, const uint32_t* positions = nullptr, uint64_t n_positions = 0) {
   if (field_id >= b->fields.size()) fail(QWGPU_EINVALID_ARG, "add_term: bad field id");
   if (n == 0) return;
   bool has_freqs = (b->fields[field_id].flags & QW_FIELD_HAS_FREQS) != 0;
+  const bool has_pos = (b->fields[field_id].flags & QW_FIELD_HAS_POSITIONS) != 0;
+  if (has_pos) {
+    if (!has_freqs || !tfs || !positions) fail(QWGPU_EINVALID_ARG, "add_term: a field with positions needs tfs and positions");
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      if (tfs[i] == 0) fail(QWGPU_EINVALID_ARG, "add_term: tf 0");
+      for (uint32_t k = 1; k < tfs[i]; k++)
+        if (total + k >= n_positions || positions[total + k] <= positions[total + k - 1]) fail(QWGPU_EINVALID_ARG, "add_term: positions of a posting must be strictly increasing");
+      total += tfs[i];
+    }
+    if (total != n_positions) fail(QWGPU_EINVALID_ARG, "add_term: %llu positions for a tf sum of %llu", (unsigned long long)n_positions, (unsigned long long)total);
+  }
   bool has_fn = (b->fields[field_id].flags & QW_FIELD_HAS_FIELDNORMS) != 0;
   const std::vector<uint8_t>& fnorms = b->fields[field_id].fieldnorms;
   BTerm t;
@@ -150,6 +164,15 @@ static void add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint
     t.first_docs.push_back(docs[start]);
     t.tf_len += 16u * s.tf_bits;
     prev = s.last_doc;
+  }
+  if (has_pos) {
+    t.positions.assign(positions, positions + n_positions);
+    uint32_t acc = 0;
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+      t.first_pos.push_back(acc);
+      for (uint32_t i = blk * QW_BLOCK_LEN; i < std::min(n, (blk + 1) * QW_BLOCK_LEN); i++) acc += tfs[i];
+    }
+    t.first_pos.push_back(acc);
   }
   // window index: granularity 2^win_shift docs, about <= 2 entries per block, never below 4096 docs
   uint32_t shift = QW_MIN_WIN_SHIFT;
@@ -304,6 +327,10 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     o.fn_len = t.fn_len;
     o.widx_off = doff; doff = align16(doff + t.widx.size() * sizeof(QwWinIdx));
     o.sub_off = doff; doff = align16(doff + t.subs.size() * sizeof(QwSubIdx));
+    if (!t.first_pos.empty()) {
+      o.pidx_off = doff; doff = align16(doff + t.first_pos.size() * 4);
+      o.pos_off = doff; doff = align16(doff + t.positions.size() * 4 + 16);
+    }
   }
   for (uint32_t f = 0; f < nf; f++) { F[f].first_term = 0; F[f].num_terms = 0; }
   for (uint32_t i = 0; i < nt; i++) {
@@ -352,6 +379,10 @@ static void finish(qwgpu_imgb* b, uint8_t** out, uint64_t* out_len) {
     if (!t.data.empty()) memcpy(data + T[i].data_off, t.data.data(), t.data.size());
     if (!t.widx.empty()) memcpy(data + T[i].widx_off, t.widx.data(), t.widx.size() * sizeof(QwWinIdx));
     if (!t.subs.empty()) memcpy(data + T[i].sub_off, t.subs.data(), t.subs.size() * sizeof(QwSubIdx));
+    if (!t.first_pos.empty()) {
+      memcpy(data + T[i].pidx_off, t.first_pos.data(), t.first_pos.size() * 4);
+      if (!t.positions.empty()) memcpy(data + T[i].pos_off, t.positions.data(), t.positions.size() * 4);
+    }
   }
   for (uint32_t c = 0; c < nc; c++) {
     const BColumn& bc = b->columns[c];
@@ -525,6 +556,14 @@ int qwgpu_imgb_add_term(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, u
                         const uint32_t* docs, const uint32_t* tfs, uint32_t n) {
   QW_API_BEGIN
   qw::add_term(b, field_id, term, term_len, docs, tfs, n);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_imgb_add_term_positions(qwgpu_imgb* b, uint32_t field_id, const uint8_t* term, uint32_t term_len,
+                                  const uint32_t* docs, const uint32_t* tfs, uint32_t n, const uint32_t* positions, uint64_t n_positions) {
+  QW_API_BEGIN
+  qw::add_term(b, field_id, term, term_len, docs, tfs, n, positions, n_positions);
   return 0;
   QW_API_END
 }

@@ -127,7 +127,8 @@ static int64_t truncate_ns(int64_t ns, int64_t prec) {  // DateTime::truncate
 
 // ---- TantivyQueryAst mirror ------------------------------------------------------------------------
 struct TQ {
-  enum Kind { Bool, Term, Range, Exists, All, None } kind = None;
+  enum Kind { Bool, Term, Range, Exists, All, None, Phrase } kind = None;
+  std::vector<uint32_t> phrase_terms;  // Phrase: term ords in phrase order (offset k = position k)
   bool opaque = false;  // wrapped in a BoostQuery leaf: not subject to bool flattening / const folding
   std::vector<TQ> must, must_not, should, filter;
   bool has_msm = false;
@@ -298,7 +299,7 @@ static TQ range_leaf(uint32_t column, uint64_t lo, uint64_t hi) {
 
 // full_text_query / FullTextParams::make_query (full_text_query.rs:103-160, utils.rs:73-200)
 static TQ full_text(const Ctx& cx, const std::string& field, const std::string& text, const std::string& tokenizer_override,
-                    const std::string& mode, bool op_and, int zero_terms_all, bool lenient) {
+                    const std::string& mode, bool op_and, int zero_terms_all, bool lenient, uint32_t slop = 0) {
   int f = cx.img.find_field(field);
   if (f < 0) {
     int c = cx.img.find_column(field);
@@ -329,7 +330,18 @@ static TQ full_text(const Ctx& cx, const std::string& field, const std::string& 
   if (mode == "phrase" || (mode == "phrase_fallback_to_intersection" && has_positions)) {
     if (!has_positions)
       fail(QWGPU_EINVALID_QUERY, "invalid query: Applied phrase query on field which does not have positions indexed");
-    fail(QWGPU_EUNSUPPORTED, "phrase queries are not implemented on the GPU path yet");
+    if (slop != 0) fail(QWGPU_EUNSUPPORTED, "phrase queries with slop > 0 are not implemented on the GPU path yet");
+    if (tokens.size() > QW_MAX_PHRASE_TERMS) fail(QWGPU_EUNSUPPORTED, "phrases of more than %d terms are not implemented on the GPU path", QW_MAX_PHRASE_TERMS);
+    // TantivyPhraseQuery::new_with_offset(terms) (full_text_query.rs:140-156): a term missing from the split
+    // means no doc can match
+    TQ ph;
+    ph.kind = TQ::Phrase;
+    for (auto& t : tokens) {
+      int ord = cx.img.find_term((uint32_t)f, (const uint8_t*)t.data(), (uint32_t)t.size());
+      if (ord < 0) return tq_none();
+      ph.phrase_terms.push_back((uint32_t)ord);
+    }
+    return ph;
   }
   if (mode == "bool_prefix") fail(QWGPU_EUNSUPPORTED, "bool_prefix queries are not implemented on the GPU path yet");
   TQ b;
@@ -419,16 +431,18 @@ static TQ build(const Ctx& cx, const Json& q, int depth) {
     std::string tok, mode = "bool";
     bool op_and = false;
     int zero_all = 0;
+    uint32_t slop = 0;
     if (params) {
       tok = params->str_or("tokenizer", "");
       if (const Json* m = params->get("mode")) {
         mode = m->str_or("type", "bool");
+        if (const Json* sl = m->get("slop")) slop = (uint32_t)sl->as_f64();
         std::string op = m->str_or("operator", "Or");
         op_and = op == "And" || op == "AND" || op == "and";
       }
       zero_all = params->str_or("zero_terms_query", "none") == "all";
     }
-    return full_text(cx, q.str_or("field", ""), q.str_or("text", ""), tok, mode, op_and, zero_all, q.bool_or("lenient", false));
+    return full_text(cx, q.str_or("field", ""), q.str_or("text", ""), tok, mode, op_and, zero_all, q.bool_or("lenient", false), slop);
   }
   if (type == "range") return range_query(cx, q.str_or("field", ""), q.get("lower_bound"), q.get("upper_bound"));
   if (type == "field_presence") {
@@ -496,6 +510,28 @@ static void emit(const TQ& t, uint32_t occur, const ImageView& img, std::vector<
         // Bm25Weight: idf * (1 + K1), then boost_by(boost)
         float w = bm25_idf(it.doc_freq, img.hdr->num_docs) * (1.0f + BM25_K1);
         n.bm25_weight = w * t.boost;
+      }
+      break;
+    }
+    case TQ::Phrase: {
+      // PhraseWeight: Bm25Weight::for_terms = (sum of the terms' idf, duplicates included) * (1 + K1) * boost
+      n.kind = QW_NODE_PHRASE;
+      float idf_sum = 0.0f;
+      for (uint32_t ord : t.phrase_terms) idf_sum += bm25_idf(img.terms[ord].doc_freq, img.hdr->num_docs);
+      const uint32_t field_id = img.terms[t.phrase_terms[0]].field_id;
+      n.field_id = field_id;
+      n.bm25_weight = idf_sum * (1.0f + BM25_K1) * t.boost;
+      const size_t first = out.size();  // (`n` dangles after the resize below)
+      out[idx].first_child = (uint32_t)first;
+      out[idx].num_children = (uint32_t)t.phrase_terms.size();
+      out.resize(first + t.phrase_terms.size());
+      for (size_t k = 0; k < t.phrase_terms.size(); k++) {
+        QwPlanNode& c = out[first + k];
+        memset(&c, 0, sizeof c);
+        c.kind = QW_NODE_TERM; c.occur = QW_OCCUR_MUST; c.boost = 1.0f; c.min_should_match = 0xFFFFFFFFu;
+        c.term_ord = t.phrase_terms[k]; c.field_id = field_id; c.column = 0xFFFFFFFFu;
+        c.bm25_weight = bm25_idf(img.terms[c.term_ord].doc_freq, img.hdr->num_docs) * (1.0f + BM25_K1);
+        c.lo = k;  // position offset inside the phrase
       }
       break;
     }

@@ -20,7 +20,7 @@ FIELD_HAS_FREQS, FIELD_HAS_FIELDNORMS, FIELD_HAS_POSITIONS = 1, 2, 4
 TOK_RAW, TOK_DEFAULT = 0, 1
 COL_U64, COL_I64, COL_F64, COL_BOOL, COL_DATETIME, COL_STR = range(6)
 CARD_FULL, CARD_OPTIONAL, CARD_MULTI = range(3)
-NODE_TERM, NODE_RANGE, NODE_BOOL, NODE_ALL, NODE_NONE, NODE_EXISTS = 1, 2, 3, 4, 5, 6
+NODE_TERM, NODE_RANGE, NODE_BOOL, NODE_ALL, NODE_NONE, NODE_EXISTS, NODE_PHRASE = 1, 2, 3, 4, 5, 6, 7
 OCCUR_MUST, OCCUR_SHOULD, OCCUR_MUST_NOT, OCCUR_FILTER = range(4)
 SORT_NONE, SORT_DOCID, SORT_SCORE, SORT_COLUMN = range(4)
 ORDER_ASC, ORDER_DESC = 0, 1
@@ -52,7 +52,7 @@ class QwImgTerm(C.Structure):
                 ("doc_freq", C.c_uint32), ("num_blocks", C.c_uint32), ("win_shift", C.c_uint32),
                 ("skip_off", C.c_uint64), ("data_off", C.c_uint64), ("data_len", C.c_uint64),
                 ("widx_off", C.c_uint64), ("tf_len", C.c_uint64), ("fn_len", C.c_uint64),
-                ("sub_off", C.c_uint64)]
+                ("sub_off", C.c_uint64), ("pos_off", C.c_uint64), ("pidx_off", C.c_uint64)]
 
 
 class QwImgColumn(C.Structure):
@@ -193,10 +193,12 @@ def lib() -> C.CDLL:
     bind("qwgpu_imgb_free", [vp], None)
     bind("qwgpu_imgb_add_field", [vp, cp, u32, u32, vp, u64])
     bind("qwgpu_imgb_add_term", [vp, u32, vp, u32, vp, vp, u32])
+    bind("qwgpu_imgb_add_term_positions", [vp, u32, vp, u32, vp, vp, u32, vp, u64])
     bind("qwgpu_imgb_add_column", [vp, cp, u32, u32, vp, u64, vp, vp, vp, u32])
     bind("qwgpu_imgb_finish", [vp, C.POINTER(vp), C.POINTER(u64)])
     bind("qwgpu_synth_split", [C.POINTER(SynthSpec), C.POINTER(vp), C.POINTER(u64)])
     bind("qwgpu_bm25_weight", [u64, u64, C.c_float], C.c_float)
+    bind("qwgpu_bm25_phrase_weight", [vp, u32, u64, C.c_float], C.c_float)
     bind("qwgpu_fieldnorm_to_id", [u32], C.c_uint8)
     bind("qwgpu_id_to_fieldnorm", [C.c_uint8], u32)
     if missing and not os.environ.get("QWGPU_DEV_PARTIAL"):
@@ -220,10 +222,12 @@ def img_lib():
                 ("qwgpu_imgb_new", [u32], vp), ("qwgpu_imgb_free", [vp], None),
                 ("qwgpu_imgb_add_field", [vp, cp, u32, u32, vp, u64], C.c_int),
                 ("qwgpu_imgb_add_term", [vp, u32, vp, u32, vp, vp, u32], C.c_int),
+                ("qwgpu_imgb_add_term_positions", [vp, u32, vp, u32, vp, vp, u32, vp, u64], C.c_int),
                 ("qwgpu_imgb_add_column", [vp, cp, u32, u32, vp, u64, vp, vp, vp, u32], C.c_int),
                 ("qwgpu_imgb_finish", [vp, C.POINTER(vp), C.POINTER(u64)], C.c_int),
                 ("qwgpu_synth_split", [C.POINTER(SynthSpec), C.POINTER(vp), C.POINTER(u64)], C.c_int),
                 ("qwgpu_bm25_weight", [u64, u64, C.c_float], C.c_float),
+                ("qwgpu_bm25_phrase_weight", [vp, u32, u64, C.c_float], C.c_float),
                 ("qwgpu_fieldnorm_to_id", [u32], C.c_uint8), ("qwgpu_id_to_fieldnorm", [C.c_uint8], u32)]:
             fn = getattr(L, name)
             fn.argtypes, fn.restype = argtypes, restype

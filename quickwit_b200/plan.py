@@ -38,6 +38,18 @@ def term(img: SplitImage, field: str, text: str, occur=ffi.OCCUR_MUST, boost: fl
     return Node(ffi.NODE_TERM, occur, boost, term_ord=t, weight=bm25_weight(img.doc_freq(t), img.num_docs, boost))
 
 
+def phrase(img: SplitImage, field: str, terms: Sequence[str], occur=ffi.OCCUR_MUST, boost: float = 1.0) -> Node:
+    """tantivy PhraseQuery (slop 0) over `terms` in order; any term absent from the split -> matches nothing."""
+    ords = [img.term_ord(field, t) for t in terms]
+    if any(o < 0 for o in ords) or len(ords) < 2:
+        return Node(ffi.NODE_NONE, occur)
+    dfs = (C.c_uint64 * len(ords))(*[img.doc_freq(o) for o in ords])
+    w = float(ffi.img_lib().qwgpu_bm25_phrase_weight(dfs, len(ords), img.num_docs, boost))
+    kids = [Node(ffi.NODE_TERM, ffi.OCCUR_MUST, 1.0, term_ord=o, field_id=img.field_names().index(field), weight=bm25_weight(img.doc_freq(o), img.num_docs), lo=k)
+            for k, o in enumerate(ords)]
+    return Node(ffi.NODE_PHRASE, occur, boost, children=kids, field_id=img.field_names().index(field), weight=w)
+
+
 def range_(img: SplitImage, column: str, lo: int, hi: int, occur=ffi.OCCUR_FILTER, boost=1.0) -> Node:
     c = img.column_ord(column)
     return Node(ffi.NODE_RANGE, occur, boost, column=c if c >= 0 else ffi.ABSENT, lo=lo, hi=hi)

@@ -186,13 +186,18 @@ class _Builder:
         p = fieldnorm_ids.ctypes.data if fieldnorm_ids is not None else None
         return ffi.img_check(self.L.qwgpu_imgb_add_field(self.b, name.encode(), flags, tok, p, total_tokens))
 
-    def add_term(self, field_id: int, term: bytes, docs: np.ndarray, tfs: Optional[np.ndarray]):
+    def add_term(self, field_id: int, term: bytes, docs: np.ndarray, tfs: Optional[np.ndarray], positions: Optional[np.ndarray] = None):
         docs = np.ascontiguousarray(docs, dtype=np.uint32)
         tfp = None
         if tfs is not None:
             tfs = np.ascontiguousarray(tfs, dtype=np.uint32)
             tfp = tfs.ctypes.data
         buf = C.create_string_buffer(term, len(term))
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=np.uint32)
+            ffi.img_check(self.L.qwgpu_imgb_add_term_positions(self.b, field_id, C.addressof(buf), len(term), docs.ctypes.data, tfp,
+                                                               len(docs), positions.ctypes.data, len(positions)))
+            return
         ffi.img_check(self.L.qwgpu_imgb_add_term(self.b, field_id, C.addressof(buf), len(term),
                                              docs.ctypes.data, tfp, len(docs)))
 
@@ -310,16 +315,22 @@ def build_split(docs: Sequence[Dict[str, Any]], doc_mapping: Dict[str, Any], spl
             fieldnorms = bool(m.get("fieldnorms", False))
             if m.get("indexed", True):
                 flags = (ffi.FIELD_HAS_FREQS if record in ("freq", "position") else 0) | \
-                        (ffi.FIELD_HAS_FIELDNORMS if fieldnorms else 0)
+                        (ffi.FIELD_HAS_FIELDNORMS if fieldnorms else 0) | (ffi.FIELD_HAS_POSITIONS if record == "position" else 0)
                 postings: Dict[bytes, Dict[int, int]] = {}
+                positions: Dict[bytes, Dict[int, List[int]]] = {}
                 lengths = np.zeros(n, dtype=np.uint32)
                 for d, vs in enumerate(values):
+                    # token positions run across the values of a multi-valued field with a gap of one between
+                    # values (tantivy postings_writer: end_position + POSITION_GAP)
+                    start = 0
                     for v in vs:
                         toks = tokenize(str(v), tokenizer)
                         lengths[d] += len(toks)
-                        for t in toks:
+                        for i, t in enumerate(toks):
                             postings.setdefault(t.encode(), {}).setdefault(d, 0)
                             postings[t.encode()][d] += 1
+                            positions.setdefault(t.encode(), {}).setdefault(d, []).append(start + i)
+                        start += len(toks) + 1
                 L = ffi.img_lib()
                 fn = np.array([L.qwgpu_fieldnorm_to_id(int(x)) for x in lengths], dtype=np.uint8) if fieldnorms else None
                 fid = b.add_field(name, flags, ffi.TOK_RAW if tokenizer == "raw" else ffi.TOK_DEFAULT, fn, int(lengths.sum()))
@@ -327,7 +338,10 @@ def build_split(docs: Sequence[Dict[str, Any]], doc_mapping: Dict[str, Any], spl
                     dd = postings[term]
                     ds = np.array(sorted(dd), dtype=np.uint32)
                     tfs = np.array([dd[int(x)] for x in ds], dtype=np.uint32) if flags & ffi.FIELD_HAS_FREQS else None
-                    b.add_term(fid, term, ds, tfs)
+                    pos = None
+                    if flags & ffi.FIELD_HAS_POSITIONS:
+                        pos = np.array([p for x in ds for p in positions[term][int(x)]], dtype=np.uint32)
+                    b.add_term(fid, term, ds, tfs, pos)
             if m.get("fast", False):
                 dictionary = sorted({str(v).encode() for vs in values for v in vs})
                 ords = {t: i for i, t in enumerate(dictionary)}

@@ -383,3 +383,62 @@ def test_cpu_baseline_fast_path_equals_the_oracle():
     # a shape the fast path does not cover falls back to the oracle proper
     pl = P.make_plan(P.bool_([P.term(img, "body", "t0"), P.term(img, "body", "t1")]), 10, [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)])
     assert O.split_search(img, pl, fast=True).hits == O.split_search(img, pl).hits
+
+
+# ---- phrase queries (full_text mode `phrase`, slop 0): semantics of rest-api-tests es_compatibility/0013-phrase-query.yaml
+# ("zone of explosion" does not match the phrase `zone explosion`), PhraseScorer / Bm25Weight::for_terms scoring ------------
+PHRASE_MAPPING = {"field_mappings": [{"name": "body", "type": "text", "record": "position", "fieldnorms": True},
+                                     {"name": "tags", "type": "text", "record": "position"},
+                                     {"name": "nopos", "type": "text", "record": "freq"}]}
+PHRASE_DOCS = [{"body": "the quick brown fox jumps over the lazy dog", "nopos": "quick brown"},
+               {"body": "quick fox brown quick brown fox"}, {"body": "brown fox"}, {"body": "a quick brown"},
+               {"body": "quick brown quick brown quick brown", "tags": ["alpha beta", "gamma alpha", "beta"]},
+               {"body": "there is a zone of explosion and a sign decoration"}, {"tags": ["alpha", "beta gamma"]}]
+
+
+def phrase_ast(field, text, slop=None):
+    mode = {"type": "phrase"}
+    if slop is not None:
+        mode["slop"] = slop
+    return {"type": "full_text", "field": field, "text": text, "params": {"mode": mode}, "lenient": False}
+
+
+def test_phrase_queries():
+    img = S.build_split(PHRASE_DOCS, PHRASE_MAPPING, "phrases")
+    run = lambda ast, **kw: cpu_root_search([img], ast, PHRASE_MAPPING, max_hits=10, **kw)
+    ids = lambda res: sorted(h["doc_id"] for h in res["partial_hits"])
+    assert ids(run(phrase_ast("body", "quick brown"))) == [0, 1, 3, 4]
+    assert ids(run(phrase_ast("body", "Quick, BROWN fox!"))) == [0, 1]
+    assert ids(run(phrase_ast("body", "fox quick"))) == [] and ids(run(phrase_ast("body", "quick quick"))) == []
+    assert ids(run(phrase_ast("body", "zone explosion"))) == [] and ids(run(phrase_ast("body", "zone of explosion"))) == [5]
+    assert ids(run(phrase_ast("body", "sign decoration"))) == [5]
+    assert ids(run(phrase_ast("body", "quick unknownword"))) == []          # a term missing from the split
+    assert ids(run(phrase_ast("body", "brown"))) == [0, 1, 2, 3, 4]         # one token: a plain term query
+    # values of a multi-valued field are one position apart: no phrase across two values
+    assert ids(run(phrase_ast("tags", "alpha beta"))) == [4] and ids(run(phrase_ast("tags", "beta gamma"))) == [6]
+    assert ids(run(phrase_ast("tags", "gamma alpha"))) == [4] and ids(run(phrase_ast("tags", "beta alpha"))) == []
+    # inside a bool, with other clauses
+    both = bool_(must=[phrase_ast("body", "quick brown")], must_not=[term("body", "lazy")])
+    assert ids(run(both)) == [1, 3, 4]
+    # scores: (sum of the terms' idf) * 2.2 * count / (count + K1 * (1 - B + B * len / avg_len)), f32
+    res = run(phrase_ast("body", "quick brown"), sort_fields=[("_score", DESC)])
+    n = len(PHRASE_DOCS)
+    f32 = np.float32
+    idf = lambda df: f32(np.log(f32(1) + (f32(n - df) + f32(0.5)) / (f32(df) + f32(0.5))))
+    lens = [len(d.get("body", "").split()) for d in PHRASE_DOCS]
+    avg = f32(sum(lens)) / f32(n)
+    weight = (idf(4) + idf(5)) * f32(2.2)
+    counts = {0: 1, 1: 1, 3: 1, 4: 3}
+    want = {d: weight * (f32(c) / (f32(c) + f32(1.2) * (f32(0.25) + f32(0.75) * f32(lens[d]) / avg))) for d, c in counts.items()}
+    got = {h["doc_id"]: h["sort_value"][1] for h in res["partial_hits"]}
+    assert set(got) == set(want)
+    for d in want:
+        assert abs(got[d] - float(want[d])) <= 1e-6 * float(want[d]), (d, got[d], want[d])
+    assert [h["doc_id"] for h in res["partial_hits"]] == [4, 3, 1, 0]
+    # errors: no positions on the field; slop is not implemented
+    with pytest.raises(ffi.QwGpuError) as e:
+        run(phrase_ast("nopos", "quick brown"))
+    assert e.value.code == ffi.EINVALID_QUERY and "does not have positions indexed" in e.value.msg
+    with pytest.raises(ffi.QwGpuError) as e:
+        run(phrase_ast("body", "zone explosion", slop=1))
+    assert e.value.code == ffi.EUNSUPPORTED
