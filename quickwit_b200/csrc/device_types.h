@@ -26,19 +26,40 @@
 #define QW_MAX_TOPK 4096
 #define QW_SMEM_AGG_CELLS 4096
 
-enum { OP_TERM = 1, OP_RANGE = 2, OP_EXISTS = 3, OP_ALL = 4, OP_BOOL_BEGIN = 5, OP_BOOL_END = 6 };
+enum { OP_TERM = 1, OP_RANGE = 2, OP_EXISTS = 3, OP_ALL = 4, OP_BOOL_BEGIN = 5, OP_BOOL_END = 6, OP_PHRASE = 7 };
 enum { IF_SCORED = 1u, IF_HAS_TF = 2u, IF_HAS_FN = 4u, IF_BITS_FROM_SCORE = 8u };
 #define QW_TFF_ROWS 16 /* tf-factor table: tff[tf][fieldnorm_id] = tf / (tf + norm[id]) for tf < 16 */
 
 struct DInstr {  // 64 bytes
   uint32_t op, level, occur, flags;
-  uint64_t a, b, c;  // TERM: data_off, widx_off, skip_off | RANGE: lo, hi
+  uint64_t a, b, c;  // TERM: data_off, widx_off, skip_off | RANGE: lo, hi | PHRASE: a = VBlk[] (device address), c = driver skip_off
   uint32_t n;        // TERM: num_blocks   | BOOL_END: n_req
   uint32_t m;        // TERM: win_shift    | BOOL_END: n_should
   uint32_t r;        // TERM: fn slot      | RANGE/EXISTS: column | BOOL_END: required_should
   float f;           // TERM: bm25 weight  | const-score leaves: boost
   uint32_t t;        // TERM: term slot (index among the plan's TERM instructions)
   uint32_t pad;
+};
+
+// A phrase evaluated by the pre-pass (phrase_kernel.cuh): one uncompressed posting block per 128-posting block of
+// the phrase's driver term — doc = 0xFFFFFFFF where the driver posting's doc does not hold the phrase.
+struct VBlk {
+  uint32_t doc[QW_BLOCK_LEN];
+  float val[QW_BLOCK_LEN];  // score contribution (0 when the phrase is not scored)
+};
+struct DPhraseTerm {
+  uint64_t data_off, skip_off, pos_off, pidx_off;  // data-relative (QwImgTerm)
+  uint32_t nblk, offset;                           // offset = position of the term inside the phrase
+};
+struct DPhrase {
+  uint64_t data_base;  // the split's data region (device address)
+  uint64_t out;        // VBlk[driver blocks] (device address)
+  uint64_t fn_off;     // per-document fieldnorm ids, data-relative; ~0 = the field keeps none (constant id 1)
+  uint64_t tab;        // the field's BM25 tables (device address): float[256] norms, then tff[16][256]
+  float weight;        // (sum of the terms' idf) * (1 + K1) * boost
+  uint32_t n_terms, driver, scored;
+  uint32_t first_work, pad[3];  // prefix of driver blocks over the batch's phrases
+  DPhraseTerm t[QW_MAX_PHRASE_TERMS];
 };
 
 struct DCol {  // 48 bytes

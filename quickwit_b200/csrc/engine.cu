@@ -11,6 +11,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "union_kernel.cuh"
+#include "phrase_kernel.cuh"
 #include "agg_kernel.cuh"
 
 namespace qw {
@@ -205,6 +206,8 @@ struct Lowered {
   int fn_field[2] = {-1, -1};
   uint64_t postings = 0, alg_bytes = 0, min_required_df = ~0ull;
   std::vector<std::pair<uint32_t, uint64_t>> range_cols;  // (col, driver df) for roofline accounting
+  std::vector<DPhrase> phrases;         // phrase pre-pass descriptors (out / first_work filled per batch)
+  std::vector<uint32_t> phrase_instr;   // instruction that consumes phrases[i]
 };
 
 static uint32_t use_col(Lowered& L, const SplitDev& sp, uint32_t c) {
@@ -337,7 +340,49 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
       L.instrs.push_back(en);
       break;
     }
-    case QW_NODE_PHRASE: fail(QWGPU_EUNSUPPORTED, "phrase queries are compiled but not executed on the GPU yet");
+    case QW_NODE_PHRASE: {
+      // evaluated by the pre-pass (phrase_kernel.cuh) into one uncompressed posting block per block of its
+      // rarest term; the window program consumes those blocks (OP_PHRASE)
+      if (n.num_children < 2 || n.num_children > QW_MAX_PHRASE_TERMS || n.first_child + n.num_children > nn)
+        fail(QWGPU_EINVALID_ARG, "phrase node with %u terms", n.num_children);
+      DPhrase ph;
+      memset(&ph, 0, sizeof ph);
+      ph.data_base = (uint64_t)sp.d_data;
+      ph.n_terms = n.num_children;
+      ph.weight = n.bm25_weight;
+      ph.scored = scored ? 1 : 0;
+      uint64_t best_df = ~0ull;
+      const QwImgField* fld = nullptr;
+      uint32_t field_id = 0;
+      for (uint32_t k = 0; k < n.num_children; k++) {
+        const QwPlanNode& c = nodes[n.first_child + k];
+        if (c.kind != QW_NODE_TERM || c.term_ord >= sp.view.hdr->num_terms) fail(QWGPU_EINVALID_ARG, "phrase term %u is not a term of this split", k);
+        const QwImgTerm& t = sp.view.terms[c.term_ord];
+        if (!t.pidx_off) fail(QWGPU_EINVALID_ARG, "phrase over a field without positions");
+        if (k && t.field_id != field_id) fail(QWGPU_EINVALID_ARG, "phrase terms of different fields");
+        field_id = t.field_id;
+        fld = &sp.view.fields[t.field_id];
+        ph.t[k].data_off = t.data_off; ph.t[k].skip_off = t.skip_off; ph.t[k].pos_off = t.pos_off; ph.t[k].pidx_off = t.pidx_off;
+        ph.t[k].nblk = t.num_blocks; ph.t[k].offset = (uint32_t)c.lo;
+        if (t.doc_freq < best_df) { best_df = t.doc_freq; ph.driver = k; }
+        L.alg_bytes += t.data_len - t.fn_len;
+      }
+      const QwImgTerm& drv = sp.view.terms[nodes[n.first_child + ph.driver].term_ord];
+      L.postings += drv.doc_freq;
+      L.alg_bytes += (uint64_t)drv.doc_freq * 4 * n.num_children;  // positions probed per candidate (lower bound)
+      if (occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER) L.min_required_df = std::min<uint64_t>(L.min_required_df, drv.doc_freq);
+      ph.fn_off = (fld->flags & QW_FIELD_HAS_FIELDNORMS) ? fld->fieldnorm_off : ~0ull;
+      ph.tab = (uint64_t)(sp.d_tabs + (size_t)(256 + QW_TFF_ROWS * 256) * field_id);
+      in.op = OP_PHRASE;
+      in.c = drv.skip_off;
+      in.n = drv.num_blocks;
+      in.f = n.bm25_weight;
+      if (scored) L.score_max += n.bm25_weight > 0 ? n.bm25_weight : 0.f;
+      L.phrase_instr.push_back((uint32_t)L.instrs.size());
+      L.phrases.push_back(ph);
+      L.instrs.push_back(in);
+      break;
+    }
     default: fail(QWGPU_EINVALID_ARG, "unknown plan node kind %u", n.kind);
   }
 }
@@ -819,11 +864,15 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       fw_smp[i + 1] = fw_smp[i] + cnt;
     } else fw_smp[i + 1] = fw_smp[i] + (nw > phase ? (nw - phase + stride - 1) / stride : 0);
   }
+  // phrases: one uncompressed posting block per block of each phrase's driver term (phrase_kernel.cuh)
+  uint32_t n_phrases = 0, phrase_blocks = 0;
+  for (auto& L : low)
+    for (size_t k = 0; k < L.phrases.size(); k++) { n_phrases++; phrase_blocks += L.instrs[L.phrase_instr[k]].n; }
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), o_rank = al(o_bounds + (size_t)tot_bounds * 8),
-         o_smp = al(o_rank + (size_t)n * 4), blob_bytes = al(o_smp + sample_win.size() * 4);
+         o_smp = al(o_rank + (size_t)n * 4), o_phr = al(o_smp + sample_win.size() * 4), blob_bytes = al(o_phr + (size_t)n_phrases * sizeof(DPhrase));
   // device-side cross-split merge: the per-split hit lists stay in scratch, only the merged top-K comes back
   const bool do_merge = merge && merged && merge->k > 0 && any_topk && merge->rank.size() == n_in;
   uint32_t kmax = 1;
@@ -834,7 +883,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          s_hits = al(s_cand + (any_topk ? (size_t)n * QW_CAND_CAP * 24 : 0)),
          s_cut = al(s_hits + (do_merge ? (size_t)n * kmax * sizeof(QwHit) : 0)),
          s_grecv = al(s_cut + (size_t)std::max<uint32_t>(n, 64) * 4 + 1024),
-         scratch_bytes = al(s_grecv + (gather && gather->world > 1 && do_merge ? (size_t)gather->world * (64 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : 0));
+         s_vblk = al(s_grecv + (gather && gather->world > 1 && do_merge ? (size_t)gather->world * (64 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : 0)),
+         scratch_bytes = al(s_vblk + (size_t)phrase_blocks * sizeof(VBlk));
   // out: per split [hdr 32B][hits][cells]
   std::vector<size_t> out_off(n + 1);
   out_off[0] = 0;
@@ -874,6 +924,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   slot->ensure(blob_bytes, scratch_bytes, out_bytes);
   cudaStream_t st = slot->stream;
 
+  uint32_t phr_done = 0, phr_blocks_done = 0;
   for (uint32_t i = 0; i < n; i++) {
     DSplitPlan& P = low[i].P;
     // privatised counters + stats triples must fit the (dead at collect time) staging area
@@ -886,6 +937,15 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     P.out_cells = (uint64_t)(ob + 32 + (do_merge ? 0 : (size_t)P.max_hits * sizeof(QwHit)));
     P.out_hist = (uint64_t)(slot->d_scratch + s_hist + (size_t)i * QW_HIST_BINS * 4);
     P.out_cands = (uint64_t)(slot->d_scratch + s_cand + (size_t)i * QW_CAND_CAP * 24);
+    for (size_t k = 0; k < low[i].phrases.size(); k++) {
+      DPhrase& ph = low[i].phrases[k];
+      DInstr& pin = low[i].instrs[low[i].phrase_instr[k]];
+      ph.first_work = phr_blocks_done;
+      ph.out = (uint64_t)(slot->d_scratch + s_vblk + (size_t)phr_blocks_done * sizeof(VBlk));
+      pin.a = ph.out;
+      phr_blocks_done += pin.n;
+      memcpy(slot->h_blob + o_phr + (size_t)phr_done++ * sizeof(DPhrase), &ph, sizeof ph);
+    }
     memcpy(slot->h_blob + o_plans + i * sizeof(DSplitPlan), &P, sizeof P);
     memcpy(slot->h_blob + o_instr + P.instr_base * sizeof(DInstr), low[i].instrs.data(), P.n_instr * sizeof(DInstr));
     if (P.n_cols) memcpy(slot->h_blob + o_cols + P.col_base * sizeof(DCol), low[i].cols.data(), P.n_cols * sizeof(DCol));
@@ -901,6 +961,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
   stats.h2d_bytes += blob_bytes;
+  if (phrase_blocks) {
+    // phrase pre-pass: every phrase of the batch becomes a posting list in scratch, read by every later pass
+    qwk::k_phrase<<<(phrase_blocks + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, 0, st>>>((const DPhrase*)(slot->d_blob + o_phr), n_phrases, phrase_blocks);
+    stats.launches++;
+  }
 
   KParams kp;
   memset(&kp, 0, sizeof kp);

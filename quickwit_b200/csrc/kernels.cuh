@@ -276,6 +276,27 @@ __device__ __forceinline__ void fold_block_dyn(uint32_t blk_off, const uint8_t* 
   else { if (cn) fold_block<false, true, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); else fold_block<false, false, STAGED>(blk_off, gblk, ws, rlo, rlen, tg, lane); }
 }
 
+// A phrase's pre-computed posting block (phrase_kernel.cuh): doc ids and score contributions are already
+// decoded, 4 entries per lane; same targets as fold_block (score add in clause order, should counter, bitmap).
+__device__ __forceinline__ void fold_vblock(const VBlk* vb, uint32_t ws, uint32_t rlen, const TermTarget& tg, uint32_t lane) {
+  const uint4 d = __ldg(reinterpret_cast<const uint4*>(&vb->doc[lane * 4]));
+  const float4 v = __ldg(reinterpret_cast<const float4*>(&vb->val[lane * 4]));
+  const uint32_t doc[4] = {d.x, d.y, d.z, d.w};
+  const float val[4] = {v.x, v.y, v.z, v.w};
+  uint32_t* bits = reinterpret_cast<uint32_t*>(qw_smem + tg.bits);
+  float* score = reinterpret_cast<float*>(qw_smem + tg.score);
+  uint8_t* cnt = qw_smem + tg.cnt;
+  const bool sc = tg.score != 0xFFFFFFFFu, cn = tg.cnt != 0xFFFFFFFFu;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t rel = doc[j] - ws;  // (0xFFFFFFFF = no phrase match at this driver posting: never inside a window)
+    if (doc[j] == 0xFFFFFFFFu || rel >= rlen) continue;
+    if (sc) score[rel] = __fadd_rn(score[rel], val[j]);
+    if (cn) cnt[rel] = (uint8_t)(cnt[rel] + 1);
+    atomicOr(&bits[rel >> 5], 1u << (rel & 31));
+  }
+}
+
 // BM25-union pipeline, first half: decode a STAGED posting block and compute the score contribution
 // of each of the lane's 4 postings (weight * tf-factor) WITHOUT touching the accumulator, so that it
 // can run ahead of the clause order; `inmask` bit j = posting j exists and lies inside the window.
@@ -1080,7 +1101,7 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           req_init &= ~(1u << level);
           __syncthreads();
           ip++;
-        } else if (op == OP_TERM) {
+        } else if (op == OP_TERM || op == OP_PHRASE) {
           const bool required = occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER;
           const uint32_t slot = in.t;
           const bool from_score = (in.flags & IF_BITS_FROM_SCORE) != 0;  // bitmap derived at BOOL_END
@@ -1101,7 +1122,18 @@ __global__ void __launch_bounds__(QW_THREADS, QW_MIN_BLOCKS_PER_SM) k_window(con
           tg.has_tf = (in.flags & IF_HAS_TF) != 0;
           tg.fn = (scored && (in.flags & IF_HAS_FN)) ? p.sm.fn[in.r] : 0xFFFFFFFFu;
           tg.gtab = scored ? (const float*)P.bm25_tab[in.r] : nullptr;
-          if (s_rng[4 * slot + 2] != 0xFFFFFFFFu) {
+          if (op == OP_PHRASE) {
+            // blocks of the phrase's posting list = blocks of its driver term: found through that term's skip list
+            const QwSkip* skips = (const QwSkip*)(base + in.c);
+            const VBlk* vblks = (const VBlk*)in.a;
+            const uint32_t nblk = in.n;
+            const uint32_t bfirst = first_block_ge(skips, nblk, ws, lane);
+            for (uint32_t bb = bfirst + warp; bb < nblk; bb += QW_WARPS) {
+              const uint32_t prev = __ldg(&skips[bb].prev_last_doc);
+              if (prev != QW_NO_PREV_DOC && prev + 1 >= we) break;
+              fold_vblock(vblks + bb, ws, wlen, tg, lane);
+            }
+          } else if (s_rng[4 * slot + 2] != 0xFFFFFFFFu) {
             const uint32_t g0 = s_tblk[2 * slot], nb = s_tblk[2 * slot + 1];
             const bool sc = tg.score != 0xFFFFFFFFu, cn = tg.cnt != 0xFFFFFFFFu;
             if (sc && !cn && from_score) { for (uint32_t k = warp; k < nb; k += QW_WARPS) fold_block<true, false, true, false>(p.sm.stage + s_blk[g0 + k].soff, nullptr, ws, 0, wlen, tg, lane); }

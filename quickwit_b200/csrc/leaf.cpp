@@ -337,8 +337,9 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
         if (!j.dev) fail(QWGPU_ENOTFOUND, "split `%s` is not resident on this GPU", so.split_id.c_str());
         j.plan = compile_plan(j.dev->view, so.split_id, *req, dm, &so, &ast);
       } catch (const Error& e) {
-        // malformed queries / aggregations fail the whole request like the reference (service.rs:182-184)
-        if (e.code == QWGPU_EINVALID_QUERY || e.code == QWGPU_EINVALID_AGG || e.code == QWGPU_EINVALID_ARG) throw;
+        // malformed queries / aggregations fail the whole request like the reference (service.rs:182-184); so does
+        // a query or aggregation shape this library does not compile: every split would fail the same way
+        if (e.code == QWGPU_EINVALID_QUERY || e.code == QWGPU_EINVALID_AGG || e.code == QWGPU_EINVALID_ARG || e.code == QWGPU_EUNSUPPORTED) throw;
         j.error = e.what();
         j.error_code = e.code;
       }

@@ -213,3 +213,62 @@ def test_random_plans_against_the_oracle(gpu_ctx, clustered, kids, msm, sort, k,
         aggs = [terms_agg(img, "code", children=[stats_agg(img, "timestamp")]), stats_agg(img, "opt")]
     plan = P.make_plan(root, k, _sort(img, sort), aggs=aggs)
     run_both(gpu_ctx, img, plan, ctx=f"kids={kids} msm={msm} sort={sort} k={k} aggs={with_aggs}")
+
+
+# ---- phrases ------------------------------------------------------------------------------------------------------
+_VOCAB = ["alpha", "beta", "gamma", "delta", "eps", "zeta", "eta", "theta"]
+
+
+@pytest.fixture(scope="module")
+def phrase_split(gpu_ctx):
+    """20 000 docs of 3..40 random words over 8 words (every word in most docs, every 2-word phrase frequent, long
+    phrases rare), a multi-valued field, many posting blocks per term."""
+    rnd = random.Random(11)
+    docs = []
+    for i in range(20_000):
+        n = 3 + (i * 37) % 38
+        doc = {"body": " ".join(rnd.choice(_VOCAB) for _ in range(n)), "n": i % 50}
+        if i % 3 == 0:
+            doc["tags"] = [" ".join(rnd.choice(_VOCAB[:4]) for _ in range(1 + i % 3)) for _ in range(1 + i % 4)]
+        if i % 1000 == 0:
+            doc["body"] += " " + " ".join(["alpha beta"] * 20)   # phrase_count above the tf-factor table
+        docs.append(doc)
+    mapping = {"field_mappings": [{"name": "body", "type": "text", "record": "position", "fieldnorms": True},
+                                  {"name": "tags", "type": "text", "record": "position"},
+                                  {"name": "n", "type": "u64", "fast": True}]}
+    img = S.build_split(docs, mapping, "phrases-0")
+    gpu_ctx.register_split(img)
+    yield img
+    gpu_ctx.unregister_split(img.split_id)
+
+
+def test_phrases_against_the_oracle(gpu_ctx, phrase_split):
+    img = phrase_split
+    rnd = random.Random(3)
+    cases = [["alpha", "beta"], ["beta", "alpha"], ["alpha", "alpha"], ["alpha", "beta", "gamma"], ["eta", "eta", "eta"],
+             ["alpha", "beta", "gamma", "delta"], ["theta", "zeta", "eta", "eps", "delta", "gamma", "beta", "alpha"]]
+    cases += [[rnd.choice(_VOCAB) for _ in range(rnd.randint(2, 5))] for _ in range(12)]
+    n_hits = []
+    for terms in cases:
+        for k, sort in ((10, SCORE_DESC), (300, DOC_ASC), (0, DOC_DESC)):
+            got, _ = run_both(gpu_ctx, img, P.make_plan(P.phrase(img, "body", terms), k, sort), ctx=f"phrase {terms} k={k}")
+        n_hits.append(got.num_hits)
+    assert max(n_hits) > 5000 and 0 < min(x for x in n_hits if x) < 200      # frequent and rare phrases both occurred
+    # multi-valued field without fieldnorms
+    for terms in (["alpha", "beta"], ["gamma", "delta", "alpha"], ["beta", "beta"]):
+        run_both(gpu_ctx, img, P.make_plan(P.phrase(img, "tags", terms), 50, SCORE_DESC), ctx=f"tags {terms}")
+    # phrases as clauses: must + should + must_not, two phrases in a union, a range filter, an aggregation
+    ph = lambda terms, occ, boost=1.0, field="body": P.phrase(img, field, terms, occur=occ, boost=boost)
+    t = lambda name, occ: P.term(img, "body", name, occur=occ)
+    plans = [
+        P.bool_([ph(["alpha", "beta"], ffi.OCCUR_MUST), t("gamma", ffi.OCCUR_SHOULD), ph(["delta", "delta"], ffi.OCCUR_MUST_NOT)]),
+        P.bool_([ph(["alpha", "beta"], ffi.OCCUR_SHOULD, 2.0), ph(["gamma", "delta"], ffi.OCCUR_SHOULD), t("eta", ffi.OCCUR_SHOULD)]),
+        P.bool_([ph(["alpha", "beta"], ffi.OCCUR_SHOULD), ph(["gamma", "delta"], ffi.OCCUR_SHOULD), ph(["alpha", "gamma"], ffi.OCCUR_SHOULD, field="tags")],
+                min_should_match=2),
+        P.bool_([ph(["zeta", "eta"], ffi.OCCUR_MUST), P.range_(img, "n", 10, 30, occur=ffi.OCCUR_FILTER)]),
+        P.bool_([t("alpha", ffi.OCCUR_MUST), ph(["beta", "gamma", "delta"], ffi.OCCUR_FILTER)]),
+    ]
+    for i, root in enumerate(plans):
+        for k, sort in ((25, SCORE_DESC), (1000, [col_sort(img, "n", ffi.ORDER_ASC), (ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)])):
+            run_both(gpu_ctx, img, P.make_plan(root, k, sort), ctx=f"phrase plan {i} k={k}")
+    run_both(gpu_ctx, img, P.make_plan(ph(["alpha", "beta"], ffi.OCCUR_MUST), 0, DOC_DESC, aggs=[terms_agg(img, "n")]), ctx="phrase + terms agg")

@@ -97,3 +97,7 @@ def test_merge_goldens():
     G.test_merge_partial_hits_with_tie()
     G.test_merge_collectors()
     G.test_merge_empty_intermediate_aggregation_result()
+
+
+def test_phrase_queries(on_gpu):
+    G.test_phrase_queries()
