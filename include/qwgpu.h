@@ -179,6 +179,18 @@ void qwgpu_comm_destroy(qwgpu_ctx* ctx);
 int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* leaf_search_request_pb, size_t len,
                                 uint8_t** merged_resp, size_t* merged_len);
 
+/* ---- real `.split` files ------------------------------------------------------------------------
+ * Reads the footer of a Quickwit split bundle: `tail` = the last `tail_len` bytes of the split file (at least
+ * [split_footer_start, split_footer_end) of SplitIdAndFooterOffsets, search.proto:489-503), `split_file_len` =
+ * the size of the whole file. Layout (quickwit-storage/src/bundle_storage.rs:92-174,
+ * quickwit-directories/src/hot_directory.rs:40-80): ...files | BundleStorageFileOffsets (versioned header + JSON)
+ * | u32 len | hotcache (versioned header + postcard HotDirectoryMeta + cached slices) | u32 len.
+ * `json_out` (qwgpu_buf_free): {"files": [{"path", "start", "end"}] sorted by offset, "bundle_metadata": {"offset",
+ * "len"}, "footer_start", "footer_end", "hotcache": {"offset", "len", "file_lengths": {path: len}, "slices":
+ * [{"path", "offset"}]}} — every offset is a byte offset in the split file. Host only; the first step of ingesting
+ * a real split: it locates the tantivy .term / .idx / .pos / .fast / .fieldnorm files. */
+int qwgpu_parse_split_footer(const uint8_t* tail, uint64_t tail_len, uint64_t split_file_len, uint8_t** json_out, size_t* json_len);
+
 /* ---- split image writer ------------------------------------------------------------------------ */
 
 qwgpu_imgb* qwgpu_imgb_new(uint32_t num_docs);

@@ -180,6 +180,7 @@ def lib() -> C.CDLL:
     bind("qwgpu_merge_leaf_responses", [vp, sz, u32, C.POINTER(vp), C.POINTER(sz),
                                         C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_optimize_leaf_request", [vp, sz, C.POINTER(vp), C.POINTER(sz)])
+    bind("qwgpu_parse_split_footer", [vp, u64, u64, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_finalize_aggregation", [cp, vp, sz, C.POINTER(vp)])
     bind("qwgpu_partial_size", [vp, sz, C.POINTER(u64)])
     bind("qwgpu_response_to_partial", [vp, sz, vp, sz, vp, u64])

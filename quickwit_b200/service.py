@@ -144,6 +144,17 @@ def optimize_leaf_request(leaf_search_request_pb: bytes) -> list:
     return json.loads(ffi.take_bytes(out, n.value))
 
 
+def parse_split_footer(tail: bytes, split_file_len: int) -> dict:
+    """BundleStorageFileOffsets + HotDirectoryMeta of a `.split` file from its last bytes
+    (bundle_storage.rs:92-174, hot_directory.rs:40-80): where the tantivy files and the hotcache lie. Host only."""
+    import json
+    L = ffi.lib()
+    buf = C.create_string_buffer(tail, len(tail))
+    out, n = C.c_void_p(), C.c_size_t()
+    ffi.check(L.qwgpu_parse_split_footer(C.addressof(buf), len(tail), split_file_len, C.byref(out), C.byref(n)))
+    return json.loads(ffi.take_bytes(out, n.value))
+
+
 def merge_leaf_responses(search_request_pb: bytes, responses: Sequence[bytes]) -> bytes:
     """merge_leaf_responses / QuickwitCollector::merge_fruits (collector.rs:832-974)."""
     L = ffi.lib()

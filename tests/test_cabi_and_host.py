@@ -285,3 +285,57 @@ def test_partial_exchange_carries_failed_splits_and_rejects_corrupt_partials():
     with pytest.raises(ffi.QwGpuError) as e:
         service.response_to_partial(req, many, buf.data_ptr(), nbytes)
     assert e.value.code == ffi.EUNSUPPORTED
+
+
+def test_split_bundle_footer():
+    """A `.split` file's footer built byte by byte the way the reference writes it (bundle_storage.rs:92-174:
+    versioned header magic 403881646 / version 1 + JSON, u32 length; hot_directory.rs:40-80: magic 2557869106 /
+    version 1, u32 length, postcard HotDirectoryMeta, slices; u32 length) and read back."""
+    import struct
+    files = {"a.term": b"T" * 100, "a.idx": b"I" * 3000, "a.pos": b"P" * 70, "b.fast": b"F" * 555, "meta.json": b"{}"}
+    body, ranges = b"", {}
+    for name, data in files.items():
+        ranges[name] = {"start": len(body), "end": len(body) + len(data)}
+        body += data
+    meta = struct.pack("<II", 403881646, 1) + json.dumps({"files": ranges}).encode()
+
+    def varint(v):
+        out = b""
+        while True:
+            b7 = v & 0x7F
+            v >>= 7
+            out += bytes([b7 | (0x80 if v else 0)])
+            if not v:
+                return out
+    pstr = lambda s: varint(len(s)) + s.encode()
+    file_lengths = {"a.term": 100, "a.idx": 3000, "b.fast": 555}
+    slice_offsets = [("a.term", 0), ("a.idx", 130), ("b.fast", 400)]
+    pc = varint(len(file_lengths)) + b"".join(pstr(k) + varint(v) for k, v in file_lengths.items())
+    pc += varint(len(slice_offsets)) + b"".join(pstr(k) + varint(v) for k, v in slice_offsets)
+    slices = b"S" * 1000
+    hot = struct.pack("<III", 2557869106, 1, len(pc)) + pc + slices
+    split = body + meta + struct.pack("<I", len(meta)) + hot + struct.pack("<I", len(hot))
+    footer_start = len(body)
+    for tail_from in (footer_start, 0, footer_start - 17):      # exactly the footer, the whole file, a bit more than the footer
+        got = service.parse_split_footer(split[tail_from:], len(split))
+        assert [(f["path"], f["start"], f["end"]) for f in got["files"]] == [(k, v["start"], v["end"]) for k, v in ranges.items()]
+        assert got["footer_start"] == footer_start and got["footer_end"] == len(split)
+        assert got["bundle_metadata"] == {"offset": footer_start, "len": len(meta)}
+        h = got["hotcache"]
+        assert h["offset"] == footer_start + len(meta) + 4 and h["len"] == len(hot) and h["file_lengths"] == file_lengths
+        first_slice = h["offset"] + 12 + len(pc)
+        assert [(s["path"], s["offset"]) for s in h["slices"]] == [(k, first_slice + o) for k, o in slice_offsets]
+        assert split[h["slices"][0]["offset"]:h["slices"][0]["offset"] + 4] == b"SSSS"
+    # corrupt footers are rejected, not followed
+    bad = bytearray(split)
+    bad[footer_start] ^= 0xFF                                    # bundle magic
+    with pytest.raises(ffi.QwGpuError) as e:
+        service.parse_split_footer(bytes(bad[footer_start:]), len(split))
+    assert e.value.code == ffi.EINVALID_ARG and "magic number" in e.value.msg
+    for cut in (3, 40, len(split) - footer_start - 10):         # the tail does not hold the whole footer
+        with pytest.raises(ffi.QwGpuError):
+            service.parse_split_footer(split[-cut:], len(split))
+    bad = bytearray(split)
+    bad[-4:] = struct.pack("<I", len(split) + 5)                 # hotcache longer than the file
+    with pytest.raises(ffi.QwGpuError):
+        service.parse_split_footer(bytes(bad[footer_start:]), len(split))
