@@ -72,6 +72,24 @@ int qwgpu_split_unregister(qwgpu_ctx* ctx, const char* split_id);
 /* Bytes resident on the device for this ctx. */
 uint64_t qwgpu_resident_bytes(qwgpu_ctx* ctx);
 
+/* Residency manager — the GPU-side counterpart of a searcher's split cache and of the open + warmup step of a
+ * leaf search (quickwit-search/src/leaf.rs:210-251 open_split_bundle, :269-472 warmup):
+ *   qwgpu_set_residency_budget  cap on the bytes of split data kept in HBM (0 = none). A registration that does
+ *                               not fit evicts the least recently searched splits that no running call uses; a
+ *                               search on an evicted split reports it in failed_splits (retryable: the caller
+ *                               registers it again), exactly like a split that was never registered.
+ *   qwgpu_split_register_async  returns at once; the data region is uploaded by a background thread through
+ *                               pinned staging buffers on its own stream, searches on other splits keep running.
+ *                               `img` must stay valid until qwgpu_split_wait(split_id) has returned. A search
+ *                               that names a split still loading waits for it.
+ *   qwgpu_split_wait            blocks until the upload has finished; returns its error, if any.
+ *   qwgpu_residency_info        bytes resident, budget, number of splits, evictions so far (NULL = not wanted). */
+int qwgpu_set_residency_budget(qwgpu_ctx* ctx, uint64_t bytes);
+int qwgpu_split_register_async(qwgpu_ctx* ctx, const char* split_id, const uint8_t* img, uint64_t img_len);
+int qwgpu_split_wait(qwgpu_ctx* ctx, const char* split_id);
+int qwgpu_residency_info(qwgpu_ctx* ctx, uint64_t* resident_bytes, uint64_t* budget_bytes, uint64_t* num_splits, uint64_t* evictions);
+int qwgpu_split_is_resident(qwgpu_ctx* ctx, const char* split_id);
+
 /* ---- seam A / B: protobuf in, protobuf out ---------------------------------------------------- */
 
 /* req = quickwit.search.LeafSearchRequest, resp = quickwit.search.LeafSearchResponse

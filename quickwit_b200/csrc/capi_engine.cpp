@@ -47,6 +47,45 @@ int qwgpu_split_unregister(qwgpu_ctx* ctx, const char* split_id) {
   QW_API_END
 }
 
+int qwgpu_split_register_async(qwgpu_ctx* ctx, const char* split_id, const uint8_t* img, uint64_t img_len) {
+  QW_API_BEGIN
+  engine_of(ctx).register_split_async(split_id, img, img_len);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_split_wait(qwgpu_ctx* ctx, const char* split_id) {
+  QW_API_BEGIN
+  engine_of(ctx).wait_split(split_id);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_set_residency_budget(qwgpu_ctx* ctx, uint64_t bytes) {
+  QW_API_BEGIN
+  engine_of(ctx).set_budget(bytes);
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_residency_info(qwgpu_ctx* ctx, uint64_t* resident_bytes, uint64_t* budget_bytes, uint64_t* num_splits, uint64_t* evictions) {
+  QW_API_BEGIN
+  qw::Engine& e = engine_of(ctx);
+  std::lock_guard<std::mutex> g(e.mu);
+  if (resident_bytes) *resident_bytes = e.resident;
+  if (budget_bytes) *budget_bytes = e.budget;
+  if (num_splits) *num_splits = e.splits.size();
+  if (evictions) *evictions = e.evictions;
+  return 0;
+  QW_API_END
+}
+
+int qwgpu_split_is_resident(qwgpu_ctx* ctx, const char* split_id) {
+  if (!ctx || !ctx->engine || !split_id) return 0;
+  std::lock_guard<std::mutex> g(ctx->engine->mu);
+  return ctx->engine->splits.count(split_id) ? 1 : 0;
+}
+
 uint64_t qwgpu_resident_bytes(qwgpu_ctx* ctx) {
   if (!ctx || !ctx->engine) return 0;
   std::lock_guard<std::mutex> g(ctx->engine->mu);

@@ -102,12 +102,14 @@ Engine::Engine(int dev) : device(dev) {
 }
 
 Engine::~Engine() {
+  for (Loader& l : loaders) if (l.t.joinable()) l.t.join();
   cudaSetDevice(device);
   for (CallSlot* s : free_slots) delete s;
   splits.clear();
 }
 
-void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
+// host half of a registration: directory copy + views (no device work)
+static std::shared_ptr<SplitDev> open_split(const char* id, const uint8_t* img, uint64_t len, ImageView* full_out) {
   ImageView full;
   full.open(img, len);
   auto sp = std::make_shared<SplitDev>();
@@ -124,13 +126,15 @@ void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
   sp->view.strings = sp->dir.data() + full.hdr->strings_off;
   sp->view.data = nullptr;
   sp->data_len = full.hdr->data_len;
-  CUDA_CHECK(cudaSetDevice(device));
-  CUDA_CHECK(cudaMalloc(&sp->d_data, std::max<uint64_t>(sp->data_len, 16)));
-  CUDA_CHECK(cudaMemcpy(sp->d_data, full.data, sp->data_len, cudaMemcpyHostToDevice));
-  // Bm25Weight cache per field: K1 * (1 - B + B * fieldnorm(id) / avg)
-  uint32_t nf = full.hdr->num_fields;
-  // followed, per field, by the tf-factor table tff[tf][id] = tf / (tf + norm[id]) (tf < 16), built with
-  // the same IEEE f32 ops the kernel would use, so table lookups are bit-identical to dividing
+  *full_out = full;
+  return sp;
+}
+
+// Bm25Weight cache per field: K1 * (1 - B + B * fieldnorm(id) / avg), followed, per field,
+// by the tf-factor table tff[tf][id] = tf / (tf + norm[id]) (tf < 16), built with the same IEEE f32 ops the kernel
+// would use, so table lookups are bit-identical to dividing
+static std::vector<float> bm25_tables(const ImageView& full) {
+  const uint32_t nf = full.hdr->num_fields;
   const size_t kTab = 256 + QW_TFF_ROWS * 256;
   std::vector<float> tabs((size_t)std::max(nf, 1u) * kTab);
   for (uint32_t f = 0; f < nf; f++) {
@@ -145,27 +149,143 @@ void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
         t[256 + tf * 256 + i] = num / den;
       }
   }
+  return tabs;
+}
+
+// Makes room for `need` more bytes under the budget: drops the least recently searched splits that nothing but
+// the table references (a split in use by a running call, or still loading, stays). Caller holds `mu`.
+static void evict_for(Engine& e, uint64_t need, const std::string& keep) {
+  if (!e.budget) return;
+  while (e.resident + need > e.budget) {
+    auto victim = e.splits.end();
+    for (auto it = e.splits.begin(); it != e.splits.end(); ++it) {
+      if (it->first == keep || it->second.use_count() > 1 || it->second->state == 0) continue;
+      if (victim == e.splits.end() || it->second->last_use < victim->second->last_use) victim = it;
+    }
+    if (victim == e.splits.end()) break;  // everything left is in use: over budget until those calls end
+    e.resident -= victim->second->data_len;
+    e.splits.erase(victim);
+    e.evictions++;
+  }
+}
+
+static void publish(Engine& e, const std::shared_ptr<SplitDev>& sp) {
+  auto it = e.splits.find(sp->id);
+  if (it != e.splits.end()) e.resident -= it->second->data_len;
+  sp->last_use = ++e.tick;
+  e.splits[sp->id] = sp;
+  e.resident += sp->data_len;
+}
+
+void Engine::register_split(const char* id, const uint8_t* img, uint64_t len) {
+  ImageView full;
+  auto sp = open_split(id, img, len, &full);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (budget && sp->data_len > budget) fail(QWGPU_EINVALID_ARG, "split `%s` needs %llu bytes, the residency budget is %llu", id, (unsigned long long)sp->data_len, (unsigned long long)budget);
+    evict_for(*this, sp->data_len, sp->id);
+  }
+  CUDA_CHECK(cudaSetDevice(device));
+  CUDA_CHECK(cudaMalloc(&sp->d_data, std::max<uint64_t>(sp->data_len, 16)));
+  CUDA_CHECK(cudaMemcpy(sp->d_data, full.data, sp->data_len, cudaMemcpyHostToDevice));
+  std::vector<float> tabs = bm25_tables(full);
   CUDA_CHECK(cudaMalloc(&sp->d_tabs, tabs.size() * sizeof(float)));
   CUDA_CHECK(cudaMemcpy(sp->d_tabs, tabs.data(), tabs.size() * sizeof(float), cudaMemcpyHostToDevice));
   std::lock_guard<std::mutex> g(mu);
-  auto it = splits.find(sp->id);
-  if (it != splits.end()) resident -= it->second->data_len;
-  splits[sp->id] = sp;
-  resident += sp->data_len;
+  publish(*this, sp);
+}
+
+// Background upload: the split is visible (loading) at once; a loader thread stages the data region through two
+// pinned buffers (pageable -> pinned memcpy of chunk i+1 overlaps the DMA of chunk i) on its own stream, so
+// searches on other splits keep the GPU while a cold split comes in (leaf.rs:269-472 warmup runs beside searches).
+void Engine::register_split_async(const char* id, const uint8_t* img, uint64_t len) {
+  ImageView full;
+  auto sp = open_split(id, img, len, &full);
+  sp->state = 0;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (budget && sp->data_len > budget) fail(QWGPU_EINVALID_ARG, "split `%s` needs %llu bytes, the residency budget is %llu", id, (unsigned long long)sp->data_len, (unsigned long long)budget);
+    evict_for(*this, sp->data_len, sp->id);
+  }
+  CUDA_CHECK(cudaSetDevice(device));
+  CUDA_CHECK(cudaMalloc(&sp->d_data, std::max<uint64_t>(sp->data_len, 16)));
+  std::vector<float> tabs = bm25_tables(full);
+  CUDA_CHECK(cudaMalloc(&sp->d_tabs, tabs.size() * sizeof(float)));
+  std::lock_guard<std::mutex> g(mu);
+  publish(*this, sp);
+  // loaders that have finished (state set, lock released) are reaped here
+  for (size_t i = 0; i < loaders.size();) {
+    if (loaders[i].sp->state != 0) { loaders[i].t.join(); loaders[i] = std::move(loaders.back()); loaders.pop_back(); }
+    else i++;
+  }
+  loaders.push_back(Loader{std::thread(), sp});
+  loaders.back().t = std::thread([this, sp, full, tabs]() {
+    std::string err;
+    cudaStream_t st = nullptr;
+    uint8_t* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    const size_t kChunk = 8u << 20;
+    auto ok = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && err.empty()) err = std::string(what) + ": " + cudaGetErrorString(e); return e == cudaSuccess; };
+    if (ok(cudaSetDevice(device), "cudaSetDevice") && ok(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate")) {
+      for (int i = 0; i < 2; i++) { ok(cudaMallocHost(&pin[i], kChunk), "cudaMallocHost"); ok(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming), "cudaEventCreate"); }
+      uint64_t off = 0;
+      for (int k = 0; err.empty() && off < sp->data_len; k ^= 1) {
+        const size_t nb = (size_t)std::min<uint64_t>(kChunk, sp->data_len - off);
+        ok(cudaEventSynchronize(ev[k]), "upload event");  // the DMA that last used this buffer is done
+        memcpy(pin[k], full.data + off, nb);
+        ok(cudaMemcpyAsync(sp->d_data + off, pin[k], nb, cudaMemcpyHostToDevice, st), "H2D of the split data");
+        ok(cudaEventRecord(ev[k], st), "upload event");
+        off += nb;
+      }
+      ok(cudaMemcpyAsync(sp->d_tabs, tabs.data(), tabs.size() * sizeof(float), cudaMemcpyHostToDevice, st), "H2D of the BM25 tables");
+      ok(cudaStreamSynchronize(st), "upload stream");
+    }
+    for (int i = 0; i < 2; i++) { if (pin[i]) cudaFreeHost(pin[i]); if (ev[i]) cudaEventDestroy(ev[i]); }
+    if (st) cudaStreamDestroy(st);
+    {
+      std::lock_guard<std::mutex> g2(mu);
+      sp->load_error = err;
+      sp->state = err.empty() ? 1 : 2;
+    }
+    loaded_cv.notify_all();
+  });
+}
+
+void Engine::wait_split(const char* id) {
+  std::unique_lock<std::mutex> g(mu);
+  auto it = splits.find(id);
+  if (it == splits.end()) fail(QWGPU_ENOTFOUND, "split '%s' is not registered", id);
+  std::shared_ptr<SplitDev> sp = it->second;
+  loaded_cv.wait(g, [&] { return sp->state != 0; });
+  if (sp->state == 2) fail(QWGPU_EINTERNAL, "upload of split '%s' failed: %s", id, sp->load_error.c_str());
+}
+
+void Engine::set_budget(uint64_t bytes) {
+  std::lock_guard<std::mutex> g(mu);
+  budget = bytes;
+  evict_for(*this, 0, "");
 }
 
 void Engine::unregister_split(const char* id) {
-  std::lock_guard<std::mutex> g(mu);
+  std::unique_lock<std::mutex> g(mu);
   auto it = splits.find(id);
   if (it == splits.end()) fail(QWGPU_ENOTFOUND, "split '%s' is not registered", id);
-  resident -= it->second->data_len;
-  splits.erase(it);
+  std::shared_ptr<SplitDev> sp = it->second;
+  loaded_cv.wait(g, [&] { return sp->state != 0; });  // (its loader still writes the device buffer)
+  it = splits.find(id);
+  if (it != splits.end() && it->second == sp) { resident -= sp->data_len; splits.erase(it); }
 }
 
+// A search takes the split in use: recency for the LRU; a split that is still loading is waited for.
 std::shared_ptr<SplitDev> Engine::find(const std::string& id) {
-  std::lock_guard<std::mutex> g(mu);
+  std::unique_lock<std::mutex> g(mu);
   auto it = splits.find(id);
-  return it == splits.end() ? nullptr : it->second;
+  if (it == splits.end()) return nullptr;
+  std::shared_ptr<SplitDev> sp = it->second;
+  loaded_cv.wait(g, [&] { return sp->state != 0; });
+  if (sp->state == 2) return nullptr;
+  sp->last_use = ++tick;
+  return sp;
 }
 
 uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t>* bases) {

@@ -1,8 +1,10 @@
 // engine.h — host-side engine: split residency in HBM + batched plan execution on the GPU.
 #pragma once
+#include <condition_variable>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -17,6 +19,10 @@ struct SplitDev {
   uint8_t* d_data = nullptr; // device copy of the data region
   float* d_tabs = nullptr;   // device float[num_fields][256] BM25 norm tables
   uint64_t data_len = 0;
+  // residency: recency for the LRU, state of an asynchronous upload (0 loading, 1 ready, 2 failed)
+  uint64_t last_use = 0;
+  int state = 1;
+  std::string load_error;
   ~SplitDev();
 };
 
@@ -73,12 +79,25 @@ struct Engine {
   std::map<std::string, std::shared_ptr<SplitDev>> splits;
   std::vector<CallSlot*> free_slots;
   uint64_t resident = 0;
+  // residency manager: byte budget for the data regions of the resident splits (0 = no limit). Registering a
+  // split beyond it evicts the least recently searched splits that no call is using (the counterpart of the
+  // searcher's split cache, quickwit-storage split_cache + leaf.rs:210-251 open_split_bundle: a leaf keeps hot
+  // splits local and drops cold ones). Uploads can run in the background (register_split_async): `find` waits
+  // for a split that is still loading.
+  uint64_t budget = 0, tick = 0, evictions = 0;
+  std::condition_variable loaded_cv;
+  struct Loader { std::thread t; std::shared_ptr<SplitDev> sp; };
+  std::vector<Loader> loaders;
   int sm_count = 148;
   int max_smem_optin = 0;
 
   explicit Engine(int dev);
   ~Engine();
   void register_split(const char* id, const uint8_t* img, uint64_t len);
+  // returns at once; `img` must stay valid until wait_split(id) has returned
+  void register_split_async(const char* id, const uint8_t* img, uint64_t len);
+  void wait_split(const char* id);  // throws the upload's error, if any
+  void set_budget(uint64_t bytes);
   void unregister_split(const char* id);
   std::shared_ptr<SplitDev> find(const std::string& id);
   // Runs plan[i] on splits[i]; fills outs[i] (status per split). Throws only on whole-call errors.

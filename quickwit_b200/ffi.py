@@ -170,6 +170,11 @@ def lib() -> C.CDLL:
     bind("qwgpu_split_register", [vp, cp, vp, u64])
     bind("qwgpu_split_unregister", [vp, cp])
     bind("qwgpu_resident_bytes", [vp], u64)
+    bind("qwgpu_set_residency_budget", [vp, u64])
+    bind("qwgpu_split_register_async", [vp, cp, vp, u64])
+    bind("qwgpu_split_wait", [vp, cp])
+    bind("qwgpu_residency_info", [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)])
+    bind("qwgpu_split_is_resident", [vp, cp])
     bind("qwgpu_leaf_search", [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_invoke_leaf_search", [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_compile_plan", [vp, u64, cp, vp, sz, cp, C.POINTER(vp), C.POINTER(sz)])

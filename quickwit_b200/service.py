@@ -66,6 +66,25 @@ class SearcherContext:
     def resident_bytes(self) -> int:
         return int(self._L.qwgpu_resident_bytes(self._ctx))
 
+    def set_residency_budget(self, nbytes: int):
+        """Cap on the split data kept in HBM; registrations beyond it evict the least recently searched splits."""
+        ffi.check(self._L.qwgpu_set_residency_budget(self._ctx, nbytes))
+
+    def register_split_async(self, img: SplitImage, split_id: Optional[str] = None):
+        """Background upload; `img` must stay alive until wait_split() has returned."""
+        ffi.check(self._L.qwgpu_split_register_async(self._ctx, (split_id or img.split_id).encode(), img.ptr, img.nbytes))
+
+    def wait_split(self, split_id: str):
+        ffi.check(self._L.qwgpu_split_wait(self._ctx, split_id.encode()))
+
+    def is_resident(self, split_id: str) -> bool:
+        return bool(self._L.qwgpu_split_is_resident(self._ctx, split_id.encode()))
+
+    def residency_info(self) -> dict:
+        v = [C.c_uint64() for _ in range(4)]
+        ffi.check(self._L.qwgpu_residency_info(self._ctx, *[C.byref(x) for x in v]))
+        return dict(zip(("resident_bytes", "budget_bytes", "num_splits", "evictions"), (int(x.value) for x in v)))
+
     # -- seam C -------------------------------------------------------------------------------------
     def split_search(self, split_ids: Sequence[str], plans: Sequence[bytes]) -> List[SplitSearchResult]:
         n = len(split_ids)

@@ -199,3 +199,36 @@ def test_pre_search_pruning_keeps_the_response(gpu_ctx):
     lreq = proto.enc_leaf_search_request(search_request(MATCH_ALL, max_hits=5, sort_fields=[("ts", DESC)]), offs, json.dumps(mapping))
     leaf = proto.dec_leaf_search_response(gpu_ctx.leaf_search(lreq))
     assert leaf["num_hits"] == 323 and not leaf["failed_splits"] and leaf["num_successful_splits"] == 6
+
+
+def test_residency_budget_lru_and_background_upload():
+    """Residency manager (qwgpu.h): a byte budget evicts the least recently SEARCHED splits, an evicted split
+    shows up as a retryable failed split, background uploads are waited for by the searches that need them."""
+    ctx = service.SearcherContext(0)
+    imgs = [S.synth_split(30_000, 100 + i, FRACS[:4], split_id=f"lru-{i}", ts_start_secs=1_700_000_000) for i in range(5)]
+    one = None
+    for im in imgs[:3]:
+        ctx.register_split(im)
+        one = ctx.resident_bytes() if one is None else one
+    assert ctx.residency_info()["num_splits"] == 3 and ctx.resident_bytes() >= 2.9 * one
+    leaf = lambda ids: proto.dec_leaf_search_response(ctx.leaf_search(proto.enc_leaf_search_request(
+        search_request(term("body", "t0"), max_hits=3), [proto.enc_split_offsets(i, 30_000) for i in ids], json.dumps(SYNTH_MAPPING))))
+    leaf(["lru-0"])                                    # lru-0 is now the most recently used, lru-1 the least
+    ctx.set_residency_budget(int(3.5 * one))
+    ctx.register_split(imgs[3])                        # needs room: evicts lru-1
+    assert [ctx.is_resident(f"lru-{i}") for i in range(4)] == [True, False, True, True]
+    assert ctx.residency_info()["evictions"] == 1 and ctx.resident_bytes() <= int(3.5 * one)
+    resp = leaf(["lru-0", "lru-1"])
+    assert resp["num_successful_splits"] == 1 and resp["failed_splits"][0]["split_id"] == "lru-1" and resp["failed_splits"][0]["retryable_error"]
+    # background upload of two splits: the search that names them waits for the upload and sees every doc
+    ctx.register_split_async(imgs[4])
+    ctx.register_split_async(imgs[1])                  # back in: evicts the least recently used of the rest
+    resp = leaf(["lru-4", "lru-1"])
+    assert resp["num_successful_splits"] == 2 and not resp["failed_splits"]
+    want = [proto.dec_leaf_search_response(cpu_split_response(imgs[i], search_request(term("body", "t0"), max_hits=3), SYNTH_MAPPING)) for i in (4, 1)]
+    assert resp["num_hits"] == sum(w["num_hits"] for w in want)
+    ctx.wait_split("lru-4"); ctx.wait_split("lru-1")
+    info = ctx.residency_info()
+    assert info["resident_bytes"] <= info["budget_bytes"] and info["num_splits"] == 3 and info["evictions"] == 3
+    with pytest.raises(ffi.QwGpuError):
+        ctx.set_residency_budget(one // 2) or ctx.register_split(imgs[0])   # a split larger than the whole budget
