@@ -896,7 +896,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // order-free accumulation (union_kernel.cuh, FREE = 1) when few docs can collect three or more contributions:
   // at most one posting per doc on average. A window that still overflows its late-arrival list raises a flag
   // and the batch is repeated in ordered mode (tl_ordered_union).
-  static const bool no_free = getenv("QWGPU_ORDERED_UNION") != nullptr;
+  // (opt-in through QWGPU_FREE_UNION=1 until it has a full GPU validation run behind it; QWGPU_ORDERED_UNION wins)
+  static const bool no_free = getenv("QWGPU_ORDERED_UNION") != nullptr || getenv("QWGPU_FREE_UNION") == nullptr;
   bool free_mode = use_union && !no_free && !tl_ordered_union;
   if (free_mode)
     for (auto& L : low) if (L.postings > L.P.num_docs) { free_mode = false; break; }

@@ -8,6 +8,7 @@
    takes at all (33+ terms -> generic window kernel).
 3. hypothesis-driven random bool trees x sort specs x K x aggregations against the oracle.
 Everything is bit-exact: doc ids, f32 score bits, sort values, hit counts, bucket counts."""
+import os
 import random
 
 import numpy as np
@@ -120,7 +121,8 @@ def test_order_free_accumulation_paths(gpu_ctx, clustered):
         assert got.exact_fallbacks == 0
     dense = ["c0", "ends", "c1", "c2"]                               # 3 contributions on 36 000 consecutive docs
     got, _ = run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t, boost=1.0 + 0.21 * i) for i, t in enumerate(dense)]), 100, SCORE_DESC), ctx="overflow")
-    assert got.exact_fallbacks >= 1
+    if os.environ.get("QWGPU_FREE_UNION") and not os.environ.get("QWGPU_ORDERED_UNION"):
+        assert got.exact_fallbacks >= 1      # the order-free pipeline ran, overflowed and was repeated in ordered mode
     mixed = ["c0", "m0", "c1", "m1", "s3", "m2"]                     # two planes + list + sparse clauses
     run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t) for t in mixed]), 500, SCORE_DESC), ctx="mixed")
 
