@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "union_kernel.cuh"
 #include "phrase_kernel.cuh"
+#include "driver_kernel.cuh"
 #include "agg_kernel.cuh"
 
 namespace qw {
@@ -864,12 +865,29 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // by a candidates-only pass over the few windows that can hold candidates
   bool rec_l0 = true, rangeq = false;
   // every plan has the BM25 top-K shape => the specialised UNION instantiation of the collect kernel
-  bool all_union = true;
+  bool all_union = true, all_driver = true;
   for (auto& L : low) {
     if (!(L.P.fused_score_root && L.P.max_hits && !L.P.sa.present && !L.P.n_aggs && L.P.key.kind[0] == QW_SORT_SCORE &&
           L.P.key.order[0] == QW_ORDER_DESC))
       all_union = false;
     if (L.P.n_terms > QU_MAX_TERMS || L.P.n_instr != L.P.n_terms + 2) all_union = false;  // [BOOL_BEGIN, TERM x n, BOOL_END]
+    {
+      // one driving posting list + required column filters, no aggregations: the posting-driven kernel
+      // (driver_kernel.cuh). [BOOL_BEGIN, TERM, (RANGE | EXISTS) x 0..4, BOOL_END] at level 0.
+      const std::vector<DInstr>& I = L.instrs;
+      bool d = L.P.n_aggs == 0 && I.size() >= 3 && I.size() <= 3 + QD_MAX_FILTERS && I[0].op == OP_BOOL_BEGIN && I[1].op == OP_TERM &&
+               I.back().op == OP_BOOL_END && I.back().level == 0;
+      if (d) {
+        const bool req = I[1].occur == QW_OCCUR_MUST || I[1].occur == QW_OCCUR_FILTER;
+        if (!req && !(I[1].occur == QW_OCCUR_SHOULD && I.size() == 3 && I.back().r == 1 && I.back().n == 0)) d = false;
+        for (size_t k = 2; k + 1 < I.size() && d; k++) {
+          const bool colpred = I[k].op == OP_RANGE || I[k].op == OP_EXISTS;
+          const bool unscored_req = I[k].occur == QW_OCCUR_FILTER || (I[k].occur == QW_OCCUR_MUST && !(I[k].flags & IF_SCORED));
+          if (!colpred || !unscored_req || I[k].level != 0) d = false;
+        }
+      }
+      if (!d) all_driver = false;
+    }
     if (L.P.max_hits && L.P.key.kind[0] == QW_SORT_SCORE) rec_l0 = false;
     max_key_bits = std::max(max_key_bits, L.P.key.total_bits);
     for (const DInstr& in : L.instrs)
@@ -892,7 +910,11 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // BM25-union batches run the TMA + mbarrier pipeline (union_kernel.cuh): fixed 16384-doc windows,
   // two blocks per SM; QWGPU_OLD_UNION=1 keeps the round-1 window kernel for A/B runs
   static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
-  const bool use_union = all_union && !old_union;
+  // (opt-in through QWGPU_DRIVER=1 until it has a full GPU validation run behind it)
+  static const bool driver_on = getenv("QWGPU_DRIVER") != nullptr;
+  const bool use_driver = all_driver && driver_on;
+  if (use_driver) rec_l0 = false;
+  const bool use_union = all_union && !old_union && !use_driver;
   // order-free accumulation (union_kernel.cuh, FREE = 1) when few docs can collect three or more contributions:
   // at most one posting per doc on average. A window that still overflows its late-arrival list raises a flag
   // and the batch is repeated in ordered mode (tl_ordered_union).
@@ -967,6 +989,9 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // histogram pass but the looser threshold costs about as much in the collect pass)
   static const uint32_t stride_cap = getenv("QWGPU_STRIDE_CAP") ? (uint32_t)atoi(getenv("QWGPU_STRIDE_CAP")) : 16u;
   uint32_t stride = std::min(std::max(stride_cap, 1u), std::max(1u, max_windows / 8));
+  if (use_driver) stride = 1;  // a posting-driven pass costs what the sample would: exact radix select, no sampling
+  std::vector<uint32_t> fw_drv(n + 1, 0);  // posting-driven kernel: prefix of the driving term's block counts
+  if (use_driver) for (uint32_t i = 0; i < n; i++) fw_drv[i + 1] = fw_drv[i] + low[i].instrs[1].n;
   // the generic kernels sample an explicit window list: strided windows + the first and last window of each
   // split (weight 1 in the histogram); the union pipeline keeps the plain strided sample (scores do not
   // follow doc order)
@@ -993,7 +1018,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   size_t o_plans = 0, o_instr = al(o_plans + n * sizeof(DSplitPlan)), o_cols = al(o_instr + tot_instr * sizeof(DInstr)),
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), o_rank = al(o_bounds + (size_t)tot_bounds * 8),
-         o_smp = al(o_rank + (size_t)n * 4), o_phr = al(o_smp + sample_win.size() * 4), blob_bytes = al(o_phr + (size_t)n_phrases * sizeof(DPhrase));
+         o_smp = al(o_rank + (size_t)n * 4), o_phr = al(o_smp + sample_win.size() * 4), o_fwd = al(o_phr + (size_t)n_phrases * sizeof(DPhrase)),
+         blob_bytes = al(o_fwd + (use_driver ? (size_t)(n + 1) * 4 : 0));
   // device-side cross-split merge: the per-split hit lists stay in scratch, only the merged top-K comes back
   const bool do_merge = merge && merged && merge->k > 0 && any_topk && merge->rank.size() == n_in;
   uint32_t kmax = 1;
@@ -1078,6 +1104,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   }
   if (do_merge) for (uint32_t i = 0; i < n; i++) ((uint32_t*)(slot->h_blob + o_rank))[i] = merge->rank[idx[i]];
   if (!sample_win.empty()) memcpy(slot->h_blob + o_smp, sample_win.data(), sample_win.size() * 4);
+  if (use_driver) memcpy(slot->h_blob + o_fwd, fw_drv.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
@@ -1120,6 +1147,19 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     q.rec_l0 = (flags & F_REC) ? 1 : 0;
     q.refine = (flags & F_REFINE) ? 1 : 0;
     q.cands_only = (flags & F_CANDS_ONLY) ? 1 : 0;
+    if (use_driver && flags == 0) {
+      qwk::DrvParams d;
+      memset(&d, 0, sizeof d);
+      d.plans = kp.plans; d.instrs = kp.instrs; d.cols = kp.cols; d.thresh = kp.thresh;
+      d.first_work = (const uint32_t*)(slot->d_blob + o_fwd); d.n_splits = n; d.total_work = fw_drv[n];
+      d.level = level; d.use_prefix = use_prefix;
+      if (d.total_work == 0) return;
+      const uint32_t dgrid = std::min<uint32_t>((d.total_work + QD_WARPS - 1) / QD_WARPS, (uint32_t)(sm_count * 4));
+      if (mode == qwk::MODE_HIST) qwk::k_driver<qwk::MODE_HIST><<<dgrid, QD_WARPS * 32, 0, st>>>(d);
+      else qwk::k_driver<qwk::MODE_COLLECT><<<dgrid, QD_WARPS * 32, 0, st>>>(d);
+      stats.launches++;
+      return;
+    }
     if (q.total_work == 0) return;
     if (use_aggscan && mode == qwk::MODE_COLLECT && flags == 0) {
       qwk::AParams a;
