@@ -419,6 +419,13 @@ def main():
         dist.broadcast(uid, 0)
         all_ids = [f"bench-{g:04d}" for g in range(world * a.splits)]
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, all_ids)
+        # one communicator ("lane") per concurrent query of a step: query q of every step runs on lane q on every
+        # rank, so each communicator sees its collectives in the same order everywhere
+        for lane in range(1, Q_SETS):
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(SearcherContext.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            ctx.comm_init_lane(lane, bytes(uid.cpu().numpy().tobytes()), rank, world)
     if world > 1 and not device_exchange:
         # one fixed-size partial per query of the step; the step's partials travel in ONE all-gather
         part_host = torch.zeros(Q_SETS * part_bytes, dtype=torch.uint8).pin_memory()
@@ -464,14 +471,16 @@ def main():
     def step_e2e():
         t0 = time.perf_counter()
         if device_exchange:
-            # collectives must be issued in the same order on every rank: one query after the other; the
-            # search, the NCCL all-gather of the per-rank records and the cross-rank merge all run inside
-            # qwgpu_leaf_search_allgather on the call's stream (no host bounce, no Python in between)
-            resps = []
-            for q in range(Q_SETS):
+            # the step's queries run concurrently, query q on communicator lane q (a communicator's collectives are
+            # issued in the same order on every rank); the search, the NCCL all-gather of the per-rank records and
+            # the cross-rank merge all run inside qwgpu_leaf_search_allgather on the call's stream (no host bounce,
+            # no Python in between)
+            def one_collective(q):
                 t = time.perf_counter()
-                resps.append(ctx.leaf_search_allgather(lreqs[q]))
+                r = ctx.leaf_search_allgather(lreqs[q], lane=q)
                 lat.append(time.perf_counter() - t)
+                return r
+            resps = list(pool.map(one_collective, range(Q_SETS)))
             phase[0] += time.perf_counter() - t0
         else:
             resps = list(pool.map(one_query, range(Q_SETS)))

@@ -196,6 +196,13 @@ int qwgpu_comm_set_split_table(qwgpu_ctx* ctx, uint32_t n, const char* const* sp
 void qwgpu_comm_destroy(qwgpu_ctx* ctx);
 int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* leaf_search_request_pb, size_t len,
                                 uint8_t** merged_resp, size_t* merged_len);
+/* Lanes: the collectives of one NCCL communicator must be issued in the same order on every rank, so one
+ * communicator serialises the searches that use it. A context holds up to 16 communicators ("lanes", each with
+ * its own unique id; lane 0 = qwgpu_comm_init): concurrent searches — one host thread per lane, the same
+ * assignment of requests to lanes on every rank — overlap like concurrent qwgpu_leaf_search calls do. */
+int qwgpu_comm_init_lane(qwgpu_ctx* ctx, uint32_t lane, const uint8_t* id128, int rank, int world);
+int qwgpu_leaf_search_allgather_lane(qwgpu_ctx* ctx, uint32_t lane, const uint8_t* leaf_search_request_pb, size_t len,
+                                     uint8_t** merged_resp, size_t* merged_len);
 
 /* ---- real `.split` files ------------------------------------------------------------------------
  * Reads the footer of a Quickwit split bundle: `tail` = the last `tail_len` bytes of the split file (at least

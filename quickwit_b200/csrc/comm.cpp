@@ -120,4 +120,7 @@ int comm_split_rank(const Comm* c, const std::string& split_id) {
 
 }  // namespace qw
 
-qwgpu_ctx::~qwgpu_ctx() { qw::comm_destroy(comm); }
+qwgpu_ctx::~qwgpu_ctx() {
+  for (qw::Comm*& c : lanes) { qw::comm_destroy(c); c = nullptr; }
+  comm = nullptr;
+}

@@ -28,6 +28,7 @@ struct DrvParams {
   const uint32_t* first_work;  // prefix over splits of the driving term's block counts; [n_splits + 1]
   uint32_t n_splits, total_work;
   uint32_t level, use_prefix;  // MODE_HIST
+  uint32_t stride;             // threshold sample: work item k of split s = block k * stride + s % stride (1 = every block)
 };
 
 template <int MODE>
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(QD_WARPS * 32) k_driver(const DrvParams p) {
     uint32_t my_hits = 0, my_elig = 0;
 
     for (uint32_t w = seg + warp; w < seg_end; w += QD_WARPS) {
-      const uint32_t bb = w - fw;
+      const uint32_t bb = (w - fw) * p.stride + (p.stride > 1 ? split % p.stride : 0);
       const uint8_t* blk = tdata + __ldg(&skips[bb].byte_off);
       const uint4 h = __ldg(reinterpret_cast<const uint4*>(blk));  // QwSkip: last_doc, prev_last_doc, byte_off, bits/count
       const uint32_t prev = h.y, doc_bits = h.w & 0xFF, tf_bits = (h.w >> 8) & 0xFF, count = h.w >> 16;

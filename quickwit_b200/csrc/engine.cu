@@ -327,6 +327,7 @@ struct Lowered {
   int fn_field[2] = {-1, -1};
   uint64_t postings = 0, alg_bytes = 0, min_required_df = ~0ull;
   std::vector<std::pair<uint32_t, uint64_t>> range_cols;  // (col, driver df) for roofline accounting
+  bool empty = false;                   // a required clause of the root cannot match in this split: no work at all
   std::vector<DPhrase> phrases;         // phrase pre-pass descriptors (out / first_work filled per batch)
   std::vector<uint32_t> phrase_instr;   // instruction that consumes phrases[i]
 };
@@ -359,6 +360,7 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
   switch (n.kind) {
     case QW_NODE_TERM: {
       in.op = OP_TERM;
+      if (n.term_ord == 0xFFFFFFFFu && level == 0 && (occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER)) L.empty = true;
       in.t = L.P.n_terms++;
       if (L.P.n_terms > QW_MAX_TERMS) fail(QWGPU_EUNSUPPORTED, "more than %d term clauses", QW_MAX_TERMS);
       in.r = 0;
@@ -396,7 +398,14 @@ static void lower_node(Lowered& L, const SplitDev& sp, const QwPlanNode* nodes, 
         in.r = use_col(L, sp, n.column);
         in.a = n.lo; in.b = n.hi;
         if (n.column != 0xFFFFFFFFu) L.range_cols.push_back({n.column, 0});
+        // a range that misses the column's [min, max] (the split's own value range) matches nothing
+        if (n.kind == QW_NODE_RANGE && n.column != 0xFFFFFFFFu) {
+          const QwImgColumn& ic = sp.view.columns[n.column];
+          if (ic.num_vals == 0 || n.hi < ic.min_value || n.lo > ic.max_value) in.r = 0xFFFFFFFFu;
+        }
       }
+      // a required clause at the root that cannot match: the split has no hits (its windows are skipped)
+      if (in.r == 0xFFFFFFFFu && in.op != OP_ALL && level == 0 && (occur == QW_OCCUR_MUST || occur == QW_OCCUR_FILTER)) L.empty = true;
       in.f = n.boost;
       if (scored) L.score_max += n.boost > 0 ? n.boost : 0.f;
       L.instrs.push_back(in);
@@ -982,20 +991,31 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   std::vector<uint32_t> fw_all(n + 1), fw_smp(n + 1);
   uint32_t max_windows = 0;
   for (uint32_t i = 0; i < n; i++) {
-    low[i].P.num_windows = (low[i].P.num_docs + W - 1) / W;
+    low[i].P.num_windows = low[i].empty ? 0 : (low[i].P.num_docs + W - 1) / W;
     max_windows = std::max(max_windows, low[i].P.num_windows);
   }
   // sampling stride of the threshold-estimation pass: 1/16 of the windows (24 or 32 save ~15 us in the
   // histogram pass but the looser threshold costs about as much in the collect pass)
   static const uint32_t stride_cap = getenv("QWGPU_STRIDE_CAP") ? (uint32_t)atoi(getenv("QWGPU_STRIDE_CAP")) : 16u;
   uint32_t stride = std::min(std::max(stride_cap, 1u), std::max(1u, max_windows / 8));
-  if (use_driver) stride = 1;  // a posting-driven pass costs what the sample would: exact radix select, no sampling
-  std::vector<uint32_t> fw_drv(n + 1, 0);  // posting-driven kernel: prefix of the driving term's block counts
-  if (use_driver) for (uint32_t i = 0; i < n; i++) fw_drv[i + 1] = fw_drv[i] + low[i].instrs[1].n;
+  // posting-driven kernel: the work list is the driving term's posting blocks; the threshold sample takes every
+  // stride-th BLOCK (128 postings, fine enough for keys that follow doc order: what lies between two sampled
+  // blocks is < 2K postings)
+  std::vector<uint32_t> fw_drv(n + 1, 0), fw_dsm(n + 1, 0);
+  if (use_driver) {
+    uint32_t max_blocks = 0;
+    for (uint32_t i = 0; i < n; i++) max_blocks = std::max(max_blocks, low[i].empty ? 0u : low[i].instrs[1].n);
+    stride = std::min(std::max(stride_cap, 1u), std::max(1u, max_blocks / 64));
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t nb = low[i].empty ? 0u : low[i].instrs[1].n, phase = stride > 1 ? i % stride : 0;
+      fw_drv[i + 1] = fw_drv[i] + nb;
+      fw_dsm[i + 1] = fw_dsm[i] + (nb > phase ? (nb - phase + stride - 1) / stride : 0);
+    }
+  }
   // the generic kernels sample an explicit window list: strided windows + the first and last window of each
   // split (weight 1 in the histogram); the union pipeline keeps the plain strided sample (scores do not
   // follow doc order)
-  const bool edge_sample = !use_union && stride > 1;
+  const bool edge_sample = !use_union && !use_driver && stride > 1;
   std::vector<uint32_t> sample_win;
   fw_all[0] = fw_smp[0] = 0;
   for (uint32_t i = 0; i < n; i++) {
@@ -1019,7 +1039,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
          o_aggs = al(o_cols + std::max(tot_cols, 1u) * sizeof(DCol)), o_fwa = al(o_aggs + std::max(tot_aggs, 1u) * sizeof(DAgg)),
          o_fws = al(o_fwa + (n + 1) * 4), o_bounds = al(o_fws + (n + 1) * 4), o_rank = al(o_bounds + (size_t)tot_bounds * 8),
          o_smp = al(o_rank + (size_t)n * 4), o_phr = al(o_smp + sample_win.size() * 4), o_fwd = al(o_phr + (size_t)n_phrases * sizeof(DPhrase)),
-         blob_bytes = al(o_fwd + (use_driver ? (size_t)(n + 1) * 4 : 0));
+         o_fwds = al(o_fwd + (use_driver ? (size_t)(n + 1) * 4 : 0)), blob_bytes = al(o_fwds + (use_driver ? (size_t)(n + 1) * 4 : 0));
   // device-side cross-split merge: the per-split hit lists stay in scratch, only the merged top-K comes back
   const bool do_merge = merge && merged && merge->k > 0 && any_topk && merge->rank.size() == n_in;
   uint32_t kmax = 1;
@@ -1104,7 +1124,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   }
   if (do_merge) for (uint32_t i = 0; i < n; i++) ((uint32_t*)(slot->h_blob + o_rank))[i] = merge->rank[idx[i]];
   if (!sample_win.empty()) memcpy(slot->h_blob + o_smp, sample_win.data(), sample_win.size() * 4);
-  if (use_driver) memcpy(slot->h_blob + o_fwd, fw_drv.data(), (n + 1) * 4);
+  if (use_driver) { memcpy(slot->h_blob + o_fwd, fw_drv.data(), (n + 1) * 4); memcpy(slot->h_blob + o_fwds, fw_dsm.data(), (n + 1) * 4); }
   memcpy(slot->h_blob + o_fwa, fw_all.data(), (n + 1) * 4);
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
@@ -1151,8 +1171,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       qwk::DrvParams d;
       memset(&d, 0, sizeof d);
       d.plans = kp.plans; d.instrs = kp.instrs; d.cols = kp.cols; d.thresh = kp.thresh;
-      d.first_work = (const uint32_t*)(slot->d_blob + o_fwd); d.n_splits = n; d.total_work = fw_drv[n];
-      d.level = level; d.use_prefix = use_prefix;
+      d.first_work = (const uint32_t*)(slot->d_blob + (sampled ? o_fwds : o_fwd)); d.n_splits = n; d.total_work = sampled ? fw_dsm[n] : fw_drv[n];
+      d.level = level; d.use_prefix = use_prefix; d.stride = sampled ? stride : 1;
       if (d.total_work == 0) return;
       const uint32_t dgrid = std::min<uint32_t>((d.total_work + QD_WARPS - 1) / QD_WARPS, (uint32_t)(sm_count * 4));
       if (mode == qwk::MODE_HIST) qwk::k_driver<qwk::MODE_HIST><<<dgrid, QD_WARPS * 32, 0, st>>>(d);

@@ -115,6 +115,10 @@ uint64_t agg_cell_layout(const QwAggNode* aggs, uint32_t n, std::vector<uint32_t
 namespace qw { struct Comm; }
 struct qwgpu_ctx {
   std::unique_ptr<qw::Engine> engine;  // null for host-only contexts
-  qw::Comm* comm = nullptr;            // NCCL communicator + global split table (comm.cpp); null until qwgpu_comm_init
+  // NCCL communicators + the global split table (comm.cpp). One communicator per LANE: the collectives of one
+  // communicator must be issued in the same order on every rank, so concurrent searches (one host thread each)
+  // take one lane each. comm == lanes[0]; null until qwgpu_comm_init.
+  qw::Comm* comm = nullptr;
+  qw::Comm* lanes[16] = {nullptr};
   ~qwgpu_ctx();
 };

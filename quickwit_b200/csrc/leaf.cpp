@@ -690,32 +690,32 @@ int qwgpu_comm_unique_id(uint8_t* out128) {
   return 0;
   QW_API_END
 }
-int qwgpu_comm_init(qwgpu_ctx* ctx, const uint8_t* id128, int rank, int world) {
+int qwgpu_comm_init_lane(qwgpu_ctx* ctx, uint32_t lane, const uint8_t* id128, int rank, int world) {
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
   if (!id128) qw::fail(QWGPU_EINVALID_ARG, "null unique id");
-  if (ctx->comm) { qw::comm_destroy(ctx->comm); ctx->comm = nullptr; }
-  ctx->comm = qw::comm_create(eng.device, id128, rank, world);
+  if (lane >= 16) qw::fail(QWGPU_EINVALID_ARG, "lane %u (at most 16 lanes)", lane);
+  if (ctx->lanes[lane]) { qw::comm_destroy(ctx->lanes[lane]); ctx->lanes[lane] = nullptr; }
+  ctx->lanes[lane] = qw::comm_create(eng.device, id128, rank, world);
+  if (lane && ctx->lanes[0]) ctx->lanes[lane]->split_ids = ctx->lanes[0]->split_ids;
+  ctx->comm = ctx->lanes[0];
   return 0;
   QW_API_END
 }
+int qwgpu_comm_init(qwgpu_ctx* ctx, const uint8_t* id128, int rank, int world) { return qwgpu_comm_init_lane(ctx, 0, id128, rank, world); }
 int qwgpu_comm_set_split_table(qwgpu_ctx* ctx, uint32_t n, const char* const* split_ids) {
   QW_API_BEGIN
   if (!ctx || !ctx->comm) qw::fail(QWGPU_EINVALID_ARG, "no communicator: call qwgpu_comm_init first");
-  qw::comm_set_split_table(ctx->comm, n, split_ids);
+  for (qw::Comm* c : ctx->lanes) if (c) qw::comm_set_split_table(c, n, split_ids);
   return 0;
   QW_API_END
 }
 void qwgpu_comm_destroy(qwgpu_ctx* ctx) {
-  if (ctx && ctx->comm) { qw::comm_destroy(ctx->comm); ctx->comm = nullptr; }
+  if (!ctx) return;
+  for (qw::Comm*& c : ctx->lanes) { qw::comm_destroy(c); c = nullptr; }
+  ctx->comm = nullptr;
 }
 
-// leaf_search on every rank + the root merge as ONE device-side exchange: each rank searches its own splits,
-// merges them on the device, all-gathers its fixed-size record {counters, best k hits} over NCCL on the call's
-// stream and merges the gathered lists on the device again. Every rank returns the same merged
-// LeafSearchResponse (what merge_leaf_responses over all ranks' responses yields, collector.rs:914-974).
-// Aggregation partials and failed-split entries are variable-length: they travel in a second, host-staged
-// all-gather, only when the request has aggregations / some rank reports a failed split.
 // The host-staged exchange: this rank's LeafSearchResponse -> fixed-layout partial -> all ranks (only the used
 // prefix travels: one 8-byte all-gather of the lengths, one of the longest prefix) -> merge_leaf_responses over
 // the gathered partials. Carries everything a response holds (hits, aggregation bytes, failed_splits, stats).
@@ -739,10 +739,14 @@ static void exchange_responses(qw::Comm& comm, const qw::pb::SearchRequest& mreq
 }
 
 int qwgpu_leaf_search_allgather(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
+  return qwgpu_leaf_search_allgather_lane(ctx, 0, req, req_len, resp, resp_len);
+}
+
+int qwgpu_leaf_search_allgather_lane(qwgpu_ctx* ctx, uint32_t lane, const uint8_t* req, size_t req_len, uint8_t** resp, size_t* resp_len) {
   QW_API_BEGIN
   qw::Engine& eng = engine_of(ctx);
-  if (!ctx->comm) qw::fail(QWGPU_EINVALID_ARG, "no communicator: call qwgpu_comm_init first");
-  qw::Comm& comm = *ctx->comm;
+  if (lane >= 16 || !ctx->lanes[lane]) qw::fail(QWGPU_EINVALID_ARG, "no communicator on lane %u: call qwgpu_comm_init_lane first", lane);
+  qw::Comm& comm = *ctx->lanes[lane];
   qw::pb::LeafSearchRequest lr = qw::pb::decode_leaf_search_request(req, req_len);
   qw::pb::SearchRequest mreq = lr.search_request;
   mreq.max_hits += mreq.start_offset;

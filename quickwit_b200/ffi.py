@@ -195,6 +195,8 @@ def lib() -> C.CDLL:
     bind("qwgpu_comm_set_split_table", [vp, u32, C.POINTER(cp)])
     bind("qwgpu_comm_destroy", [vp], None)
     bind("qwgpu_leaf_search_allgather", [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)])
+    bind("qwgpu_comm_init_lane", [vp, u32, vp, C.c_int, C.c_int])
+    bind("qwgpu_leaf_search_allgather_lane", [vp, u32, vp, sz, C.POINTER(vp), C.POINTER(sz)])
     bind("qwgpu_imgb_new", [u32], vp)
     bind("qwgpu_imgb_free", [vp], None)
     bind("qwgpu_imgb_add_field", [vp, cp, u32, u32, vp, u64])

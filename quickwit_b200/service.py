@@ -131,10 +131,20 @@ class SearcherContext:
         arr = (C.c_char_p * n)(*[s.encode() for s in all_split_ids])
         ffi.check(self._L.qwgpu_comm_set_split_table(self._ctx, n, arr))
 
-    def leaf_search_allgather(self, leaf_search_request: bytes) -> bytes:
+    def comm_init_lane(self, lane: int, unique_id: bytes, rank: int, world: int):
+        """One more communicator on this context (its own unique id): concurrent collective searches take one
+        lane each, the same request-to-lane assignment on every rank."""
+        idb = C.create_string_buffer(unique_id, 128)
+        ffi.check(self._L.qwgpu_comm_init_lane(self._ctx, lane, C.addressof(idb), rank, world))
+
+    def leaf_search_allgather(self, leaf_search_request: bytes, lane: int = 0) -> bytes:
         """Collective: leaf_search on this rank's splits + the device-side all-gather / merge that stands in
         for the root merge; every rank returns the merged LeafSearchResponse."""
-        return self._bytes_call(self._L.qwgpu_leaf_search_allgather, leaf_search_request)
+        L = self._L
+        buf = C.create_string_buffer(leaf_search_request, len(leaf_search_request))
+        out, n = C.c_void_p(), C.c_size_t()
+        ffi.check(L.qwgpu_leaf_search_allgather_lane(self._ctx, lane, C.addressof(buf), len(leaf_search_request), C.byref(out), C.byref(n)))
+        return ffi.take_bytes(out, n.value)
 
     def invoke_leaf_search(self, leaf_search_request: bytes) -> bytes:
         """LambdaLeafSearchInvoker::invoke_leaf_search -> LambdaSearchResponses bytes."""
