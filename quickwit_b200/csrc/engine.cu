@@ -919,8 +919,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   // BM25-union batches run the TMA + mbarrier pipeline (union_kernel.cuh): fixed 16384-doc windows,
   // two blocks per SM; QWGPU_OLD_UNION=1 keeps the round-1 window kernel for A/B runs
   static const bool old_union = getenv("QWGPU_OLD_UNION") != nullptr;
-  // (opt-in through QWGPU_DRIVER=1 until it has a full GPU validation run behind it)
-  static const bool driver_on = getenv("QWGPU_DRIVER") != nullptr;
+  // (QWGPU_NO_DRIVER=1 keeps the window engine for these shapes: A/B runs)
+  static const bool driver_on = getenv("QWGPU_NO_DRIVER") == nullptr;
   const bool use_driver = all_driver && driver_on;
   if (use_driver) rec_l0 = false;
   const bool use_union = all_union && !old_union && !use_driver;
