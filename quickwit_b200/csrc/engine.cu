@@ -94,10 +94,8 @@ Engine::Engine(int dev) : device(dev) {
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_COLLECT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_window<qwk::MODE_HIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_HIST, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_COLLECT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_HIST, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
-  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_COLLECT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_HIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
+  CUDA_CHECK(cudaFuncSetAttribute(qwk::k_union<qwk::MODE_COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_aggscan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin));
   CUDA_CHECK(cudaFuncSetAttribute(qwk::k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8 * QW_CAND_CAP));
 }
@@ -770,17 +768,12 @@ static SmemLayout make_layout(uint32_t W, uint32_t n_levels, uint32_t need_cnt, 
 
 // shared-memory arena of the BM25-union pipeline (union_kernel.cuh): score array, QU_SLOTS staging slots
 // (block payload + records + per-term table + header), mbarriers, MODE_HIST histogram
-static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget, bool free_mode) {
+static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget) {
   qwk::USmem L;
   memset(&L, 0, sizeof L);
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t o = off; off = (off + bytes + 15) & ~15u; return o; };
   L.score = take(W * 4);
-  if (free_mode) {
-    L.pa = take(W * 4);
-    L.pb = take(W * 4);
-    L.over = take(QU_OVER * 8 + 16);
-  }
   L.bars = take(8 * (2 * QU_SLOTS + QU_CHAIN));
   if (hist) L.hist = take(QW_HIST_BINS * 4);
   L.cands = take(QU_NCW * QU_CANDS * 8 + QU_NCW * 4);
@@ -797,9 +790,6 @@ static qwk::USmem make_union_layout(uint32_t W, bool hist, uint32_t budget, bool
   L.total = off;
   return L;
 }
-
-// set while a batch whose order-free union pass overflowed is repeated in ordered mode
-static thread_local bool tl_ordered_union = false;
 
 void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std::vector<const uint8_t*>& plans,
                     const std::vector<size_t>& plan_lens, std::vector<SplitOutput>& outs, BatchStats& stats,
@@ -924,14 +914,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   const bool use_driver = all_driver && driver_on;
   if (use_driver) rec_l0 = false;
   const bool use_union = all_union && !old_union && !use_driver;
-  // order-free accumulation (union_kernel.cuh, FREE = 1) when few docs can collect three or more contributions:
-  // at most one posting per doc on average. A window that still overflows its late-arrival list raises a flag
-  // and the batch is repeated in ordered mode (tl_ordered_union).
-  // (opt-in through QWGPU_FREE_UNION=1 until it has a full GPU validation run behind it; QWGPU_ORDERED_UNION wins)
-  static const bool no_free = getenv("QWGPU_ORDERED_UNION") != nullptr || getenv("QWGPU_FREE_UNION") == nullptr;
-  bool free_mode = use_union && !no_free && !tl_ordered_union;
-  if (free_mode)
-    for (auto& L : low) if (L.postings > L.P.num_docs) { free_mode = false; break; }
   const uint32_t u_budget = (uint32_t)(max_smem_optin + 1024) / QU_MINB - 1024 - 64;
   // match_all + flat terms / histogram aggregations, no hits: the streaming column kernel (agg_kernel.cuh)
   static const bool old_aggs = getenv("QWGPU_OLD_AGGS") != nullptr;
@@ -971,7 +953,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (use_aggscan) W = QA_CHUNK;  // the flat work list is the list of 8192-doc chunks
   qwk::USmem ulay_c, ulay_h;
   if (use_union && !getenv("QWGPU_W"))
-    W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : (free_mode ? 6144u : 15360u) * 2 / QU_MINB;
+    W = getenv("QWGPU_UW") ? (uint32_t)atoi(getenv("QWGPU_UW")) : 15360u * 2 / QU_MINB;
   SmemLayout lay;
   for (;;) {
     lay = make_layout(W, n_levels, need_cnt, need_msum, need_ssum, max_instr, max_cols, max_aggs, n_fn, rec_l0, rangeq);
@@ -982,8 +964,8 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (use_aggscan && W != QA_CHUNK) use_aggscan = false;
   if (use_union) {
     // (the generic layout above stays valid for the same W: exact radix passes below level 0 use k_window)
-    ulay_c = make_union_layout(W, false, u_budget, free_mode);
-    ulay_h = make_union_layout(W, true, u_budget, free_mode);
+    ulay_c = make_union_layout(W, false, u_budget);
+    ulay_h = make_union_layout(W, true, u_budget);
   }
   if ((int)lay.total > max_smem_optin) fail(QWGPU_EUNSUPPORTED, "query needs %u bytes of shared memory per block", lay.total);
 
@@ -1200,20 +1182,14 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       u.plans = kp.plans; u.instrs = kp.instrs; u.cols = kp.cols; u.thresh = kp.thresh;
       u.first_work = q.first_work; u.n_splits = n; u.total_work = q.total_work; u.stride = q.stride; u.W = W;
       u.sm = mode == qwk::MODE_HIST ? ulay_h : ulay_c;
-      u.oflag = (uint32_t*)(slot->d_scratch + s_ctr) + 63;
 #ifdef QU_PROFILE
       static unsigned long long* d_prof = nullptr;
       if (!d_prof) CUDA_CHECK(cudaMalloc(&d_prof, 16 * 8));
       if (mode == qwk::MODE_COLLECT) { CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 16 * 8, st)); u.prof = d_prof; }
 #endif
       const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * QU_MINB));
-      if (mode == qwk::MODE_HIST) {
-        if (free_mode) qwk::k_union<qwk::MODE_HIST, 1><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
-        else qwk::k_union<qwk::MODE_HIST, 0><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
-      } else {
-        if (free_mode) qwk::k_union<qwk::MODE_COLLECT, 1><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
-        else qwk::k_union<qwk::MODE_COLLECT, 0><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
-      }
+      if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
+      else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
 #ifdef QU_PROFILE
       if (u.prof && getenv("QWGPU_UPROF")) {
         unsigned long long h[16];
@@ -1240,7 +1216,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaEventRecord(slot->ev2, st));
     launch_window(qwk::MODE_COLLECT, false, 0, 0, flags);
     CUDA_CHECK(cudaEventRecord(slot->ev3, st));
-    if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans, kp.cols, free_mode ? (const uint32_t*)(slot->d_scratch + s_ctr) + 63 : nullptr); stats.launches++; }
+    if (any_topk) { qwk::k_select<<<n, 1024, sel_smem, st>>>(kp.plans, kp.cols); stats.launches++; }
     if (do_merge) {
       uint32_t* d_cut = (uint32_t*)(slot->d_scratch + s_cut);
       const qwk::SrcSplits src{kp.plans, (const uint32_t*)(slot->d_blob + o_rank), do_gather ? 1u : 0u};
@@ -1269,15 +1245,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     return all;
   };
 
-  // order-free union passes: a window ran out of room for late contributions (flag copied next to the first
-  // split's counters by k_select) -> the whole batch again, clause-ordered
-  auto union_overflowed = [&]() { return free_mode && *(const uint32_t*)(slot->h_out + out_off[0] + 24) != 0; };
-  auto rerun_ordered = [&]() {
-    stats.exact_fallbacks++;
-    struct Flag { Flag() { tl_ordered_union = true; } ~Flag() { tl_ordered_union = false; } } flag;
-    search(sp, plans, plan_lens, outs, stats, merge, merged, gather, rank_headers);
-  };
-
   const auto t_staged = tclock::now();
   CUDA_CHECK(cudaEventRecord(slot->ev0, st));
   CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));  // thresholds, histograms, refinement state
@@ -1293,7 +1260,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     run_collect(rec_l0 ? F_REC : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (union_overflowed()) { rerun_ordered(); return; }
     ok = verify();
     if (!ok) {
       float ms = 0;
@@ -1345,7 +1311,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     run_collect(refine ? (F_REFINE | F_CANDS_ONLY) : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (union_overflowed()) { rerun_ordered(); return; }
     if (!verify()) fail(QWGPU_EINTERNAL, "top-K candidate selection failed verification");
   }
   if (do_gather) {

@@ -1595,11 +1595,9 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
 //   2. compaction of the candidates >= that word (all ties kept) — normally ~K of the ~2-3K candidates;
 //   3. bitonic sort of the survivors with the full 192-bit comparison (the reference total order).
 #define QW_SEL_MAX 2048  /* survivors sorted in shared memory; more ties than this => sort everything */
-__global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const DCol* all_cols, const uint32_t* oflag) {
+__global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const DCol* all_cols) {
   const DSplitPlan& P = plans[blockIdx.x];
   const uint32_t tid = threadIdx.x;
-  // the order-free union pipeline's overflow flag travels back with the split's counters (header word 6)
-  if (oflag && tid == 0) ((uint32_t*)P.out_num_hits)[6] = *oflag;
   if (P.max_hits == 0) { if (tid == 0) *(uint32_t*)P.out_nhits = 0; return; }
   uint32_t n = *(const uint32_t*)P.out_cand_count;
   if (n > QW_CAND_CAP) n = QW_CAND_CAP;  // overflow is detected by the host (cand_count > cap)

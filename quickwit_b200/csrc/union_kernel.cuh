@@ -52,14 +52,11 @@ namespace qwk {
 #ifndef QU_MINB
 #define QU_MINB 2               /* blocks per SM */
 #endif
-#define QU_OVER 1024            /* free mode: per-window list of third-and-later contributions */
 
 enum { QU_F_FIRST = 1u, QU_F_LAST = 2u, QU_F_END = 4u };
 
 struct USmem {
-  uint32_t score;                       // float[W] (ordered mode) / uint32 clause mask[W] (free mode)
-  uint32_t pa, pb;                      // free mode: float[W] first / second contribution of each doc
-  uint32_t over;                        // free mode: uint2[QU_OVER] third and later contributions, then uint32 count[2]
+  uint32_t score;                       // float[W]
   uint32_t slot0, slot_stride;          // QU_SLOTS slots
   uint32_t payload, recs, ttab, hdr;    // offsets inside a slot
   uint32_t bars;                        // full[QU_SLOTS], empty[QU_SLOTS], chain[QU_CHAIN]
@@ -77,7 +74,6 @@ struct UParams {
   const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
   uint32_t n_splits, total_work, stride, W;
   unsigned long long* prof;    // QU_PROFILE builds: cycle counters (see k_union)
-  uint32_t* oflag;             // free mode: set when a window had more late contributions than QU_OVER
   USmem sm;
 };
 #ifdef QU_PROFILE
@@ -154,45 +150,7 @@ __device__ __noinline__ void union_emit(const DSplitPlan* plans, const DThresh* 
   }
 }
 
-// Free mode, rare path of the sweep: a doc with three or more contributions. `m` = its clause mask, `a` /
-// `bbits` = the first / second contribution to arrive (the sign bit of `bbits`: the second one's clause is
-// the lower of the two), `over` = the window's list of later arrivals {rel doc << 8 | clause, f32 bits}.
-// Rebuilds the reference's sum: contributions added in clause order, starting from the first one.
-__device__ __noinline__ float union_fold(uint32_t m, float a, uint32_t bbits, const uint2* over, uint32_t n_over, uint32_t r) {
-  uint32_t late = 0;
-  for (uint32_t i = 0; i < n_over; i++) {
-    const uint32_t k = over[i].x;
-    if ((k >> 8) == r) late |= 1u << (k & 31u);
-  }
-  const uint32_t rest = m & ~late;  // the clauses of `a` and `b`
-  const uint32_t lo = (uint32_t)__ffs(rest) - 1u, hi = 31u - __clz(rest);
-  const uint32_t ca = (bbits >> 31) ? hi : lo, cb = (bbits >> 31) ? lo : hi;
-  float s = 0.f;
-  bool first = true;
-  for (uint32_t mm = m; mm; mm &= mm - 1u) {
-    const uint32_t c = (uint32_t)__ffs(mm) - 1u;
-    float v = 0.f;
-    if (c == ca) v = a;
-    else if (c == cb) v = __uint_as_float(bbits & 0x7FFFFFFFu);
-    else {
-      const uint32_t want = (r << 8) | c;
-      for (uint32_t i = 0; i < n_over; i++) if (over[i].x == want) { v = __uint_as_float(over[i].y); break; }
-    }
-    s = first ? v : __fadd_rn(s, v);
-    first = false;
-  }
-  return s;
-}
-
-// FREE = 0: clause-ordered read-modify-write of one f32 accumulator per doc (any union the pipeline takes).
-// FREE = 1: order-free accumulation. f32 addition is commutative, so a doc with one or two contributions has
-//   the same sum in any order; only three or more need the clause order. Every posting ORs its clause bit into
-//   the doc's mask word with one shared-memory atomic; the returned mask says whether it is the first (value
-//   -> plane A), second (-> plane B, sign bit = "my clause is the lower one") or a later arrival (-> the
-//   window's overflow list). The sweep adds A + B, or folds the rare docs with >= 3 contributions in clause
-//   order. No clause stages: a warp never waits inside a window. A window whose overflow list fills up sets
-//   `oflag`; the host then repeats the batch in ordered mode.
-template <int MODE, int FREE>
+template <int MODE>
 __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t W = p.W;
@@ -430,18 +388,10 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
     // ================================ consumers =====================================================
     float* score = (float*)(qw_smem + p.sm.score);
     uint32_t* hist = (uint32_t*)(qw_smem + p.sm.hist);
-    // free mode planes
-    uint32_t* mask = (uint32_t*)(qw_smem + p.sm.score);
-    float* pa = (float*)(qw_smem + p.sm.pa);
-    uint32_t* pb = (uint32_t*)(qw_smem + p.sm.pb);
-    uint2* over = (uint2*)(qw_smem + p.sm.over);
-    uint32_t* novr = (uint32_t*)(qw_smem + p.sm.over + QU_OVER * 8);  // [2]: by window parity
-    uint32_t wpar = 0;
     {
       float4* q = reinterpret_cast<float4*>(score);
       for (uint32_t i = tid; i < (W >> 2); i += QU_NCT) q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (MODE == MODE_HIST) for (uint32_t i = tid; i < QW_HIST_BINS; i += QU_NCT) hist[i] = 0;
-      if (FREE && tid < 2) novr[tid] = 0;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_chain(0));
@@ -461,7 +411,8 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
     auto pass_to = [&](uint32_t st) {  // arrive at every stage below st
       if (my_stage < st) {
         __syncwarp();
-        if (lane == 0) for (uint32_t s = my_stage; s < st; s++) mbar_arrive(bar_chain(s));
+        // one lane per stage (a warp that skips several clauses arrives at all of them with one instruction)
+        for (uint32_t s0 = my_stage; s0 < st; s0 += 32) if (s0 + lane < st) mbar_arrive(bar_chain(s0 + lane));
         my_stage = st;
       }
     };
@@ -545,6 +496,12 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         const bool on = g0 + half < G;
         const uint4 rec = *(const uint4*)(qw_smem + recs + 16u * (on ? g0 + half : g0));  // prev_last_doc, shared address, widths/count, clause | interior
         const uint32_t t = rec.w & 0xFFu;
+        // This warp is done with every clause below the one it is about to decode: say so NOW, not after the
+        // decode — the warps that wait for those stages are on the window's critical path (one hop per clause).
+        const uint32_t st = wbase + t;
+        const uint32_t st_lo = __shfl_sync(QW_FULL, st, 0);
+        const uint32_t st_hi = __shfl_sync(QW_FULL, on ? st : 0u, 16);  // (0: the upper half has no block)
+        pass_to(st_lo);
         const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
         const float weight = __uint_as_float(tt.x);
         const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
@@ -621,35 +578,11 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
           }
         }
         // ---- ordered accumulate: everything of the earlier clauses must be in -------------------------
-        const uint32_t st = wbase + (FREE ? 0u : t);  // free mode: one accumulate stage per window
-        const uint32_t st_lo = __shfl_sync(QW_FULL, st, 0);
-        const uint32_t st_hi = __shfl_sync(QW_FULL, on ? st : 0u, 16);  // (0: the upper half has no block)
         const uint32_t count = rec.z >> 16;
         const uint32_t nvalid = !on ? 0u : (count > hl * 8u ? count - hl * 8u : 0u);  // postings of this lane that exist
         const bool all_interior = __all_sync(QW_FULL, on && (rec.w & 256u));
         auto apply = [&]() {
-          if (FREE) {
-            const uint32_t bit = 1u << t;
-            bool in[8];
-            uint32_t old[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              in[j] = all_interior || ((uint32_t)j < nvalid && r[j] < wlen);
-              old[j] = 0;
-              if (in[j]) old[j] = atomicOr(&mask[r[j]], bit);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              if (!in[j]) continue;
-              if (old[j] == 0) pa[r[j]] = c[j];
-              else if ((old[j] & (old[j] - 1u)) == 0) pb[r[j]] = __float_as_uint(c[j]) | (old[j] > bit ? 0x80000000u : 0u);
-              else {
-                const uint32_t pos = atomicAdd(&novr[wpar], 1u);
-                if (pos < QU_OVER) over[pos] = make_uint2((r[j] << 8) | t, __float_as_uint(c[j]));
-                else if (pos == QU_OVER) atomicOr(p.oflag, 1u);
-              }
-            }
-          } else if (all_interior) {
+          if (all_interior) {
             // both blocks: all 128 postings exist and lie inside the window
             float o[8];
 #pragma unroll
@@ -669,7 +602,6 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
             for (int j = 0; j < 8; j++) if (in[j]) score[r[j]] = __fadd_rn(o[j], c[j]);
           }
         };
-        pass_to(st_lo);
         wait_below(st_lo);
         if (st_hi == st_lo || st_hi == 0u) apply();  // (lanes of an absent upper block have nvalid == 0)
         else {
@@ -687,10 +619,10 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(slot));
       if (!(flags & QU_F_LAST)) {
-        pass_to(wbase + (FREE ? 0u : t_last));  // the slot's last clause may continue in the next slot
+        pass_to(wbase + t_last);  // the slot's last clause may continue in the next slot
         continue;
       }
-      const uint32_t end_stage = wbase + (FREE ? 1u : n_terms);
+      const uint32_t end_stage = wbase + n_terms;
       pass_to(end_stage);
       QU_T(te0);
       wait_below(end_stage);  // every contribution of the window is in
@@ -698,50 +630,23 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       QU_T(ts0);
       // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
       float4* sc4 = reinterpret_cast<float4*>(score);
-      // one group of four docs: scores (0 = no match) + match flags; the accumulator is cleared on the way
-      const uint32_t n_over = FREE ? min(novr[wpar], (uint32_t)QU_OVER) : 0u;
-      if (FREE && tid == 0) novr[wpar ^ 1u] = 0;  // the next window's list (its last readers swept a window ago)
-      auto quad = [&](uint32_t q, float (&vv)[4], uint32_t& any) {
-        if (!FREE) {
-          const float4 v = sc4[q];
-          sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
-          any = 1;
-        } else {
-          uint4* m4 = reinterpret_cast<uint4*>(mask);
-          const uint4 m = m4[q];
-          any = m.x | m.y | m.z | m.w;
-          if (any) {
-            m4[q] = make_uint4(0, 0, 0, 0);
-            const float4 a = reinterpret_cast<const float4*>(pa)[q];
-            const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
-            const float aa[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              float v = 0.f;
-              if (mm[j]) {
-                v = aa[j];
-                if (mm[j] & (mm[j] - 1u)) {
-                  const uint32_t bb = pb[4 * q + j];
-                  if (__popc(mm[j]) == 2) v = __fadd_rn(aa[j], __uint_as_float(bb & 0x7FFFFFFFu));
-                  else v = union_fold(mm[j], aa[j], bb, over, n_over, 4 * q + j);
-                }
-              }
-              vv[j] = v;
-            }
-          }
-        }
+      // one group of four docs: scores (0 = no match); the accumulator is cleared on the way
+      auto quad = [&](uint32_t q, float (&vv)[4]) {
+        const float4 v = sc4[q];
+        sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
       };
       if (MODE == MODE_COLLECT) {
         const float s_lo = hdr_f;
+        const uint32_t s_lo_bits = s_lo > 0.0f ? __float_as_uint(s_lo) : 1u;  // no threshold yet: every match goes on
 #pragma unroll 4
         for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
           float vv[4];
-          uint32_t any;
-          quad(q, vv, any);
-          if (!any) continue;
-          my_hits += (vv[0] > 0.0f) + (vv[1] > 0.0f) + (vv[2] > 0.0f) + (vv[3] > 0.0f);
-          if (fmaxf(fmaxf(vv[0], vv[1]), fmaxf(vv[2], vv[3])) >= s_lo) {
+          quad(q, vv);
+          // (scores are sums of positive contributions: as integers, 0 = no match and the order is the float order)
+          const uint32_t u0 = __float_as_uint(vv[0]), u1 = __float_as_uint(vv[1]), u2 = __float_as_uint(vv[2]), u3 = __float_as_uint(vv[3]);
+          my_hits += min(u0, 1u) + min(u1, 1u) + min(u2, 1u) + min(u3, 1u);
+          if (__vimax3_u32(__vimax3_u32(u0, u1, u2), u3, 0u) >= s_lo_bits) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               if (vv[j] > 0.0f && vv[j] >= s_lo) {
@@ -768,9 +673,7 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         };
         for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
           float vv[4];
-          uint32_t any;
-          quad(q, vv, any);
-          if (!any) continue;
+          quad(q, vv);
 #pragma unroll
           for (int j = 0; j < 4; j++) if (vv[j] > 0.0f) atomicAdd(&hist[lin(vv[j])], 1u);
         }
@@ -788,7 +691,6 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         my_stage = end_stage + 2;
         next_base = end_stage + 2;
       }
-      wpar ^= 1u;
     }
     flush_hits();
 #ifdef QU_PROFILE

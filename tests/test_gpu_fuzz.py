@@ -8,7 +8,6 @@
    takes at all (33+ terms -> generic window kernel).
 3. hypothesis-driven random bool trees x sort specs x K x aggregations against the oracle.
 Everything is bit-exact: doc ids, f32 score bits, sort values, hit counts, bucket counts."""
-import os
 import random
 
 import numpy as np
@@ -50,9 +49,8 @@ def _clustered_split(split_id="clustered-0", n=N, seed=5):
     add(body, "half_b", [d for d in range(n) if (d * 40503) % 89 < 45])
     for i in range(40):                                                      # many sparse terms (slot overflow, > 32 clauses)
         add(body, f"s{i}", rnd.sample(range(n), 150 + 13 * i))
-    # order-free accumulation (k_union FREE): few postings per doc overall, but many contributions on the SAME
-    # docs — three dense clauses over one region (the late-arrival list overflows -> ordered rerun) and five
-    # clauses on every 97th doc (clause-order fold of 3+ contributions inside the list's capacity)
+    # few postings per doc overall, but many contributions on the SAME docs: three dense clauses over one region
+    # and five clauses on every 97th doc
     for i in range(3):
         add(body, f"c{i}", range(10_000, 46_000), np.array([1 + ((d + i) % 5) for d in range(36_000)], dtype=np.uint32))
     for i in range(5):
@@ -110,19 +108,17 @@ def test_clustered_unions(gpu_ctx, clustered):
                                        [(ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT), col_sort(img, "timestamp", ffi.ORDER_ASC)]), ctx="score then ts")
 
 
-def test_order_free_accumulation_paths(gpu_ctx, clustered):
-    """Unions light enough for the order-free pipeline (postings <= docs): docs with 3+ contributions are
-    folded in clause order from the late-arrival list; a window that overflows the list repeats the batch in
-    ordered mode. Either way every f32 score equals the oracle's clause-order sum bit for bit."""
+def test_many_contributions_per_doc(gpu_ctx, clustered):
+    """Unions with few postings per doc overall but many contributions on the SAME docs (five clauses on every
+    97th doc, three dense clauses over one region): every f32 score equals the oracle's clause-order sum bit
+    for bit."""
     img = clustered
     fold = ["m3", "m0", "rare", "m4", "m1", "m2", "burst"]          # 5 contributions on every 97th doc
     for k in (10, 2000):
         got, _ = run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t, boost=1.0 + 0.37 * i) for i, t in enumerate(fold)]), k, SCORE_DESC), ctx=f"fold k={k}")
         assert got.exact_fallbacks == 0
     dense = ["c0", "ends", "c1", "c2"]                               # 3 contributions on 36 000 consecutive docs
-    got, _ = run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t, boost=1.0 + 0.21 * i) for i, t in enumerate(dense)]), 100, SCORE_DESC), ctx="overflow")
-    if os.environ.get("QWGPU_FREE_UNION") and not os.environ.get("QWGPU_ORDERED_UNION"):
-        assert got.exact_fallbacks >= 1      # the order-free pipeline ran, overflowed and was repeated in ordered mode
+    run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t, boost=1.0 + 0.21 * i) for i, t in enumerate(dense)]), 100, SCORE_DESC), ctx="dense")
     mixed = ["c0", "m0", "c1", "m1", "s3", "m2"]                     # two planes + list + sparse clauses
     run_both(gpu_ctx, img, P.make_plan(P.bool_([B(img, t) for t in mixed]), 500, SCORE_DESC), ctx="mixed")
 

@@ -41,6 +41,10 @@ def configs(n_splits):
         ("C1b term(body:t0, 20% of docs) top-10 by BM25", term("body", "t0"), dict(max_hits=10, sort_fields=[("_score", 1)])),
         ("C2 10-term OR, BM25 top-1000", or10, dict(max_hits=1000, sort_fields=[("_score", 1)])),
         ("C2b 10-term OR, count only", or10, dict(max_hits=0)),
+        # experiments on the clause chain of the BM25-union pipeline: only the 4 dense terms / only the 6 sparse ones
+        ("X2d 4 dense terms OR, BM25 top-1000", {"type": "bool", "should": [term("body", f"t{i}") for i in range(4)]}, dict(max_hits=1000, sort_fields=[("_score", 1)])),
+        ("X2s 6 sparse terms OR, BM25 top-1000", {"type": "bool", "should": [term("body", f"t{i}") for i in range(4, 10)]}, dict(max_hits=1000, sort_fields=[("_score", 1)])),
+        ("X2t 2 dense terms OR, BM25 top-1000", {"type": "bool", "should": [term("body", f"t{i}") for i in range(2)]}, dict(max_hits=1000, sort_fields=[("_score", 1)])),
         ("C3 term AND timestamp range (half the span), top-1000 by timestamp desc", {"type": "bool", "must": [term("body", "t2")]},
          dict(max_hits=1000, sort_fields=[("timestamp", 1)], start_timestamp=T0 + span // 4, end_timestamp=T0 + 3 * span // 4)),
         ("C3b 2-term AND NOT third, top-100 by (tenant_id asc, timestamp desc)",
@@ -79,7 +83,7 @@ def main():
     offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
     rows = []
     for name, ast, kw in configs(a.splits):
-        if a.only and not name.startswith(a.only + " "):
+        if a.only and not any(name.startswith(o + " ") for o in a.only.split(",")):
             continue
         kw = dict(kw)
         aggs = kw.pop("aggs", None)
