@@ -1187,7 +1187,10 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       if (!d_prof) CUDA_CHECK(cudaMalloc(&d_prof, 16 * 8));
       if (mode == qwk::MODE_COLLECT) { CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 16 * 8, st)); u.prof = d_prof; }
 #endif
-      const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * QU_MINB));
+      // cross-rank calls leave a few block slots free: the persistent grid would otherwise hold every SM's shared
+      // memory, a concurrent call's NCCL kernel would take the place of one of its blocks, and that block — with its
+      // static share of the windows — would only start when another one has finished (twice the kernel time)
+      const uint32_t ugrid = std::min<uint32_t>(q.total_work, (uint32_t)(sm_count * QU_MINB) - (do_gather ? 4u : 0u));
       if (mode == qwk::MODE_HIST) qwk::k_union<qwk::MODE_HIST><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
       else qwk::k_union<qwk::MODE_COLLECT><<<ugrid, QU_THREADS, u.sm.total, st>>>(u);
 #ifdef QU_PROFILE
