@@ -15,7 +15,11 @@ import sys
 def rows_of(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    return rows[0], rows[2:]
+    return rows[0], rows[1], rows[2:]
+
+
+# the raw page prints each metric in the unit of its own column (row 2 of the csv): scale to bytes / ns
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "": 1.0}
 
 
 def main():
@@ -24,14 +28,14 @@ def main():
     for spec in specs:
         key, rest = spec.split("=", 1)
         rep, sub, workload = rest.split(":", 2)
-        hdr, rows = rows_of(rep)
+        hdr, units, rows = rows_of(rep)
+        unit = dict(zip(hdr, units))
         tot, n, dur = 0.0, 0, 0.0
         for r in rows:
             d = dict(zip(hdr, r))
             if sub not in d.get("Kernel Name", ""):
                 continue
-            f = lambda k: float(d[k].replace(",", "")) if d.get(k) else 0.0
-            # units are bytes in --page raw (ncu prints the base unit with --csv raw page: check the unit row when in doubt)
+            f = lambda k: float(d[k].replace(",", "")) * SCALE[unit.get(k, "")] if d.get(k) else 0.0
             tot += f("dram__bytes_read.sum") + f("dram__bytes_write.sum")
             dur += f("gpu__time_duration.sum")
             n += 1
