@@ -70,13 +70,16 @@ def parse_args():
     return ap.parse_args()
 
 
-def build_splits(rank: int, n_splits: int, docs: int, threads: int):
+MSG_VOCAB = 64  # vocabulary of the positions field "msg" (phrase queries of BASELINE config 5)
+
+
+def build_splits(rank: int, n_splits: int, docs: int, threads: int, msg_vocab: int = 0):
     from quickwit_b200 import splitgen as S
 
     def one(i):
         gid = rank * n_splits + i
         return S.synth_split(docs, gid, FRACS * Q_SETS, seed=0x5157, ts_start_secs=1_700_000_000 + 86_400 * gid,
-                             split_id=f"bench-{gid:04d}")
+                             split_id=f"bench-{gid:04d}", msg_vocab=msg_vocab)
     with ThreadPoolExecutor(max_workers=threads) as ex:
         return list(ex.map(one, range(n_splits)))
 
@@ -236,7 +239,8 @@ T0_SECS = 1_700_000_000
 SYNTH_MAPPING = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
                                     {"name": "severity_text", "type": "text", "tokenizer": "raw", "fast": True},
                                     {"name": "timestamp", "type": "datetime", "fast": True, "fast_precision": "seconds"},
-                                    {"name": "tenant_id", "type": "u64", "fast": True}], "timestamp_field": "timestamp"}
+                                    {"name": "tenant_id", "type": "u64", "fast": True},
+                                    {"name": "msg", "type": "text", "record": "position", "fieldnorms": True}], "timestamp_field": "timestamp"}
 
 
 def other_configs(ctx, imgs, peak, reps: int = 20, lat_runs: int = 60):
@@ -337,6 +341,92 @@ def config4_strong(ctx, imgs, world: int, rank: int, reps: int = 10):
             "api": "qwgpu_leaf_search_allgather (aggregation partials: host-staged NCCL all-gather inside the library)"}
 
 
+def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_per_thread: int = 6):
+    """BASELINE config 5's shape on one GPU's share of the index: a mixed term / phrase / bool / range / aggregation
+    query set issued from `concurrency` host threads against the rank's resident splits through qwgpu_leaf_search
+    (host protobuf bytes in and out). With N ranks every rank serves its own 32 splits (256 splits / 1 B docs at
+    N = 8 with 3.9 M-doc splits; here docs_per_split as configured) — the per-leaf view of a root that fans every
+    query out to all leaves — so the job-level QPS is the slowest rank's. Reports QPS, latency percentiles, the mean
+    latency per query type and the HBM fraction the mix sustains (algorithmic bytes of the executed queries / wall /
+    measured peak). Every response under concurrency is compared with the same request issued alone."""
+    import random
+    from quickwit_b200 import proto, service
+    n = len(imgs)
+    span = 86_400 * n
+    term = lambda f, v: {"type": "term", "field": f, "value": v}
+    or10 = {"type": "bool", "should": [term("body", f"t{i}") for i in range(10)]}
+    phrase = lambda text: {"type": "full_text", "field": "msg", "text": text, "params": {"mode": {"type": "phrase"}}}
+    mix = [
+        ("term_top10", term("severity_text", "ERROR"), dict(max_hits=10), None, 3),
+        ("term_bm25_top10", term("body", "t13"), dict(max_hits=10, sort_fields=[("_score", 1)]), None, 2),
+        ("phrase_top10", phrase("w1 w2"), dict(max_hits=10, sort_fields=[("_score", 1)]), None, 2),
+        ("phrase3_top10", phrase("w0 w3 w1"), dict(max_hits=10, sort_fields=[("_score", 1)]), None, 1),
+        ("bool_and_not_top100", {"type": "bool", "must": [term("body", "t0"), term("body", "t1")], "must_not": [term("body", "t4")]},
+         dict(max_hits=100, sort_fields=[("tenant_id", 0), ("timestamp", 1)]), None, 2),
+        ("range_top1000_by_ts", {"type": "bool", "must": [term("body", "t2")]},
+         dict(max_hits=1000, sort_fields=[("timestamp", 1)], start_timestamp=T0_SECS + span // 4, end_timestamp=T0_SECS + 3 * span // 4), None, 2),
+        ("or10_bm25_top1000", or10, dict(max_hits=1000, sort_fields=[("_score", 1)]), None, 1),
+        ("agg_terms_date_histogram", {"type": "match_all"}, dict(max_hits=0), C4_AGGS, 2),
+        ("agg_terms_stats_over_or10", or10, dict(max_hits=0),
+         {"tenants": {"terms": {"field": "tenant_id", "size": 10}, "aggs": {"ts": {"stats": {"field": "timestamp"}}}}}, 1),
+    ]
+    dm = json.dumps(SYNTH_MAPPING)
+    ids = [im.split_id for im in imgs]
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in imgs]
+    reqs, alone, algb, weights = {}, {}, {}, []
+    for name, ast, kw, aggs, wgt in mix:
+        sreq = proto.enc_search_request(json.dumps(ast), aggregation_request=json.dumps(aggs) if aggs else None, **kw)
+        reqs[name] = proto.enc_leaf_search_request(sreq, offsets, dm)
+        rs = RawSearch(ctx, ids, [service.compile_plan(im, sreq, dm) for im in imgs])
+        r = rs.run(); rs.free()
+        algb[name] = r["alg_bytes"]
+        for _ in range(2):
+            alone[name] = ctx.leaf_search(reqs[name])
+        weights += [name] * wgt
+    rng = random.Random(5)
+    plan = [[rng.choice(weights) for _ in range(queries_per_thread)] for _ in range(concurrency)]
+    lat, got = [[] for _ in range(concurrency)], [[] for _ in range(concurrency)]
+    start = threading.Barrier(concurrency + 1)
+
+    def worker(t):
+        start.wait()
+        for name in plan[t]:
+            t0 = time.perf_counter()
+            resp = ctx.leaf_search(reqs[name])
+            lat[t].append((name, time.perf_counter() - t0))
+            got[t].append((name, resp))
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(concurrency)]
+    for th in ths:
+        th.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for th in ths:
+        th.join()
+    wall = time.perf_counter() - t0
+    # outside the timed region: every response (distinct byte strings decoded once) against the sequential one
+    key = lambda r: (lambda d: (d["num_hits"], d["partial_hits"], d["intermediate_aggregation_result"]))(proto.dec_leaf_search_response(r))
+    want = {name: key(r) for name, r in alone.items()}
+    seen = {(name, resp) for g in got for name, resp in g}
+    mismatches = sorted({name for name, resp in seen if key(resp) != want[name]})
+    if mismatches:
+        raise RuntimeError(f"config 5: responses under concurrency differ from the sequential ones: {mismatches}")
+    flat = sorted(x for l in lat for _, x in l)
+    per_type = {}
+    for l in lat:
+        for name, x in l:
+            per_type.setdefault(name, []).append(x)
+    nq = len(flat)
+    bytes_total = sum(algb[name] for l in lat for name, _ in l)
+    pct = lambda q: 1e3 * flat[min(nq - 1, int(q * nq))]
+    return {"workload": "c5_mixed_term_phrase_bool_range_agg", "concurrency": concurrency, "queries": nq,
+            "splits_per_gpu": n, "docs_per_gpu": sum(im.num_docs for im in imgs), "n_gpus": world,
+            "qps": nq / wall, "latency_ms": {"p50": pct(0.50), "p90": pct(0.90), "p99": pct(0.99), "max": 1e3 * flat[-1]},
+            "mean_latency_ms_by_type": {k: 1e3 * sum(v) / len(v) for k, v in sorted(per_type.items())},
+            "mix_weights": {m[0]: m[4] for m in mix},
+            "hbm": {"algorithmic_bytes": bytes_total, "achieved_gbs": bytes_total / wall / 1e9, "peak": peak, "frac": bytes_total / wall / 1e9 / peak},
+            "api": "qwgpu_leaf_search from 64 host threads; responses checked against the sequential ones"}
+
+
 def main():
     a = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -392,7 +482,8 @@ def main():
     from quickwit_b200.service import SearcherContext
 
     t_build = time.perf_counter()
-    imgs = build_splits(rank, a.splits, a.docs_per_split, threads=max(1, min(cores // max(world, 1), 32)))
+    imgs = build_splits(rank, a.splits, a.docs_per_split, threads=max(1, min(cores // max(world, 1), 32)),
+                        msg_vocab=0 if a.no_configs else MSG_VOCAB)
     plans = make_plans(imgs)
     ctx = SearcherContext(local_rank)
     for img in imgs:
@@ -568,6 +659,27 @@ def main():
             c4_strong = config4_strong(ctx, imgs, world, rank)
         except AssertionError as e:  # (the same data on every rank: a mismatch shows on all of them)
             c4_strong = {"error": str(e)}
+    # BASELINE config 5's shape (mixed query set, concurrency 64) on every rank's share of the index; the job-level
+    # figures are the slowest rank's
+    c5 = None
+    if not a.no_configs:
+        peak5 = 6650.0
+        try:
+            peak5 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except Exception:
+            pass
+        if world > 1:
+            dist.barrier()
+        c5 = config5_mixed(ctx, imgs, peak5, world)
+        if world > 1:
+            v = torch.tensor([-c5["qps"], c5["latency_ms"]["p50"], c5["latency_ms"]["p90"], c5["latency_ms"]["p99"], c5["latency_ms"]["max"], -c5["hbm"]["frac"]],
+                             dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            q, p50, p90, p99, mx, fr = [float(x) for x in v.tolist()]
+            c5["qps"] = -q
+            c5["latency_ms"] = {"p50": p50, "p90": p90, "p99": p99, "max": mx}
+            c5["hbm"]["frac"] = -fr
+            c5["aggregate"] = "slowest rank (every query is answered by every rank's leaf)"
     if world > 1:
         t = torch.tensor([gpu_s, wall, main_s, wall_c], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -600,7 +712,7 @@ def main():
                 "exchange": ("device: qwgpu_leaf_search_allgather (NCCL all-gather + merge inside the library)" if device_exchange else ("host partials" if world > 1 else None)),
                 "cold_split_register_ms": cold_ms, "phase_ms_per_step": {"leaf_search": 1e3 * phase[0] / a.steps, "all_gather": 1e3 * phase[1] / a.steps, "root_merge": 1e3 * phase[2] / a.steps}, "mean_query_latency_ms": 1e3 * sum(lat) / max(len(lat), 1),
                 "h2d_bytes_per_step": accs[0]["h2d"] + sum(len(x) for x in lreqs),
-                "d2h_bytes_per_step": Q_SETS * a.splits * (32 + 32 * K),
+                "d2h_bytes_per_step": Q_SETS * (a.splits * 32 + 64 + 40 * K),  # per split 32 B of counters + the merged top-K record (device merge)
                 "seam_c_wall_value": postings / wall_c},
         "gpu_launches": launches,
         "exact_fallbacks": sum(x["fallbacks"] for x in accs),
@@ -616,6 +728,8 @@ def main():
         out["configs"] = other_configs(ctx, imgs, peak)
     if c4_strong:
         out["config4_strong"] = c4_strong
+    if c5:
+        out["config5_mixed"] = c5
     if not a.no_cpu_baseline and world == 1:
         n_s = a.cpu_sample_splits or min(a.splits, max(4, min(cores, 32)))
         threads = min(cores, n_s)

@@ -250,6 +250,10 @@ typedef struct qwgpu_synth_spec {
   int64_t ts_start_secs; /* first timestamp; docs advance monotonically, 1 s resolution */
   uint32_t ts_span_secs; /* timestamps cover [ts_start, ts_start + span) */
   uint32_t num_tenants;
+  /* > 0: a second text field "msg", indexed with positions (`record: position`): 4..8 tokens per doc drawn
+   * Zipf(1) from the vocabulary "w0".."w<msg_vocab-1>" — the field the phrase queries of BASELINE config 5 run on */
+  uint32_t msg_vocab;
+  uint32_t reserved;
 } qwgpu_synth_spec;
 int qwgpu_synth_split(const qwgpu_synth_spec* spec, uint8_t** img, uint64_t* img_len);
 

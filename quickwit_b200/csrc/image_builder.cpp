@@ -477,6 +477,46 @@ static void synth_split(const qwgpu_synth_spec* sp, uint8_t** img, uint64_t* img
     int n = snprintf(name, sizeof name, "t%u", t);
     add_term(b.get(), 0, (const uint8_t*)name, (uint32_t)n, docs.data(), tfs.data(), (uint32_t)docs.size());
   }
+  // msg: optional text field with positions (phrase queries): 4..8 tokens per doc, Zipf(1) over "w<k>"
+  if (sp->msg_vocab) {
+    const uint32_t nv = sp->msg_vocab;
+    const uint32_t fid = (uint32_t)b->fields.size();
+    BField f;
+    f.name = "msg";
+    f.flags = QW_FIELD_HAS_FREQS | QW_FIELD_HAS_FIELDNORMS | QW_FIELD_HAS_POSITIONS;
+    f.tokenizer = QW_TOK_DEFAULT;
+    f.fieldnorms.resize(nd);
+    std::vector<double> cdf(nv);
+    double z = 0;
+    for (uint32_t i = 0; i < nv; i++) { z += 1.0 / (double)(i + 1); cdf[i] = z; }
+    struct Acc { std::vector<uint32_t> docs, tfs, pos; };
+    std::vector<Acc> acc(nv);
+    Rng r(base_seed ^ 0x3596);
+    uint64_t total = 0;
+    for (uint32_t d = 0; d < nd; d++) {
+      const uint32_t len = 4 + (uint32_t)(r.next() % 5);
+      total += len;
+      f.fieldnorms[d] = fieldnorm_to_id(len);
+      for (uint32_t t = 0; t < len; t++) {
+        const double u = r.uniform() * z;
+        uint32_t k = (uint32_t)(std::lower_bound(cdf.begin(), cdf.end(), u) - cdf.begin());
+        if (k >= nv) k = nv - 1;
+        Acc& a = acc[k];
+        if (a.docs.empty() || a.docs.back() != d) { a.docs.push_back(d); a.tfs.push_back(0); }
+        a.tfs.back()++;
+        a.pos.push_back(t);
+      }
+    }
+    f.total_tokens = total;
+    b->fields.push_back(std::move(f));
+    for (uint32_t k = 0; k < nv; k++) {
+      char name[32];
+      const int n = snprintf(name, sizeof name, "w%u", k);
+      const Acc& a = acc[k];
+      if (!a.docs.empty())
+        add_term(b.get(), fid, (const uint8_t*)name, (uint32_t)n, a.docs.data(), a.tfs.data(), (uint32_t)a.docs.size(), a.pos.data(), a.pos.size());
+    }
+  }
   // timestamp: datetime, seconds precision, monotone within the split
   {
     std::vector<uint64_t> ts(nd);

@@ -1536,12 +1536,16 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
   uint32_t loc[8], sum = 0;
 #pragma unroll
   for (int j = 0; j < 8; j++) { loc[j] = h[hi - 1 - j]; sum += loc[j]; }
-  s_part[tid] = sum;
+  // exclusive prefix over threads (bins above mine): warp scan + the totals of the warps before mine
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)(tid & 31) >= o) incl += t; }
+  if ((tid & 31) == 31) s_part[tid >> 5] = incl;
   if (tid == 0) { s_sel[0] = 0xFFFFFFFFu; s_sel[1] = 0; }
   __syncthreads();
-  // exclusive prefix over threads (bins above mine)
-  uint32_t above_me = 0;
-  for (uint32_t t = 0; t < tid; t++) above_me += s_part[t];
+  uint32_t above_me = incl - sum, total_all = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < 8; w++) { const uint32_t t = s_part[w]; total_all += t; if (w < (tid >> 5)) above_me += t; }
   uint32_t K = P.max_hits;
   uint32_t target, base_above = 0;
   if (sampled == 2) {
@@ -1565,8 +1569,7 @@ __global__ void __launch_bounds__(256) k_pick(const DSplitPlan* plans, DThresh* 
   __syncthreads();
   if (tid == 0) {
     uint32_t digit = s_sel[0];
-    uint32_t total = 0;
-    for (uint32_t t = 0; t < 256; t++) total += s_part[t];
+    const uint32_t total = total_all;
     if (digit == 0xFFFFFFFFu) {
       // fewer than `target` ranked docs: keep everything that matches the current prefix
       T.done = 1;
@@ -1606,7 +1609,7 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const 
   // shared memory: all first words [QW_CAND_CAP], then the compacted survivors (3 x sort capacity)
   uint64_t* a0 = (uint64_t*)qw_smem;
   __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_sel[3];  // [0] digit, [1] count above digit, [2] survivor counter
+  __shared__ uint32_t s_sel[4];  // [0] digit, [1] count above digit, [2] survivor counter, [3] count in the digit's bin
   for (uint32_t i = tid; i < n; i += 1024) a0[i] = src[3ull * i];
   if (tid == 0) s_sel[2] = 0;
   __syncthreads();
@@ -1614,13 +1617,25 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const 
   if (n > K) {
     uint64_t prefix = 0;
     uint32_t need = K;  // rank of the wanted element among those matching the prefix
+    // the sort below pads to a power of two anyway: once the candidates above the current bin plus the bin itself
+    // fit that size, the remaining digits need not be resolved (the whole bin is kept)
+    uint32_t cap = 32;
+    while (cap < K) cap <<= 1;
     for (int shift = 56; shift >= 0; shift -= 8) {
       if (tid < 256) s_hist[tid] = 0;
       __syncthreads();
       const uint64_t himask = shift == 56 ? 0ull : (~0ull << (shift + 8));
-      for (uint32_t i = tid; i < n; i += 1024) {
-        const uint64_t v = a0[i];
-        if ((v & himask) == prefix) atomicAdd(&s_hist[(uint32_t)(v >> shift) & 255u], 1u);
+      for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint64_t v = i < n ? a0[i] : 0ull;
+        const bool in = i < n && (v & himask) == prefix;
+        const uint32_t bin = (uint32_t)(v >> shift) & 255u;
+        // candidates near the threshold share their leading digits: one atomic per distinct bin of the warp
+        const uint32_t act = __ballot_sync(0xFFFFFFFFu, in);
+        if (in) {
+          const uint32_t peers = __match_any_sync(act, bin);
+          if ((tid & 31) == (uint32_t)__ffs(peers) - 1u) atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+        }
       }
       __syncthreads();
       if (tid < 32) {
@@ -1636,15 +1651,17 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const 
         for (int j = 0; j < 8; j++) {
           const uint32_t before = run;
           run += loc[j];
-          if (before < need && run >= need) { s_sel[0] = 255 - (tid * 8 + j); s_sel[1] = before; }
+          if (before < need && run >= need) { s_sel[0] = 255 - (tid * 8 + j); s_sel[1] = before; s_sel[3] = loc[j]; }
         }
       }
       __syncthreads();
       prefix |= (uint64_t)s_sel[0] << shift;
       need -= s_sel[1];
+      const uint32_t in_bin = s_sel[3];
       __syncthreads();
+      if ((K - need) + in_bin <= cap) break;  // (block-uniform: every operand comes from shared memory)
     }
-    thr = prefix;  // the exact K-th largest first word
+    thr = prefix;  // K-th largest first word with its unresolved low digits cleared: everything >= thr is kept
   }
   // count survivors; too many ties on the first word => sort every candidate instead
   uint32_t mine = 0;
@@ -1671,16 +1688,54 @@ __global__ void __launch_bounds__(1024) k_select(const DSplitPlan* plans, const 
     k0 = a0 + QW_CAND_CAP; k1 = k0 + QW_SEL_MAX; k2 = k1 + QW_SEL_MAX;
     if (tid == 0) s_sel[2] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += 1024) {
-      const uint64_t v = a0[i];
-      if (v >= thr) {
-        const uint32_t pos = atomicAdd(&s_sel[2], 1u);
+    for (uint32_t base = 0; base < n; base += 1024) {
+      const uint32_t i = base + tid;
+      const uint64_t v = i < n ? a0[i] : 0ull;
+      const bool keep = i < n && v >= thr;
+      const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);  // one atomic per warp
+      uint32_t wpos = 0;
+      if ((tid & 31) == 0 && km) wpos = atomicAdd(&s_sel[2], (uint32_t)__popc(km));
+      wpos = __shfl_sync(0xFFFFFFFFu, wpos, 0);
+      if (keep) {
+        const uint32_t pos = wpos + __popc(km & ((1u << (tid & 31)) - 1u));
         k0[pos] = v; k1[pos] = src[3ull * i + 1]; k2[pos] = src[3ull * i + 2];
       }
     }
     for (uint32_t i = m + tid; i < N; i += 1024) { k0[i] = 0; k1[i] = 0; k2[i] = 0; }
   }
   __syncthreads();
+  if (N <= 1024 && !all) {
+    // One key per thread, in registers: the compare-exchange partner of thread i at distance `stride` is thread
+    // i ^ stride, reached with warp shuffles below 32 and through shared memory (two buffers in turn: one barrier
+    // per exchange) from 32 up — 15 barriers for 1024 keys instead of the 55 of the generic network below.
+    const bool act = tid < N;
+    Key mine{0, 0, 0};
+    if (act) mine = Key{k0[tid], k1[tid], k2[tid]};
+    uint32_t pb = 1;  // exchange buffer: 1 = the first-word array (dead by now), 0 = the survivor arrays
+    __syncthreads();
+    for (uint32_t size = 2; size <= N; size <<= 1) {
+      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        Key other{0, 0, 0};
+        if (stride >= 32) {
+          uint64_t *b0 = pb ? a0 : k0, *b1 = pb ? a0 + 1024 : k1, *b2 = pb ? a0 + 2048 : k2;
+          if (act) { b0[tid] = mine.w0; b1[tid] = mine.w1; b2[tid] = mine.w2; }
+          __syncthreads();
+          if (act) other = Key{b0[tid ^ stride], b1[tid ^ stride], b2[tid ^ stride]};
+          pb ^= 1;
+        } else if (act) {
+          other.w0 = __shfl_xor_sync(0xFFFFFFFFu, mine.w0, stride);
+          other.w1 = __shfl_xor_sync(0xFFFFFFFFu, mine.w1, stride);
+          other.w2 = __shfl_xor_sync(0xFFFFFFFFu, mine.w2, stride);
+        }
+        // descending runs where (i & size) == 0; the lower index of a pair keeps the larger key there
+        const bool want_larger = ((tid & stride) == 0) == ((tid & size) == 0);
+        if (act && want_larger == key_lt(mine, other)) mine = other;
+      }
+    }
+    __syncthreads();
+    if (act) { k0[tid] = mine.w0; k1[tid] = mine.w1; k2[tid] = mine.w2; }
+    __syncthreads();
+  } else
   for (uint32_t size = 2; size <= N; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       for (uint32_t i = tid; i < (N >> 1); i += 1024) {
@@ -1816,7 +1871,8 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_l
     return;
   }
   uint32_t nonempty = 0;
-  for (uint32_t s = 0; s < n_lists; s++) nonempty += src.count(s) ? 1u : 0u;
+  for (uint32_t s = lane; s < n_lists; s += 32) nonempty += src.count(s) ? 1u : 0u;  // (one round of loads per warp)
+  nonempty = __reduce_add_sync(0xFFFFFFFFu, nonempty);
   const uint32_t m = nonempty ? (K + nonempty - 1) / nonempty : 0;
   for (uint32_t s = warp; s < n_lists; s += nw) {
     if (lane == 0) {
@@ -1840,18 +1896,26 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_l
   __syncthreads();
   const MKey tau = s_tau;
   for (uint32_t s = warp; s < n_lists; s += nw) {
-    if (lane != 0) continue;
     const uint32_t nh = min(src.count(s), K);
     uint32_t lo = 0, hi = nh;  // first index whose hit is worse than tau
     if (s_prune) {
+      // 32-ary search: the lanes probe evenly spaced hits of [lo, hi) at once (the list is sorted best-first, so the
+      // hits that are not worse than tau form a prefix of the probes): two or three rounds of loads for 1000 hits
       while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        uint32_t rk;
-        const QwHit h = src.hit(s, mid, rk);
-        if (mkey_gt(tau, merge_key(h, rk, o1, o2))) hi = mid; else lo = mid + 1;
+        const uint32_t step = (hi - lo + 31) / 32, idx = lo + lane * step;
+        bool keep = false;
+        if (idx < hi) {
+          uint32_t rk;
+          const QwHit h = src.hit(s, idx, rk);
+          keep = !mkey_gt(tau, merge_key(h, rk, o1, o2));
+        }
+        const uint32_t c = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, keep));
+        if (c == 0) { hi = lo; break; }
+        hi = min(hi, lo + c * step);
+        lo = lo + (c - 1) * step + 1;
       }
     } else lo = nh;
-    cut[s] = lo;
+    if (lane == 0) cut[s] = lo;
   }
 }
 template <class Src>

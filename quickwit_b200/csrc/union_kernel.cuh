@@ -74,6 +74,7 @@ struct UParams {
   const uint32_t* first_work;  // prefix over splits of (sampled) window counts; [n_splits + 1]
   uint32_t n_splits, total_work, stride, W;
   unsigned long long* prof;    // QU_PROFILE builds: cycle counters (see k_union)
+  uint32_t* work_ctr;          // dynamic hand-out of the windows (zero at launch); null = static chunks per block
   USmem sm;
 };
 #ifdef QU_PROFILE
@@ -253,18 +254,33 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       return (work - __ldg(p.first_work + split)) * p.stride + (p.stride > 1 ? split % p.stride : 0);
     };
 
-    uint32_t split = 0;
-    if (w_begin < w_end) {
-      uint32_t a = 0, b = p.n_splits;
-      while (b - a > 1) {
-        const uint32_t mid = (a + b) >> 1;
-        if (__ldg(p.first_work + mid) <= w_begin) a = mid; else b = mid;
+    // Work items (windows) come either from this block's static chunk of the flat list or, when the host passes a
+    // counter, one at a time from that counter: blocks that start late (their SM was busy with another call's
+    // kernel) or hit denser windows simply take fewer, so the kernel's duration does not hinge on full residency.
+    const bool dyn = p.work_ctr != nullptr;
+    const uint32_t w_limit = dyn ? p.total_work : w_end;
+    uint32_t grabbed = 0;
+    auto grab_issue = [&]() { if (dyn && lane == 0) grabbed = atomicAdd(p.work_ctr, 1u); };
+    auto grab_take = [&](uint32_t after) { return dyn ? __shfl_sync(QW_FULL, grabbed, 0) : after + 1; };
+    // split of a work item: number of prefix entries <= work, minus one (lane-parallel; empty splits share their entry)
+    auto split_of = [&](uint32_t work) {
+      uint32_t cnt = 0;
+      for (uint32_t b0 = 0; b0 < p.n_splits; b0 += 32) {
+        const uint32_t i = b0 + lane;
+        cnt += __popc(__ballot_sync(QW_FULL, i < p.n_splits && __ldg(p.first_work + i) <= work));
       }
-      split = a;
+      return cnt - 1;
+    };
+    uint32_t split = 0;
+    uint32_t work = w_begin, next_work = w_begin + 1;
+    if (dyn) { grab_issue(); work = grab_take(0); grab_issue(); next_work = grab_take(0); }
+    if (work < w_limit) {
+      split = split_of(work);
       load_plan(split);
-      load_widx(window_of(w_begin, split));
+      load_widx(window_of(work, split));
     }
-    for (uint32_t work = w_begin; work < w_end; work++) {
+    for (; work < w_limit; ) {
+      grab_issue();  // the item after next: its latency hides behind this window's packing
       QU_T(pt_w0);
       const uint32_t window = window_of(work, split);
       ws = window * W;
@@ -305,10 +321,11 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       if (G) round_loads(0, t, r, ck, dat, tfl);
       // the next window's index entries fly while this window is packed (same split: same term constants)
       uint32_t nx_split = split;
-      const bool have_next = work + 1 < w_end;
+      const bool have_next = next_work < w_limit;
       if (have_next) {
-        while (__ldg(p.first_work + nx_split + 1) <= work + 1) nx_split++;
-        if (nx_split == split) load_widx(window_of(work + 1, split));
+        if (dyn) nx_split = split_of(next_work);
+        else while (__ldg(p.first_work + nx_split + 1) <= next_work) nx_split++;
+        if (nx_split == split) load_widx(window_of(next_work, split));
       }
       for (uint32_t q0 = 0; q0 < G; q0 += 32) {
         const uint32_t q = q0 + lane;
@@ -367,8 +384,10 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       if (have_next && nx_split != split) {
         split = nx_split;
         load_plan(split);
-        load_widx(window_of(work + 1, split));
+        load_widx(window_of(next_work, split));
       }
+      work = next_work;
+      next_work = grab_take(next_work);
     }
     // terminal slot
     open_slot();
@@ -508,8 +527,28 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         const uint32_t blk = rec.y - sbase;  // offset inside qw_smem
         const uint32_t doc_bits = rec.z & 0xFFu, tf_bits = (rec.z >> 8) & 0xFFu;
         // ---- doc ids: two positions x 4 values per lane, in-lane prefix, then a 16-lane scan -------------
+        // Both positions of a lane are adjacent in the packed stream: for widths <= 16 the 32 bits that start at
+        // the first position hold the second one too, so ONE pair of 16-byte words serves both (half the
+        // shared-memory loads of the general path).
+        const bool narrow = __all_sync(QW_FULL, doc_bits <= 16u && tf_bits <= 16u);
         uint32_t d[8];
-        {
+        if (narrow) {
+          const uint32_t bp0 = 2u * hl * doc_bits;
+          const uint8_t* a0 = qw_smem + blk + ((bp0 >> 5) << 4);
+          const uint4 A0 = *(const uint4*)a0, B0 = *(const uint4*)(a0 + 16);
+          const uint32_t sh0 = bp0 & 31u;
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, doc_bits);
+          const uint32_t x0 = __funnelshift_r(A0.x, B0.x, sh0), x1 = __funnelshift_r(A0.y, B0.y, sh0);
+          const uint32_t x2 = __funnelshift_r(A0.z, B0.z, sh0), x3 = __funnelshift_r(A0.w, B0.w, sh0);
+          d[0] = (x0 & mask) + 1u;
+          d[1] = d[0] + (x1 & mask) + 1u;
+          d[2] = d[1] + (x2 & mask) + 1u;
+          d[3] = d[2] + (x3 & mask) + 1u;
+          d[4] = d[3] + ((x0 >> doc_bits) & mask) + 1u;
+          d[5] = d[4] + ((x1 >> doc_bits) & mask) + 1u;
+          d[6] = d[5] + ((x2 >> doc_bits) & mask) + 1u;
+          d[7] = d[6] + ((x3 >> doc_bits) & mask) + 1u;
+        } else {
           const uint32_t bp0 = 2u * hl * doc_bits, bp1 = bp0 + doc_bits;
           const uint8_t* a0 = qw_smem + blk + ((bp0 >> 5) << 4);
           const uint8_t* a1 = qw_smem + blk + ((bp1 >> 5) << 4);
@@ -536,7 +575,17 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         uint32_t f[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) f[j] = 1;
-        if (tf_bits) {
+        if (tf_bits && narrow) {
+          const uint32_t bp0 = 2u * hl * tf_bits;
+          const uint8_t* a0 = qw_smem + blk + 16u * doc_bits + ((bp0 >> 5) << 4);
+          const uint4 A0 = *(const uint4*)a0, B0 = *(const uint4*)(a0 + 16);
+          const uint32_t sh0 = bp0 & 31u;
+          const uint32_t mask = __funnelshift_lc(0xFFFFFFFFu, 0u, tf_bits);
+          const uint32_t x0 = __funnelshift_r(A0.x, B0.x, sh0), x1 = __funnelshift_r(A0.y, B0.y, sh0);
+          const uint32_t x2 = __funnelshift_r(A0.z, B0.z, sh0), x3 = __funnelshift_r(A0.w, B0.w, sh0);
+          f[0] = x0 & mask; f[1] = x1 & mask; f[2] = x2 & mask; f[3] = x3 & mask;
+          f[4] = (x0 >> tf_bits) & mask; f[5] = (x1 >> tf_bits) & mask; f[6] = (x2 >> tf_bits) & mask; f[7] = (x3 >> tf_bits) & mask;
+        } else if (tf_bits) {
           const uint32_t bp0 = 2u * hl * tf_bits, bp1 = bp0 + tf_bits;
           const uint8_t* a0 = qw_smem + blk + 16u * doc_bits + ((bp0 >> 5) << 4);
           const uint8_t* a1 = qw_smem + blk + 16u * doc_bits + ((bp1 >> 5) << 4);

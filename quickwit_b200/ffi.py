@@ -123,7 +123,7 @@ class SynthSpec(C.Structure):
     _fields_ = [("num_docs", C.c_uint32), ("split_ord", C.c_uint32), ("seed", C.c_uint64),
                 ("num_terms", C.c_uint32), ("term_fracs", C.POINTER(C.c_double)),
                 ("ts_start_secs", C.c_int64), ("ts_span_secs", C.c_uint32),
-                ("num_tenants", C.c_uint32)]
+                ("num_tenants", C.c_uint32), ("msg_vocab", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class QwGpuError(RuntimeError):

@@ -357,12 +357,13 @@ def build_split(docs: Sequence[Dict[str, Any]], doc_mapping: Dict[str, Any], spl
 
 def synth_split(num_docs: int, split_ord: int, term_fracs: Iterable[float], seed: int = 0x5157,
                 ts_start_secs: int = 1_700_000_000, ts_span_secs: int = 86_400, num_tenants: int = 100,
-                split_id: Optional[str] = None) -> SplitImage:
-    """Synthetic hdfs-logs-shaped split; generation is done by the C++ writer."""
+                split_id: Optional[str] = None, msg_vocab: int = 0) -> SplitImage:
+    """Synthetic hdfs-logs-shaped split; generation is done by the C++ writer.
+    msg_vocab > 0 adds the text field "msg" with positions (phrase queries, BASELINE config 5)."""
     L = ffi.img_lib()
     fr = np.ascontiguousarray(list(term_fracs), dtype=np.float64)
     spec = ffi.SynthSpec(num_docs, split_ord, seed, len(fr), fr.ctypes.data_as(C.POINTER(C.c_double)),
-                         ts_start_secs, ts_span_secs, num_tenants)
+                         ts_start_secs, ts_span_secs, num_tenants, msg_vocab, 0)
     out, n = C.c_void_p(), C.c_uint64()
     ffi.img_check(L.qwgpu_synth_split(C.byref(spec), C.byref(out), C.byref(n)))
     arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()

@@ -270,3 +270,24 @@ def test_phrases_against_the_oracle(gpu_ctx, phrase_split):
         for k, sort in ((25, SCORE_DESC), (1000, [col_sort(img, "n", ffi.ORDER_ASC), (ffi.SORT_SCORE, ffi.ORDER_DESC, ffi.ABSENT)])):
             run_both(gpu_ctx, img, P.make_plan(root, k, sort), ctx=f"phrase plan {i} k={k}")
     run_both(gpu_ctx, img, P.make_plan(ph(["alpha", "beta"], ffi.OCCUR_MUST), 0, DOC_DESC, aggs=[terms_agg(img, "n")]), ctx="phrase + terms agg")
+
+
+@pytest.mark.gpu
+def test_phrases_over_the_synthetic_positions_field(gpu_ctx):
+    """The bench corpus' optional `msg` field (positions, Zipf vocabulary): frequent 2-word and rarer 3-word
+    phrases at a size where every term spans thousands of posting blocks — the BASELINE config 5 queries."""
+    img = S.synth_split(400_000, 7, [0.2, 0.05], split_id="synth-msg-7", msg_vocab=64)
+    gpu_ctx.register_split(img)
+    try:
+        counts = []
+        for terms in (["w1", "w2"], ["w0", "w3", "w1"], ["w40", "w50"], ["w5", "w5"]):
+            for k, sort in ((10, SCORE_DESC), (200, DOC_DESC)):
+                got, _ = run_both(gpu_ctx, img, P.make_plan(P.phrase(img, "msg", terms), k, sort), ctx=f"msg phrase {terms} k={k}")
+            counts.append(got.num_hits)
+        assert counts[0] > 5000 and counts[1] > 100 and counts[2] < counts[0]
+        # a phrase next to a scored body term and a timestamp sort
+        root = P.bool_([P.phrase(img, "msg", ["w1", "w2"], occur=ffi.OCCUR_MUST), P.term(img, "body", "t0", occur=ffi.OCCUR_SHOULD)])
+        run_both(gpu_ctx, img, P.make_plan(root, 100, SCORE_DESC), ctx="msg phrase + body term")
+        run_both(gpu_ctx, img, P.make_plan(root, 100, [col_sort(img, "timestamp", ffi.ORDER_DESC)]), ctx="msg phrase by timestamp")
+    finally:
+        gpu_ctx.unregister_split(img.split_id)
