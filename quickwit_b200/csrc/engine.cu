@@ -986,9 +986,21 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   static const uint32_t hdiv = getenv("QWGPU_HDIV") ? std::max(1u, (uint32_t)atoi(getenv("QWGPU_HDIV"))) : 1u;
   const uint32_t W_h = use_union ? std::max(1024u, (W / hdiv) & ~1023u) : W;
   if (use_union) {
-    uint32_t mw = 0;
-    for (uint32_t i = 0; i < n; i++) mw = std::max(mw, low[i].empty ? 0u : (low[i].P.num_docs + W_h - 1) / W_h);
+    uint32_t mw = 0, tw = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t nw = low[i].empty ? 0u : (low[i].P.num_docs + W_h - 1) / W_h;
+      mw = std::max(mw, nw);
+      tw += nw;
+    }
     stride = std::min(std::max(stride_cap, 1u), std::max(1u, mw / 8));
+    // Large requests: at most ONE sampled window per resident block (the sampled pass is latency bound — a block
+    // that gets two windows doubles its duration), up to a stride of 32. Bench workload (6528 windows, 296 blocks):
+    // stride 23 instead of 16, 1.146 against 1.186 ms per 4-query step (32: 1.169 — the looser threshold then costs
+    // more candidates in the collect pass than the sampled pass saves).
+    if (!getenv("QWGPU_STRIDE_CAP")) {
+      const uint32_t per_block = (tw + (uint32_t)(sm_count * QU_MINB) - 1) / (uint32_t)(sm_count * QU_MINB);
+      stride = std::max(stride, std::min({per_block, 32u, std::max(1u, mw / 8)}));
+    }
   }
   // posting-driven kernel: the work list is the driving term's posting blocks; the threshold sample takes every
   // stride-th BLOCK (128 postings, fine enough for keys that follow doc order: what lies between two sampled
