@@ -391,6 +391,10 @@ def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_pe
     start = threading.Barrier(concurrency + 1)
 
     def worker(t):
+        # untimed warm-up: the thread's whole plan once, so that every in-flight call slot of the library (stream,
+        # pinned staging, device scratch: allocated on first use, grown to the largest request seen) exists
+        for name in plan[t]:
+            ctx.leaf_search(reqs[name])
         start.wait()
         for name in plan[t]:
             t0 = time.perf_counter()

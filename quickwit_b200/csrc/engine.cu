@@ -1093,7 +1093,17 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       e->free_slots.push_back(s);
     }
   } rel{this, slot};
-  slot->ensure(blob_bytes, scratch_bytes, out_bytes);
+  size_t want_blob, want_scratch, want_out;
+  {
+    // slots are sized to the largest request the context has seen: a slot that meets a bigger request later would
+    // have to cudaFree / cudaMalloc (device-synchronising) in the middle of concurrent searches
+    std::lock_guard<std::mutex> g(mu);
+    hw_blob = std::max(hw_blob, blob_bytes); hw_scratch = std::max(hw_scratch, scratch_bytes); hw_out = std::max(hw_out, out_bytes);
+    // (only while the marks stay moderate: one huge aggregation request must not size every slot after itself)
+    auto sized = [](size_t hw, size_t need) { return hw <= ((size_t)64 << 20) ? hw : need; };
+    want_blob = sized(hw_blob, blob_bytes); want_scratch = sized(hw_scratch, scratch_bytes); want_out = sized(hw_out, out_bytes);
+  }
+  slot->ensure(want_blob, want_scratch, want_out);
   cudaStream_t st = slot->stream;
 
   uint32_t phr_done = 0, phr_blocks_done = 0;

@@ -78,6 +78,7 @@ struct Engine {
   std::mutex mu;
   std::map<std::string, std::shared_ptr<SplitDev>> splits;
   std::vector<CallSlot*> free_slots;
+  size_t hw_blob = 0, hw_scratch = 0, hw_out = 0;  // largest per-call buffers requested so far (slot sizing)
   uint64_t resident = 0;
   // residency manager: byte budget for the data regions of the resident splits (0 = no limit). Registering a
   // split beyond it evicts the least recently searched splits that no call is using (the counterpart of the

@@ -1862,7 +1862,8 @@ struct SrcGathered {
 template <class Src>
 __global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_lists, uint32_t K, uint32_t o1, uint32_t o2, uint32_t* cut) {
   __shared__ MKey s_key[64];
-  __shared__ uint32_t s_have[64];
+  __shared__ MKey s_keyK[64];
+  __shared__ uint32_t s_have[64], s_full[64];
   __shared__ MKey s_tau;
   __shared__ uint32_t s_prune;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -1879,6 +1880,10 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_l
       const uint32_t nh = min(src.count(s), K), ms = min(m, nh);
       s_have[s] = ms;
       if (ms) { uint32_t rk; const QwHit h = src.hit(s, ms - 1, rk); s_key[s] = merge_key(h, rk, o1, o2); }
+      // a list that holds K hits by itself: its own K-th hit bounds the merged K-th hit as well (the bound that
+      // bites when the lists are skewed — time-sorted hits of time-partitioned splits all come from one split)
+      s_full[s] = (K > 0 && nh >= K) ? 1u : 0u;
+      if (s_full[s]) { uint32_t rk; const QwHit h = src.hit(s, K - 1, rk); s_keyK[s] = merge_key(h, rk, o1, o2); }
     }
   }
   __syncthreads();
@@ -1890,8 +1895,11 @@ __global__ void __launch_bounds__(1024) k_merge_prep(const Src src, uint32_t n_l
       have += s_have[s];
       if (s_have[s] && (first || mkey_gt(tau, s_key[s]))) { tau = s_key[s]; first = 0; }
     }
+    uint32_t prune = have >= K ? 1u : 0u;
+    for (uint32_t s = 0; s < n_lists; s++)
+      if (s_full[s] && (!prune || mkey_gt(s_keyK[s], tau))) { tau = s_keyK[s]; prune = 1; }  // the tighter of the valid bounds
     s_tau = tau;
-    s_prune = have >= K ? 1u : 0u;
+    s_prune = prune;
   }
   __syncthreads();
   const MKey tau = s_tau;
