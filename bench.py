@@ -341,7 +341,7 @@ def config4_strong(ctx, imgs, world: int, rank: int, reps: int = 10):
             "api": "qwgpu_leaf_search_allgather (aggregation partials: host-staged NCCL all-gather inside the library)"}
 
 
-def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_per_thread: int = 6):
+def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_per_thread: int = 6, announce: bool = False):
     """BASELINE config 5's shape on one GPU's share of the index: a mixed term / phrase / bool / range / aggregation
     query set issued from `concurrency` host threads against the rank's resident splits through qwgpu_leaf_search
     (host protobuf bytes in and out). With N ranks every rank serves its own 32 splits (256 splits / 1 B docs at
@@ -397,6 +397,8 @@ def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_pe
             ctx.leaf_search(reqs[name])
         start.wait()
         for name in plan[t]:
+            if announce:  # (with QWGPU_TRACE=1: labels the library's per-call phase timings on stderr)
+                print(f"[c5] {name}", file=sys.stderr, flush=True)
             t0 = time.perf_counter()
             resp = ctx.leaf_search(reqs[name])
             lat[t].append((name, time.perf_counter() - t0))

@@ -37,6 +37,7 @@ SplitDev::~SplitDev() {
 struct CallSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that yield the CPU (many calls in flight)
   uint8_t *d_blob = nullptr, *h_blob = nullptr;
   size_t blob_cap = 0;
   uint8_t* d_scratch = nullptr;
@@ -71,6 +72,7 @@ struct CallSlot {
     if (d_out) cudaFree(d_out);
     if (h_out) cudaFreeHost(h_out);
     if (ev0) cudaEventDestroy(ev0);
+    if (ev_block) cudaEventDestroy(ev_block);
     if (ev1) cudaEventDestroy(ev1);
     if (ev2) cudaEventDestroy(ev2);
     if (ev3) cudaEventDestroy(ev3);
@@ -1070,11 +1072,25 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   const size_t o_ghdr = al(o_merged + rec_bytes), o_final = al(o_ghdr + (do_gather ? (size_t)gather->world * 64 : 0));
   size_t out_bytes = do_merge ? (do_gather ? al(o_final + 16 + (size_t)merge->k * sizeof(qwk::DMergedHit)) : al(o_merged + rec_bytes)) : out_off[n];
 
+  // Admission: at most QWGPU_MAX_IN_FLIGHT (default 16) searches drive the device at once; further callers wait here
+  // on a condition variable (no CUDA calls, no spinning). Measured on the mixed config-5 query set: 16 host threads
+  // sustain 1860 queries/s, 64 unthrottled threads 920 — beyond a dozen or so submitters the driver's per-context
+  // lock and 64 interleaved streams cost more than the extra overlap brings.
+  static const int max_in_flight = getenv("QWGPU_MAX_IN_FLIGHT") ? std::max(1, atoi(getenv("QWGPU_MAX_IN_FLIGHT"))) : 16;
   CallSlot* slot = nullptr;
   {
-    std::lock_guard<std::mutex> g(mu);
+    std::unique_lock<std::mutex> g(mu);
+    cv_admit.wait(g, [&] { return admitted < max_in_flight; });
+    admitted++;
     if (!free_slots.empty()) { slot = free_slots.back(); free_slots.pop_back(); }
   }
+  struct Admit {  // (released on every path, including a throw before the slot guard below exists)
+    Engine* e;
+    ~Admit() {
+      { std::lock_guard<std::mutex> g(e->mu); e->admitted--; }
+      e->cv_admit.notify_one();
+    }
+  } admit{this};
   if (!slot) {
     slot = new CallSlot();
     CUDA_CHECK(cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking));
@@ -1082,6 +1098,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaEventCreate(&slot->ev1));
     CUDA_CHECK(cudaEventCreate(&slot->ev2));
     CUDA_CHECK(cudaEventCreate(&slot->ev3));
+    CUDA_CHECK(cudaEventCreateWithFlags(&slot->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
   }
   // the slot goes back to the pool only once its stream is idle: on an error path copies / kernels of this
   // call may still be in flight, and the next call would reuse the pinned buffers under them
@@ -1089,10 +1106,23 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     Engine* e; CallSlot* s;
     ~Release() {
       cudaStreamSynchronize(s->stream);
+      e->in_flight.fetch_sub(1);
       std::lock_guard<std::mutex> g(e->mu);
       e->free_slots.push_back(s);
     }
   } rel{this, slot};
+  in_flight.fetch_add(1);
+  // Waiting for the call's stream: cudaStreamSynchronize spins on a CPU core, which is the fastest wake-up while a
+  // few calls are in flight (single-query latency) and a disaster when more host threads wait than there are cores
+  // to spare — the spinners starve the threads that still have plans to compile. Beyond a quarter of the cores the
+  // wait goes through a blocking event instead (the thread sleeps until the driver's interrupt).
+  static const uint32_t spin_limit = getenv("QWGPU_SPIN_LIMIT") ? (uint32_t)atoi(getenv("QWGPU_SPIN_LIMIT")) : std::max(2u, std::thread::hardware_concurrency() / 4);
+  auto wait_stream = [&]() {
+    if (in_flight.load(std::memory_order_relaxed) > (int)spin_limit) {
+      CUDA_CHECK(cudaEventRecord(slot->ev_block, slot->stream));
+      CUDA_CHECK(cudaEventSynchronize(slot->ev_block));
+    } else CUDA_CHECK(cudaStreamSynchronize(slot->stream));
+  };
   size_t want_blob, want_scratch, want_out;
   {
     // slots are sized to the largest request the context has seen: a slot that meets a bigger request later would
@@ -1144,11 +1174,6 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   memcpy(slot->h_blob + o_fws, fw_smp.data(), (n + 1) * 4);
   CUDA_CHECK(cudaMemcpyAsync(slot->d_blob, slot->h_blob, blob_bytes, cudaMemcpyHostToDevice, st));
   stats.h2d_bytes += blob_bytes;
-  if (phrase_blocks) {
-    // phrase pre-pass: every phrase of the batch becomes a posting list in scratch, read by every later pass
-    qwk::k_phrase<<<(phrase_blocks + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, 0, st>>>((const DPhrase*)(slot->d_blob + o_phr), n_phrases, phrase_blocks);
-    stats.launches++;
-  }
 
   KParams kp;
   memset(&kp, 0, sizeof kp);
@@ -1237,7 +1262,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       if (u.prof && getenv("QWGPU_UPROF")) {
         unsigned long long h[16];
         CUDA_CHECK(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        wait_stream();
         const double np = (double)ugrid, nc = (double)h[15];
         fprintf(stderr, "[uprof] producer/CTA: total %.0f cyc, empty-wait %.0f, phaseA %.0f, window(A+B) %.0f, windows %.1f, slots %.1f | consumer/warp: total %.0f, full-wait %.0f, chain-wait %.0f (end-of-window %.0f), sweep %.0f, block-loop %.0f, blocks %.1f\n",
                 h[0] / np, h[1] / np, h[2] / np, h[3] / np, h[4] / np, h[5] / np, h[8] / nc, h[9] / nc, h[10] / nc, h[11] / nc, h[12] / nc, h[13] / nc, h[14] / nc);
@@ -1291,6 +1316,15 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   const auto t_staged = tclock::now();
   CUDA_CHECK(cudaEventRecord(slot->ev0, st));
   CUDA_CHECK(cudaMemsetAsync(slot->d_scratch, 0, s_cand, st));  // thresholds, histograms, refinement state
+  if (phrase_blocks) {
+    // phrase pre-pass (inside the timed device region): every phrase of the batch becomes a posting list in
+    // scratch (beyond s_cand: never cleared), read by every later pass
+    uint32_t max_terms = 1;
+    for (auto& L : low) for (auto& ph : L.phrases) max_terms = std::max(max_terms, ph.n_terms);
+    const size_t psm = (size_t)QP_WARPS * QP_SMEM_WORDS(max_terms) * 4;
+    qwk::k_phrase<<<(phrase_blocks + QP_WARPS - 1) / QP_WARPS, QP_WARPS * 32, psm, st>>>((const DPhrase*)(slot->d_blob + o_phr), n_phrases, phrase_blocks, max_terms);
+    stats.launches++;
+  }
   bool ok = true;
   float main_ms = 0;
   auto add_main = [&]() { float ms = 0; cudaEventElapsedTime(&ms, slot->ev2, slot->ev3); main_ms += ms; };
@@ -1302,7 +1336,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     if (rec_l0) CUDA_CHECK(cudaMemsetAsync(slot->d_scratch + s_hist, 0, (size_t)n * QW_HIST_BINS * 4, st));
     run_collect(rec_l0 ? F_REC : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    wait_stream();
     ok = verify();
     if (!ok) {
       float ms = 0;
@@ -1316,7 +1350,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
   if (!any_topk) {
     run_collect(0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    wait_stream();
   } else if (stride == 1 || !ok) {
     // exact radix select over the composite key: one histogram pass per 11-bit digit until the
     // candidate set of every split fits QW_CAND_CAP. After a failed sampled threshold with the
@@ -1336,7 +1370,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, 0, 0, 1, d_state);
       stats.launches++;
       CUDA_CHECK(cudaMemcpyAsync(th.data(), slot->d_scratch + s_thr, n * sizeof(DThresh), cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      wait_stream();
       done = all_done();
       level = 1;
     } else {
@@ -1348,12 +1382,12 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
       qwk::k_pick<<<n, 256, 0, st>>>(kp.plans, kp.thresh, level, 0, 1, d_state);
       stats.launches++;
       CUDA_CHECK(cudaMemcpyAsync(th.data(), slot->d_scratch + s_thr, n * sizeof(DThresh), cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
+      wait_stream();
       done = all_done();
     }
     run_collect(refine ? (F_REFINE | F_CANDS_ONLY) : 0);
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    wait_stream();
     if (!verify()) fail(QWGPU_EINTERNAL, "top-K candidate selection failed verification");
   }
   if (do_gather) {
@@ -1373,7 +1407,7 @@ void Engine::search(const std::vector<std::shared_ptr<SplitDev>>& sp, const std:
     CUDA_CHECK(cudaMemcpy2DAsync(slot->d_out + o_ghdr, 64, g_recv, rec_bytes, 64, (size_t)gather->world, cudaMemcpyDeviceToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(slot->h_out + o_ghdr, slot->d_out + o_ghdr, out_bytes - o_ghdr, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaEventRecord(slot->ev1, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    wait_stream();
     stats.launches += 4;
     stats.d2h_bytes += out_bytes - o_ghdr;
   }

@@ -1,6 +1,7 @@
 // engine.h — host-side engine: split residency in HBM + batched plan execution on the GPU.
 #pragma once
 #include <condition_variable>
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -78,6 +79,9 @@ struct Engine {
   std::mutex mu;
   std::map<std::string, std::shared_ptr<SplitDev>> splits;
   std::vector<CallSlot*> free_slots;
+  std::atomic<int> in_flight{0};  // searches between slot acquisition and release
+  int admitted = 0;               // searches past the admission gate (guarded by mu)
+  std::condition_variable cv_admit;
   size_t hw_blob = 0, hw_scratch = 0, hw_out = 0;  // largest per-call buffers requested so far (slot sizing)
   uint64_t resident = 0;
   // residency manager: byte budget for the data regions of the resident splits (0 = no limit). Registering a

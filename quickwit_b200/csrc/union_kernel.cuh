@@ -52,6 +52,9 @@ namespace qwk {
 #ifndef QU_MINB
 #define QU_MINB 2               /* blocks per SM */
 #endif
+#ifndef QU_DEFER_SWEEP
+#define QU_DEFER_SWEEP 1        /* COLLECT: sweep a finished window after the first decode of the next one */
+#endif
 
 enum { QU_F_FIRST = 1u, QU_F_LAST = 2u, QU_F_END = 4u };
 
@@ -487,6 +490,46 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       my_hits = 0;
     };
 
+    // COLLECT: the sweep of a finished window is DEFERRED until this warp has decoded its first pair of blocks of the
+    // next window (decode needs no ordering): the wait for the window's last clauses — a third of the warps hold the
+    // sparse tail while the others idle — overlaps with useful work instead of a parked warp.
+    constexpr bool DEFER = (MODE == MODE_COLLECT) && (QU_DEFER_SWEEP != 0);
+    bool pend = false;
+    uint32_t p_ws = 0, p_split = 0, p_end = 0;
+    float p_hdr = 0.f;
+    auto collect_sweep = [&](const uint32_t ws, const uint32_t split, const float s_lo, const uint32_t end_stage) {
+      QU_T(te0);
+      wait_below(end_stage);  // every contribution of the window is in
+      QU_ACC(ct_endwait, te0);
+      QU_T(ts0);
+      float4* sc4 = reinterpret_cast<float4*>(score);
+      const uint32_t s_lo_bits = s_lo > 0.0f ? __float_as_uint(s_lo) : 1u;  // no threshold yet: every match goes on
+#pragma unroll 4
+      for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
+        const float4 v = sc4[q];
+        sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        // (scores are sums of positive contributions: as integers, 0 = no match and the order is the float order)
+        const uint32_t u0 = __float_as_uint(vv[0]), u1 = __float_as_uint(vv[1]), u2 = __float_as_uint(vv[2]), u3 = __float_as_uint(vv[3]);
+        my_hits += min(u0, 1u) + min(u1, 1u) + min(u2, 1u) + min(u3, 1u);
+        if (__vimax3_u32(__vimax3_u32(u0, u1, u2), u3, 0u) >= s_lo_bits) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (vv[j] > 0.0f && vv[j] >= s_lo) {
+              const uint32_t pos = atomicAdd(ncand, 1u);
+              if (pos < QU_CANDS) cands[pos] = make_uint2(ws + 4 * q + j, __float_as_uint(vv[j]));
+              else union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + j, vv[j]);  // buffer full: slow road now
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_chain(end_stage));
+      my_stage = end_stage + 1;
+      if (*ncand >= QU_CANDS / 2) flush_cands();  // (after the arrival: nobody waits for the global atomics)
+      QU_ACC(ct_sweep, ts0);
+    };
+
     for (uint32_t seq = 0;; seq++) {
       const uint32_t slot = seq % QU_SLOTS;
       QU_T(tf0);
@@ -499,9 +542,16 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       const uint32_t ws = h0.x, wlen = h0.y, split = h0.z, flags = h0.w;
       const uint32_t G = h1.x, n_terms = h1.y, t_last = h1.z;
       const float hdr_f = __uint_as_float(h1.w);
-      if (flags & QU_F_END) break;
+      if (flags & QU_F_END) {
+        if (pend) collect_sweep(p_ws, p_split, p_hdr, p_end);
+        break;
+      }
       if (flags & QU_F_FIRST) wbase = next_base;
-      if (split != cur_split) { flush_hits(); cur_split = split; }
+      if (split != cur_split) {
+        if (pend) { collect_sweep(p_ws, p_split, p_hdr, p_end); pend = false; }  // (its hits belong to the old split)
+        flush_hits();
+        cur_split = split;
+      }
       const uint32_t recs = sl + p.sm.recs, ttab = sl + p.sm.ttab;
 
       // Two blocks per warp step: half-warp `half` decodes block g0 + half, 16 lanes x 8 postings each (two
@@ -520,7 +570,8 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
         const uint32_t st = wbase + t;
         const uint32_t st_lo = __shfl_sync(QW_FULL, st, 0);
         const uint32_t st_hi = __shfl_sync(QW_FULL, on ? st : 0u, 16);  // (0: the upper half has no block)
-        pass_to(st_lo);
+        const bool deferred = DEFER && pend;  // (warp-uniform) the previous window's sweep comes after this decode
+        if (!deferred) pass_to(st_lo);
         const uint4 tt = *(const uint4*)(qw_smem + ttab + 16u * t);
         const float weight = __uint_as_float(tt.x);
         const float* tab = (const float*)(((uint64_t)tt.w << 32) | tt.z);
@@ -651,6 +702,11 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
             for (int j = 0; j < 8; j++) if (in[j]) score[r[j]] = __fadd_rn(o[j], c[j]);
           }
         };
+        if (deferred) {
+          collect_sweep(p_ws, p_split, p_hdr, p_end);
+          pend = false;
+          pass_to(st_lo);
+        }
         wait_below(st_lo);
         if (st_hi == st_lo || st_hi == 0u) apply();  // (lanes of an absent upper block have nvalid == 0)
         else {
@@ -664,6 +720,7 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
 #ifdef QU_PROFILE
       ct_blocks += clock64() - tb0;
 #endif
+      if (DEFER && pend) { collect_sweep(p_ws, p_split, p_hdr, p_end); pend = false; }  // (no block of this slot was this warp's)
       // this warp is done reading the slot
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(slot));
@@ -673,47 +730,22 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       }
       const uint32_t end_stage = wbase + n_terms;
       pass_to(end_stage);
-      QU_T(te0);
-      wait_below(end_stage);  // every contribution of the window is in
-      QU_ACC(ct_endwait, te0);
-      QU_T(ts0);
-      // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
-      float4* sc4 = reinterpret_cast<float4*>(score);
       // one group of four docs: scores (0 = no match); the accumulator is cleared on the way
+      float4* sc4 = reinterpret_cast<float4*>(score);
       auto quad = [&](uint32_t q, float (&vv)[4]) {
         const float4 v = sc4[q];
         sc4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         vv[0] = v.x; vv[1] = v.y; vv[2] = v.z; vv[3] = v.w;
       };
+      (void)quad;
       if (MODE == MODE_COLLECT) {
-        const float s_lo = hdr_f;
-        const uint32_t s_lo_bits = s_lo > 0.0f ? __float_as_uint(s_lo) : 1u;  // no threshold yet: every match goes on
-#pragma unroll 4
-        for (uint32_t q = tid; q < (W >> 2); q += QU_NCT) {
-          float vv[4];
-          quad(q, vv);
-          // (scores are sums of positive contributions: as integers, 0 = no match and the order is the float order)
-          const uint32_t u0 = __float_as_uint(vv[0]), u1 = __float_as_uint(vv[1]), u2 = __float_as_uint(vv[2]), u3 = __float_as_uint(vv[3]);
-          my_hits += min(u0, 1u) + min(u1, 1u) + min(u2, 1u) + min(u3, 1u);
-          if (__vimax3_u32(__vimax3_u32(u0, u1, u2), u3, 0u) >= s_lo_bits) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              if (vv[j] > 0.0f && vv[j] >= s_lo) {
-                const uint32_t pos = atomicAdd(ncand, 1u);
-                if (pos < QU_CANDS) cands[pos] = make_uint2(ws + 4 * q + j, __float_as_uint(vv[j]));
-                else union_emit(p.plans, p.thresh, p.cols, split, ws + 4 * q + j, vv[j]);  // buffer full: slow road now
-              }
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_chain(end_stage));
-        my_stage = end_stage + 1;
+        // ---- sweep: count matches (score > 0), test against the threshold, clear ----------------------
         next_base = end_stage + 1;
-        if (*ncand >= QU_CANDS / 2) flush_cands();  // (after the arrival: nobody waits for the global atomics)
-        QU_ACC(ct_sweep, ts0);
+        if (DEFER) { pend = true; p_ws = ws; p_split = split; p_hdr = hdr_f; p_end = end_stage; }
+        else collect_sweep(ws, split, hdr_f, end_stage);
       } else {
         // level-0 digit histogram of the sampled windows: digit = [1 | lin:10] (score_lin)
+        wait_below(end_stage);  // every contribution of the window is in
         const float scale = hdr_f;
         auto lin = [&](float s) -> uint32_t {
           const float x = __fmul_rn(s, scale);
