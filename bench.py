@@ -59,7 +59,7 @@ def ncu_traffic(kernel: str):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qwgpu", choices=["qwgpu", "reference"])
     ap.add_argument("--splits", type=int, default=32, help="splits per GPU")

@@ -4,7 +4,7 @@
 // Replaces tantivy's BufferedUnionScorer + Bm25Weight + TopDocs loop behind `searcher.search`
 // (quickwit-search/src/leaf.rs:637) for the headline query shape.
 //
-// One 512-thread block = 15 consumer warps + 1 producer warp, two blocks per SM. The block owns one
+// One 448-thread block = 13 consumer warps + 1 producer warp, two blocks per SM. The block owns one
 // 16384-doc window of one split at a time (f32 score accumulator of the window in shared memory);
 // windows are handed out dynamically from a global counter.
 //
@@ -36,7 +36,10 @@
 namespace qwk {
 
 #ifndef QU_THREADS
-#define QU_THREADS 512
+/* 13 consumer warps + the producer, two blocks per SM: 72 registers per thread. Measured against 512 threads (64
+ * registers: 232 B of spills and re-materialised shared-window addresses in the block loop): 186.8 vs 196.0 us per launch
+ * (384 threads / 80 registers: 188.4 us). */
+#define QU_THREADS 448
 #endif
 #define QU_NCW (QU_THREADS / 32 - 1)   /* consumer warps; warp QU_NCW is the producer */
 #define QU_NCT (QU_NCW * 32)
@@ -53,7 +56,10 @@ namespace qwk {
 #define QU_MINB 2               /* blocks per SM */
 #endif
 #ifndef QU_DEFER_SWEEP
-#define QU_DEFER_SWEEP 1        /* COLLECT: sweep a finished window after the first decode of the next one */
+/* 1 = COLLECT sweeps a finished window only after the warp's first decode of the next window (overlaps the wait for the
+ * window's last clauses with work). Measured: 369 us against 195 us per launch — the decoded pair has to stay live
+ * across the sweep loop, and under the 64-register cap that spills the inner loop (384 B of spill stores) — so it is off. */
+#define QU_DEFER_SWEEP 0
 #endif
 
 enum { QU_F_FIRST = 1u, QU_F_LAST = 2u, QU_F_END = 4u };
@@ -490,9 +496,9 @@ __global__ void __launch_bounds__(QU_THREADS, QU_MINB) k_union(const UParams p) 
       my_hits = 0;
     };
 
-    // COLLECT: the sweep of a finished window is DEFERRED until this warp has decoded its first pair of blocks of the
-    // next window (decode needs no ordering): the wait for the window's last clauses — a third of the warps hold the
-    // sparse tail while the others idle — overlaps with useful work instead of a parked warp.
+    // QU_DEFER_SWEEP builds: the sweep of a finished window is deferred until this warp has decoded its first pair of
+    // blocks of the next window (decode needs no ordering), so that the wait for the window's last clauses overlaps
+    // with work. Off by default (see the macro).
     constexpr bool DEFER = (MODE == MODE_COLLECT) && (QU_DEFER_SWEEP != 0);
     bool pend = false;
     uint32_t p_ws = 0, p_split = 0, p_end = 0;

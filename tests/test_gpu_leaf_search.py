@@ -167,6 +167,34 @@ def test_concurrent_leaf_searches_match_sequential(gpu_ctx, synth):
             assert got == want
 
 
+def test_more_callers_than_the_admission_gate_admits(gpu_ctx, synth):
+    """40 host threads against the default gate of 16 searches in flight: the surplus callers wait inside the
+    library and every response equals the sequential one."""
+    import threading
+    offsets = [proto.enc_split_offsets(im.split_id, im.num_docs) for im in synth]
+    dm = json.dumps(SYNTH_MAPPING)
+    reqs = [proto.enc_leaf_search_request(search_request(bool_(should=[term("body", f"t{(q + i) % 10}") for i in range(1 + q % 3)]),
+                                                         max_hits=20 + q, sort_fields=[("_score", DESC)]), offsets, dm) for q in range(5)]
+    key = lambda resp: (lambda d: (d["num_hits"], d["partial_hits"]))(proto.dec_leaf_search_response(resp))
+    want = [key(gpu_ctx.leaf_search(r)) for r in reqs]
+    got, errs = [[] for _ in range(40)], []
+
+    def worker(t):
+        try:
+            for k in range(3):
+                q = (t + k) % len(reqs)
+                got[t].append((q, gpu_ctx.leaf_search(reqs[q])))
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(40)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    assert not errs, errs
+    assert all(key(resp) == want[q] for g in got for q, resp in g) and sum(len(g) for g in got) == 120
+
+
 def test_pre_search_pruning_keeps_the_response(gpu_ctx):
     """a16: with the split metadata in the request (time ranges, doc counts) match-all top-K requests demote the
     splits that cannot reach the top to count-only / metadata-count requests (leaf.rs:1141-1242, 525-528).
