@@ -341,6 +341,49 @@ def config4_strong(ctx, imgs, world: int, rank: int, reps: int = 10):
             "api": "qwgpu_leaf_search_allgather (aggregation partials: host-staged NCCL all-gather inside the library)"}
 
 
+def config2_strong(ctx, imgs, world: int, rank: int, reps: int = 20):
+    """The headline query on BASELINE's own index size at N > 1 (strong scaling): the 32-split / 100 M-doc corpus sharded
+    over the N GPUs (32 / N splits per rank), BM25 10-term OR, top-1000. One qwgpu_leaf_search_allgather per query on
+    every rank (device merge + NCCL all-gather of the per-rank top-K records + device merge of the gathered lists);
+    timed end to end with host bytes in / out, barrier on both sides, max over ranks. The merged response of every rank
+    is checked against the host road (per-rank response -> partial -> torch all-gather -> qwgpu_merge_partials)."""
+    import torch
+    import torch.distributed as dist
+    from quickwit_b200 import proto, service
+    per = max(1, len(imgs) // world)
+    mine = imgs[:per]
+    sreq = proto.enc_search_request(json.dumps({"type": "bool", "should": [{"type": "term", "field": "body", "value": f"t{i}"} for i in range(10)]}),
+                                    max_hits=K, sort_fields=[("_score", 1)])
+    lreq = proto.enc_leaf_search_request(sreq, [proto.enc_split_offsets(im.split_id, im.num_docs) for im in mine], json.dumps(SYNTH_MAPPING))
+    got = proto.dec_leaf_search_response(ctx.leaf_search_allgather(lreq))
+    nb = service.partial_size(sreq)
+    pbuf = torch.zeros(nb, dtype=torch.uint8).pin_memory()
+    service.response_to_partial(sreq, ctx.leaf_search(lreq), pbuf.data_ptr(), nb)
+    gd = torch.zeros(world * nb, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(gd, pbuf.cuda())
+    gh = gd.cpu()
+    want = proto.dec_leaf_search_response(service.merge_partials(sreq, world, gh.data_ptr(), nb))
+    assert got["num_hits"] == want["num_hits"] and got["partial_hits"] == want["partial_hits"], "cross-rank top-K differs from the host merge"
+    from quickwit_b200 import plan as P
+    postings = sum(im.doc_freq(P.term(im, "body", f"t{i}").term_ord) for im in mine for i in range(10))
+    for _ in range(3):
+        ctx.leaf_search_allgather(lreq)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.leaf_search_allgather(lreq)
+    torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item()) / reps
+    c = torch.tensor([postings], dtype=torch.int64, device="cuda")
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    total = int(c.item())
+    return {"workload": "c2_bm25_or10_top1000, corpus sharded over the ranks (strong scaling)", "docs": world * sum(im.num_docs for im in mine),
+            "splits_per_rank": per, "ms_per_query": 1e3 * wall, "postings_per_s": total / wall, "postings_per_query": total,
+            "api": "qwgpu_leaf_search_allgather (device merge + ncclAllGather of the top-K records + device merge)"}
+
+
 def config5_mixed(ctx, imgs, peak, world: int, concurrency: int = 64, queries_per_thread: int = 6, announce: bool = False):
     """BASELINE config 5's shape on one GPU's share of the index: a mixed term / phrase / bool / range / aggregation
     query set issued from `concurrency` host threads against the rank's resident splits through qwgpu_leaf_search
@@ -662,11 +705,16 @@ def main():
     n_main = a.steps * Q_SETS
     postings_rank0 = postings
     c4_strong = None
+    c2_strong = None
     if world > 1 and device_exchange and not a.no_configs and a.splits % world == 0:
         try:
             c4_strong = config4_strong(ctx, imgs, world, rank)
         except AssertionError as e:  # (the same data on every rank: a mismatch shows on all of them)
             c4_strong = {"error": str(e)}
+        try:
+            c2_strong = config2_strong(ctx, imgs, world, rank)
+        except AssertionError as e:
+            c2_strong = {"error": str(e)}
     # BASELINE config 5's shape (mixed query set, concurrency 64) on every rank's share of the index; the job-level
     # figures are the slowest rank's
     c5 = None
@@ -736,6 +784,8 @@ def main():
         out["configs"] = other_configs(ctx, imgs, peak)
     if c4_strong:
         out["config4_strong"] = c4_strong
+    if c2_strong:
+        out["config2_strong"] = c2_strong
     if c5:
         out["config5_mixed"] = c5
     if not a.no_cpu_baseline and world == 1:

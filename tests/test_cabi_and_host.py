@@ -339,3 +339,23 @@ def test_split_bundle_footer():
     bad[-4:] = struct.pack("<I", len(split) + 5)                 # hotcache longer than the file
     with pytest.raises(ffi.QwGpuError):
         service.parse_split_footer(bytes(bad[footer_start:]), len(split))
+
+
+def test_synthetic_positions_field_is_deterministic_and_consistent():
+    """qwgpu_synth_split with msg_vocab > 0 (the positions field behind BASELINE config 5's phrase queries): same
+    spec => same bytes; without it the image is the plain corpus; a phrase can only match
+    documents that hold all of its words."""
+    from quickwit_b200 import plan as P
+    from oracle import oracle as O
+    a = S.synth_split(30_000, 3, [0.2, 0.05], split_id="m", msg_vocab=32)
+    b = S.synth_split(30_000, 3, [0.2, 0.05], split_id="m", msg_vocab=32)
+    plain = S.synth_split(30_000, 3, [0.2, 0.05], split_id="m")
+    assert a.array.tobytes() == b.array.tobytes() and plain.nbytes < a.nbytes
+    by_doc = [(ffi.SORT_DOCID, ffi.ORDER_DESC, ffi.ABSENT)]
+    n = lambda root, img=a: O.split_search(img, P.make_plan(root, 0, by_doc)).num_hits
+    assert 0 < n(P.phrase(a, "msg", ["w3", "w3"])) < n(P.term(a, "msg", "w3"))   # the word twice in a row: a subset
+    both = n(P.bool_([P.term(a, "msg", "w1", occur=ffi.OCCUR_MUST), P.term(a, "msg", "w2", occur=ffi.OCCUR_MUST)]))
+    ph12, ph21 = n(P.phrase(a, "msg", ["w1", "w2"])), n(P.phrase(a, "msg", ["w2", "w1"]))
+    assert 0 < ph12 <= both and 0 < ph21 <= both
+    # the body terms are untouched by the extra field
+    assert n(P.term(a, "body", "t0")) == n(P.term(plain, "body", "t0"), plain)
