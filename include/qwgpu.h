@@ -142,8 +142,10 @@ int qwgpu_build_leaf_response(const uint8_t* img, uint64_t img_len, const char* 
 /* Pre-search pruning, host only: what qwgpu_leaf_search does to the request of every
  * split before it searches — CanSplitDoBetter::{from_request, optimize_split_order, optimize}
  * (quickwit-search/src/leaf.rs:1072-1242), disable_search_request_hits (leaf.rs:1438-1443) and
- * is_metadata_count_request_with_ast (root.rs:665-686; leaf.rs:525-528 answers such a split from num_docs).
- * `json_out` (qwgpu_buf_free) = [{"split_id", "max_hits", "hits_disabled", "metadata_count"}, ...] in the
+ * is_metadata_count_request_with_ast (root.rs:665-686; leaf.rs:525-528 answers such a split from num_docs) and
+ * simplify_search_request (leaf.rs:1399-1433: under CountHits::Underestimate a split that has neither hits nor an
+ * aggregation left to compute is not searched at all — "skipped").
+ * `json_out` (qwgpu_buf_free) = [{"split_id", "max_hits", "hits_disabled", "metadata_count", "skipped"}, ...] in the
  * reference's processing order, one entry per split of the request. */
 int qwgpu_optimize_leaf_request(const uint8_t* leaf_search_request_pb, size_t req_len, uint8_t** json_out, size_t* json_len);
 

@@ -251,6 +251,7 @@ struct SplitRequest {
   size_t input_pos;         // position of the split in the LeafRequestRef
   bool hits_disabled;       // demoted to a count-only request
   bool metadata_count;      // answered from num_docs
+  bool skipped;             // simplify_search_request returned None: nothing to compute, the split is not searched
 };
 // the splits of one LeafRequestRef in the reference's processing order, with the per-split request rewrite
 static std::vector<SplitRequest> optimize_split_requests(const pb::SearchRequest& r, const Json& ast, const std::string& timestamp_field,
@@ -264,7 +265,7 @@ static std::vector<SplitRequest> optimize_split_requests(const pb::SearchRequest
   else if (f.kind == SplitFilter::SplitTimestampHigher) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ts_end(a) > ts_end(b); });
   else if (f.kind == SplitFilter::SplitTimestampLower) std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ts_start(a) < ts_start(b); });
   std::vector<SplitRequest> out;
-  for (size_t i : order) out.push_back({i, false, false});
+  for (size_t i : order) out.push_back({i, false, false, false});
   if (is_simple_all_query(r, ast)) {
     const uint64_t wanted = r.start_offset + r.max_hits;
     // splits guaranteed to deliver enough docs: the first prefix whose doc counts reach `wanted`
@@ -290,7 +291,10 @@ static std::vector<SplitRequest> optimize_split_requests(const pb::SearchRequest
   for (SplitRequest& q : out) {
     pb::SearchRequest rr = r;  // (only the fields the test reads)
     if (q.hits_disabled) disable_search_request_hits(rr);
-    q.metadata_count = is_metadata_count_request(rr, ast);
+    // simplify_search_request (leaf.rs:1399-1433): no hits wanted (any more), no aggregation, and the caller accepts an
+    // underestimate of the hit count (CountHits::Underestimate = 1) => the split is pruned before warmup
+    q.skipped = rr.max_hits == 0 && !rr.aggregation_request && r.count_hits == 1;
+    q.metadata_count = !q.skipped && is_metadata_count_request(rr, ast);
   }
   return out;
 }
@@ -320,6 +324,7 @@ static void run_leaf_raw(Engine& eng, const pb::LeafSearchRequest& lr, LeafRun& 
     for (size_t si = 0; si < ref.split_offsets.size(); si++) {
       const pb::SplitIdAndFooterOffsets& so = ref.split_offsets[si];
       const SplitRequest& q = *by_pos[si];
+      if (q.skipped && !comm && !no_prune) continue;  // (PrunedBeforeWarmup: contributes nothing, not even to the split counters)
       SplitJob j;
       j.meta = so;
       if (q.metadata_count && !comm && !no_prune) {
@@ -658,7 +663,7 @@ int qwgpu_leaf_search(qwgpu_ctx* ctx, const uint8_t* req, size_t req_len, uint8_
 }
 
 // Host only: the per-split request rewrite of a LeafSearchRequest as JSON, in the reference's processing order:
-// [{"split_id", "max_hits", "hits_disabled", "metadata_count"} ...] per LeafRequestRef (concatenated).
+// [{"split_id", "max_hits", "hits_disabled", "metadata_count", "skipped"} ...] per LeafRequestRef (concatenated).
 int qwgpu_optimize_leaf_request(const uint8_t* req, size_t req_len, uint8_t** out, size_t* out_len) {
   QW_API_BEGIN
   if (!req || !out || !out_len) qw::fail(QWGPU_EINVALID_ARG, "null argument");
@@ -673,7 +678,8 @@ int qwgpu_optimize_leaf_request(const uint8_t* req, size_t req_len, uint8_t** ou
       std::string id;
       for (char c : ref.split_offsets[q.input_pos].split_id) { if (c == '"' || c == '\\') id += '\\'; id += c; }
       js += "{\"split_id\":\"" + id + "\",\"max_hits\":" + std::to_string(q.hits_disabled ? 0 : lr.search_request.max_hits) +
-            ",\"hits_disabled\":" + (q.hits_disabled ? "true" : "false") + ",\"metadata_count\":" + (q.metadata_count ? "true" : "false") + "}";
+            ",\"hits_disabled\":" + (q.hits_disabled ? "true" : "false") + ",\"metadata_count\":" + (q.metadata_count ? "true" : "false") +
+            ",\"skipped\":" + (q.skipped ? "true" : "false") + "}";
     }
   }
   js += "]";

@@ -254,6 +254,24 @@ def test_can_split_do_better_static_pruning():
     assert not any(r["metadata_count"] for r in _optimized(term("body", "x"), splits, max_hits=0))
 
 
+def test_underestimate_count_skips_splits_with_nothing_left_to_compute():
+    """simplify_search_request (leaf.rs:1399-1433): under CountHits::Underestimate a split whose hits were disabled (or
+    never wanted) and that has no aggregation to feed is pruned before warmup; CountAll keeps it as a count request."""
+    UNDER = 1
+    splits = [("a", 2, None, None), ("b", 5, None, None), ("c", 1, None, None), ("0", 9, None, None)]
+    row = lambda r: (r["split_id"], r["hits_disabled"], r["metadata_count"], r["skipped"])
+    got = _optimized(MATCH_ALL, splits, max_hits=2, start_offset=1, count_hits=UNDER)
+    assert [row(r) for r in got] == [("c", False, False, False), ("b", False, False, False), ("a", True, False, True), ("0", True, False, True)]
+    got = _optimized(MATCH_ALL, splits, max_hits=2, start_offset=1)   # CountAll: counted from the metadata instead
+    assert [row(r) for r in got] == [("c", False, False, False), ("b", False, False, False), ("a", True, True, False), ("0", True, True, False)]
+    # an aggregation keeps every split; a term query is never demoted, so nothing is skipped while hits are wanted
+    assert not any(r["skipped"] for r in _optimized(MATCH_ALL, splits, max_hits=2, count_hits=UNDER, aggs={"c": {"terms": {"field": "n"}}}))
+    assert not any(r["skipped"] for r in _optimized(term("body", "x"), splits, max_hits=2, count_hits=UNDER))
+    # a pure count request under Underestimate computes nothing at all (the reference returns Some only for CountAll)
+    assert all(r["skipped"] for r in _optimized(term("body", "x"), splits, max_hits=0, count_hits=UNDER))
+    assert not any(r["skipped"] for r in _optimized(term("body", "x"), splits, max_hits=0))
+
+
 def test_partial_exchange_carries_failed_splits_and_rejects_corrupt_partials():
     """The fixed-size per-rank partial: hits, aggregation bytes, failed_splits entries and resource
     statistics survive response -> partial -> merge; sizes claimed inside a gathered partial are checked."""
