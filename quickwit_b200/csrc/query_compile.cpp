@@ -279,7 +279,60 @@ static const char* col_type_name(uint32_t t) {
 struct Ctx {
   const ImageView& img;
   const DocMapperInfo& dm;
+  bool scoring = false;             // the request ranks by _score
+  mutable int unscored_depth = 0;   // > 0 while building a must_not / filter subtree (its scores are never read)
 };
+
+// Constant-score set queries (TermSetQuery, wildcard -> AutomatonWeight): tantivy gives every matching document the
+// score 1.0 (ConstScorer over a bitset). The plan has no constant-score node, so these compile to an unscored filter —
+// exact for every sort except BM25 ranking with the node in a scoring position, which is refused instead of ranked
+// differently.
+static void refuse_const_score_under_ranking(const Ctx& cx, const char* what) {
+  if (cx.scoring && cx.unscored_depth == 0)
+    fail(QWGPU_EUNSUPPORTED, "`%s` in a scoring clause of a query ranked by _score is not implemented on the GPU path (constant score 1.0)", what);
+}
+
+// ---- wildcard queries (quickwit-query/src/query_ast/wildcard_query.rs) ------------------------------------------
+struct GlobPart { int kind; std::string text; };  // 0 = text, 1 = `*`, 2 = `?`
+// parse_wildcard_query (wildcard_query.rs:43-72): `*`, `?`, backslash escapes the next character
+static std::vector<GlobPart> parse_wildcard(const std::string& q) {
+  std::vector<GlobPart> out;
+  auto text = [&](const std::string& t) { if (!out.empty() && out.back().kind == 0) out.back().text += t; else out.push_back({0, t}); };
+  size_t i = 0;
+  auto utf8_len = [](unsigned char c) { return c < 0x80 ? 1u : (c >> 5) == 6 ? 2u : (c >> 4) == 14 ? 3u : (c >> 3) == 30 ? 4u : 1u; };
+  while (i < q.size()) {
+    const char c = q[i];
+    if (c == '*') { out.push_back({1, ""}); i++; }
+    else if (c == '?') { out.push_back({2, ""}); i++; }
+    else if (c == '\\') {
+      if (i + 1 >= q.size()) break;  // a trailing escape is dropped
+      const size_t n = std::min<size_t>(utf8_len((unsigned char)q[i + 1]), q.size() - i - 1);
+      text(q.substr(i + 1, n));
+      i += 1 + n;
+    } else { text(std::string(1, c)); i++; }
+  }
+  return out;
+}
+static bool glob_match(const std::vector<GlobPart>& parts, size_t pi, const uint8_t* s, size_t n, size_t si) {
+  auto cp_len = [&](size_t at) { const unsigned char c = s[at]; size_t l = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1; return std::min(l, n - at); };
+  for (; pi < parts.size(); pi++) {
+    const GlobPart& p = parts[pi];
+    if (p.kind == 0) {
+      if (n - si < p.text.size() || memcmp(s + si, p.text.data(), p.text.size()) != 0) return false;
+      si += p.text.size();
+    } else if (p.kind == 2) {
+      if (si >= n) return false;
+      si += cp_len(si);
+    } else {
+      // `.*`: every suffix that starts on a code point boundary
+      for (size_t k = si;; k += cp_len(k)) {
+        if (glob_match(parts, pi + 1, s, n, k)) return true;
+        if (k >= n) return false;
+      }
+    }
+  }
+  return si == n;
+}
 
 static TQ term_leaf(const Ctx& cx, uint32_t field, const std::string& token) {
   TQ t;
@@ -419,9 +472,11 @@ static TQ build(const Ctx& cx, const Json& q, int depth) {
     TQ b;
     b.kind = TQ::Bool;
     b.must = build_list(cx, q.get("must"), depth);
-    b.must_not = build_list(cx, q.get("must_not"), depth);
     b.should = build_list(cx, q.get("should"), depth);
+    cx.unscored_depth++;
+    b.must_not = build_list(cx, q.get("must_not"), depth);
     b.filter = build_list(cx, q.get("filter"), depth);
+    cx.unscored_depth--;
     if (const Json* m = q.get("minimum_should_match")) if (m->is_num()) { b.has_msm = true; b.msm = (size_t)m->as_f64(); }
     return b;
   }
@@ -454,7 +509,47 @@ static TQ build(const Ctx& cx, const Json& q, int depth) {
     t.column = (uint32_t)c;
     return t;
   }
+  if (type == "wildcard") {
+    const std::string field = q.str_or("field", ""), value = q.str_or("value", "");
+    const bool lenient = q.bool_or("lenient", false), ci = q.bool_or("case_insensitive", false);
+    const int f = cx.img.find_field(field);
+    if (f < 0) {
+      if (cx.img.find_column(field) >= 0 && cx.img.columns[cx.img.find_column(field)].type != QW_COL_STR)
+        fail(QWGPU_EINVALID_QUERY, "invalid query: trying to run a Wildcard query on a non-text field");
+      bool known = false;
+      for (auto& fd : cx.dm.fields) if (fd.name == field) { known = true; if (fd.type != "text" && fd.type != "json") fail(QWGPU_EINVALID_QUERY, "invalid query: trying to run a Wildcard query on a non-text field"); }
+      if (lenient || known) return tq_none();  // (declared in the doc mapping but without a single term in this split)
+      fail(QWGPU_EINVALID_QUERY, "invalid query: field does not exist: `%s`", field.c_str());
+    }
+    refuse_const_score_under_ranking(cx, "wildcard");
+    // sub_query_parts_to_regex: text parts go through the field tokenizer's NORMALIZER (raw: unchanged; default:
+    // lower-cased), `*` = `.*`, `?` = `.`; case_insensitive = the regex flag (?i) (ASCII folding here)
+    std::vector<GlobPart> parts = parse_wildcard(value);
+    const bool lower = cx.img.fields[f].tokenizer != QW_TOK_RAW;
+    auto fold = [](std::string& t) { for (char& c : t) if ((unsigned char)c < 0x80) c = (char)tolower((unsigned char)c); };
+    for (GlobPart& p : parts) if (p.kind == 0 && (lower || ci)) fold(p.text);
+    TQ b;
+    b.kind = TQ::Bool;
+    const QwImgField& F = cx.img.fields[f];
+    std::string folded;
+    for (uint32_t t = F.first_term; t < F.first_term + F.num_terms; t++) {
+      const QwImgTerm& T = cx.img.terms[t];
+      const uint8_t* bytes = cx.img.term_bytes + T.bytes_off;
+      if (ci) { folded.assign((const char*)bytes, T.bytes_len); fold(folded); bytes = (const uint8_t*)folded.data(); }
+      if (!glob_match(parts, 0, bytes, T.bytes_len, 0)) continue;
+      TQ leaf;
+      leaf.kind = TQ::Term;
+      leaf.term_ord = t;
+      b.should.push_back(std::move(leaf));
+    }
+    if (b.should.empty()) return tq_none();
+    TQ outer;  // constant-score membership test, like term_set below
+    outer.kind = TQ::Bool;
+    outer.filter.push_back(std::move(b));
+    return outer;
+  }
   if (type == "term_set") {
+    refuse_const_score_under_ranking(cx, "term_set");
     TQ b;
     b.kind = TQ::Bool;
     if (const Json* tpf = q.get("terms_per_field"))
@@ -482,7 +577,7 @@ static TQ build(const Ctx& cx, const Json& q, int depth) {
   }
   if (type == "user_input")
     fail(QWGPU_EINVALID_QUERY, "invalid query: user_input queries must be parsed by the root before reaching a leaf");
-  if (type == "wildcard" || type == "regex" || type == "phrase_prefix")
+  if (type == "regex" || type == "phrase_prefix")
     fail(QWGPU_EUNSUPPORTED, "`%s` queries are not implemented on the GPU path yet", type.c_str());
   fail(QWGPU_EINVALID_QUERY, "invalid query: unknown query type `%s`", type.c_str());
 }
@@ -636,6 +731,7 @@ CompiledPlan compile_plan(const ImageView& img, const std::string& split_id, con
   // rewrite_request (leaf.rs:712-729)
   if (req.max_hits == 0 && req.start_offset == 0) req.sort_fields.clear();
   Ctx cx{img, dm};
+  for (const pb::SortField& sf : req.sort_fields) if (sf.field_name == "_score") cx.scoring = true;
   Json local_ast;
   if (!parsed_ast) { local_ast = parse_json(req.query_ast, QWGPU_EINVALID_QUERY); parsed_ast = &local_ast; }
   TQ root = build(cx, *parsed_ast, 0);

@@ -395,3 +395,71 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["steps"] == 2 and d["config"]["workload"] == "c2_bm25_or10_top1000"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "postings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_wildcard_queries_expand_over_the_split_dictionary():
+    """WildcardQuery (quickwit-query/src/query_ast/wildcard_query.rs): `*` / `?` / backslash escapes, text parts through the
+    field tokenizer's normalizer (default: lower-cased, raw: unchanged), case_insensitive, lenient; matching documents
+    compared with a brute force over the documents' tokens. Constant-score semantics: refused under BM25 ranking in a
+    scoring position (like term_set), fine as a filter or under any other sort."""
+    mapping = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
+                                  {"name": "tag", "type": "text", "tokenizer": "raw"}, {"name": "n", "type": "u64", "fast": True}]}
+    words = ["alpha", "alpine", "beta", "betamax", "gamma", "Alphabet", "al", "élan", "a*b", "delta"]
+    tags = ["Prod-EU", "prod-us", "Dev", "staging?"]
+    docs = [{"body": f"{words[i % 10]} {words[(i * 3) % 10]} filler", "tag": tags[i % 4], "n": i} for i in range(200)]
+    img = S.build_split(docs, mapping, "wc-0")
+    dm = json.dumps(mapping)
+
+    def run(ast, **kw):
+        return O.split_search(img, service.compile_plan(img, search_request(ast, **kw), dm))
+
+    def to_regex(pat):  # the reference's translation: text escaped, `*` -> `.*`, `?` -> `.`
+        out, i = "", 0
+        while i < len(pat):
+            c = pat[i]
+            if c == "*":
+                out += ".*"
+            elif c == "?":
+                out += "."
+            elif c == "\\":
+                if i + 1 >= len(pat):
+                    break
+                out += re.escape(pat[i + 1]); i += 1
+            else:
+                out += re.escape(c)
+            i += 1
+        return out
+
+    def brute(field, pat, ci=False):
+        if field == "body":
+            rx = re.compile(to_regex(pat.lower() if not ci else pat.lower()), re.S)
+            toks = lambda d: [t.lower() for t in re.findall(r"[^\W_]+", d["body"], re.U)]
+        else:
+            rx = re.compile(to_regex(pat), re.S | (re.I if ci else 0))
+            toks = lambda d: [d["tag"]]
+        return sorted((i for i, d in enumerate(docs) if any(rx.fullmatch(t) for t in toks(d))), reverse=True)
+
+    wc = lambda field, value, **kw: {"type": "wildcard", "field": field, "value": value, **kw}
+    for field, pat, ci in [("body", "al*", False), ("body", "AL*", False), ("body", "?eta", False), ("body", "*ma*", False), ("body", "a\\*b", False),
+                           ("body", "é?an", False), ("body", "*", False), ("body", "zz*", False), ("tag", "prod*", False), ("tag", "Prod*", False),
+                           ("tag", "prod*", True), ("tag", "staging\\?", False), ("tag", "stag*\\", False), ("tag", "???", False)]:
+        r = run(wc(field, pat, case_insensitive=ci), max_hits=200)
+        want = brute(field, pat, ci)
+        assert r.num_hits == len(want) and [h[0] for h in r.hits] == want, (field, pat, ci, r.num_hits, len(want))
+    assert run(wc("body", "al*"), max_hits=0).num_hits == 120
+    # scoring: refused in a scoring position under BM25 ranking, accepted as a filter
+    with pytest.raises(ffi.QwGpuError) as ei:
+        run(wc("body", "al*"), max_hits=5, sort_fields=[("_score", DESC)])
+    assert ei.value.code == ffi.EUNSUPPORTED
+    with pytest.raises(ffi.QwGpuError):
+        run({"type": "term_set", "terms_per_field": {"body": ["alpha", "beta"]}}, max_hits=5, sort_fields=[("_score", DESC)])
+    flt = run(bool_(must=[term("body", "filler")], filter=[wc("body", "al*")]), max_hits=5, sort_fields=[("_score", DESC)])
+    assert flt.num_hits == 120
+    assert run({"type": "term_set", "terms_per_field": {"body": ["alpha", "beta"]}}, max_hits=0).num_hits == len(brute("body", "alpha", False) + [i for i in brute("body", "beta", False) if i not in brute("body", "alpha", False)])
+    # errors and leniency
+    with pytest.raises(ffi.QwGpuError) as ei:
+        run(wc("n", "1*"), max_hits=0)
+    assert ei.value.code == ffi.EINVALID_QUERY and "non-text" in ei.value.msg
+    with pytest.raises(ffi.QwGpuError):
+        run(wc("nope", "x*"), max_hits=0)
+    assert run(wc("nope", "x*", lenient=True), max_hits=0).num_hits == 0
