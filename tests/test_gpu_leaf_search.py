@@ -8,6 +8,7 @@ import pytest
 
 from quickwit_b200 import ffi, proto, service, splitgen as S
 from quickwit_b200.proto import ASC, DESC
+from oracle import oracle as O
 from pipeline import MATCH_ALL, bool_, cpu_root_search, cpu_split_response, full_text, leafify, search_request, term
 from test_oracle_goldens import (AGG_MAPPING, AGG_SPLIT1, AGG_SPLIT2, BM25_DOCS, BM25_MAPPING, SORT_DATA, SORT_MAPPING,
                                  _expected_order)
@@ -222,6 +223,18 @@ def test_pre_search_pruning_keeps_the_response(gpu_ctx):
         assert n_meta >= 1, (kw, plan)
         on_device = leaf["resource_stats"]["localexec_num_splits"] if leaf["resource_stats"] else 0
         assert on_device == 5 - n_meta, (kw, plan)
+    # CountHits::Underestimate (= 1): the demoted splits are not searched at all (simplify_search_request returns None,
+    # leaf.rs:1399-1433): same hits, a smaller count, fewer splits attempted
+    kw = dict(max_hits=5, sort_fields=[("ts", DESC)])
+    lreq = proto.enc_leaf_search_request(search_request(MATCH_ALL, count_hits=1, **kw), offsets, json.dumps(mapping))
+    plan = service.optimize_leaf_request(lreq)
+    leaf_bytes = gpu_ctx.leaf_search(lreq)
+    leaf = proto.dec_leaf_search_response(leaf_bytes)
+    got = proto.dec_leaf_search_response(service.merge_leaf_responses(search_request(MATCH_ALL, count_hits=1, **kw), [leaf_bytes]))
+    n_skip = sum(r["skipped"] for r in plan)
+    assert n_skip >= 1 and not any(r["metadata_count"] for r in plan)
+    assert got["partial_hits"] == cpu_root_search(imgs, MATCH_ALL, mapping, **kw)["partial_hits"]
+    assert leaf["num_hits"] == 40 * (5 - n_skip) and leaf["num_attempted_splits"] == 5 - n_skip and not leaf["failed_splits"]
     # a non-resident split that only has to be counted is answered from its metadata
     offs = offsets + [proto.enc_split_offsets("prune-ghost", 123, t0 - 500, t0 - 400)]
     lreq = proto.enc_leaf_search_request(search_request(MATCH_ALL, max_hits=5, sort_fields=[("ts", DESC)]), offs, json.dumps(mapping))
@@ -260,3 +273,30 @@ def test_residency_budget_lru_and_background_upload():
     assert info["resident_bytes"] <= info["budget_bytes"] and info["num_splits"] == 3 and info["evictions"] == 3
     with pytest.raises(ffi.QwGpuError):
         ctx.set_residency_budget(one // 2) or ctx.register_split(imgs[0])   # a split larger than the whole budget
+
+
+def test_wildcard_queries_on_the_device(gpu_ctx):
+    """Wildcard queries compile (on the host) into a filter over the union of the matching dictionary terms: the device
+    result must equal the oracle's for the same plan, through seam C and through qwgpu_leaf_search."""
+    mapping = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True},
+                                  {"name": "tag", "type": "text", "tokenizer": "raw"}, {"name": "n", "type": "u64", "fast": True}]}
+    words = ["alpha", "alpine", "beta", "betamax", "gamma", "Alphabet", "al", "delta", "epsilon", "zeta"]
+    docs = [{"body": f"{words[i % 10]} {words[(i * 7) % 10]} filler", "tag": ["Prod-EU", "prod-us", "Dev", "staging"][i % 4], "n": i} for i in range(3000)]
+    img = S.build_split(docs, mapping, "wc-gpu-0")
+    gpu_ctx.register_split(img)
+    try:
+        dm = json.dumps(mapping)
+        wc = lambda field, value, **kw: {"type": "wildcard", "field": field, "value": value, **kw}
+        for ast, kw in [(wc("body", "al*"), dict(max_hits=50)), (wc("body", "*eta*"), dict(max_hits=20, sort_fields=[("n", ASC)])),
+                        (wc("tag", "prod*", case_insensitive=True), dict(max_hits=0)),
+                        (bool_(must=[term("body", "filler")], filter=[wc("body", "?eta")]), dict(max_hits=30, sort_fields=[("_score", DESC)]))]:
+            sreq = search_request(ast, **kw)
+            plan = service.compile_plan(img, sreq, dm)
+            got = gpu_ctx.split_search([img.split_id], [plan])[0]
+            want = O.split_search(img, plan)
+            assert got.num_hits == want.num_hits > 0 and [h[:4] for h in got.hits] == [h[:4] for h in want.hits], ast
+            lreq = proto.enc_leaf_search_request(sreq, [proto.enc_split_offsets(img.split_id, img.num_docs)], dm)
+            leaf = proto.dec_leaf_search_response(gpu_ctx.leaf_search(lreq))
+            assert leaf["num_hits"] == want.num_hits and not leaf["failed_splits"]
+    finally:
+        gpu_ctx.unregister_split(img.split_id)
