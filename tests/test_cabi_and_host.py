@@ -456,6 +456,16 @@ def test_wildcard_queries_expand_over_the_split_dictionary():
     flt = run(bool_(must=[term("body", "filler")], filter=[wc("body", "al*")]), max_hits=5, sort_fields=[("_score", DESC)])
     assert flt.num_hits == 120
     assert run({"type": "term_set", "terms_per_field": {"body": ["alpha", "beta"]}}, max_hits=0).num_hits == len(brute("body", "alpha", False) + [i for i in brute("body", "beta", False) if i not in brute("body", "alpha", False)])
+    # the reference's own translation vectors (wildcard_query.rs:224-302: "MyString Wh1ch?a.nOrMal Tokenizer would*cut" ->
+    # `MyString Wh1ch.a\.nOrMal Tokenizer would.*cut` on a raw field, everything escaped when `?` / `*` are escaped),
+    # checked as behaviour on raw terms: `.` stays a literal, `?` is one character, `*` any run
+    vec_docs = [{"tag": t, "body": "x", "n": i} for i, t in enumerate([
+        "MyString Wh1chXa.nOrMal Tokenizer wouldZZcut", "MyString Wh1ch?a.nOrMal Tokenizer would*cut",
+        "MyString Wh1chXaXnOrMal Tokenizer wouldcut", "mystring wh1chxa.normal tokenizer wouldcut", "MyString Wh1cha.nOrMal Tokenizer wouldcut"])]
+    vimg = S.build_split(vec_docs, mapping, "wc-vec")
+    vrun = lambda value: sorted(h[0] for h in O.split_search(vimg, service.compile_plan(vimg, search_request(wc("tag", value), max_hits=10), dm)).hits)
+    assert vrun("MyString Wh1ch?a.nOrMal Tokenizer would*cut") == [0, 1]
+    assert vrun("MyString Wh1ch\\?a.nOrMal Tokenizer would\\*cut") == [1]
     # errors and leniency
     with pytest.raises(ffi.QwGpuError) as ei:
         run(wc("n", "1*"), max_hits=0)
