@@ -473,3 +473,58 @@ def test_wildcard_queries_expand_over_the_split_dictionary():
     with pytest.raises(ffi.QwGpuError):
         run(wc("nope", "x*"), max_hits=0)
     assert run(wc("nope", "x*", lenient=True), max_hits=0).num_hits == 0
+
+
+def test_merge_leaf_responses_against_an_independent_restatement_of_the_order():
+    """Root / leaf merge at scale (collector.rs:914-992, 1120-1153; SortOrder::compare_opt, quickwit-proto/src/lib.rs:122-140):
+    random per-leaf hit lists with ties, None sort values, one or two sort keys and both directions — qwgpu_merge_leaf_responses
+    against a Python restatement written from the reference's comparator, not from the product's code."""
+    import functools
+    import random
+    rng = random.Random(7)
+
+    def cmp_opt(a, b, order):  # greater = better; Some beats None in both directions
+        if a is None or b is None:
+            return (a is not None) - (b is not None)
+        return ((a > b) - (a < b)) * (1 if order == DESC else -1)
+
+    def better(x, y, o1, o2):
+        c = cmp_opt(x.get("sort_value", (None, None))[1] if x.get("sort_value") else None,
+                    y.get("sort_value", (None, None))[1] if y.get("sort_value") else None, o1)
+        if c == 0:
+            c = cmp_opt(x.get("sort_value2", (None, None))[1] if x.get("sort_value2") else None,
+                        y.get("sort_value2", (None, None))[1] if y.get("sort_value2") else None, o2)
+        if c == 0:
+            ax, ay = (x["split_id"], x["segment_ord"], x["doc_id"]), (y["split_id"], y["segment_ord"], y["doc_id"])
+            c = ((ax > ay) - (ax < ay)) * (1 if o1 == DESC else -1)
+        return c
+
+    for trial in range(60):
+        o1, o2 = rng.choice([ASC, DESC]), rng.choice([ASC, DESC])
+        two = rng.random() < 0.5
+        k = rng.choice([1, 3, 10, 40])
+        leaves, everything, total = [], [], 0
+        for leaf in range(rng.randint(1, 6)):
+            hits = []
+            for _ in range(rng.randint(0, 25)):
+                h = {"split_id": f"split-{rng.randint(0, 3)}", "segment_ord": 0, "doc_id": rng.randint(0, 12)}
+                v1 = None if rng.random() < 0.15 else rng.randint(-3, 3)
+                h["sort_value"] = None if v1 is None else ("i64", v1)
+                if two:
+                    v2 = None if rng.random() < 0.2 else rng.randint(0, 2)
+                    h["sort_value2"] = None if v2 is None else ("i64", v2)
+                hits.append(h)
+            # a leaf never reports the same document twice, and reports its hits best first
+            uniq = {(h["split_id"], h["doc_id"]): h for h in hits}
+            hits = sorted(uniq.values(), key=functools.cmp_to_key(lambda a, b: -better(a, b, o1, o2)))
+            for h in hits:
+                h["split_id"] = f"{h['split_id']}-leaf{leaf}"   # distinct splits per leaf, like a real fan-out
+            nh = len(hits) + rng.randint(0, 50)
+            total += nh
+            leaves.append(proto.enc_leaf_search_response(nh, hits, num_attempted_splits=1, num_successful_splits=1))
+            everything += hits
+        sort_fields = [("a", o1)] + ([("b", o2)] if two else [])
+        got = proto.dec_leaf_search_response(service.merge_leaf_responses(proto.enc_search_request("{}", max_hits=k, sort_fields=sort_fields), leaves))
+        want = sorted(everything, key=functools.cmp_to_key(lambda a, b: -better(a, b, o1, o2)))[:k]
+        norm = lambda h: (h["split_id"], h["doc_id"], h.get("sort_value"), h.get("sort_value2") if two else None)
+        assert got["num_hits"] == total and [norm(h) for h in got["partial_hits"]] == [norm(h) for h in want], (trial, o1, o2, two, k)
