@@ -528,3 +528,64 @@ def test_merge_leaf_responses_against_an_independent_restatement_of_the_order():
         want = sorted(everything, key=functools.cmp_to_key(lambda a, b: -better(a, b, o1, o2)))[:k]
         norm = lambda h: (h["split_id"], h["doc_id"], h.get("sort_value"), h.get("sort_value2") if two else None)
         assert got["num_hits"] == total and [norm(h) for h in got["partial_hits"]] == [norm(h) for h in want], (trial, o1, o2, two, k)
+
+
+def test_query_ast_compiler_against_a_brute_force_over_documents():
+    """QueryAst -> plan (query_compile.cpp: BoolQuery lowering + TantivyBoolQuery::simplify, tantivy_query_ast.rs:166-377;
+    bool_query.rs:20-36: a boolean query is a filtering predicate aligned with Elasticsearch) pinned at scale: random
+    nested bool / term / range / match_all / match_none trees evaluated document by document in Python, against the
+    compiled plan run by the oracle. Doc sets only (no scores)."""
+    import random
+    rng = random.Random(11)
+    vocab = ["red", "green", "blue", "cyan", "pink", "gray"]
+    mapping = {"field_mappings": [{"name": "body", "type": "text"}, {"name": "n", "type": "u64", "fast": True}]}
+    docs = [{"body": " ".join(rng.sample(vocab, rng.randint(1, 4))), "n": rng.randint(0, 9)} for _ in range(300)]
+    img = S.build_split(docs, mapping, "ast-fuzz")
+    dm = json.dumps(mapping)
+
+    def gen(depth):
+        r = rng.random()
+        if depth >= 3 or r < 0.35:
+            r = rng.random()
+            if r < 0.6:
+                return term("body", rng.choice(vocab + ["absent"]))
+            if r < 0.85:
+                lo, hi = sorted((rng.randint(0, 9), rng.randint(0, 9)))
+                return {"type": "range", "field": "n", "lower_bound": {"Included": lo}, "upper_bound": {rng.choice(["Included", "Excluded"]): hi}}
+            return {"type": rng.choice(["match_all", "match_none"])}
+        q = {"type": "bool"}
+        for occur, p in (("must", 0.45), ("should", 0.6), ("must_not", 0.3), ("filter", 0.3)):
+            if rng.random() < p:
+                q[occur] = [gen(depth + 1) for _ in range(rng.randint(1, 3))]
+        if "should" in q and rng.random() < 0.3:
+            q["minimum_should_match"] = rng.randint(1, len(q["should"]))
+        return q
+
+    def matches(q, d):
+        t = q["type"]
+        if t == "match_all":
+            return True
+        if t == "match_none":
+            return False
+        if t == "term":
+            return q["value"] in d["body"].split()
+        if t == "range":
+            (lk, lv), = q["lower_bound"].items()
+            (uk, uv), = q["upper_bound"].items()
+            return (d["n"] >= lv if lk == "Included" else d["n"] > lv) and (d["n"] <= uv if uk == "Included" else d["n"] < uv)
+        must, should, must_not, flt = q.get("must", []), q.get("should", []), q.get("must_not", []), q.get("filter", [])
+        if any(not matches(c, d) for c in must + flt) or any(matches(c, d) for c in must_not):
+            return False
+        n_should = sum(matches(c, d) for c in should)
+        if "minimum_should_match" in q:
+            return n_should >= q["minimum_should_match"]
+        return n_should >= 1 if (should and not must and not flt) else True
+
+    n_nonempty = 0
+    for trial in range(150):
+        ast = gen(0)
+        want = sorted((i for i, d in enumerate(docs) if matches(ast, d)), reverse=True)
+        r = O.split_search(img, service.compile_plan(img, search_request(ast, max_hits=len(docs)), dm))
+        assert r.num_hits == len(want) and [h[0] for h in r.hits] == want, (trial, json.dumps(ast), r.num_hits, len(want))
+        n_nonempty += bool(want) and len(want) < len(docs)
+    assert n_nonempty > 50   # the generator produced discriminating queries, not only all / none
