@@ -589,3 +589,60 @@ def test_query_ast_compiler_against_a_brute_force_over_documents():
         assert r.num_hits == len(want) and [h[0] for h in r.hits] == want, (trial, json.dumps(ast), r.num_hits, len(want))
         n_nonempty += bool(want) and len(want) < len(docs)
     assert n_nonempty > 50   # the generator produced discriminating queries, not only all / none
+
+
+def test_aggregations_end_to_end_against_a_brute_force_over_documents():
+    """Leaf aggregation cells -> intermediate bytes -> merge over splits -> finalize (a12, a13/a14, a15) against results
+    computed straight from the documents: terms (count-desc / key-asc order, nested stats), histogram (gap filling,
+    min_doc_count 0), range buckets, metric aggregations — the Elasticsearch shapes docs/reference/aggregation.md gives
+    (`buckets`, `doc_count`, `sum_other_doc_count`, `doc_count_error_upper_bound`, `key`, `from` / `to`, `value`)."""
+    import random
+    from pipeline import cpu_root_search
+    rng = random.Random(23)
+    mapping = {"field_mappings": [{"name": "body", "type": "text"}, {"name": "n", "type": "u64", "fast": True},
+                                  {"name": "price", "type": "f64", "fast": True}, {"name": "sev", "type": "text", "tokenizer": "raw", "fast": True}]}
+    sevs = ["INFO", "WARN", "ERROR", "DEBUG"]
+    all_docs = [{"body": rng.choice(["red", "blue"]) + " x", "n": rng.randint(0, 12), "price": rng.randint(0, 400) / 4.0,
+                 "sev": rng.choices(sevs, [60, 25, 10, 5])[0]} for _ in range(600)]
+    parts = [all_docs[0:250], all_docs[250:420], all_docs[420:600]]
+    imgs = [S.build_split(p, mapping, f"agg-fuzz-{i}") for i, p in enumerate(parts)]
+    aggs = {
+        "by_n": {"terms": {"field": "n", "size": 50}, "aggs": {"p": {"stats": {"field": "price"}}}},
+        "by_sev": {"terms": {"field": "sev", "size": 10}},
+        "hist": {"histogram": {"field": "price", "interval": 12.5}},
+        "ranges": {"range": {"field": "n", "ranges": [{"to": 3}, {"from": 3, "to": 8}, {"from": 8}]}},
+        "avg_price": {"avg": {"field": "price"}}, "max_n": {"max": {"field": "n"}}, "cnt": {"value_count": {"field": "n"}},
+    }
+    for ast, keep in ((MATCH_ALL, lambda d: True), (term("body", "red"), lambda d: d["body"].startswith("red"))):
+        got = cpu_root_search(imgs, ast, mapping, max_hits=0, aggs=aggs)["aggregations"]
+        docs = [d for d in all_docs if keep(d)]
+        # terms on n with nested stats
+        by = {}
+        for d in docs:
+            by.setdefault(d["n"], []).append(d["price"])
+        want_terms = sorted(by.items(), key=lambda kv: (-len(kv[1]), kv[0]))
+        gb = got["by_n"]["buckets"]
+        assert [(b["key"], b["doc_count"]) for b in gb] == [(k, len(v)) for k, v in want_terms]
+        assert got["by_n"]["sum_other_doc_count"] == 0 and got["by_n"]["doc_count_error_upper_bound"] == 0
+        for b, (k, v) in zip(gb, want_terms):
+            st = b["p"]
+            assert st["count"] == len(v) and st["min"] == min(v) and st["max"] == max(v)
+            assert abs(st["sum"] - sum(v)) < 1e-9 * max(1.0, abs(sum(v))) and abs(st["avg"] - sum(v) / len(v)) < 1e-9 * max(1.0, sum(v) / len(v))
+        # terms on a string fast field
+        cs = {}
+        for d in docs:
+            cs[d["sev"]] = cs.get(d["sev"], 0) + 1
+        assert [(b["key"], b["doc_count"]) for b in got["by_sev"]["buckets"]] == sorted(cs.items(), key=lambda kv: (-kv[1], kv[0]))
+        # histogram: floor(price / interval) * interval, every bucket between the first and the last one present
+        hb = {}
+        for d in docs:
+            k = (d["price"] // 12.5) * 12.5
+            hb[k] = hb.get(k, 0) + 1
+        lo, hi = min(hb), max(hb)
+        want_h = [(lo + 12.5 * i, hb.get(lo + 12.5 * i, 0)) for i in range(int(round((hi - lo) / 12.5)) + 1)]
+        assert [(b["key"], b["doc_count"]) for b in got["hist"]["buckets"]] == want_h
+        # range buckets: [from, to)
+        rb = got["ranges"]["buckets"]
+        assert [b["doc_count"] for b in rb] == [sum(d["n"] < 3 for d in docs), sum(3 <= d["n"] < 8 for d in docs), sum(d["n"] >= 8 for d in docs)]
+        assert abs(got["avg_price"]["value"] - sum(d["price"] for d in docs) / len(docs)) < 1e-9 * 100
+        assert got["max_n"]["value"] == max(d["n"] for d in docs) and got["cnt"]["value"] == len(docs)
