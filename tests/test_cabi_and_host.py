@@ -646,3 +646,55 @@ def test_aggregations_end_to_end_against_a_brute_force_over_documents():
         assert [b["doc_count"] for b in rb] == [sum(d["n"] < 3 for d in docs), sum(3 <= d["n"] < 8 for d in docs), sum(d["n"] >= 8 for d in docs)]
         assert abs(got["avg_price"]["value"] - sum(d["price"] for d in docs) / len(docs)) < 1e-9 * 100
         assert got["max_n"]["value"] == max(d["n"] for d in docs) and got["cnt"]["value"] == len(docs)
+
+
+def test_bm25_scores_against_a_numpy_restatement_at_corpus_scale():
+    """Bm25Weight (tantivy; formula verified against the reference golden in SURVEY.md Appendix B.1) restated in numpy
+    float32 from the document lengths and term frequencies themselves: idf = ln(1 + (N - n + 0.5) / (n + 0.5)),
+    weight = idf * (1 + k1), norm = k1 * (1 - b + b * fieldnorm / avg_fieldnorm) with the fieldnorm QUANTISED through the
+    256-entry id table, score = weight * tf / (tf + norm); a two-term OR adds the contributions in clause order. 4000
+    documents of 1..400 tokens (long documents exercise the quantisation) against the oracle's scores, rel. 1e-6
+    (logf implementations may differ in the last place; everything else is the same IEEE operations)."""
+    import random
+    rng = random.Random(5)
+    vocab = ["red", "green", "blue"]
+    docs = []
+    for _ in range(4000):
+        n_tok = rng.choice([1, 2, 3, 5, 8, 13, 40, 41, 60, 100, 250, 400])
+        toks = [rng.choice(vocab) if rng.random() < 0.3 else "pad" for _ in range(n_tok)]
+        docs.append({"body": " ".join(toks)})
+    mapping = {"field_mappings": [{"name": "body", "type": "text", "record": "freq", "fieldnorms": True}]}
+    img = S.build_split(docs, mapping, "bm25-scale")
+    dm = json.dumps(mapping)
+    L = ffi.img_lib()
+    L.qwgpu_fieldnorm_to_id.restype = C.c_uint8
+    L.qwgpu_fieldnorm_to_id.argtypes = [C.c_uint32]
+    L.qwgpu_id_to_fieldnorm.restype = C.c_uint32
+    L.qwgpu_id_to_fieldnorm.argtypes = [C.c_uint8]
+    f32 = np.float32
+    lens = np.array([len(d["body"].split()) for d in docs], dtype=np.int64)
+    quant = np.array([L.qwgpu_id_to_fieldnorm(L.qwgpu_fieldnorm_to_id(int(x))) for x in lens], dtype=np.float32)
+    avg = f32(lens.sum()) / f32(len(docs))
+    k1, b = f32(1.2), f32(0.75)
+    norm = k1 * (f32(1) - b + b * quant / avg)
+
+    def contributions(word):
+        tf = np.array([d["body"].split().count(word) for d in docs], dtype=np.float32)
+        n = int((tf > 0).sum())
+        idf = np.log(f32(1) + (f32(len(docs) - n) + f32(0.5)) / (f32(n) + f32(0.5)), dtype=np.float32)
+        weight = idf * (f32(1) + k1)
+        with np.errstate(invalid="ignore"):
+            return np.where(tf > 0, weight * (tf / (tf + norm)), f32(0)).astype(np.float32)
+
+    def check(ast, expected):
+        r = O.split_search(img, service.compile_plan(img, search_request(ast, max_hits=len(docs), sort_fields=[("_score", DESC)]), dm))
+        assert r.num_hits == int((expected > 0).sum())
+        got = {h[0]: np.float32(h[4]) for h in r.hits}
+        for doc, s in got.items():
+            assert abs(float(s) - float(expected[doc])) <= 1e-6 * float(expected[doc]), (doc, float(s), float(expected[doc]))
+        # the ranking itself: scores descending, doc id descending among equal scores
+        order = [(float(np.float32(h[4])), h[0]) for h in r.hits]
+        assert order == sorted(order, key=lambda x: (-x[0], -x[1]))
+
+    check(term("body", "red"), contributions("red"))
+    check(bool_(should=[term("body", "red"), term("body", "blue")]), (contributions("red") + contributions("blue")).astype(np.float32))
