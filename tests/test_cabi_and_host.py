@@ -698,3 +698,58 @@ def test_bm25_scores_against_a_numpy_restatement_at_corpus_scale():
 
     check(term("body", "red"), contributions("red"))
     check(bool_(should=[term("body", "red"), term("body", "blue")]), (contributions("red") + contributions("blue")).astype(np.float32))
+
+
+def test_sort_keys_and_search_after_paging_against_a_python_order():
+    """SegmentPartialHitSortingKey (collector.rs:1082-1118: sort value 1, sort value 2 with None last in both
+    directions, then doc id in the direction of the first key) and search_after (top_k_collector.rs:821-873) at a
+    few hundred documents with missing values: the full order paged K at a time through search_after must equal a
+    Python sort of the documents."""
+    import functools
+    import random
+    rng = random.Random(31)
+    mapping = {"field_mappings": [{"name": "body", "type": "text"}, {"name": "a", "type": "u64", "fast": True}, {"name": "b", "type": "i64", "fast": True}]}
+    docs = []
+    for _ in range(400):
+        d = {"body": "x"}
+        if rng.random() < 0.8:
+            d["a"] = rng.randint(0, 6)
+        if rng.random() < 0.7:
+            d["b"] = rng.randint(-3, 3)
+        docs.append(d)
+    img = S.build_split(docs, mapping, "sort-page")
+    dm = json.dumps(mapping)
+
+    def cmp_opt(x, y, order):
+        if x is None or y is None:
+            return (x is not None) - (y is not None)
+        return ((x > y) - (x < y)) * (1 if order == DESC else -1)
+
+    for o1, o2, two in [(DESC, DESC, True), (ASC, DESC, True), (DESC, ASC, True), (ASC, ASC, False), (DESC, DESC, False)]:
+        def better(i, j):
+            c = cmp_opt(docs[i].get("a"), docs[j].get("a"), o1)
+            if c == 0 and two:
+                c = cmp_opt(docs[i].get("b"), docs[j].get("b"), o2)
+            if c == 0:
+                c = ((i > j) - (i < j)) * (1 if o1 == DESC else -1)
+            return c
+        want = sorted(range(len(docs)), key=functools.cmp_to_key(lambda i, j: -better(i, j)))
+        sort_fields = [("a", o1)] + ([("b", o2)] if two else [])
+        got, after, k = [], None, 37
+        while True:
+            kw = dict(max_hits=k, sort_fields=sort_fields)
+            if after is not None:
+                kw["search_after"] = after
+            resp = proto.dec_leaf_search_response(cpu_split_response_bytes(img, search_request(MATCH_ALL, **kw), dm))
+            assert resp["num_hits"] == len(docs)
+            page = resp["partial_hits"]
+            got += [h["doc_id"] for h in page]
+            if len(page) < k:
+                break
+            after = dict(page[-1])
+        assert got == want, (o1, o2, two)
+
+
+def cpu_split_response_bytes(img, req_pb, dm):
+    r = O.split_search(img, service.compile_plan(img, req_pb, dm))
+    return service.build_leaf_response(img, req_pb, dm, r.num_hits, r.hits, r.cells)
