@@ -753,3 +753,45 @@ def test_sort_keys_and_search_after_paging_against_a_python_order():
 def cpu_split_response_bytes(img, req_pb, dm):
     r = O.split_search(img, service.compile_plan(img, req_pb, dm))
     return service.build_leaf_response(img, req_pb, dm, r.num_hits, r.hits, r.cells)
+
+
+def test_phrase_queries_against_a_brute_force_over_token_positions():
+    """PhraseQuery, slop 0 (full_text mode `phrase`, full_text_query.rs:140-156; tantivy PhraseScorer + Bm25Weight::for_terms):
+    a document matches when the words occur at consecutive positions, phrase_count = number of such starts, score =
+    (sum of the words' idf) * (1 + k1) * tf_factor(fieldnorm, phrase_count). Documents and counts from a Python scan of
+    the token lists, scores from a numpy float32 restatement (rel. 1e-6)."""
+    import random
+    rng = random.Random(17)
+    vocab = ["a", "b", "c", "d"]
+    docs = [{"body": " ".join(rng.choice(vocab) for _ in range(rng.choice([2, 3, 5, 9, 20, 45])))} for _ in range(1500)]
+    mapping = {"field_mappings": [{"name": "body", "type": "text", "record": "position", "fieldnorms": True}]}
+    img = S.build_split(docs, mapping, "phrase-brute")
+    dm = json.dumps(mapping)
+    L = ffi.img_lib()
+    L.qwgpu_fieldnorm_to_id.restype = C.c_uint8
+    L.qwgpu_fieldnorm_to_id.argtypes = [C.c_uint32]
+    L.qwgpu_id_to_fieldnorm.restype = C.c_uint32
+    L.qwgpu_id_to_fieldnorm.argtypes = [C.c_uint8]
+    f32 = np.float32
+    toks = [d["body"].split() for d in docs]
+    lens = np.array([len(t) for t in toks], dtype=np.int64)
+    quant = np.array([L.qwgpu_id_to_fieldnorm(L.qwgpu_fieldnorm_to_id(int(x))) for x in lens], dtype=np.float32)
+    avg = f32(lens.sum()) / f32(len(docs))
+    k1, b = f32(1.2), f32(0.75)
+    norm = k1 * (f32(1) - b + b * quant / avg)
+    df = {w: sum(w in t for t in toks) for w in vocab}
+    idf = lambda w: np.log(f32(1) + (f32(len(docs) - df[w]) + f32(0.5)) / (f32(df[w]) + f32(0.5)), dtype=np.float32)
+    for words in (["a", "b"], ["c", "c"], ["a", "b", "c"], ["d", "a", "d"]):
+        counts = np.array([sum(t[i:i + len(words)] == words for i in range(len(t) - len(words) + 1)) for t in toks], dtype=np.float32)
+        weight = f32(0)
+        for w in words:
+            weight = weight + idf(w)
+        weight = weight * (f32(1) + k1)
+        with np.errstate(invalid="ignore"):
+            expected = np.where(counts > 0, weight * (counts / (counts + norm)), f32(0)).astype(np.float32)
+        ast = {"type": "full_text", "field": "body", "text": " ".join(words), "params": {"mode": {"type": "phrase"}}}
+        r = O.split_search(img, service.compile_plan(img, search_request(ast, max_hits=len(docs), sort_fields=[("_score", DESC)]), dm))
+        assert r.num_hits == int((counts > 0).sum()) > 0, words
+        assert sorted(h[0] for h in r.hits) == [i for i in range(len(docs)) if counts[i] > 0]
+        for h in r.hits:
+            assert abs(float(np.float32(h[4])) - float(expected[h[0]])) <= 1e-6 * float(expected[h[0]]), (words, h[0])
